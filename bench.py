@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: accepted particles / s on the batched Euclidean-distance + threshold
+path (BASELINE.json config #2: 1e6 particles x 128-dim summaries per GPU, fp64).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # CPU arm (oracle port, all cores)
+
+One "step" = one pass of the hot path over one batch of synthetic summaries:
+distances (bit-exact cdist order) + acceptance test + compaction of accepted row indices.
+`value`     : whole-job accepted particles/s with inputs resident in HBM.
+`e2e`       : same metric through the host-buffer C-ABI entry point (pinned host input,
+              H2D of the batch and D2H of distances/indices inside the timed region).
+`roofline`  : algorithmic bytes (B*D*8 read + B*8 written) / CUDA-event time of the distance
+              kernel alone, against MEASURED_PEAKS.json's HBM copy bandwidth.
+Multi-GPU: the batch shards by rows (each rank owns B particles, weak scaling); no data-path
+collective (the per-generation all-gather belongs to the SMC driver, not to this step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 1_000_000
+D = 128
+ACCEPT_Q = 0.01
+WORKLOAD = 'rejection_dist_thr_B1e6_D128_f64'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(mx)) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    return rank, local, world
+
+
+def cpu_oracle_rate(seconds_budget=12.0, threads=None, sample_rows=None):
+    """Times the oracle port (sequential-order cdist + threshold + index compaction) on the
+    host cores; returns accepted particles/s and a description of the sample."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import elfi_oracle as o
+    threads = threads or os.cpu_count() or 1
+    rows = sample_rows or min(B_PER_GPU, max(20000, 25000 * threads))
+    rs = np.random.RandomState(0)
+    S = rs.standard_normal((rows, D))
+    obs = rs.standard_normal(D)
+    d = o.cdist_euclid(S, obs, threads=threads)
+    thr = float(np.quantile(d, ACCEPT_Q))
+    reps, t_total, n_acc = 0, 0.0, 0
+    while t_total < seconds_budget and reps < 50:
+        t0 = time.perf_counter()
+        d = o.cdist_euclid(S, obs, threads=threads)
+        idx = o.accept_indices(d, thr)
+        t_total += time.perf_counter() - t0
+        n_acc = len(idx)
+        reps += 1
+    per_pass = t_total / reps
+    return {'value': n_acc / per_pass, 'unit': 'accepted particles/s', 'cores': threads,
+            'kind': 'port',
+            'sample': '{} rows x {} fp64, {} passes, oracle C port of cdist+threshold '
+                      '({} threads), evaluated {:.3e} particles/s'.format(
+                          rows, D, reps, threads, rows / per_pass),
+            'evaluated_per_s': rows / per_pass, 'rows': rows, 'ms_per_pass': per_pass * 1e3}
+
+
+def run_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import elfi_oracle as o
+    rows = min(B_PER_GPU, max(50000, 25000 * threads))
+    rs = np.random.RandomState(0)
+    S = rs.standard_normal((rows, D))
+    obs = rs.standard_normal(D)
+    d = o.cdist_euclid(S, obs, threads=threads)
+    thr = float(np.quantile(d, ACCEPT_Q))
+    for _ in range(args.warmup):
+        o.accept_indices(o.cdist_euclid(S, obs, threads=threads), thr)
+    t0 = time.perf_counter()
+    n_acc = 0
+    for _ in range(args.steps):
+        d = o.cdist_euclid(S, obs, threads=threads)
+        n_acc = len(o.accept_indices(d, thr))
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_acc / dt
+    sample = '{} rows x {} fp64 per step (bounded sample of the {}-row batch)'.format(
+        rows, D, B_PER_GPU)
+    line = {
+        'impl': 'reference', 'metric': 'accepted particles/sec', 'value': value,
+        'unit': 'accepted particles/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B_PER_GPU, 'summary_dim': D,
+                   'accept_quantile': ACCEPT_Q, 'sampled_rows': rows},
+        'evaluated_particles_per_s': rows / dt,
+        'cpu_baseline': {'value': value, 'unit': 'accepted particles/s', 'cores': threads,
+                         'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'accepted particles/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local, world = dist_env()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    from elfi_b200 import _lib, ops
+    from elfi_b200 import device as dev
+    import ctypes
+
+    B = B_PER_GPU
+    gen = torch.Generator(device='cuda').manual_seed(1234 + rank)
+    S = torch.randn(B, D, dtype=torch.float64, device='cuda', generator=gen)
+    obs = torch.randn(D, dtype=torch.float64, device='cuda',
+                      generator=torch.Generator(device='cuda').manual_seed(99))
+    d0, _ = ops.dist_euclid(S, obs)
+    thr = float(torch.quantile(d0[:200000], ACCEPT_Q))
+    thr_arr = np.array([thr], dtype=np.float64)
+    d = torch.empty(B, dtype=torch.float64, device='cuda')
+    idx = torch.empty(B, dtype=torch.int32, device='cuda')
+    n_acc = torch.zeros(1, dtype=torch.int64, device='cuda')
+    ctx = dev.context()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        _lib.call('elfi_b200_dist_euclid_thr_f64', ctx, dev.ptr(S), D, B, D, dev.ptr(obs), None, 1,
+                  dev.ptr(thr_arr), dev.ptr(d), dev.ptr(idx), dev.ptr(n_acc),
+                  ctypes.c_void_p(stream.cuda_stream))
+
+    def kernel_only():
+        _lib.call('elfi_b200_dist_euclid_thr_f64', ctx, dev.ptr(S), D, B, D, dev.ptr(obs), None, 1,
+                  dev.ptr(thr_arr), dev.ptr(d), None, None, ctypes.c_void_p(stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # dominant kernel alone (distance + mask), per launch, CUDA events on the launch stream
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    for a, b in kev:
+        a.record()
+        kernel_only()
+        b.record()
+    torch.cuda.synchronize()
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop() if rank == 0 else None
+    accepted = int(n_acc.item())
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+    acc_t = torch.tensor([accepted], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(acc_t, op=dist.ReduceOp.SUM)
+    ms_step = float(t.item()) / args.steps
+    total_acc = float(acc_t.item())
+    value = total_acc / (ms_step * 1e-3)
+    evaluated = B * world / (ms_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host input) --------------
+    e2e_steps = max(2, min(args.steps, 5))
+    S_host = torch.empty(B, D, dtype=torch.float64).pin_memory()
+    S_host.copy_(S)
+    S_np = S_host.numpy()
+    obs_np = obs.cpu().numpy()
+    d_host = torch.empty(B, dtype=torch.float64).pin_memory().numpy()
+    idx_host = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
+    n_host = ctypes.c_int64(0)
+
+    def e2e_step():
+        _lib.call('elfi_b200_dist_euclid_thr_f64_host', ctx, dev.ptr(S_np), D, B, D,
+                  dev.ptr(obs_np), None, 1, dev.ptr(thr_arr), dev.ptr(d_host), dev.ptr(idx_host),
+                  ctypes.byref(n_host))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([dt], dtype=torch.float64, device='cuda')
+    ae = torch.tensor([float(n_host.value)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ae, op=dist.ReduceOp.SUM)
+    e2e_value = float(ae.item()) / float(te.item())
+    h2d = B * D * 8 + D * 8
+    d2h = B * 8 + int(n_host.value) * 4 + 8
+
+    if rank == 0:
+        peak, how = peaks()
+        alg_bytes = B * D * 8 + B * 8
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        cpu = cpu_oracle_rate()
+        line = {
+            'metric': 'accepted particles/sec', 'value': value, 'unit': 'accepted particles/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'summary_dim': D,
+                       'accept_quantile': ACCEPT_Q, 'threshold': thr,
+                       'l2_policy': 'input (1.02 GB) larger than L2 (126 MB)',
+                       'parallelism': 'rows sharded x{}'.format(world)},
+            'evaluated_particles_per_s': evaluated, 'accepted_per_step': total_acc,
+            'gpu_launches': 2 * args.steps,
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'accepted particles/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': float(te.item()) * 1e3,
+                    'evaluated_particles_per_s': B * world / float(te.item()),
+                    'note': 'pinned host S -> chunked H2D overlapped with the kernel; '
+                            'PCIe-bound'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': None, 'peak_source': how,
+                         'kernel': 'rowstream_kernel<EuclidConsumer>',
+                         'kernel_ms': kernel_ms, 'algorithmic_bytes': alg_bytes,
+                         'frac_of_nominal_8TBs': achieved / 8000.0},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,10 @@
+"""elfi_b200 -- B200-native (sm_100a) implementation of ELFI's data-parallel hot path.
+
+The package mirrors the operator / sampler API of elfi-dev/elfi for the batched
+summary -> distance -> threshold/top-n selection -> SMC weight path and the BOLFI GP
+surrogate, with the arithmetic in hand-written CUDA reached through a C ABI
+(include/elfi_b200.h).  See DESIGN.md and INTEGRATION.md.
+"""
+__version__ = '0.1.0'
+
+from . import _lib  # noqa: F401

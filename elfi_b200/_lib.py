@@ -1,0 +1,72 @@
+"""ctypes binding of libelfi_b200.so (the C ABI declared in include/elfi_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception is
+raised.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+LIB_PATH = os.environ.get(
+    'ELFI_B200_LIB',
+    os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libelfi_b200.so'))
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_ptr = ctypes.c_void_p
+
+# name -> (argtypes); every function returns int (0 = ok) unless listed in _SPECIAL_RESTYPE
+SIGNATURES = {
+    'elfi_b200_version': [],
+    'elfi_b200_last_error': [],
+    'elfi_b200_ctx_create': [c_int, ctypes.POINTER(c_ptr)],
+    'elfi_b200_ctx_destroy': [c_ptr],
+    'elfi_b200_ctx_sm_count': [c_ptr],
+    'elfi_b200_dist_euclid_thr_f64': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,
+                                      c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'elfi_b200_dist_euclid_thr_f64_host': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,
+                                           c_ptr, c_ptr, c_ptr, c_ptr],
+}
+_SPECIAL_RESTYPE = {'elfi_b200_last_error': ctypes.c_char_p}
+_NO_STATUS = {'elfi_b200_version', 'elfi_b200_last_error', 'elfi_b200_ctx_sm_count'}
+
+
+class ElfiB200Error(RuntimeError):
+    """A call into libelfi_b200.so failed."""
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare all signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ElfiB200Error(
+            "libelfi_b200.so not found at {}. The CUDA extension must be built "
+            "(__graft_entry__.build()); elfi_b200 has no CPU fallback.".format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.argtypes = argtypes
+        fn.restype = _SPECIAL_RESTYPE.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().elfi_b200_last_error()
+    return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def call(name, *args):
+    """Call a status-returning entry point; raise ElfiB200Error on a non-zero code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name in _NO_STATUS:
+        return rc
+    if rc != 0:
+        raise ElfiB200Error('{} failed ({}): {}'.format(name, rc, last_error()))
+    return rc

@@ -1,0 +1,416 @@
+// distance.cu -- Euclidean / nested weighted distances fused with the acceptance test
+// (SURVEY.md K1, K2, K4).
+//
+// Reference semantics restated (see include/elfi_b200.h for the call sites):
+//   d[i,k] = sqrt( sum_j W[k,j] * ((S[i,j]-obs[j]) * (S[i,j]-obs[j])) ), j strictly ascending,
+// one rounding per multiply and per add (SciPy's cdist 'euclidean' with optional `w`).
+// The CUDA code uses __dmul_rn/__dadd_rn/__dsub_rn so nvcc cannot contract into FMA.
+//
+// Algorithmic traffic per particle: D*8 bytes read + K*8 bytes written (+ 1 bit of mask).
+// Roofline: HBM.  The fp64 pipe does 3 (unweighted) or 4 (weighted) issue slots per element,
+// ~20 % of the memory time at D=128 on B200, so the kernel is bandwidth bound as long as
+// the TMA pipeline keeps >= ~45 KiB in flight per SM (see rowstream.cuh).
+#include "rowstream.cuh"
+
+namespace elfi {
+
+struct DistParams {
+    const double* obs;   // (D)
+    const double* W;     // (K, D) or nullptr
+    double* d_out;       // (B, K)
+    uint32_t* mask;      // ceil(B/32) words or nullptr
+    int K;
+    int has_thr;
+    double thr[ELFI_B200_MAX_NESTED];
+};
+
+// Shared consumer area: obs padded to G*16 doubles with zeros, then W rows padded likewise.
+// Padding matters: TMA zero-fills columns >= D, obs pad 0 => (0-0)^2 = +0 is added, which
+// leaves a non-negative accumulator unchanged bit for bit.
+__device__ __forceinline__ void dist_setup_shared(uint8_t* aux, const DistParams& p, int D,
+                                                  bool weighted) {
+    const int Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    double* obs_s = reinterpret_cast<double*>(aux);
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) obs_s[j] = j < D ? p.obs[j] : 0.0;
+    if (weighted) {
+        double* w_s = obs_s + Dp;
+        for (int k = 0; k < p.K; ++k)
+            for (int j = threadIdx.x; j < Dp; j += blockDim.x)
+                w_s[size_t(k) * Dp + j] = j < D ? p.W[size_t(k) * D + j] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void dist_finish(const DistParams& p, const double* acc, int K,
+                                            int64_t row, int64_t B, int lane) {
+    bool ok = row < B;
+    if (ok) {
+        for (int k = 0; k < K; ++k) {
+            const double d = sqrt(acc[k]);
+            p.d_out[row * K + k] = d;
+            if (p.has_thr) ok = ok && (d <= p.thr[k]);
+        }
+    }
+    if (p.mask != nullptr) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok && p.has_thr);
+        if (lane == 0) p.mask[row >> 5] = bits;
+    }
+}
+
+// K = 1, unweighted: the headline kernel (config #2: 1e6 x 128).
+struct EuclidConsumer {
+    typedef DistParams Params;
+    const Params& p;
+    const double* obs_s;
+    double acc;
+
+    static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
+        dist_setup_shared(aux, p, D, false);
+    }
+    __device__ EuclidConsumer(const Params& p_, const uint8_t* aux, int, int)
+        : p(p_), obs_s(reinterpret_cast<const double*>(aux)), acc(0.0) {}
+    __device__ __forceinline__ void begin_row() { acc = 0.0; }
+    __device__ __forceinline__ void consume(int cg, const uint8_t* box_row, int sw) {
+        const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = *reinterpret_cast<const double2*>(box_row + ((c ^ sw) << 4));
+            const double2 ob = o[c];
+            const double d0 = __dsub_rn(v.x, ob.x);
+            const double d1 = __dsub_rn(v.y, ob.y);
+            acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+            acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+        }
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
+        dist_finish(p, &acc, 1, row, B, lane);
+    }
+};
+
+// 1 <= K <= KMAX weighted columns sharing one pass over S (AdaptiveDistance: the reference
+// re-reads S once per column, elfi_model.py:1150).
+template <int KMAX>
+struct NestedConsumer {
+    typedef DistParams Params;
+    const Params& p;
+    const double* obs_s;
+    const double* w_s;
+    int Dp;
+    double acc[KMAX];
+
+    static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
+        dist_setup_shared(aux, p, D, true);
+    }
+    __device__ NestedConsumer(const Params& p_, const uint8_t* aux, int D, int)
+        : p(p_), obs_s(reinterpret_cast<const double*>(aux)) {
+        Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+        w_s = obs_s + Dp;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) acc[k] = 0.0;
+    }
+    __device__ __forceinline__ void begin_row() {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) acc[k] = 0.0;
+    }
+    __device__ __forceinline__ void consume(int cg, const uint8_t* box_row, int sw) {
+        const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
+        const int K = p.K;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = *reinterpret_cast<const double2*>(box_row + ((c ^ sw) << 4));
+            const double2 ob = o[c];
+            const double d0 = __dsub_rn(v.x, ob.x);
+            const double d1 = __dsub_rn(v.y, ob.y);
+            const double s0 = __dmul_rn(d0, d0);
+            const double s1 = __dmul_rn(d1, d1);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (k < K) {
+                    const double2 w = *reinterpret_cast<const double2*>(
+                        w_s + size_t(k) * Dp + cg * RS_BOX_COLS + 2 * c);
+                    acc[k] = __dadd_rn(acc[k], __dmul_rn(w.x, s0));
+                    acc[k] = __dadd_rn(acc[k], __dmul_rn(w.y, s1));
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
+        dist_finish(p, acc, p.K, row, B, lane);
+    }
+};
+
+// Fallback for narrow (D < 16) or TMA-incompatible matrices: one thread per row, direct
+// loads.  For D <= 8 a warp still touches a contiguous span, so sectors are fully used.
+__global__ void __launch_bounds__(256)
+dist_direct_kernel(const double* __restrict__ S, int64_t ld, int64_t B, int D, DistParams p) {
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int K = p.K;
+    bool ok = row < B;
+    if (ok) {
+        const double* r = S + row * ld;
+        for (int k = 0; k < K; ++k) {
+            double acc = 0.0;
+            if (p.W != nullptr) {
+                const double* w = p.W + size_t(k) * D;
+                for (int j = 0; j < D; ++j) {
+                    const double d = __dsub_rn(__ldg(r + j), __ldg(p.obs + j));
+                    acc = __dadd_rn(acc, __dmul_rn(__ldg(w + j), __dmul_rn(d, d)));
+                }
+            } else {
+                for (int j = 0; j < D; ++j) {
+                    const double d = __dsub_rn(__ldg(r + j), __ldg(p.obs + j));
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                }
+            }
+            const double dist = sqrt(acc);
+            p.d_out[row * K + k] = dist;
+            if (p.has_thr) ok = ok && (dist <= p.thr[k]);
+        }
+    }
+    if (p.mask != nullptr) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok && p.has_thr);
+        if (lane == 0 && (row - lane) < B) p.mask[row >> 5] = bits;
+    }
+}
+
+// Mask words -> ascending accepted row indices.  CTA b owns words [b*1024, (b+1)*1024):
+// it first totals the popcounts of all earlier words (the whole mask is B/8 bytes, L2
+// resident), then scans its own and scatters.  Deterministic order, no atomics.
+__global__ void __launch_bounds__(1024)
+compact_mask_kernel(const uint32_t* __restrict__ mask, int64_t nwords, int64_t B,
+                    int32_t* __restrict__ idx, int64_t* __restrict__ n_out) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t base_s;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int wid = tid >> 5;
+    const int64_t first = int64_t(blockIdx.x) * 1024;
+
+    int64_t before = 0;
+    for (int64_t w = tid; w < first; w += 1024) before += __popc(mask[w]);
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) warp_sums[wid] = before;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t t = 0;
+        for (int i = 0; i < 32; ++i) t += warp_sums[i];
+        base_s = t;
+    }
+    __syncthreads();
+    const int64_t base = base_s;
+    __syncthreads();
+
+    const int64_t w = first + tid;
+    const uint32_t bits = w < nwords ? mask[w] : 0u;
+    const int cnt = __popc(bits);
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t v = warp_sums[lane];
+        int64_t inc2 = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) inc2 += t;
+        }
+        warp_sums[lane] = inc2 - v;  // exclusive
+        if (lane == 31 && blockIdx.x == gridDim.x - 1 && n_out != nullptr) *n_out = base + inc2;
+    }
+    __syncthreads();
+    int64_t pos = base + warp_sums[wid] + (incl - cnt);
+    if (idx != nullptr) {
+        uint32_t b = bits;
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            idx[pos++] = int32_t(w * 32 + bit);
+        }
+    }
+}
+
+int launch_compact_mask(const uint32_t* mask, int64_t B, int32_t* idx, int64_t* n_out,
+                        cudaStream_t stream) {
+    const int64_t nwords = (B + 31) / 32;
+    if (nwords == 0) {
+        if (n_out) ELFI_CUDA_OK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), stream));
+        return ELFI_B200_OK;
+    }
+    const unsigned blocks = unsigned((nwords + 1023) / 1024);
+    compact_mask_kernel<<<blocks, 1024, 0, stream>>>(mask, nwords, B, idx, n_out);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+// Distances (+ mask when thresholds are given) for a device-resident matrix.
+int launch_dist(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int64_t D,
+                const double* obs, const double* W, int64_t K, const double* thr_host,
+                double* d_out, uint32_t* mask, cudaStream_t stream) {
+    DistParams p;
+    memset(&p, 0, sizeof(p));
+    p.obs = obs;
+    p.W = W;
+    p.d_out = d_out;
+    p.mask = mask;
+    p.K = int(K);
+    p.has_thr = thr_host != nullptr;
+    if (thr_host)
+        for (int k = 0; k < K; ++k) p.thr[k] = thr_host[k];
+    if (B == 0) return ELFI_B200_OK;
+
+    const int64_t Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    const bool use_tma = D >= RS_BOX_COLS && tma_compatible(S, ldS);
+    if (use_tma) {
+        const size_t aux = size_t(Dp) * 8 * (W ? (1 + K) : 1);
+        if (rs_pick_stages(ctx->smem_optin, aux) >= 2) {
+            if (W == nullptr) return rowstream_launch<EuclidConsumer>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 2) return rowstream_launch<NestedConsumer<2>>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 4) return rowstream_launch<NestedConsumer<4>>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 8) return rowstream_launch<NestedConsumer<8>>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 16) return rowstream_launch<NestedConsumer<16>>(ctx, S, ldS, B, D, aux, p, stream);
+            return rowstream_launch<NestedConsumer<32>>(ctx, S, ldS, B, D, aux, p, stream);
+        }
+    }
+    const unsigned blocks = unsigned((B + 255) / 256);
+    dist_direct_kernel<<<blocks, 256, 0, stream>>>(S, ldS, B, int(D), p);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+static int check_dist_args(const void* S, int64_t ldS, int64_t B, int64_t D, const void* obs,
+                           const void* W, int64_t K, const void* thr, const void* acc_idx) {
+    ELFI_REQUIRE(B >= 0 && D >= 1, "dist: bad shape B=%lld D=%lld", (long long)B, (long long)D);
+    ELFI_REQUIRE(B == 0 || S != nullptr, "dist: S is NULL");
+    ELFI_REQUIRE(obs != nullptr, "dist: obs is NULL");
+    ELFI_REQUIRE(ldS >= D, "dist: ldS (%lld) < D (%lld)", (long long)ldS, (long long)D);
+    ELFI_REQUIRE(K >= 1 && K <= ELFI_B200_MAX_NESTED, "dist: K=%lld outside [1, %d]",
+                 (long long)K, ELFI_B200_MAX_NESTED);
+    ELFI_REQUIRE(W != nullptr || K == 1, "dist: K=%lld needs a weight matrix", (long long)K);
+    ELFI_REQUIRE(acc_idx == nullptr || thr != nullptr, "dist: acc_idx requires thresholds");
+    ELFI_REQUIRE(B < (int64_t(1) << 31), "dist: B must fit int32 row indices");
+    return ELFI_B200_OK;
+}
+
+}  // namespace elfi
+
+extern "C" {
+
+int elfi_b200_dist_euclid_thr_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                  int64_t D, const double* obs, const double* W, int64_t K,
+                                  const double* thr_host, double* d_out, int32_t* acc_idx,
+                                  int64_t* n_acc, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "dist: ctx is NULL");
+    int rc = check_dist_args(S, ldS, B, D, obs, W, K, thr_host, acc_idx);
+    if (rc) return rc;
+    ELFI_REQUIRE(B == 0 || d_out != nullptr, "dist: d_out is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    uint32_t* mask = nullptr;
+    if (thr_host != nullptr) {
+        const size_t nwords = size_t((B + 31) / 32);
+        mask = static_cast<uint32_t*>(ctx_scratch(ctx, nwords * 4 + 256));
+        if (!mask) return ELFI_B200_ERR_NOMEM;
+    }
+    rc = launch_dist(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, mask, stream);
+    if (rc) return rc;
+    if (thr_host != nullptr && (acc_idx != nullptr || n_acc != nullptr))
+        return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_dist_euclid_thr_f64_host(elfi_b200_ctx* ctx, const double* S_host, int64_t ldS,
+                                       int64_t B, int64_t D, const double* obs_host,
+                                       const double* W_host, int64_t K, const double* thr_host,
+                                       double* d_out_host, int32_t* acc_idx_host,
+                                       int64_t* n_acc_host) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "dist_host: ctx is NULL");
+    int rc = check_dist_args(S_host, ldS, B, D, obs_host, W_host, K, thr_host, acc_idx_host);
+    if (rc) return rc;
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+
+    // Device staging: two row chunks (ping-pong), obs, W, distances, mask, indices, count.
+    const int64_t row_bytes = D * 8;
+    int64_t chunk_rows = (int64_t(32) << 20) / row_bytes;
+    chunk_rows = (chunk_rows / 32) * 32;
+    if (chunk_rows < 32) chunk_rows = 32;
+    if (chunk_rows > B) chunk_rows = ((B + 31) / 32) * 32;
+    const size_t chunk_bytes = size_t(chunk_rows) * row_bytes;
+    const size_t nwords = size_t((B + 31) / 32);
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t off_chunk1 = align(chunk_bytes);
+    const size_t off_obs = off_chunk1 + align(chunk_bytes);
+    const size_t off_w = off_obs + align(size_t(D) * 8);
+    const size_t off_d = off_w + align(size_t(K) * D * 8);
+    const size_t off_mask = off_d + align(size_t(B) * K * 8);
+    const size_t off_idx = off_mask + align(nwords * 4 + 4);
+    const size_t off_n = off_idx + align(size_t(B) * 4 + 4);
+    const size_t total = off_n + 256;
+    if (total > ctx->dev_stage_bytes) {
+        ELFI_CUDA_OK(cudaDeviceSynchronize());
+        if (ctx->dev_stage) ELFI_CUDA_OK(cudaFree(ctx->dev_stage));
+        ctx->dev_stage = nullptr;
+        ctx->dev_stage_bytes = 0;
+        ELFI_CUDA_OK(cudaMalloc(&ctx->dev_stage, total));
+        ctx->dev_stage_bytes = total;
+    }
+    uint8_t* base = static_cast<uint8_t*>(ctx->dev_stage);
+    double* chunk[2] = {reinterpret_cast<double*>(base), reinterpret_cast<double*>(base + off_chunk1)};
+    double* obs_d = reinterpret_cast<double*>(base + off_obs);
+    double* w_d = W_host ? reinterpret_cast<double*>(base + off_w) : nullptr;
+    double* d_d = reinterpret_cast<double*>(base + off_d);
+    uint32_t* mask_d = thr_host ? reinterpret_cast<uint32_t*>(base + off_mask) : nullptr;
+    int32_t* idx_d = reinterpret_cast<int32_t*>(base + off_idx);
+    int64_t* n_d = reinterpret_cast<int64_t*>(base + off_n);
+
+    cudaStream_t s0 = ctx->copy_stream[0], s1 = ctx->copy_stream[1];
+    ELFI_CUDA_OK(cudaMemcpyAsync(obs_d, obs_host, size_t(D) * 8, cudaMemcpyHostToDevice, s0));
+    if (W_host)
+        ELFI_CUDA_OK(cudaMemcpyAsync(w_d, W_host, size_t(K) * D * 8, cudaMemcpyHostToDevice, s0));
+    ELFI_CUDA_OK(cudaEventRecord(ctx->copy_event[0], s0));
+    ELFI_CUDA_OK(cudaStreamWaitEvent(s1, ctx->copy_event[0], 0));
+
+    int which = 0;
+    for (int64_t r0 = 0; r0 < B; r0 += chunk_rows, which ^= 1) {
+        const int64_t rows = (B - r0) < chunk_rows ? (B - r0) : chunk_rows;
+        cudaStream_t st = which ? s1 : s0;
+        if (ldS == D) {
+            ELFI_CUDA_OK(cudaMemcpyAsync(chunk[which], S_host + r0 * ldS, size_t(rows) * row_bytes,
+                                         cudaMemcpyHostToDevice, st));
+        } else {
+            ELFI_CUDA_OK(cudaMemcpy2DAsync(chunk[which], size_t(row_bytes), S_host + r0 * ldS,
+                                           size_t(ldS) * 8, size_t(row_bytes), size_t(rows),
+                                           cudaMemcpyHostToDevice, st));
+        }
+        rc = launch_dist(ctx, chunk[which], D, rows, D, obs_d, w_d, K, thr_host, d_d + r0 * K,
+                         mask_d ? mask_d + r0 / 32 : nullptr, st);
+        if (rc) return rc;
+    }
+    // join s1 into s0, compact, copy back
+    ELFI_CUDA_OK(cudaEventRecord(ctx->copy_event[1], s1));
+    ELFI_CUDA_OK(cudaStreamWaitEvent(s0, ctx->copy_event[1], 0));
+    ELFI_CUDA_OK(cudaEventRecord(ctx->copy_event[2], s0));
+    ELFI_CUDA_OK(cudaStreamWaitEvent(s1, ctx->copy_event[2], 0));
+    if (d_out_host && B > 0)
+        ELFI_CUDA_OK(cudaMemcpyAsync(d_out_host, d_d, size_t(B) * K * 8, cudaMemcpyDeviceToHost, s1));
+    int64_t n_acc = 0;
+    if (thr_host != nullptr) {
+        rc = launch_compact_mask(mask_d, B, acc_idx_host ? idx_d : nullptr, n_d, s0);
+        if (rc) return rc;
+        ELFI_CUDA_OK(cudaMemcpyAsync(&n_acc, n_d, 8, cudaMemcpyDeviceToHost, s0));
+        ELFI_CUDA_OK(cudaStreamSynchronize(s0));
+        if (acc_idx_host && n_acc > 0)
+            ELFI_CUDA_OK(cudaMemcpyAsync(acc_idx_host, idx_d, size_t(n_acc) * 4,
+                                         cudaMemcpyDeviceToHost, s0));
+        if (n_acc_host) *n_acc_host = n_acc;
+    }
+    ELFI_CUDA_OK(cudaStreamSynchronize(s0));
+    ELFI_CUDA_OK(cudaStreamSynchronize(s1));
+    return ELFI_B200_OK;
+}
+
+}  // extern "C"

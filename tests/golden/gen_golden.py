@@ -1,0 +1,155 @@
+"""Generate the golden fixtures from the UNMODIFIED reference (/root/reference).
+
+Run in the build container only (the reference is not present on the GPU box):
+
+    python tests/golden/gen_golden.py
+
+Writes tests/golden/*.npz / *.json.  The reference is imported through oracle/ref_shim.py
+(stubs for packages that are absent here and that the sampler path never touches).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+from ref_shim import import_reference  # noqa: E402
+
+elfi = import_reference()
+from elfi.examples import gauss, ma2  # noqa: E402
+from elfi.methods.utils import (GMDistribution, weighted_sample_quantile,  # noqa: E402
+                                weighted_var)
+from elfi.model.extensions import ModelPrior  # noqa: E402
+from elfi.utils import get_sub_seed  # noqa: E402
+
+
+def save(name, **arrays):
+    np.savez(os.path.join(HERE, name + '.npz'), **arrays)
+    print('wrote', name, {k: np.shape(v) for k, v in arrays.items()})
+
+
+def sample_arrays(res, prefix=''):
+    out = {prefix + 'threshold': np.float64(res.threshold), prefix + 'n_sim': np.int64(res.n_sim),
+           prefix + 'n_batches': np.int64(res.n_batches)}
+    for k, v in res.outputs.items():
+        out[prefix + 'out_' + k] = np.asarray(v)
+    if getattr(res, 'weights', None) is not None:
+        out[prefix + 'weights'] = np.asarray(res.weights)
+    return out
+
+
+def main():
+    meta = {'numpy': np.__version__}
+    import scipy
+    meta['scipy'] = scipy.__version__
+
+    # --- sub seeds (elfi/utils.py:71-127)
+    meta['sub_seeds_123'] = [int(get_sub_seed(123, i)) for i in range(8)]
+    meta['sub_seeds_1_hi'] = [int(get_sub_seed(1, i)) for i in (10, 100, 1000)]
+
+    # --- MA2 forward pass (elfi_model.py:265-299 generate)
+    m = ma2.get_model(seed_obs=4)
+    gen = m.generate(1000, ['t1', 't2', 'MA2', 'S1', 'S2', 'd'], seed=123)
+    save('ma2_generate', observed_MA2=np.asarray(m.observed['MA2']),
+         obs_S1=np.asarray(m['S1'].observed), obs_S2=np.asarray(m['S2'].observed),
+         **{k: np.asarray(v) for k, v in gen.items()})
+
+    # --- config #1: Rejection quantile / threshold / n_sim modes
+    r = elfi.Rejection(m['d'], batch_size=1000, seed=123).sample(100, quantile=0.01, bar=False)
+    save('ma2_rejection_quantile', **sample_arrays(r))
+    r = elfi.Rejection(m['d'], batch_size=1000, seed=123).sample(150, threshold=0.2, bar=False)
+    save('ma2_rejection_threshold', **sample_arrays(r))
+    r = elfi.Rejection(m['d'], batch_size=500, seed=7, output_names=['S1', 'S2']).sample(
+        64, n_sim=3000, bar=False)
+    save('ma2_rejection_nsim', **sample_arrays(r))
+
+    # --- SMC with quantiles and thresholds
+    s = elfi.SMC(m['d'], batch_size=1000, seed=123).sample(200, quantiles=[.5, .5, .5], bar=False)
+    arrs = sample_arrays(s)
+    for i, pop in enumerate(s.populations):
+        arrs.update(sample_arrays(pop, 'pop{}_'.format(i)))
+        arrs['pop{}_cov'.format(i)] = np.asarray(pop.cov)
+    arrs['n_pops'] = np.int64(len(s.populations))
+    save('ma2_smc_quantiles', **arrs)
+    s = elfi.SMC(m['d'], batch_size=1000, seed=20).sample(150, thresholds=[.6, .3, .15], bar=False)
+    arrs = sample_arrays(s)
+    for i, pop in enumerate(s.populations):
+        arrs.update(sample_arrays(pop, 'pop{}_'.format(i)))
+        arrs['pop{}_cov'.format(i)] = np.asarray(pop.cov)
+    arrs['n_pops'] = np.int64(len(s.populations))
+    save('ma2_smc_thresholds', **arrs)
+
+    # --- AdaptiveDistanceSMC on MA2
+    m2 = ma2.get_model(seed_obs=4)
+    m2['d'].become(elfi.AdaptiveDistance(m2['S1'], m2['S2']))
+    ad = elfi.AdaptiveDistanceSMC(m2['d'], batch_size=500, seed=11)
+    s = ad.sample(100, rounds=3, quantile=0.5, bar=False)
+    arrs = sample_arrays(s)
+    for i, pop in enumerate(s.populations):
+        arrs.update(sample_arrays(pop, 'pop{}_'.format(i)))
+        arrs['pop{}_cov'.format(i)] = np.asarray(pop.cov)
+        arrs['pop{}_w'.format(i)] = np.asarray(
+            pop.adaptive_distance_w if pop.adaptive_distance_w is not None else np.nan)
+    arrs['n_pops'] = np.int64(len(s.populations))
+    save('ma2_adaptive_distance_smc', **arrs)
+
+    # --- Gaussian model forward pass + SMC
+    g = gauss.get_model(n_obs=50, seed_obs=3)
+    gen = g.generate(500, ['mu', 'sigma', 'gauss', 'ss_mean', 'ss_var', 'd'], seed=5)
+    save('gauss_generate', observed_gauss=np.asarray(g.observed['gauss']),
+         obs_ss_mean=np.asarray(g['ss_mean'].observed), obs_ss_var=np.asarray(g['ss_var'].observed),
+         **{k: np.asarray(v) for k, v in gen.items()})
+    s = elfi.SMC(g['d'], batch_size=1000, seed=9).sample(300, quantiles=[.3, .3, .3], bar=False)
+    arrs = sample_arrays(s)
+    for i, pop in enumerate(s.populations):
+        arrs.update(sample_arrays(pop, 'pop{}_'.format(i)))
+        arrs['pop{}_cov'.format(i)] = np.asarray(pop.cov)
+    arrs['n_pops'] = np.int64(len(s.populations))
+    save('gauss_smc_quantiles', **arrs)
+
+    # --- utilities: known-answer vectors (tests/unit/test_utils.py:64-121 in the reference)
+    rs = np.random.RandomState(42)
+    x = rs.randn(5000)
+    w = rs.rand(5000)
+    qs = np.array([0.0, 0.01, 0.25, 0.5, 0.9, 1.0])
+    save('weighted_quantile', x=x, w=w, alphas=qs,
+         q_w=np.array([weighted_sample_quantile(x, a, w) for a in qs]),
+         q_unw=np.array([weighted_sample_quantile(x, a) for a in qs]))
+    x2 = rs.randn(4000, 3) * np.array([1., 5., .1]) + np.array([0., 3., -2.])
+    w2 = rs.rand(4000)
+    save('weighted_var', x=x2, w=w2, var_w=weighted_var(x2, w2), var_unw=weighted_var(x2))
+
+    means = rs.randn(300, 2) * .5
+    wts = rs.rand(300)
+    cov = np.diag([0.3, 0.05])
+    pts = rs.randn(400, 2)
+    save('gm_logpdf', means=means, weights=wts, cov=cov, x=pts,
+         logpdf=GMDistribution.logpdf(pts, means, cov, wts),
+         pdf=GMDistribution.pdf(pts, means, cov, wts))
+    cov_full = np.array([[0.3, 0.1], [0.1, 0.2]])
+    save('gm_logpdf_fullcov', means=means, weights=wts, cov=cov_full, x=pts,
+         logpdf=GMDistribution.logpdf(pts, means, cov_full, wts))
+
+    # ModelPrior.logpdf on MA2 (extensions.py:180-211)
+    prior = ModelPrior(m)
+    theta = np.column_stack([rs.uniform(-2.5, 2.5, 500), rs.uniform(-1.5, 1.5, 500)])
+    with np.errstate(divide='ignore'):
+        lp = prior.logpdf(theta)
+    save('ma2_prior_logpdf', theta=theta, logpdf=lp)
+    gprior = ModelPrior(g)
+    theta = np.column_stack([rs.uniform(-3, 11, 500), rs.uniform(-1, 12, 500)])
+    with np.errstate(divide='ignore'):
+        lp = gprior.logpdf(theta)
+    save('gauss_prior_logpdf', theta=theta, logpdf=lp)
+
+    with open(os.path.join(HERE, 'meta.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+    print(meta)
+
+
+if __name__ == '__main__':
+    main()
