@@ -59,6 +59,7 @@ __device__ __forceinline__ void dist_finish(const DistParams& p, const double* a
 // K = 1, unweighted: the headline kernel (config #2: 1e6 x 128).
 struct EuclidConsumer {
     typedef DistParams Params;
+    static constexpr int PASSES = 1;
     const Params& p;
     const double* obs_s;
     double acc;
@@ -69,7 +70,7 @@ struct EuclidConsumer {
     __device__ EuclidConsumer(const Params& p_, const uint8_t* aux, int, int)
         : p(p_), obs_s(reinterpret_cast<const double*>(aux)), acc(0.0) {}
     __device__ __forceinline__ void begin_row() { acc = 0.0; }
-    __device__ __forceinline__ void consume(int cg, const uint8_t* box_row, int sw) {
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
         const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -91,6 +92,7 @@ struct EuclidConsumer {
 template <int KMAX>
 struct NestedConsumer {
     typedef DistParams Params;
+    static constexpr int PASSES = 1;
     const Params& p;
     const double* obs_s;
     const double* w_s;
@@ -111,7 +113,7 @@ struct NestedConsumer {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) acc[k] = 0.0;
     }
-    __device__ __forceinline__ void consume(int cg, const uint8_t* box_row, int sw) {
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
         const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
         const int K = p.K;
 #pragma unroll

@@ -59,9 +59,12 @@ inline int rs_pick_stages(size_t smem_optin, size_t aux_bytes) {
 //   struct Params;                                    // POD passed by value to the kernel
 //   static void setup_shared(uint8_t* aux, const Params&, int D);   // CTA-cooperative
 //   Consumer(const Params&, const uint8_t* aux, int D, int lane);
+//   static constexpr int PASSES;                      // times a tile's boxes are streamed
 //   void begin_row();
-//   void consume(int cg, const uint8_t* box_row, int sw);  // 16 columns of this lane's row
+//   void consume(int pass, int cg, const uint8_t* box_row, int sw);  // 16 columns of my row
 //   void end_row(int64_t row, int64_t B, int lane);   // row may be >= B (zero-filled tile)
+// With PASSES > 1 a tile's column groups are requested again right after the first sweep
+// (second sweep hits L2: a tile is at most a few tens of KiB), e.g. mean then variance.
 template <class Consumer>
 __global__ void __launch_bounds__(RS_WARPS * 32, 1)
 rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int ns,
@@ -84,7 +87,8 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
     }
     __syncthreads();  // setup_shared visible; barriers initialised
 
-    const int G = (D + RS_BOX_COLS - 1) / RS_BOX_COLS;
+    const int Gc = (D + RS_BOX_COLS - 1) / RS_BOX_COLS;   // column groups per sweep
+    const int G = Gc * Consumer::PASSES;                  // boxes per tile
     const int64_t ntiles = (B + RS_BOX_ROWS - 1) / RS_BOX_ROWS;
     const int64_t gw = int64_t(blockIdx.x) * RS_WARPS + warp;
     const int64_t GW = int64_t(gridDim.x) * RS_WARPS;
@@ -94,14 +98,16 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
     // producer cursor (lane 0 only): next box to request
     int64_t p_tile = gw;
     int p_cg = 0;
+    int p_col = 0;
     int64_t p_q = 0;
     int p_s = 0;
     auto issue = [&]() {
         mbar_arrive_expect_tx(bar0 + p_s * 8, RS_BOX_BYTES);
-        tma_load_2d(box0 + p_s * RS_BOX_BYTES, &map, p_cg * RS_BOX_COLS,
+        tma_load_2d(box0 + p_s * RS_BOX_BYTES, &map, p_col * RS_BOX_COLS,
                     int32_t(p_tile * RS_BOX_ROWS), bar0 + p_s * 8);
         ++p_q;
         if (++p_s == ns) p_s = 0;
+        if (++p_col == Gc) p_col = 0;
         if (++p_cg == G) { p_cg = 0; p_tile += GW; }
     };
     if (lane == 0) {
@@ -116,15 +122,18 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
     int s = 0;
     uint32_t parity = 0;
     int cg = 0;
+    int col = 0;
+    int pass = 0;
     int64_t tile = gw;
     for (int64_t q = 0; q < nbox; ++q) {
         mbar_wait(bar0 + s * 8, parity);
         if (cg == 0) c.begin_row();
-        c.consume(cg, box0_generic + size_t(s) * RS_BOX_BYTES + row_off, sw);
+        c.consume(pass, col, box0_generic + size_t(s) * RS_BOX_BYTES + row_off, sw);
         __syncwarp();
         if (lane == 0 && p_q < nbox) issue();
         if (cg == G - 1) c.end_row(tile * RS_BOX_ROWS + lane, B, lane);
-        if (++cg == G) { cg = 0; tile += GW; }
+        if (++col == Gc) { col = 0; ++pass; }
+        if (++cg == G) { cg = 0; pass = 0; tile += GW; }
         if (++s == ns) { s = 0; parity ^= 1; }
     }
 }

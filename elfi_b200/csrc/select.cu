@@ -1,0 +1,439 @@
+// select.cu -- ordering primitives of the sampler bookkeeping:
+//   * stable LSD radix sort of (fp64 key, int32 index) pairs  -> np.argsort replacement used by
+//     Rejection._merge_batch (samplers.py:232-237) and weighted_sample_quantile (utils.py:397);
+//   * row gather (the fancy-index permutation `v[:] = v[sort_mask]`, samplers.py:236-237, and
+//     `batch[node][accepted]`, samplers.py:228-230);
+//   * weighted sample quantile (methods/utils.py:379-411).
+//
+// Keys are distances (>= 0, possibly +inf / NaN).  They are mapped to order-preserving uint64
+// (NaN last, like NumPy) and sorted 8 bits per pass.  All working sets at the BASELINE sizes
+// (<= 2e6 pairs = 24 MB) are L2 resident, so the sort is latency/issue bound, not HBM bound;
+// passes whose digit is constant over all keys (typical for the high exponent bits of
+// distances) degenerate to a copy.
+#include "common.cuh"
+
+namespace elfi {
+
+constexpr int SORT_CHUNK = 1024;   // keys per warp sub-chunk
+constexpr int SORT_WARPS = 8;      // warps per block
+
+__device__ __forceinline__ uint64_t key_to_u64(double d) {
+    if (d != d) return ~uint64_t(0);                 // NaN sorts last
+    uint64_t u = static_cast<uint64_t>(__double_as_longlong(d));
+    return (u >> 63) ? ~u : (u | (uint64_t(1) << 63));
+}
+__device__ __forceinline__ double u64_to_key(uint64_t u) {
+    if (u == ~uint64_t(0)) return __longlong_as_double(0x7ff8000000000000LL);
+    u = (u >> 63) ? (u & ~(uint64_t(1) << 63)) : ~u;
+    return __longlong_as_double(static_cast<long long>(u));
+}
+
+// keys -> u64, vals -> iota, and the 8 x 256 global digit histograms in one read.
+__global__ void __launch_bounds__(256)
+sort_prepare_kernel(const double* __restrict__ keys, int64_t n, uint64_t* __restrict__ ukeys,
+                    int32_t* __restrict__ vals, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t h[8 * 256];
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t u = key_to_u64(keys[i]);
+        ukeys[i] = u;
+        vals[i] = int32_t(i);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&h[p * 256 + ((u >> (8 * p)) & 255)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x)
+        if (h[i]) atomicAdd(&ghist[i], h[i]);
+}
+
+// A pass is trivial when one bin of its histogram holds all n keys.
+__device__ __forceinline__ bool pass_trivial(const uint32_t* ghist, int pass, int64_t n,
+                                             uint64_t first_key) {
+    return ghist[pass * 256 + ((first_key >> (8 * pass)) & 255)] == uint32_t(n);
+}
+
+// Per-warp digit counts of each sub-chunk, written digit-major: whist[digit * nw + warp].
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+sort_upsweep_kernel(const uint64_t* __restrict__ ukeys, int64_t n, int pass, int64_t nw,
+                    const uint32_t* __restrict__ ghist, uint32_t* __restrict__ whist) {
+    if (pass_trivial(ghist, pass, n, ukeys[0])) return;
+    __shared__ uint32_t h[SORT_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gw = int64_t(blockIdx.x) * SORT_WARPS + warp;
+    for (int i = lane; i < 256; i += 32) h[warp][i] = 0;
+    __syncwarp();
+    if (gw < nw) {
+        const int64_t lo = gw * SORT_CHUNK;
+        const int64_t hi = (lo + SORT_CHUNK < n) ? lo + SORT_CHUNK : n;
+        for (int64_t i = lo + lane; i < hi; i += 32)
+            atomicAdd(&h[warp][(ukeys[i] >> (8 * pass)) & 255], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) whist[int64_t(d) * nw + gw] = h[warp][d];
+    }
+}
+
+// Block d turns whist[d * nw + *] into global start offsets for digit d.
+__global__ void __launch_bounds__(1024)
+sort_scan_kernel(const uint64_t* __restrict__ ukeys, int64_t n, int pass, int64_t nw,
+                 const uint32_t* __restrict__ ghist, uint32_t* __restrict__ whist) {
+    if (pass_trivial(ghist, pass, n, ukeys[0])) return;
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // base = number of keys with a smaller digit
+    uint32_t part = 0;
+    for (int i = tid; i < d; i += 1024) part += ghist[pass * 256 + i];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) warp_tot[wid] = part;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 32; ++i) t += warp_tot[i];
+        carry_s = t;
+    }
+    __syncthreads();
+    uint32_t* row = whist + int64_t(d) * nw;
+    for (int64_t base = 0; base < nw; base += 1024) {
+        const int64_t i = base + tid;
+        const uint32_t v = i < nw ? row[i] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();  // warp_tot / carry_s reads of the previous round are done
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int k = 0; k < wid; ++k) woff += warp_tot[k];
+        const uint32_t carry = carry_s;
+        if (i < nw) row[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+    }
+}
+
+// Stable scatter: each warp walks its sub-chunk in order; equal digits keep their order
+// (match_any groups + rank by lane id).  Trivial passes copy.
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+sort_scatter_kernel(const uint64_t* __restrict__ kin, const int32_t* __restrict__ vin, int64_t n,
+                    int pass, int64_t nw, const uint32_t* __restrict__ ghist,
+                    const uint32_t* __restrict__ whist, uint64_t* __restrict__ kout,
+                    int32_t* __restrict__ vout) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gw = int64_t(blockIdx.x) * SORT_WARPS + warp;
+    if (gw >= nw) return;
+    const int64_t lo = gw * SORT_CHUNK;
+    const int64_t hi = (lo + SORT_CHUNK < n) ? lo + SORT_CHUNK : n;
+    if (pass_trivial(ghist, pass, n, kin[0])) {
+        for (int64_t i = lo + lane; i < hi; i += 32) {
+            kout[i] = kin[i];
+            vout[i] = vin[i];
+        }
+        return;
+    }
+    __shared__ uint32_t off[SORT_WARPS][256];
+    for (int d = lane; d < 256; d += 32) off[warp][d] = whist[int64_t(d) * nw + gw];
+    __syncwarp();
+    for (int64_t base = lo; base < hi; base += 32) {
+        const int64_t i = base + lane;
+        const bool valid = i < hi;
+        const uint64_t k = valid ? kin[i] : 0;
+        const int32_t v = valid ? vin[i] : 0;
+        const uint32_t digit = valid ? uint32_t((k >> (8 * pass)) & 255) : 256u + lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t pos = 0;
+        if (valid) pos = off[warp][digit] + rank;
+        __syncwarp();
+        if (valid && rank == 0) off[warp][digit] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            kout[pos] = k;
+            vout[pos] = v;
+        }
+    }
+}
+
+__global__ void sort_finish_kernel(const uint64_t* __restrict__ ukeys, const int32_t* __restrict__ vals,
+                                   int64_t n, double* __restrict__ keys_out,
+                                   int32_t* __restrict__ perm_out) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (keys_out) keys_out[i] = u64_to_key(ukeys[i]);
+        if (perm_out) perm_out[i] = vals[i];
+    }
+}
+
+struct SortScratch {
+    uint64_t* k[2];
+    int32_t* v[2];
+    uint32_t* ghist;
+    uint32_t* whist;
+    int64_t nw;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+static size_t sort_scratch_bytes(int64_t n) {
+    const int64_t nw = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    return 2 * align256(size_t(n) * 8) + 2 * align256(size_t(n) * 4) + align256(8 * 256 * 4) +
+           align256(size_t(256) * nw * 4);
+}
+
+static SortScratch carve_sort(uint8_t* base, int64_t n) {
+    SortScratch s;
+    s.nw = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    size_t o = 0;
+    for (int i = 0; i < 2; ++i) { s.k[i] = reinterpret_cast<uint64_t*>(base + o); o += align256(size_t(n) * 8); }
+    for (int i = 0; i < 2; ++i) { s.v[i] = reinterpret_cast<int32_t*>(base + o); o += align256(size_t(n) * 4); }
+    s.ghist = reinterpret_cast<uint32_t*>(base + o); o += align256(8 * 256 * 4);
+    s.whist = reinterpret_cast<uint32_t*>(base + o);
+    return s;
+}
+
+// Sorts ascending; results are left in s.k[0] / s.v[0] (8 passes = even number of swaps).
+int sort_pairs_device(const double* keys, int64_t n, const SortScratch& s, int sm_count,
+                      cudaStream_t stream) {
+    ELFI_CUDA_OK(cudaMemsetAsync(s.ghist, 0, 8 * 256 * 4, stream));
+    int blocks = int((n + 256 * 8 - 1) / (256 * 8));
+    if (blocks > sm_count * 4) blocks = sm_count * 4;
+    if (blocks < 1) blocks = 1;
+    sort_prepare_kernel<<<blocks, 256, 0, stream>>>(keys, n, s.k[0], s.v[0], s.ghist);
+    const unsigned wblocks = unsigned((s.nw + SORT_WARPS - 1) / SORT_WARPS);
+    int cur = 0;
+    for (int pass = 0; pass < 8; ++pass) {
+        sort_upsweep_kernel<<<wblocks, SORT_WARPS * 32, 0, stream>>>(s.k[cur], n, pass, s.nw, s.ghist, s.whist);
+        sort_scan_kernel<<<256, 1024, 0, stream>>>(s.k[cur], n, pass, s.nw, s.ghist, s.whist);
+        sort_scatter_kernel<<<wblocks, SORT_WARPS * 32, 0, stream>>>(
+            s.k[cur], s.v[cur], n, pass, s.nw, s.ghist, s.whist, s.k[cur ^ 1], s.v[cur ^ 1]);
+        cur ^= 1;
+    }
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+// dst[i, 0:width] = src[idx[i], 0:width]
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const double* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ idx,
+                   int64_t n, int64_t width, double* __restrict__ dst, int64_t ld_dst) {
+    const int64_t total = n * width;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / width, j = t - i * width;
+        dst[i * ld_dst + j] = src[int64_t(idx[i]) * ld_src + j];
+    }
+}
+
+// Two-source gather for the running top-n merge: logical row r < nA is A[r], otherwise
+// B[mapB ? mapB[r - nA] : r - nA]  (B = the new batch, mapB = its accepted row indices).
+__global__ void __launch_bounds__(256)
+gather2_rows_kernel(const double* __restrict__ A, int64_t ldA, int64_t nA,
+                    const double* __restrict__ Bm, int64_t ldB, const int32_t* __restrict__ mapB,
+                    const int32_t* __restrict__ perm, int64_t n, int64_t width,
+                    double* __restrict__ dst, int64_t ld_dst) {
+    const int64_t total = n * width;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / width, j = t - i * width;
+        const int64_t r = perm ? perm[i] : i;
+        double v;
+        if (r < nA) {
+            v = A[r * ldA + j];
+        } else {
+            const int64_t rb = mapB ? int64_t(mapB[r - nA]) : (r - nA);
+            v = Bm[rb * ldB + j];
+        }
+        dst[i * ld_dst + j] = v;
+    }
+}
+
+// ---- weighted quantile ---------------------------------------------------------------------
+// partial[b] = sum of w[perm[i]] over block b's 4096-element slice (w == NULL -> ones)
+__global__ void __launch_bounds__(1024)
+wq_block_sums_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm, int64_t n,
+                     double* __restrict__ partial) {
+    __shared__ double ws[32];
+    const int64_t lo = int64_t(blockIdx.x) * 4096;
+    double acc = 0.0;
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = lo + k * 1024 + threadIdx.x;
+        if (i < n) acc += w ? w[perm[i]] : 1.0;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = ws[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
+// exclusive scan of the block sums (single block) + total in partial[nb]
+__global__ void __launch_bounds__(1024)
+wq_scan_partials_kernel(double* __restrict__ partial, int64_t nb, int32_t* __restrict__ count) {
+    __shared__ double ws[32];
+    __shared__ double carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { carry_s = 0.0; *count = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += 1024) {
+        const int64_t i = base + tid;
+        const double v = i < nb ? partial[i] : 0.0;
+        double incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) ws[wid] = incl;
+        __syncthreads();
+        double woff = 0.0;
+        for (int k = 0; k < wid; ++k) woff += ws[k];
+        const double carry = carry_s;
+        if (i < nb) partial[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) partial[nb] = carry_s;
+}
+
+// count of k in [0, n-2] whose normalised inclusive prefix sum is < alpha
+__global__ void __launch_bounds__(1024)
+wq_count_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm, int64_t n,
+                const double* __restrict__ partial, int64_t nb, double alpha,
+                int32_t* __restrict__ count) {
+    __shared__ double ws[32];
+    __shared__ double carry_s;
+    __shared__ int cnt_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double total = partial[nb];
+    if (tid == 0) { carry_s = partial[blockIdx.x]; cnt_s = 0; }
+    __syncthreads();
+    int local = 0;
+    const int64_t lo = int64_t(blockIdx.x) * 4096;
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = lo + k * 1024 + tid;
+        const double v = i < n ? (w ? w[perm[i]] : 1.0) : 0.0;
+        double incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) ws[wid] = incl;
+        __syncthreads();
+        double woff = 0.0;
+        for (int q = 0; q < wid; ++q) woff += ws[q];
+        const double carry = carry_s;
+        const double c = (carry + woff + incl) / total;
+        if (i < n - 1 && c < alpha) ++local;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&cnt_s, local);
+    __syncthreads();
+    if (tid == 0 && cnt_s) atomicAdd(count, cnt_s);
+}
+
+__global__ void wq_pick_kernel(const uint64_t* __restrict__ ukeys, const int32_t* __restrict__ count,
+                               int64_t n, double alpha, double* __restrict__ out) {
+    int64_t idx = alpha == 0.0 ? 0 : int64_t(*count);
+    if (idx > n - 1) idx = n - 1;
+    out[0] = u64_to_key(ukeys[idx]);
+    out[1] = double(idx);
+}
+
+}  // namespace elfi
+
+extern "C" {
+
+int elfi_b200_sort_pairs_f64(elfi_b200_ctx* ctx, const double* keys, int64_t n,
+                             double* keys_sorted, int32_t* perm, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "sort: ctx is NULL");
+    ELFI_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "sort: n=%lld out of range", (long long)n);
+    if (n == 0) return ELFI_B200_OK;
+    ELFI_REQUIRE(keys != nullptr, "sort: keys is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, sort_scratch_bytes(n)));
+    if (!base) return ELFI_B200_ERR_NOMEM;
+    SortScratch s = carve_sort(base, n);
+    int rc = sort_pairs_device(keys, n, s, ctx->sm_count, stream);
+    if (rc) return rc;
+    int blocks = int((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    sort_finish_kernel<<<blocks, 256, 0, stream>>>(s.k[0], s.v[0], n, keys_sorted, perm);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gather_rows_f64(elfi_b200_ctx* ctx, const double* src, int64_t ld_src,
+                              const int32_t* idx, int64_t n, int64_t width, double* dst,
+                              int64_t ld_dst, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "gather: ctx is NULL");
+    ELFI_REQUIRE(n >= 0 && width >= 1 && ld_src >= width && ld_dst >= width, "gather: bad shape");
+    if (n == 0) return ELFI_B200_OK;
+    ELFI_REQUIRE(src && idx && dst, "gather: NULL argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    int64_t blocks = (n * width + 255) / 256;
+    if (blocks > int64_t(ctx->sm_count) * 16) blocks = int64_t(ctx->sm_count) * 16;
+    gather_rows_kernel<<<unsigned(blocks), 256, 0, stream>>>(src, ld_src, idx, n, width, dst, ld_dst);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA, int64_t nA,
+                               const double* Bm, int64_t ldB, const int32_t* mapB,
+                               const int32_t* perm, int64_t n, int64_t width, double* dst,
+                               int64_t ld_dst, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "gather2: ctx is NULL");
+    ELFI_REQUIRE(n >= 0 && nA >= 0 && width >= 1 && ld_dst >= width, "gather2: bad shape");
+    if (n == 0) return ELFI_B200_OK;
+    ELFI_REQUIRE(dst != nullptr && (nA == 0 || A != nullptr), "gather2: NULL argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    int64_t blocks = (n * width + 255) / 256;
+    if (blocks > int64_t(ctx->sm_count) * 16) blocks = int64_t(ctx->sm_count) * 16;
+    gather2_rows_kernel<<<unsigned(blocks), 256, 0, stream>>>(A, ldA, nA, Bm, ldB, mapB, perm, n,
+                                                             width, dst, ld_dst);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w, int64_t n,
+                            double alpha, double* out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr && x != nullptr && out != nullptr, "wquantile: NULL argument");
+    ELFI_REQUIRE(n >= 1 && n < (int64_t(1) << 31), "wquantile: n=%lld out of range", (long long)n);
+    ELFI_REQUIRE(alpha >= 0.0 && alpha <= 1.0, "wquantile: alpha=%g outside [0, 1]", alpha);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const int64_t nb = (n + 4095) / 4096;
+    const size_t sort_bytes = sort_scratch_bytes(n);
+    const size_t extra = align256(size_t(nb + 1) * 8) + 256;
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, sort_bytes + extra));
+    if (!base) return ELFI_B200_ERR_NOMEM;
+    SortScratch s = carve_sort(base, n);
+    double* partial = reinterpret_cast<double*>(base + sort_bytes);
+    int32_t* count = reinterpret_cast<int32_t*>(base + sort_bytes + align256(size_t(nb + 1) * 8));
+    int rc = sort_pairs_device(x, n, s, ctx->sm_count, stream);
+    if (rc) return rc;
+    wq_block_sums_kernel<<<unsigned(nb), 1024, 0, stream>>>(w, s.v[0], n, partial);
+    wq_scan_partials_kernel<<<1, 1024, 0, stream>>>(partial, nb, count);
+    wq_count_kernel<<<unsigned(nb), 1024, 0, stream>>>(w, s.v[0], n, partial, nb, alpha, count);
+    wq_pick_kernel<<<1, 1, 0, stream>>>(s.k[0], count, n, alpha, out);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// smc.cu -- SMC-ABC population arithmetic:
+//   * column moments for AdaptiveDistance.add_data      (elfi/model/elfi_model.py:1104-1125)
+//   * weighted mean / unbiased weighted variance         (elfi/methods/utils.py:108-139)
+//   * Gaussian-mixture proposal density  q(x_i) = sum_j w_j N(x_i; m_j, Sigma)
+//     (GMDistribution.pdf/logpdf, elfi/methods/utils.py:146-197) and the importance weights
+//     w_i = exp(logprior_i - log q_i)  (elfi/methods/inference/samplers.py:511-514).
+//
+// The mixture density is the only O(N_new * N_prev) object on the path (1e12 pair terms per
+// generation at 1e6 particles): it is bound by the FP64 pipe, not by HBM.  Per pair and
+// parameter dimension p: p DSUB + p DFMA for the squared whitened distance, then
+// exp(-maha/2) by range reduction (round via the 2^52 trick, no 64-bit conversions, which run
+// at quarter rate) and a degree-7 polynomial: relative error < 1e-8 per term, far inside the
+// 1e-5 relative tolerance on the weights.  Accumulation is fp64.
+#include "common.cuh"
+
+namespace elfi {
+
+// ---------------------------------------------------------------------------------------------
+// K5: per-column shifted power sums of a (B, D) batch: s1_j = sum_i (x_ij - c_j),
+// s2_j = sum_i (x_ij - c_j)^2 with the shift c = first row (keeps s2 - s1^2/B well conditioned).
+// Grid (row slabs, column groups of 32); block (32, 8).
+__global__ void __launch_bounds__(256)
+colmoments_partial_kernel(const double* __restrict__ S, int64_t ld, int64_t B, int64_t D,
+                          int64_t rows_per_block, double* __restrict__ partial) {
+    __shared__ double s1s[8][33], s2s[8][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t c = int64_t(blockIdx.y) * 32 + tx;
+    const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < B) ? r0 + rows_per_block : B;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < D) {
+        const double shift = S[c];
+        for (int64_t r = r0 + ty; r < r1; r += 8) {
+            const double d = S[r * ld + c] - shift;
+            s1 += d;
+            s2 = fma(d, d, s2);
+        }
+    }
+    s1s[ty][tx] = s1;
+    s2s[ty][tx] = s2;
+    __syncthreads();
+    if (ty == 0 && c < D) {
+        for (int k = 1; k < 8; ++k) { s1 += s1s[k][tx]; s2 += s2s[k][tx]; }
+        partial[(int64_t(blockIdx.x) * 2 + 0) * D + c] = s1;
+        partial[(int64_t(blockIdx.x) * 2 + 1) * D + c] = s2;
+    }
+}
+
+// out[0*D + j] = batch mean_j, out[1*D + j] = batch M2_j = sum_i (x_ij - mean_j)^2
+__global__ void colmoments_final_kernel(const double* __restrict__ S, const double* __restrict__ partial,
+                                        int64_t nblocks, int64_t B, int64_t D,
+                                        double* __restrict__ out) {
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        s1 += partial[(b * 2 + 0) * D + c];
+        s2 += partial[(b * 2 + 1) * D + c];
+    }
+    const double n = double(B);
+    out[c] = S[c] + s1 / n;
+    out[D + c] = s2 - s1 * s1 / n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: weighted statistics.  pass 0: V1 = sum w, V2 = sum w^2, xw_j = sum w x_j.
+//     pass 1: num_j = sum w (x_j - xbar_j)^2.   p <= 16.
+constexpr int WS_MAXP = 16;
+
+__global__ void __launch_bounds__(256)
+wstats_partial_kernel(const double* __restrict__ x, int64_t ld, const double* __restrict__ w,
+                      int64_t N, int p, int pass, const double* __restrict__ stats,
+                      double* __restrict__ partial) {
+    __shared__ double red[8][WS_MAXP + 2];
+    double acc[WS_MAXP + 2];
+#pragma unroll
+    for (int k = 0; k < WS_MAXP + 2; ++k) acc[k] = 0.0;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const double wi = w ? w[i] : 1.0;
+        if (pass == 0) {
+            acc[0] += wi;
+            acc[1] = fma(wi, wi, acc[1]);
+#pragma unroll
+            for (int j = 0; j < WS_MAXP; ++j)
+                if (j < p) acc[2 + j] = fma(wi, x[i * ld + j], acc[2 + j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < WS_MAXP; ++j)
+                if (j < p) {
+                    const double d = x[i * ld + j] - stats[2 + j];
+                    acc[2 + j] = fma(wi, d * d, acc[2 + j]);
+                }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < WS_MAXP + 2; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < p + 2) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+        partial[int64_t(blockIdx.x) * (WS_MAXP + 2) + threadIdx.x] = v;
+    }
+}
+
+// stats layout: [V1, V2, xbar_0..p-1, s2_0..p-1]
+__global__ void wstats_final_kernel(const double* __restrict__ partial, int nblocks, int p, int pass,
+                                    double* __restrict__ stats) {
+    const int k = threadIdx.x;
+    if (k >= p + 2) return;
+    double v = 0.0;
+    for (int b = 0; b < nblocks; ++b) v += partial[int64_t(b) * (WS_MAXP + 2) + k];
+    if (pass == 0) {
+        if (k < 2) stats[k] = v;
+        __syncthreads();
+        if (k >= 2) stats[k] = v / stats[0];                 // np.average: sum(w x) / sum(w)
+    } else if (k >= 2) {
+        const double V1 = stats[0], V2 = stats[1];
+        stats[p + k] = v / (V1 - (V2 / V1));                 // utils.py:138
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: Gaussian mixture density.
+// exp(a) for a <= 0: t = a*log2(e); k = rint(t) (2^52 trick); f = t - k in [-.5, .5];
+// 2^f by a degree-7 Taylor polynomial in f*ln2 (|f ln2| <= 0.347 -> rel. error < 6e-9);
+// scaled by 2^k through the exponent field.  t < -1020 flushes to 0.
+__device__ __forceinline__ double fast_exp_neg(double a) {
+    const double t = a * 1.4426950408889634;
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double tm = t + magic;
+    const double kd = tm - magic;
+    const double f = t - kd;
+    const double z = f * 0.6931471805599453;
+    double pz = 1.0 / 5040.0;
+    pz = fma(pz, z, 1.0 / 720.0);
+    pz = fma(pz, z, 1.0 / 120.0);
+    pz = fma(pz, z, 1.0 / 24.0);
+    pz = fma(pz, z, 1.0 / 6.0);
+    pz = fma(pz, z, 0.5);
+    pz = fma(pz, z, 1.0);
+    pz = fma(pz, z, 1.0);
+    const int k = __double2loint(tm);  // low word of (t + magic) holds rint(t) as int32
+    int hi = __double2hiint(pz) + (k << 20);
+    const double r = __hiloint2double(hi, __double2loint(pz));
+    return (t >= -1020.0) ? r : ((t != t) ? t : 0.0);
+}
+
+// whitened coordinates: y = Linv * x (Linv lower triangular, row-major p x p); for the
+// components also the normalised weight in column p.
+__global__ void gm_whiten_kernel(const double* __restrict__ x, int64_t ld, int64_t n, int p,
+                                 const double* __restrict__ Linv, const double* __restrict__ w,
+                                 const double* __restrict__ wsum, double* __restrict__ out,
+                                 int out_ld) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int a = 0; a < p; ++a) {
+        double s = 0.0;
+        for (int b = 0; b <= a; ++b) s = fma(Linv[a * p + b], x[i * ld + b], s);
+        out[i * out_ld + a] = s;
+    }
+    if (out_ld > p) out[i * out_ld + p] = w ? w[i] / wsum[0] : 1.0 / double(n);
+}
+
+template <int P, int R>
+__global__ void __launch_bounds__(128)
+gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict__ mw, int64_t M,
+              double lognorm, double* __restrict__ logq) {
+    constexpr int TILE = 512;
+    __shared__ double sm[TILE * (P + 1)];
+    double x[R][P];
+    double acc[R];
+    const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        acc[r] = 0.0;
+#pragma unroll
+        for (int a = 0; a < P; ++a) x[r][a] = (i0 + r < N) ? xw[(i0 + r) * P + a] : 0.0;
+    }
+    for (int64_t j0 = 0; j0 < M; j0 += TILE) {
+        const int64_t cnt = (M - j0) < TILE ? (M - j0) : TILE;
+        __syncthreads();
+        for (int64_t t = threadIdx.x; t < cnt * (P + 1); t += blockDim.x)
+            sm[t] = mw[j0 * (P + 1) + t];
+        __syncthreads();
+        for (int j = 0; j < cnt; ++j) {
+            double m[P];
+#pragma unroll
+            for (int a = 0; a < P; ++a) m[a] = sm[j * (P + 1) + a];
+            const double wj = sm[j * (P + 1) + P];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double maha = 0.0;
+#pragma unroll
+                for (int a = 0; a < P; ++a) {
+                    const double d = x[r][a] - m[a];
+                    maha = fma(d, d, maha);
+                }
+                acc[r] = fma(wj, fast_exp_neg(-0.5 * maha), acc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (i0 + r < N) logq[i0 + r] = log(acc[r]) + lognorm;
+}
+
+// generic p (<= 16), one point per thread
+__global__ void __launch_bounds__(128)
+gm_pdf_generic_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict__ mw,
+                      int64_t M, int p, double lognorm, double* __restrict__ logq) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double x[WS_MAXP];
+    for (int a = 0; a < p; ++a) x[a] = xw[i * p + a];
+    double acc = 0.0;
+    for (int64_t j = 0; j < M; ++j) {
+        double maha = 0.0;
+        for (int a = 0; a < p; ++a) {
+            const double d = x[a] - __ldg(mw + j * (p + 1) + a);
+            maha = fma(d, d, maha);
+        }
+        acc = fma(__ldg(mw + j * (p + 1) + p), fast_exp_neg(-0.5 * maha), acc);
+    }
+    logq[i] = log(acc) + lognorm;
+}
+
+__global__ void sum_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    // single block, deterministic
+    __shared__ double ws[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) out[0] = t;
+    }
+}
+
+__global__ void smc_weights_kernel(const double* __restrict__ logprior, const double* __restrict__ logq,
+                                   int64_t n, double* __restrict__ w) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = exp(logprior[i] - logq[i]);
+}
+
+}  // namespace elfi
+
+extern "C" {
+
+int elfi_b200_colmoments_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int64_t D,
+                             double* out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && S && out, "colmoments: NULL argument");
+    ELFI_REQUIRE(B >= 1 && D >= 1 && ldS >= D, "colmoments: bad shape");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const int64_t colgroups = (D + 31) / 32;
+    int64_t slabs = (int64_t(ctx->sm_count) * 8 + colgroups - 1) / colgroups;
+    int64_t rows_per_block = (B + slabs - 1) / slabs;
+    if (rows_per_block < 64) rows_per_block = 64;
+    slabs = (B + rows_per_block - 1) / rows_per_block;
+    double* partial = static_cast<double*>(ctx_scratch(ctx, size_t(slabs) * 2 * D * 8 + 256));
+    if (!partial) return ELFI_B200_ERR_NOMEM;
+    colmoments_partial_kernel<<<dim3(unsigned(slabs), unsigned(colgroups)), dim3(32, 8), 0, stream>>>(
+        S, ldS, B, D, rows_per_block, partial);
+    colmoments_final_kernel<<<unsigned((D + 127) / 128), 128, 0, stream>>>(S, partial, slabs, B, D, out);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_weighted_stats_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, const double* w,
+                                 int64_t N, int64_t p, double* stats, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && x && stats, "weighted_stats: NULL argument");
+    ELFI_REQUIRE(N >= 1 && p >= 1 && p <= WS_MAXP && ldx >= p, "weighted_stats: bad shape (p <= %d)",
+                 WS_MAXP);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    int blocks = int((N + 255) / 256);
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    double* partial = static_cast<double*>(ctx_scratch(ctx, size_t(blocks) * (WS_MAXP + 2) * 8 + 256));
+    if (!partial) return ELFI_B200_ERR_NOMEM;
+    for (int pass = 0; pass < 2; ++pass) {
+        wstats_partial_kernel<<<blocks, 256, 0, stream>>>(x, ldx, w, N, int(p), pass, stats, partial);
+        wstats_final_kernel<<<1, 32, 0, stream>>>(partial, blocks, int(p), pass, stats);
+    }
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t N,
+                            const double* means, int64_t ldm, const double* w, int64_t M, int64_t p,
+                            const double* Linv_host, double logdet, double* logq, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && x && means && Linv_host && logq, "gm_logpdf: NULL argument");
+    ELFI_REQUIRE(N >= 0 && M >= 1 && p >= 1 && p <= WS_MAXP && ldx >= p && ldm >= p,
+                 "gm_logpdf: bad shape (p <= %d)", WS_MAXP);
+    if (N == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t off_xw = align(size_t(p) * p * 8);
+    const size_t off_mw = off_xw + align(size_t(N) * p * 8);
+    const size_t off_ws = off_mw + align(size_t(M) * (p + 1) * 8);
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, off_ws + 256));
+    if (!base) return ELFI_B200_ERR_NOMEM;
+    double* Linv = reinterpret_cast<double*>(base);
+    double* xw = reinterpret_cast<double*>(base + off_xw);
+    double* mw = reinterpret_cast<double*>(base + off_mw);
+    double* wsum = reinterpret_cast<double*>(base + off_ws);
+    ELFI_CUDA_OK(cudaMemcpyAsync(Linv, Linv_host, size_t(p) * p * 8, cudaMemcpyHostToDevice, stream));
+    if (w) sum_kernel<<<1, 1024, 0, stream>>>(w, M, wsum);
+    gm_whiten_kernel<<<unsigned((N + 255) / 256), 256, 0, stream>>>(x, ldx, N, int(p), Linv, nullptr,
+                                                                   nullptr, xw, int(p));
+    gm_whiten_kernel<<<unsigned((M + 255) / 256), 256, 0, stream>>>(means, ldm, M, int(p), Linv, w,
+                                                                   wsum, mw, int(p + 1));
+    const double lognorm = -0.5 * (double(p) * 1.8378770664093453 + logdet);  // log(2 pi)
+    constexpr int R = 4;
+    const unsigned blocks = unsigned((N + 128 * R - 1) / (128 * R));
+    switch (p) {
+        case 1: gm_pdf_kernel<1, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
+        case 2: gm_pdf_kernel<2, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
+        case 3: gm_pdf_kernel<3, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
+        case 4: gm_pdf_kernel<4, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
+        default:
+            gm_pdf_generic_kernel<<<unsigned((N + 127) / 128), 128, 0, stream>>>(xw, N, mw, M, int(p),
+                                                                              lognorm, logq);
+    }
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_smc_weights_f64(elfi_b200_ctx* ctx, const double* logprior, const double* logq,
+                              int64_t n, double* w, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (n == 0 || (logprior && logq && w)), "smc_weights: NULL argument");
+    if (n == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    smc_weights_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(logprior, logq, n, w);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+}  // extern "C"

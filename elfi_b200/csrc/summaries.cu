@@ -1,0 +1,371 @@
+// summaries.cu -- row-wise summary statistics with NumPy's pairwise summation order
+// (SURVEY.md K6): MA2 autocovariance (elfi/examples/ma2.py:40-59) and the Gaussian model's
+// mean / variance (elfi/examples/gauss.py:142-173).
+//
+// NumPy reduces each row with DOUBLE_pairwise_sum: blocks of <= 128 elements are summed with
+// 8 strided accumulators r[0..7] combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a
+// sequential tail; longer rows are split recursively at n/2 rounded down to a multiple of 8.
+// Every left part is a multiple of 8 long, so every leaf starts at an index that is a multiple
+// of 8 and only the last leaf has a tail.  PairwiseStream below consumes a row's terms strictly
+// in order and reproduces that tree bit for bit, with the accumulators indexed by compile-time
+// constants (the term index modulo 8 is fixed by the column position and the lag).
+//
+// Traffic: n*8 bytes read per row (variance re-reads the tile from L2), 8 bytes written per
+// statistic.  Roofline: HBM.
+#include "rowstream.cuh"
+
+namespace elfi {
+
+constexpr int PW_MAX_DEPTH = 26;  // recursion depth bound: rows up to 128 * 2^26 elements
+
+// Streaming evaluation of NumPy's pairwise sum over m terms fed one aligned group of 8 at a
+// time (the last group may be partial).  All lanes of a warp run identical control flow
+// because every row has the same length.
+struct PairwiseStream {
+    double r[8];
+    double res;
+    int64_t leaf_end;     // first term index after the current leaf
+    int64_t tail_start;   // first term index of the sequential tail of the current leaf
+    int64_t leaf_start;
+    int depth;
+    bool in_tail;
+    int64_t pending_right[PW_MAX_DEPTH];
+    double left_val[PW_MAX_DEPTH];
+    bool has_left[PW_MAX_DEPTH];
+
+    __device__ __forceinline__ void descend(int64_t start, int64_t n) {
+        while (n > 128) {
+            int64_t n2 = n / 2;
+            n2 -= n2 % 8;
+            pending_right[depth] = n - n2;
+            has_left[depth] = false;
+            ++depth;
+            n = n2;
+        }
+        leaf_start = start;
+        leaf_end = start + n;
+        tail_start = n < 8 ? start : start + (n - n % 8);
+        in_tail = n < 8;
+        res = 0.0;
+    }
+    __device__ __forceinline__ void begin(int64_t m) {
+        depth = 0;
+        descend(0, m);
+    }
+    __device__ __forceinline__ double leaf_value() const {
+        if (leaf_end - leaf_start < 8) return res;
+        if (in_tail) return res;
+        return __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    }
+    // Called when term index j0 (a multiple of 8) is about to be fed and j0 == leaf_end.
+    __device__ __forceinline__ void close_leaf_and_open_next() {
+        double v = leaf_value();
+        const int64_t next = leaf_end;
+        while (depth > 0) {
+            if (!has_left[depth - 1]) {
+                left_val[depth - 1] = v;
+                has_left[depth - 1] = true;
+                const int64_t n = pending_right[depth - 1];
+                descend(next, n);
+                return;
+            }
+            v = __dadd_rn(left_val[depth - 1], v);
+            --depth;
+        }
+        res = v;  // not reached while terms remain
+    }
+    // Feed up to 8 terms t[0..cnt) with global indices j0..j0+cnt-1, j0 % 8 == 0.
+    __device__ __forceinline__ void feed8(int64_t j0, const double* t, int cnt) {
+        if (j0 == leaf_end) close_leaf_and_open_next();
+        if (!in_tail && j0 == tail_start && tail_start != leaf_start) {
+            // leaf has a tail: fold the strided accumulators first, then go sequential
+            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            in_tail = true;
+        }
+        if (in_tail) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < cnt) res = __dadd_rn(res, t[k]);
+        } else if (j0 == leaf_start) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = t[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], t[k]);
+        }
+    }
+    __device__ __forceinline__ double finish() {
+        double v = leaf_value();
+        while (depth > 0) {
+            v = __dadd_rn(left_val[depth - 1], v);
+            --depth;
+        }
+        return v;
+    }
+};
+
+// Collects terms into aligned groups of 8 and forwards them to a PairwiseStream.
+struct TermGrouper {
+    PairwiseStream pw;
+    double buf[8];
+    int64_t j0;
+    int fill;
+    __device__ __forceinline__ void begin(int64_t m) {
+        pw.begin(m);
+        j0 = 0;
+        fill = 0;
+    }
+    template <int K>
+    __device__ __forceinline__ void push(double v) {  // K = term index modulo 8 (compile time)
+        buf[K] = v;
+        if (K == 7) {
+            pw.feed8(j0, buf, 8);
+            j0 += 8;
+            fill = 0;
+        } else {
+            fill = K + 1;
+        }
+    }
+    __device__ __forceinline__ double finish() {
+        if (fill > 0) pw.feed8(j0, buf, fill);
+        return pw.finish();
+    }
+};
+
+struct SummaryParams {
+    double* out;      // out[row * ld_out + col0 (+1)]
+    int64_t ld_out;
+    int n;            // row length
+    int col_a;        // output column of the first statistic
+    int col_b;        // output column of the second statistic (or -1)
+};
+
+__device__ __forceinline__ void load_box_row(const uint8_t* box_row, int sw, double* cur) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double2 v = *reinterpret_cast<const double2*>(box_row + ((c ^ sw) << 4));
+        cur[2 * c] = v.x;
+        cur[2 * c + 1] = v.y;
+    }
+}
+
+// Autocovariance at one or two compile-time lags in a single pass over the rows:
+// C_lag = mean_j( x[j+lag] * x[j] ),  j = 0 .. n-lag-1   (ma2.py:57: np.mean(x[:,lag:]*x[:,:-lag])).
+template <int LAG_A, int LAG_B>
+struct AutocovConsumer {
+    typedef SummaryParams Params;
+    static constexpr int PASSES = 1;
+    static constexpr int HMAX = (LAG_A > LAG_B ? LAG_A : LAG_B);
+    const Params& p;
+    TermGrouper ga, gb;
+    double hist[HMAX > 0 ? HMAX : 1];  // last HMAX elements of the previous column group
+
+    static __device__ void setup_shared(uint8_t*, const Params&, int) {}
+    __device__ AutocovConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
+    __device__ __forceinline__ void begin_row() {
+        ga.begin(p.n - LAG_A);
+        if (LAG_B >= 0) gb.begin(p.n - LAG_B);
+    }
+    template <int LAG, int C>
+    __device__ __forceinline__ void term(TermGrouper& g, int t, const double* cur) {
+        // element index t = cg*16 + C; product index j = t - LAG
+        if (t >= LAG && t < p.n) {
+            const double prev = (C >= LAG) ? cur[C >= LAG ? C - LAG : 0]
+                                           : hist[C >= LAG ? 0 : HMAX - LAG + C];
+            g.template push<((C - LAG) % 8 + 8) % 8>(__dmul_rn(cur[C], prev));
+        }
+    }
+    template <int C>
+    __device__ __forceinline__ void step(int t0, const double* cur) {
+        term<LAG_A, C>(ga, t0 + C, cur);
+        if (LAG_B >= 0) term<(LAG_B >= 0 ? LAG_B : 0), C>(gb, t0 + C, cur);
+        if constexpr (C + 1 < 16) step<C + 1>(t0, cur);
+    }
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
+        double cur[16];
+        load_box_row(box_row, sw, cur);
+        step<0>(cg * RS_BOX_COLS, cur);
+#pragma unroll
+        for (int h = 0; h < HMAX; ++h) hist[h] = cur[16 - HMAX + h];
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int) {
+        const double sa = ga.finish();
+        double sb = 0.0;
+        if (LAG_B >= 0) sb = gb.finish();
+        if (row < B) {
+            p.out[row * p.ld_out + p.col_a] = sa / double(p.n - LAG_A);
+            if (LAG_B >= 0) p.out[row * p.ld_out + p.col_b] = sb / double(p.n - LAG_B);
+        }
+    }
+};
+
+// np.mean / np.var along axis 1 (gauss.py:156, 173).  Sweep 0 accumulates the pairwise sum
+// of x; sweep 1 (same boxes, L2 hits) the pairwise sum of (x - mean)^2  (numpy _var).
+struct MeanVarConsumer {
+    typedef SummaryParams Params;
+    static constexpr int PASSES = 2;
+    const Params& p;
+    TermGrouper g;
+    double mean;
+
+    static __device__ void setup_shared(uint8_t*, const Params&, int) {}
+    __device__ MeanVarConsumer(const Params& p_, const uint8_t*, int, int) : p(p_), mean(0.0) {}
+    __device__ __forceinline__ void begin_row() { g.begin(p.n); }
+    template <int C>
+    __device__ __forceinline__ void step(int pass, int t0, const double* cur) {
+        if (t0 + C < p.n) {
+            if (pass == 0) {
+                g.template push<C % 8>(cur[C]);
+            } else {
+                const double c = __dsub_rn(cur[C], mean);
+                g.template push<C % 8>(__dmul_rn(c, c));
+            }
+        }
+        if constexpr (C + 1 < 16) step<C + 1>(pass, t0, cur);
+    }
+    __device__ __forceinline__ void consume(int pass, int cg, const uint8_t* box_row, int sw) {
+        double cur[16];
+        load_box_row(box_row, sw, cur);
+        if (pass == 1 && cg == 0) {
+            mean = g.finish() / double(p.n);
+            g.begin(p.n);
+        }
+        step<0>(pass, cg * RS_BOX_COLS, cur);
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int) {
+        const double var = g.finish() / double(p.n);
+        if (row < B) {
+            if (p.col_a >= 0) p.out[row * p.ld_out + p.col_a] = mean;
+            if (p.col_b >= 0) p.out[row * p.ld_out + p.col_b] = var;
+        }
+    }
+};
+
+// Generic fallback (any lag, any alignment): one thread per row straight from global memory,
+// same PairwiseStream so results are identical.  mode 0 = autocov(lag), 1 = mean+var.
+__global__ void __launch_bounds__(128)
+summary_direct_kernel(const double* __restrict__ X, int64_t ld, int64_t B, int n, int lag,
+                      int mode, SummaryParams p) {
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    const double* x = X + row * ld;
+    PairwiseStream pw;
+    double buf[8];
+    auto run = [&](int64_t m, auto term) -> double {
+        pw.begin(m);
+        for (int64_t j0 = 0; j0 < m; j0 += 8) {
+            const int cnt = (m - j0) < 8 ? int(m - j0) : 8;
+            for (int k = 0; k < 8; ++k) buf[k] = k < cnt ? term(j0 + k) : 0.0;
+            pw.feed8(j0, buf, cnt);
+        }
+        return pw.finish();
+    };
+    if (mode == 0) {
+        const int64_t m = n - lag;
+        const double s = run(m, [&](int64_t j) { return __dmul_rn(__ldg(x + j + lag), __ldg(x + j)); });
+        p.out[row * p.ld_out + p.col_a] = s / double(m);
+    } else {
+        const double mean = run(n, [&](int64_t j) { return __ldg(x + j); }) / double(n);
+        const double ss = run(n, [&](int64_t j) {
+            const double c = __dsub_rn(__ldg(x + j), mean);
+            return __dmul_rn(c, c);
+        });
+        if (p.col_a >= 0) p.out[row * p.ld_out + p.col_a] = mean;
+        if (p.col_b >= 0) p.out[row * p.ld_out + p.col_b] = ss / double(n);
+    }
+}
+
+static bool rowstream_ok(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t n) {
+    return n >= RS_BOX_COLS && tma_compatible(X, ld) && rs_pick_stages(ctx->smem_optin, 0) >= 2;
+}
+
+}  // namespace elfi
+
+extern "C" {
+
+int elfi_b200_summary_autocov_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int64_t B,
+                                  int64_t n, const int32_t* lags_host, int64_t nlags, double* out,
+                                  int64_t ld_out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (X && out)), "autocov: NULL argument");
+    ELFI_REQUIRE(B >= 0 && n >= 1 && ldX >= n, "autocov: bad shape B=%lld n=%lld ld=%lld",
+                 (long long)B, (long long)n, (long long)ldX);
+    ELFI_REQUIRE(nlags >= 1 && lags_host != nullptr && ld_out >= nlags, "autocov: bad lags/ld_out");
+    ELFI_REQUIRE(n < (int64_t(1) << 31), "autocov: row too long");
+    for (int64_t l = 0; l < nlags; ++l)
+        ELFI_REQUIRE(lags_host[l] >= 1 && lags_host[l] < n, "autocov: lag %d outside [1, n)",
+                     lags_host[l]);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    if (B == 0) return ELFI_B200_OK;
+    SummaryParams p;
+    p.out = out;
+    p.ld_out = ld_out;
+    p.n = int(n);
+    const bool fast = rowstream_ok(ctx, X, ldX, n);
+    int64_t l = 0;
+    while (l < nlags) {
+        p.col_a = int(l);
+        p.col_b = -1;
+        const int la = lags_host[l];
+        const int lb = (l + 1 < nlags) ? lags_host[l + 1] : -1;
+        int rc = -100;
+        if (fast) {
+            if (la == 1 && lb == 2) {
+                p.col_b = int(l + 1);
+                rc = rowstream_launch<AutocovConsumer<1, 2>>(ctx, X, ldX, B, n, 0, p, stream);
+                if (rc == 0) l += 2;
+            } else if (la == 1) {
+                rc = rowstream_launch<AutocovConsumer<1, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                if (rc == 0) l += 1;
+            } else if (la == 2) {
+                rc = rowstream_launch<AutocovConsumer<2, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                if (rc == 0) l += 1;
+            } else if (la == 3) {
+                rc = rowstream_launch<AutocovConsumer<3, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                if (rc == 0) l += 1;
+            } else if (la == 4) {
+                rc = rowstream_launch<AutocovConsumer<4, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                if (rc == 0) l += 1;
+            }
+            if (rc != -100 && rc != 0) return rc;
+        }
+        if (rc == -100) {
+            summary_direct_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(X, ldX, B, int(n),
+                                                                                la, 0, p);
+            ELFI_CUDA_OK(cudaGetLastError());
+            l += 1;
+        }
+    }
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int64_t B,
+                                  int64_t n, double* out, int64_t ld_out, int32_t col_mean,
+                                  int32_t col_var, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (X && out)), "meanvar: NULL argument");
+    ELFI_REQUIRE(B >= 0 && n >= 1 && ldX >= n, "meanvar: bad shape B=%lld n=%lld ld=%lld",
+                 (long long)B, (long long)n, (long long)ldX);
+    ELFI_REQUIRE(col_mean < ld_out && col_var < ld_out && (col_mean >= 0 || col_var >= 0),
+                 "meanvar: bad output columns");
+    ELFI_REQUIRE(n < (int64_t(1) << 31), "meanvar: row too long");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    if (B == 0) return ELFI_B200_OK;
+    SummaryParams p;
+    p.out = out;
+    p.ld_out = ld_out;
+    p.n = int(n);
+    p.col_a = col_mean;
+    p.col_b = col_var;
+    if (rowstream_ok(ctx, X, ldX, n))
+        return rowstream_launch<MeanVarConsumer>(ctx, X, ldX, B, n, 0, p, stream);
+    summary_direct_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(X, ldX, B, int(n), 0, 1, p);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+}  // extern "C"

@@ -79,7 +79,7 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True):
         n_acc = torch.zeros(1, dtype=torch.int64, device='cuda')
         if want_indices:
             acc_idx = dev.empty((max(B, 1),), dtype=torch.int32)
-    _lib.call('elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S), S.stride(0), B, D,
+    _lib.call('elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S), S.stride(0) if B > 1 else D, B, D,
               dev.ptr(obs_t), dev.ptr(W), K, dev.ptr(thr), dev.ptr(d), dev.ptr(acc_idx),
               dev.ptr(n_acc), dev.stream_ptr())
     if thr is not None:
@@ -119,3 +119,171 @@ def dist_euclid_host(S, obs, w=None, thresholds=None, return_distances=True):
     if d is not None and K == 1 and (w is None or np.ndim(w) == 1):
         d = d.reshape(B)
     return d, (idx[:n.value] if idx is not None else None)
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+def autocov(x, lags=(1,), out=None):
+    """MA2 autocovariance summaries (elfi/examples/ma2.py:40-59) for one or more lags.
+
+    Returns a (B, len(lags)) tensor: column l is ``np.mean(x[:, lag:] * x[:, :-lag], axis=1)``
+    bit for bit.  This is already the column-stacked summary matrix of
+    elfi/model/utils.py:39, so it can be handed to :func:`dist_euclid` directly."""
+    x = _matrix(x)
+    B, n = x.shape
+    lags_arr = np.ascontiguousarray(np.atleast_1d(lags), dtype=np.int32)
+    for lag in lags_arr:
+        if not 1 <= lag < n:
+            raise ValueError('lag {} outside [1, {})'.format(lag, n))
+    if out is None:
+        out = dev.empty((B, len(lags_arr)))
+    _lib.call('elfi_b200_summary_autocov_f64', dev.context(), dev.ptr(x), _ld(x), B, n,
+              dev.ptr(lags_arr), len(lags_arr), dev.ptr(out), out.stride(0) if B > 1 else
+              out.shape[1], dev.stream_ptr())
+    return out
+
+
+def meanvar(y, out=None):
+    """Gaussian-model summaries ss_mean / ss_var (elfi/examples/gauss.py:142-173).
+
+    Returns a (B, 2) tensor [np.mean(y, axis=1), np.var(y, axis=1)], bit for bit."""
+    y = _matrix(y)
+    B, n = y.shape
+    if out is None:
+        out = dev.empty((B, 2))
+    _lib.call('elfi_b200_summary_meanvar_f64', dev.context(), dev.ptr(y), _ld(y), B, n,
+              dev.ptr(out), out.stride(0) if B > 1 else out.shape[1], 0, 1, dev.stream_ptr())
+    return out
+
+
+def argsort(keys, return_keys=False):
+    """Stable ascending argsort of a 1-d fp64 array (NaN last) -> int32 permutation.
+
+    np.argsort of elfi/methods/inference/samplers.py:235 and elfi/methods/utils.py:397."""
+    keys = dev.to_device(keys).reshape(-1)
+    n = keys.numel()
+    perm = dev.empty((n,), dtype=torch.int32)
+    ks = dev.empty((n,)) if return_keys else None
+    _lib.call('elfi_b200_sort_pairs_f64', dev.context(), dev.ptr(keys), n, dev.ptr(ks),
+              dev.ptr(perm), dev.stream_ptr())
+    return (perm, ks) if return_keys else perm
+
+
+def _as_2d(t):
+    return t if t.dim() == 2 else t.reshape(t.shape[0], -1)
+
+
+def take_rows(src, idx):
+    """src[idx] for an fp64 array with the batch on axis 0 (samplers.py:230, 237)."""
+    src = dev.to_device(src)
+    shape = src.shape
+    s2 = _as_2d(src)
+    if s2.stride(-1) != 1 and s2.shape[1] > 0:
+        s2 = s2.contiguous()
+    idx = dev.to_device(idx, dtype=torch.int32)
+    n = idx.numel()
+    width = s2.shape[1]
+    dst = dev.empty((n, width))
+    if n and width:
+        _lib.call('elfi_b200_gather_rows_f64', dev.context(), dev.ptr(s2), _ld(s2), dev.ptr(idx),
+                  n, width, dev.ptr(dst), width, dev.stream_ptr())
+    return dst.reshape((n,) + tuple(shape[1:]))
+
+
+def take_rows2(a, b, perm, n_out, map_b=None):
+    """Rows perm[:n_out] of the virtual concatenation [a; b[map_b]] (top-n merge gather)."""
+    shape = a.shape if a is not None else b.shape
+    a2 = _as_2d(a) if a is not None else None
+    b2 = _as_2d(b) if b is not None else None
+    width = (a2 if a2 is not None else b2).shape[1]
+    n_a = a2.shape[0] if a2 is not None else 0
+    dst = dev.empty((n_out, width))
+    if n_out and width:
+        _lib.call('elfi_b200_gather2_rows_f64', dev.context(), dev.ptr(a2),
+                  _ld(a2) if a2 is not None else width, n_a, dev.ptr(b2),
+                  _ld(b2) if b2 is not None else width, dev.ptr(map_b), dev.ptr(perm), n_out,
+                  width, dev.ptr(dst), width, dev.stream_ptr())
+    return dst.reshape((n_out,) + tuple(shape[1:]))
+
+
+def weighted_sample_quantile(x, alpha, weights=None):
+    """elfi/methods/utils.py:379-411 on the device; returns a Python float."""
+    x = dev.to_device(x).reshape(-1)
+    w = None if weights is None else dev.to_device(weights).reshape(-1)
+    if w is not None and w.numel() != x.numel():
+        raise ValueError('x and weights must have the same length')
+    out = dev.empty((2,))
+    _lib.call('elfi_b200_wquantile_f64', dev.context(), dev.ptr(x), dev.ptr(w), x.numel(),
+              float(alpha), dev.ptr(out), dev.stream_ptr())
+    return float(out[0].item())
+
+
+def colmoments(S):
+    """(mean, M2) per column of one batch (AdaptiveDistance.add_data's per-batch ingredients,
+    elfi/model/elfi_model.py:1104-1125).  Returns two host arrays of length D."""
+    S = _matrix(S)
+    B, D = S.shape
+    out = dev.empty((2, D))
+    _lib.call('elfi_b200_colmoments_f64', dev.context(), dev.ptr(S), _ld(S), B, D, dev.ptr(out),
+              dev.stream_ptr())
+    out = out.cpu().numpy()
+    return out[0], out[1]
+
+
+def weighted_stats(x, weights=None):
+    """V1, V2, weighted mean and unbiased weighted variance (elfi/methods/utils.py:108-139).
+
+    Returns (V1, V2, xbar (p,), s2 (p,)) as host values."""
+    x = _matrix(x)
+    N, p = x.shape
+    w = None if weights is None else dev.to_device(weights).reshape(-1)
+    stats = dev.empty((2 + 2 * p,))
+    _lib.call('elfi_b200_weighted_stats_f64', dev.context(), dev.ptr(x), _ld(x), dev.ptr(w), N, p,
+              dev.ptr(stats), dev.stream_ptr())
+    s = stats.cpu().numpy()
+    return s[0], s[1], s[2:2 + p].copy(), s[2 + p:2 + 2 * p].copy()
+
+
+def weighted_var(x, weights=None):
+    """elfi/methods/utils.py:108-139."""
+    return weighted_stats(x, weights)[3]
+
+
+def gm_logpdf(x, means, cov=1, weights=None):
+    """GMDistribution.logpdf (elfi/methods/utils.py:174-197) on the device.
+
+    x (N, p) and means (M, p) may be host or device arrays; returns a device tensor (N,)."""
+    means = _matrix(means)
+    M, p = means.shape
+    x = dev.to_device(x)
+    x = x.reshape(-1, p) if x.dim() != 2 else x
+    x = _matrix(x)
+    N = x.shape[0]
+    cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    if cov.shape == (1, 1) and p > 1:
+        cov = np.eye(p) * cov[0, 0]
+    L = np.linalg.cholesky(cov)
+    Linv = np.ascontiguousarray(np.linalg.inv(L))
+    logdet = 2.0 * float(np.sum(np.log(np.diag(L))))
+    w = None if weights is None else dev.to_device(weights).reshape(-1)
+    if w is not None:
+        if bool((w < 0).any()):
+            raise ValueError("Weights must be positive")
+        if float(w.sum()) == 0:
+            raise ValueError("All weights are zero")
+    logq = dev.empty((N,))
+    _lib.call('elfi_b200_gm_logpdf_f64', dev.context(), dev.ptr(x), _ld(x), N, dev.ptr(means),
+              _ld(means), dev.ptr(w), M, p, dev.ptr(Linv), logdet, dev.ptr(logq), dev.stream_ptr())
+    return logq
+
+
+def smc_weights(logprior, logq):
+    """w = exp(logprior - logq) (elfi/methods/inference/samplers.py:514)."""
+    lp = dev.to_device(logprior).reshape(-1)
+    lq = dev.to_device(logq).reshape(-1)
+    w = dev.empty((lp.numel(),))
+    _lib.call('elfi_b200_smc_weights_f64', dev.context(), dev.ptr(lp), dev.ptr(lq), lp.numel(),
+              dev.ptr(w), dev.stream_ptr())
+    return w

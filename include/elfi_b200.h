@@ -85,6 +85,88 @@ int elfi_b200_dist_euclid_thr_f64_host(elfi_b200_ctx* ctx, const double* S_host,
                                        double* d_out_host, int32_t* acc_idx_host,
                                        int64_t* n_acc_host);
 
+/* ---- summary statistics ----------------------------------------------------------------
+ * Row-wise summaries with NumPy's pairwise summation order (bit-identical results).
+ *
+ * elfi_b200_summary_autocov_f64 replaces elfi/examples/ma2.py:40-59 (autocov):
+ *   out[i*ld_out + l] = mean_j( X[i, j+lag_l] * X[i, j] ),  j = 0 .. n-lag_l-1
+ * for every lag in lags_host (HOST int32 array, 1 <= lag < n).  All lags of a call are
+ * evaluated from one pass over X where possible (lags {1,2} fused), and written straight
+ * into the column-stacked (B, nlags) summary matrix that the distance kernel consumes
+ * (this is the np.column_stack of elfi/model/utils.py:39, done for free).
+ *
+ * elfi_b200_summary_meanvar_f64 replaces elfi/examples/gauss.py:142-173 (ss_mean, ss_var):
+ *   out[i*ld_out + col_mean] = np.mean(X[i]),  out[i*ld_out + col_var] = np.var(X[i])
+ * (either column index may be -1 to skip that statistic).
+ */
+int elfi_b200_summary_autocov_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int64_t B,
+                                  int64_t n, const int32_t* lags_host, int64_t nlags, double* out,
+                                  int64_t ld_out, void* stream);
+int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int64_t B,
+                                  int64_t n, double* out, int64_t ld_out, int32_t col_mean,
+                                  int32_t col_var, void* stream);
+
+/* ---- ordering primitives ---------------------------------------------------------------
+ * elfi_b200_sort_pairs_f64: stable ascending argsort of n fp64 keys (NaN last).  Replaces
+ * np.argsort in Rejection._merge_batch (elfi/methods/inference/samplers.py:232-237) and in
+ * weighted_sample_quantile (elfi/methods/utils.py:397).  keys_sorted and perm may each be
+ * NULL.  (NumPy's default argsort is unstable; the two agree whenever keys are distinct.)
+ *
+ * elfi_b200_gather_rows_f64: dst[i, 0:width] = src[idx[i], 0:width] -- the fancy-index
+ * permutation `v[:] = v[sort_mask]` / `batch[node][accepted]` (samplers.py:228-237).
+ *
+ * elfi_b200_gather2_rows_f64: same from the virtual concatenation [A (nA rows); B], where B
+ * rows may be indirected through mapB (the accepted indices of the new batch): the running
+ * top-n merge without materialising the (n + batch) buffers of samplers.py:196-205.
+ * perm == NULL means the identity.
+ */
+int elfi_b200_sort_pairs_f64(elfi_b200_ctx* ctx, const double* keys, int64_t n,
+                             double* keys_sorted, int32_t* perm, void* stream);
+int elfi_b200_gather_rows_f64(elfi_b200_ctx* ctx, const double* src, int64_t ld_src,
+                              const int32_t* idx, int64_t n, int64_t width, double* dst,
+                              int64_t ld_dst, void* stream);
+int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA, int64_t nA,
+                               const double* B, int64_t ldB, const int32_t* mapB,
+                               const int32_t* perm, int64_t n, int64_t width, double* dst,
+                               int64_t ld_dst, void* stream);
+
+/* elfi_b200_wquantile_f64: weighted_sample_quantile (elfi/methods/utils.py:379-411).
+ *   x (n), w (n) or NULL (equal weights), 0 <= alpha <= 1.
+ *   out[0] = alpha-quantile (an element of x), out[1] = its rank in sorted order (as double).
+ * The cumulative weights are accumulated by a blocked parallel scan (the reference's
+ * np.cumsum is sequential): identical unless alpha lies within ~1e-13 of a cumulative weight. */
+int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w, int64_t n,
+                            double alpha, double* out, void* stream);
+
+/* ---- SMC population arithmetic ---------------------------------------------------------
+ * elfi_b200_colmoments_f64: per-column mean and M2 = sum_i (x_ij - mean_j)^2 of one (B, D)
+ * batch: out[0:D] = mean, out[D:2D] = M2.  The host merges batches with Chan's formula,
+ * which is algebraically AdaptiveDistance.add_data (elfi/model/elfi_model.py:1104-1125);
+ * parity is tolerance-level (the reference itself only promises np.std agreement,
+ * tests/unit/test_elfi_model.py:185-253).
+ *
+ * elfi_b200_weighted_stats_f64: weighted_var and its ingredients (elfi/methods/utils.py:108-139):
+ *   stats = [V1 = sum w, V2 = sum w^2, xbar_0..p-1 = np.average(x, weights=w),
+ *            s2_0..p-1 = sum w (x - xbar)^2 / (V1 - V2/V1)],   w == NULL means all ones.
+ *
+ * elfi_b200_gm_logpdf_f64: GMDistribution.logpdf (elfi/methods/utils.py:146-197) --
+ *   logq[i] = log sum_j (w_j / sum w) N(x_i; means_j, Sigma), plain sum of densities as in the
+ *   reference (no log-sum-exp shift), Sigma shared.  Linv_host = inverse of the lower Cholesky
+ *   factor of Sigma (HOST, p x p row-major), logdet = log det Sigma.  p <= 16.
+ *   Tolerance: <= 1e-7 relative on q (fast range-reduced exp, fp64 accumulation).
+ *
+ * elfi_b200_smc_weights_f64: w_i = exp(logprior_i - logq_i) (samplers.py:514).
+ */
+int elfi_b200_colmoments_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int64_t D,
+                             double* out, void* stream);
+int elfi_b200_weighted_stats_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, const double* w,
+                                 int64_t N, int64_t p, double* stats, void* stream);
+int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t N,
+                            const double* means, int64_t ldm, const double* w, int64_t M, int64_t p,
+                            const double* Linv_host, double logdet, double* logq, void* stream);
+int elfi_b200_smc_weights_f64(elfi_b200_ctx* ctx, const double* logprior, const double* logq,
+                              int64_t n, double* w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

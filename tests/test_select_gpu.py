@@ -1,0 +1,76 @@
+"""GPU parity: sort / gather / weighted quantile / top-n merge vs NumPy and reference goldens."""
+import numpy as np
+import pytest
+
+import elfi_oracle as o
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('n', [1, 2, 31, 32, 33, 1000, 1024, 1025, 5000, 100000, 1_000_003])
+def test_argsort_matches_numpy(n):
+    from elfi_b200 import ops
+    rs = np.random.RandomState(n)
+    x = np.abs(rs.randn(n)) * 10 ** rs.uniform(-3, 3, n)
+    perm, ks = ops.argsort(x, return_keys=True)
+    ref = np.argsort(x, kind='stable')
+    assert np.array_equal(perm.cpu().numpy(), ref)
+    assert np.array_equal(ks.cpu().numpy(), x[ref])
+
+
+def test_argsort_special_values_and_stability():
+    from elfi_b200 import ops
+    x = np.array([3.0, np.inf, 0.0, -0.0, 1.5, np.nan, -2.0, 1.5, np.inf, 1.5, -np.inf, 5e-324])
+    perm = ops.argsort(x).cpu().numpy()
+    xs = x[perm]
+    assert np.isnan(xs[-1])
+    assert np.all(np.diff(xs[:-1]) >= 0)
+    ties = [i for i in perm if x[i] == 1.5]
+    assert ties == sorted(ties)                      # stable
+    x = np.repeat(np.arange(50.0), 400)[np.random.RandomState(0).permutation(20000)]
+    assert np.array_equal(ops.argsort(x).cpu().numpy(), np.argsort(x, kind='stable'))
+
+
+def test_take_rows():
+    from elfi_b200 import ops
+    rs = np.random.RandomState(1)
+    a = rs.randn(1000, 7)
+    idx = rs.randint(0, 1000, 333).astype(np.int32)
+    assert np.array_equal(ops.take_rows(a, idx).cpu().numpy(), a[idx])
+    v = rs.randn(1000)
+    assert np.array_equal(ops.take_rows(v, idx).cpu().numpy(), v[idx])
+    t3 = rs.randn(100, 3, 2)
+    assert np.array_equal(ops.take_rows(t3, idx[:50] % 100).cpu().numpy(), t3[idx[:50] % 100])
+
+
+def test_take_rows2_merge():
+    import torch
+    from elfi_b200 import ops
+    rs = np.random.RandomState(2)
+    a = rs.randn(50, 3)
+    b = rs.randn(400, 3)
+    mapb = np.sort(rs.choice(400, 120, replace=False)).astype(np.int32)
+    cat = np.vstack([a, b[mapb]])
+    perm = rs.permutation(len(cat)).astype(np.int32)
+    got = ops.take_rows2(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(),
+                         torch.from_numpy(perm).cuda(), 60, torch.from_numpy(mapb).cuda())
+    assert np.array_equal(got.cpu().numpy(), cat[perm[:60]])
+
+
+def test_weighted_quantile_golden():
+    from elfi_b200 import ops
+    g = load_golden('weighted_quantile')
+    for a, qw, qu in zip(g['alphas'], g['q_w'], g['q_unw']):
+        assert ops.weighted_sample_quantile(g['x'], a, g['w']) == qw
+        assert ops.weighted_sample_quantile(g['x'], a) == qu
+
+
+@pytest.mark.parametrize('n', [1, 2, 100, 4096, 4097, 250000])
+def test_weighted_quantile_vs_oracle(n):
+    from elfi_b200 import ops
+    rs = np.random.RandomState(n)
+    x = rs.rand(n)
+    w = rs.rand(n) ** 3
+    for a in (0.0, 0.05, 0.3333, 0.5, 0.99, 1.0):
+        assert ops.weighted_sample_quantile(x, a, w) == o.weighted_sample_quantile(x, a, w)
