@@ -10,7 +10,7 @@
 // (<= 2e6 pairs = 24 MB) are L2 resident, so the sort is latency/issue bound, not HBM bound;
 // passes whose digit is constant over all keys (typical for the high exponent bits of
 // distances) degenerate to a copy.
-#include "common.cuh"
+#include "pairwise.cuh"
 
 namespace elfi {
 
@@ -252,101 +252,96 @@ gather2_rows_kernel(const double* __restrict__ A, int64_t ldA, int64_t nA,
 }
 
 // ---- weighted quantile ---------------------------------------------------------------------
-// partial[b] = sum of w[perm[i]] over block b's 4096-element slice (w == NULL -> ones)
-__global__ void __launch_bounds__(1024)
-wq_block_sums_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm, int64_t n,
-                     double* __restrict__ partial) {
-    __shared__ double ws[32];
-    const int64_t lo = int64_t(blockIdx.x) * 4096;
-    double acc = 0.0;
-    for (int k = 0; k < 4; ++k) {
-        const int64_t i = lo + k * 1024 + threadIdx.x;
-        if (i < n) acc += w ? w[perm[i]] : 1.0;
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = ws[threadIdx.x];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+// The reference normalises with np.sum (pairwise order) and accumulates with np.cumsum
+// (strictly sequential); with equal weights and round alphas (e.g. SMC round 0, alpha = 0.5)
+// alpha sits exactly on a cumulative weight, so the rounding of that sequential sum decides
+// which order statistic is returned.  Both are therefore reproduced in the reference's order:
+// one warp streams the data through shared memory (coalesced loads, double buffered) and lane 0
+// performs the order-dependent adds.  Cost ~5 ns per element (1e6 weights: a few ms per
+// generation), negligible next to the O(N^2) weight update it feeds.
+constexpr int WQ_CHUNK = 1024;
+
+__device__ __forceinline__ void wq_stage(const double* __restrict__ src, int64_t n, int64_t base,
+                                         double* buf, int lane) {
+    for (int t = lane; t < WQ_CHUNK; t += 32) {
+        const int64_t i = base + t;
+        buf[t] = i < n ? src[i] : 0.0;
     }
 }
 
-// exclusive scan of the block sums (single block) + total in partial[nb]
-__global__ void __launch_bounds__(1024)
-wq_scan_partials_kernel(double* __restrict__ partial, int64_t nb, int32_t* __restrict__ count) {
-    __shared__ double ws[32];
-    __shared__ double carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { carry_s = 0.0; *count = 0; }
-    __syncthreads();
-    for (int64_t base = 0; base < nb; base += 1024) {
-        const int64_t i = base + tid;
-        const double v = i < nb ? partial[i] : 0.0;
-        double incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+// out[0] = np.sum(w) in NumPy's pairwise order (w == NULL: n, exactly)
+__global__ void __launch_bounds__(32)
+wq_total_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ out) {
+    __shared__ double buf[2][WQ_CHUNK];
+    const int lane = threadIdx.x;
+    if (w == nullptr) {
+        if (lane == 0) out[0] = double(n);
+        return;
+    }
+    PairwiseStream pw;
+    if (lane == 0) pw.begin(n);
+    wq_stage(w, n, 0, buf[0], lane);
+    __syncwarp();
+    int cur = 0;
+    for (int64_t base = 0; base < n; base += WQ_CHUNK, cur ^= 1) {
+        if (base + WQ_CHUNK < n) wq_stage(w, n, base + WQ_CHUNK, buf[cur ^ 1], lane);
+        if (lane == 0) {
+            const int64_t lim = (n - base) < WQ_CHUNK ? (n - base) : WQ_CHUNK;
+            for (int64_t j = 0; j < lim; j += 8) {
+                const int cnt = (lim - j) < 8 ? int(lim - j) : 8;
+                pw.feed8(base + j, &buf[cur][j], cnt);
+            }
         }
-        if (lane == 31) ws[wid] = incl;
-        __syncthreads();
-        double woff = 0.0;
-        for (int k = 0; k < wid; ++k) woff += ws[k];
-        const double carry = carry_s;
-        if (i < nb) partial[i] = carry + woff + incl - v;
-        __syncthreads();
-        if (tid == 1023) carry_s = carry + woff + incl;
-        __syncthreads();
+        __syncwarp();
     }
-    if (tid == 0) partial[nb] = carry_s;
+    if (lane == 0) out[0] = pw.finish();
 }
 
-// count of k in [0, n-2] whose normalised inclusive prefix sum is < alpha
-__global__ void __launch_bounds__(1024)
-wq_count_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm, int64_t n,
-                const double* __restrict__ partial, int64_t nb, double alpha,
-                int32_t* __restrict__ count) {
-    __shared__ double ws[32];
-    __shared__ double carry_s;
-    __shared__ int cnt_s;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const double total = partial[nb];
-    if (tid == 0) { carry_s = partial[blockIdx.x]; cnt_s = 0; }
-    __syncthreads();
-    int local = 0;
-    const int64_t lo = int64_t(blockIdx.x) * 4096;
-    for (int k = 0; k < 4; ++k) {
-        const int64_t i = lo + k * 1024 + tid;
-        const double v = i < n ? (w ? w[perm[i]] : 1.0) : 0.0;
-        double incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+// ws[i] = w[perm[i]] / total   (weights[index] of utils.py:401-402; exact IEEE division)
+__global__ void wq_normalise_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm,
+                                    int64_t n, const double* __restrict__ total,
+                                    double* __restrict__ ws) {
+    const double t = total[0];
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        ws[i] = (w ? w[perm[i]] : 1.0) / t;
+}
+
+// index_alpha = #{ k in [0, n-2] : cumsum(ws)[k] < alpha }, cumsum strictly sequential
+// (utils.py:403-406; the last cumulative weight is forced to 1.0 there, hence n-2).
+__global__ void __launch_bounds__(32)
+wq_seqscan_kernel(const double* __restrict__ ws, int64_t n, double alpha,
+                  const uint64_t* __restrict__ ukeys, double* __restrict__ out) {
+    __shared__ double buf[2][WQ_CHUNK];
+    __shared__ int done_s;
+    const int lane = threadIdx.x;
+    int64_t count = 0;
+    double c = 0.0;
+    if (lane == 0) done_s = (alpha == 0.0) ? 1 : 0;
+    wq_stage(ws, n, 0, buf[0], lane);
+    __syncwarp();
+    int cur = 0;
+    for (int64_t base = 0; base < n - 1; base += WQ_CHUNK, cur ^= 1) {
+        if (done_s) break;
+        if (base + WQ_CHUNK < n - 1) wq_stage(ws, n, base + WQ_CHUNK, buf[cur ^ 1], lane);
+        if (lane == 0) {
+            const int64_t lim = (n - 1 - base) < WQ_CHUNK ? (n - 1 - base) : WQ_CHUNK;
+            for (int64_t j = 0; j < lim; ++j) {
+                c = __dadd_rn(c, buf[cur][j]);
+                if (c < alpha) {
+                    ++count;
+                } else {
+                    done_s = 1;   // cumulative weights are non-decreasing
+                    break;
+                }
+            }
         }
-        if (lane == 31) ws[wid] = incl;
-        __syncthreads();
-        double woff = 0.0;
-        for (int q = 0; q < wid; ++q) woff += ws[q];
-        const double carry = carry_s;
-        const double c = (carry + woff + incl) / total;
-        if (i < n - 1 && c < alpha) ++local;
-        __syncthreads();
-        if (tid == 1023) carry_s = carry + woff + incl;
-        __syncthreads();
+        __syncwarp();
     }
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if (lane == 0 && local) atomicAdd(&cnt_s, local);
-    __syncthreads();
-    if (tid == 0 && cnt_s) atomicAdd(count, cnt_s);
-}
-
-__global__ void wq_pick_kernel(const uint64_t* __restrict__ ukeys, const int32_t* __restrict__ count,
-                               int64_t n, double alpha, double* __restrict__ out) {
-    int64_t idx = alpha == 0.0 ? 0 : int64_t(*count);
-    if (idx > n - 1) idx = n - 1;
-    out[0] = u64_to_key(ukeys[idx]);
-    out[1] = double(idx);
+    if (lane == 0) {
+        out[0] = u64_to_key(ukeys[count]);
+        out[1] = double(count);
+    }
 }
 
 }  // namespace elfi
@@ -418,20 +413,20 @@ int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w
     ELFI_REQUIRE(alpha >= 0.0 && alpha <= 1.0, "wquantile: alpha=%g outside [0, 1]", alpha);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
-    const int64_t nb = (n + 4095) / 4096;
     const size_t sort_bytes = sort_scratch_bytes(n);
-    const size_t extra = align256(size_t(nb + 1) * 8) + 256;
+    const size_t extra = align256(size_t(n) * 8) + 256;
     uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, sort_bytes + extra));
     if (!base) return ELFI_B200_ERR_NOMEM;
     SortScratch s = carve_sort(base, n);
-    double* partial = reinterpret_cast<double*>(base + sort_bytes);
-    int32_t* count = reinterpret_cast<int32_t*>(base + sort_bytes + align256(size_t(nb + 1) * 8));
+    double* ws = reinterpret_cast<double*>(base + sort_bytes);
+    double* total = reinterpret_cast<double*>(base + sort_bytes + align256(size_t(n) * 8));
     int rc = sort_pairs_device(x, n, s, ctx->sm_count, stream);
     if (rc) return rc;
-    wq_block_sums_kernel<<<unsigned(nb), 1024, 0, stream>>>(w, s.v[0], n, partial);
-    wq_scan_partials_kernel<<<1, 1024, 0, stream>>>(partial, nb, count);
-    wq_count_kernel<<<unsigned(nb), 1024, 0, stream>>>(w, s.v[0], n, partial, nb, alpha, count);
-    wq_pick_kernel<<<1, 1, 0, stream>>>(s.k[0], count, n, alpha, out);
+    wq_total_kernel<<<1, 32, 0, stream>>>(w, n, total);
+    int blocks = int((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    wq_normalise_kernel<<<blocks, 256, 0, stream>>>(w, s.v[0], n, total, ws);
+    wq_seqscan_kernel<<<1, 32, 0, stream>>>(ws, n, alpha, s.k[0], out);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

@@ -1,0 +1,85 @@
+"""MA2 model (mirror of elfi/examples/ma2.py) with device summaries.
+
+The simulator and priors run on the host with the per-batch RandomState exactly as in the
+reference (that is what "same seeds" means); the summaries and the distance
+run on the device.
+"""
+from functools import partial
+
+import numpy as np
+import scipy.stats as ss
+
+from .. import model as em
+from .. import ops
+
+
+def MA2(t1, t2, n_obs=100, batch_size=1, random_state=None):
+    """x_i = w_i + t1 w_{i-1} + t2 w_{i-2}, w ~ N(0,1)  (elfi/examples/ma2.py:11-37)."""
+    t1 = np.asanyarray(t1).reshape((-1, 1))
+    t2 = np.asanyarray(t2).reshape((-1, 1))
+    random_state = random_state or np.random
+    w = random_state.randn(batch_size, n_obs + 2)
+    x = w[:, 2:] + t1 * w[:, 1:-1] + t2 * w[:, :-2]
+    return x
+
+
+def autocov(x, lag=1):
+    """Autocovariance summary on the device (elfi/examples/ma2.py:40-59); returns (B,)."""
+    x = np.atleast_2d(x) if not hasattr(x, 'is_cuda') else x
+    return ops.autocov(x, lags=(lag,))[:, 0]
+
+
+class CustomPrior1:
+    """Triangular prior of t1 on [-b, b] (elfi/examples/ma2.py:96-140)."""
+
+    @classmethod
+    def rvs(cls, b, size=1, random_state=None):
+        u = ss.uniform.rvs(loc=0, scale=1, size=size, random_state=random_state)
+        return np.where(u < 0.5, np.sqrt(2. * u) * b - b, -np.sqrt(2. * (1. - u)) * b + b)
+
+    @classmethod
+    def pdf(cls, x, b):
+        p = 1. / b - np.abs(x) / (b * b)
+        return np.where(p < 0., 0., p)
+
+    @classmethod
+    def logpdf(cls, x, b):
+        with np.errstate(divide='ignore'):
+            return np.log(cls.pdf(x, b))
+
+
+class CustomPrior2:
+    """Uniform prior of t2 given t1 (elfi/examples/ma2.py:143-186)."""
+
+    @classmethod
+    def rvs(cls, t1, a, size=1, random_state=None):
+        locs = np.maximum(-a - t1, -a + t1)
+        scales = a - locs
+        return ss.uniform.rvs(loc=locs, scale=scales, size=size, random_state=random_state)
+
+    @classmethod
+    def pdf(cls, x, t1, a):
+        locs = np.maximum(-a - t1, -a + t1)
+        scales = a - locs
+        return (x >= locs) * (x <= locs + scales) * 1 / np.where(scales > 0, scales, 1)
+
+    @classmethod
+    def logpdf(cls, x, t1, a):
+        with np.errstate(divide='ignore'):
+            return np.log(cls.pdf(x, t1, a))
+
+
+def get_model(n_obs=100, true_params=None, seed_obs=None):
+    """MA2 inference task (elfi/examples/ma2.py:62-92)."""
+    if true_params is None:
+        true_params = [.6, .2]
+    y = MA2(*true_params, n_obs=n_obs, random_state=np.random.RandomState(seed_obs))
+    sim_fn = partial(MA2, n_obs=n_obs)
+    m = em.ElfiModel()
+    em.Prior(CustomPrior1, 2, model=m, name='t1')
+    em.Prior(CustomPrior2, m['t1'], 1, name='t2')
+    em.Simulator(sim_fn, m['t1'], m['t2'], observed=y, name='MA2')
+    em.Summary(autocov, m['MA2'], name='S1')
+    em.Summary(autocov, m['MA2'], 2, name='S2')
+    em.Distance('euclidean', m['S1'], m['S2'], name='d')
+    return m

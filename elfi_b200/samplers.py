@@ -1,0 +1,755 @@
+"""Rejection / SMC-ABC samplers with the population arithmetic on the device.
+
+Host control flow mirrors the reference (file:line in /root/reference):
+  ParameterInference.infer/iterate      elfi/methods/inference/parameter_inference.py:226-305
+  Rejection                             elfi/methods/inference/samplers.py:57-317
+  SMC                                   elfi/methods/inference/samplers.py:320-559
+  AdaptiveDistanceSMC                   elfi/methods/inference/samplers.py:562-659
+  ModelPrior.logpdf                     elfi/model/extensions.py:120-211
+  GMDistribution.rvs / logpdf           elfi/methods/utils.py:142-272
+What moved to the GPU: summaries + distances (+ acceptance) per batch, the running top-n merge
+(sort + gather instead of argsort + fancy indexing over n + batch_size rows), the weighted
+quantile, the O(N^2) proposal density, importance weights and weighted variance.
+
+Multi-GPU (one process per GPU, torch.distributed): batch index b is computed by rank
+b % world_size; ranks keep local top-n states and exchange them with ONE all-gather when a
+population is extracted (fixed capacity n rows per rank), after which every rank holds the same
+population.  The O(N^2) density is sharded over the new particles and all-gathered.
+"""
+import logging
+from functools import reduce
+from math import ceil
+from operator import add
+
+import numpy as np
+import scipy.stats as ss
+import torch
+
+from . import device as dev
+from . import model as em
+from . import ops
+from .results import Sample, SmcSample
+
+logger = logging.getLogger(__name__)
+
+__all__ = ['Rejection', 'SMC', 'AdaptiveDistanceSMC', 'ModelPrior', 'GMDistribution']
+
+
+# ----------------------------------------------------------------------------- communication
+class Comm:
+    """torch.distributed plumbing (NCCL on GPUs, gloo in CPU tests); identity when single."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.rank = dist.get_rank() if self.on else 0
+        self.size = dist.get_world_size() if self.on else 1
+
+    def all_gather_rows(self, t):
+        """Concatenate equally shaped tensors of all ranks along axis 0 (rank order)."""
+        if not self.on:
+            return t
+        t = t.contiguous()
+        out = torch.empty((self.size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype,
+                          device=t.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return out
+
+    def all_reduce_sum(self, value):
+        if not self.on:
+            return value
+        backend = self.dist.get_backend()
+        devname = 'cuda' if backend == 'nccl' else 'cpu'
+        t = torch.tensor([float(value)], dtype=torch.float64, device=devname)
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+
+# -------------------------------------------------------------------------------- prior, GM
+class ModelPrior:
+    """Joint prior of the model parameters (elfi/model/extensions.py:120-245): logpdf is the sum
+    of each parameter node's distribution.logpdf(x_node, *parent values), evaluated through the
+    graph so conditional priors (MA2's t2 | t1) work.  Host side: priors are arbitrary Python."""
+
+    def __init__(self, model, parameter_names=None):
+        model = model.copy()
+        self.parameter_names = parameter_names or model.parameter_names
+        for p in self.parameter_names:
+            if p not in model.parameter_names:
+                raise ValueError("Parameter '{}' not found in model parameters.".format(p))
+        self.dim = len(self.parameter_names)
+        self._model = model
+        self._nets = {}
+        for log in (False, True):
+            attr = 'logpdf' if log else 'pdf'
+            nodes = []
+            for n in model.parameter_names:
+                node = model[n]
+                op = getattr(node.distribution, attr)
+                nodes.append(em.Operation(op, node, *node.parents, model=model,
+                                          name='_{}_{}'.format(n, attr)))
+            combine = add if log else (lambda a, b: a * b)
+            joint = em.Operation(lambda *a, _c=combine: reduce(_c, a), *nodes, model=model,
+                                 name='_joint_{}*'.format(attr))
+            self._nets[log] = (joint.name, em.compile_net(model.source_net, [joint.name]))
+
+    def _evaluate(self, x, log):
+        x = np.asanyarray(x)
+        ndim = x.ndim
+        x = x.reshape((-1, self.dim))
+        name, net = self._nets[log]
+        context = em.ComputationContext(len(x), seed=0)
+        batch = {p: x[:, i] for i, p in enumerate(self.parameter_names)}
+        val = em.execute_batch(self._model, [name], context, 0, with_values=batch,
+                               compiled=net)[name]
+        if ndim == 0 or (ndim == 1 and self.dim > 1):
+            val = val[0]
+        return val
+
+    def pdf(self, x):
+        return self._evaluate(x, False)
+
+    def logpdf(self, x):
+        return self._evaluate(x, True)
+
+    def rvs(self, size=None, random_state=None):
+        random_state = np.random if random_state is None else random_state
+        context = em.ComputationContext(size or 1, seed='global')
+        batch = em.execute_batch(self._model, list(self.parameter_names), context, 0,
+                                 with_values={'_random_state': random_state})
+        rvs = np.column_stack([batch[p] for p in self.parameter_names])
+        if self.dim == 1:
+            rvs = rvs.reshape(size or 1)
+        return rvs[0] if size is None else rvs
+
+
+def normalize_weights(weights):
+    """elfi/methods/utils.py:80-88."""
+    w = np.atleast_1d(weights)
+    if np.any(w < 0):
+        raise ValueError("Weights must be positive")
+    wsum = np.sum(weights)
+    if wsum == 0:
+        raise ValueError("All weights are zero")
+    return w / wsum
+
+
+class GMDistribution:
+    """Gaussian mixture with shared covariance (elfi/methods/utils.py:142-272).
+    logpdf/pdf run on the device; rvs consumes the host RandomState like the reference."""
+
+    @classmethod
+    def logpdf(cls, x, means, cov=1, weights=None):
+        return ops.gm_logpdf(x, means, cov, weights)
+
+    @classmethod
+    def pdf(cls, x, means, cov=1, weights=None):
+        return torch.exp(ops.gm_logpdf(x, means, cov, weights))
+
+    @classmethod
+    def rvs(cls, means, cov=1, weights=None, size=1, prior_logpdf=None, random_state=None):
+        random_state = random_state or np.random
+        means = np.atleast_1d(np.squeeze(means))
+        if means.ndim > 2:
+            raise ValueError('means.ndim = {} but must be at most 2.'.format(means.ndim))
+        if weights is None:
+            weights = np.ones(len(means))
+        weights = normalize_weights(weights)
+        no_wrap = size is None
+        if no_wrap:
+            size = 1
+        output = np.empty((size,) + means.shape[1:])
+        n_accepted, n_left, trials = 0, size, 0
+        while n_accepted < size:
+            inds = random_state.choice(len(means), size=n_left, p=weights)
+            centres = means[inds]
+            perturb = ss.multivariate_normal.rvs(mean=means[0] * 0, cov=cov,
+                                                 random_state=random_state, size=n_left)
+            x = centres + perturb
+            if prior_logpdf is not None:
+                x = x[np.isfinite(prior_logpdf(x))]
+            k = len(x)
+            output[n_accepted:n_accepted + k] = x
+            n_accepted += k
+            n_left -= k
+            trials += 1
+            if trials == 100:
+                logger.warning("SMC: It appears to be difficult to find enough valid proposals "
+                               "with prior pdf > 0. ELFI will keep trying, but you may wish "
+                               "to kill the process and adjust the model priors.")
+        return output[0] if no_wrap else output
+
+
+# ----------------------------------------------------------------------------- base class
+class ParameterInference:
+    """Batch loop of elfi's ParameterInference for a single in-order device client."""
+
+    def __init__(self, model, output_names, batch_size=1, seed=None, pool=None,
+                 max_parallel_batches=None):
+        model = model.model if isinstance(model, em.NodeReference) else model
+        if not model.parameter_names:
+            raise ValueError('Model {} defines no parameters'.format(model))
+        self.model = model.copy()
+        self.output_names = self._check_outputs(output_names)
+        self.computation_context = em.ComputationContext(batch_size=batch_size, seed=seed,
+                                                         pool=pool)
+        self._compiled = em.compile_net(self.model.source_net, self.output_names)
+        self.comm = Comm()
+        self.max_parallel_batches = max_parallel_batches or self.comm.size
+        if self.max_parallel_batches <= 0:
+            raise ValueError('Value for max_parallel_batches ({}) must be at least one.'.format(
+                self.max_parallel_batches))
+        self.state = dict(n_sim=0, n_batches=0)
+        self.objective = dict()
+        self._next_batch_index = 0
+
+    @property
+    def seed(self):
+        return self.computation_context.seed
+
+    @property
+    def parameter_names(self):
+        return self.model.parameter_names
+
+    @property
+    def batch_size(self):
+        return self.computation_context.batch_size
+
+    def set_objective(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def extract_result(self):
+        raise NotImplementedError
+
+    def update(self, batch, batch_index):
+        self.state['n_batches'] += 1
+        self.state['n_sim'] += self.batch_size
+
+    def prepare_new_batch(self, batch_index):
+        pass
+
+    def _accept_hint(self):
+        return None
+
+    def _run_batch(self, batch_index, values):
+        batch = em.execute_batch(self.model, self.output_names, self.computation_context,
+                                 batch_index, with_values=values, accept=self._accept_hint(),
+                                 compiled=self._compiled)
+        self.computation_context.num_submissions += 1
+        return batch
+
+    def infer(self, *args, vis=None, bar=True, **kwargs):
+        self.set_objective(*args, **kwargs)
+        while not self.finished:
+            self.iterate()
+        return self.extract_result()
+
+    def iterate(self):
+        """One batch: prepare -> execute on the device -> update (in batch_index order)."""
+        batch_index = self._next_batch_index
+        values = self.prepare_new_batch(batch_index)
+        self._next_batch_index += 1
+        batch = self._run_batch(batch_index, values)
+        self.update(batch, batch_index)
+
+    @property
+    def finished(self):
+        return self._objective_n_batches <= self.state['n_batches']
+
+    @property
+    def _objective_n_batches(self):
+        if 'n_batches' in self.objective:
+            return self.objective['n_batches']
+        if 'n_sim' in self.objective:
+            return ceil(self.objective['n_sim'] / self.batch_size)
+        raise ValueError('Objective must define either `n_batches` or `n_sim`.')
+
+    def _extract_result_kwargs(self):
+        return {'method_name': self.__class__.__name__, 'parameter_names': self.parameter_names,
+                'seed': self.seed, 'n_sim': self.state['n_sim'],
+                'n_batches': self.state['n_batches']}
+
+    @staticmethod
+    def _resolve_model(model, target, default_reference_class=em.NodeReference):
+        if isinstance(model, em.ElfiModel) and target is None:
+            raise NotImplementedError("Please specify the target node of the inference method")
+        if isinstance(model, em.NodeReference):
+            target = model
+            model = target.model
+        if isinstance(target, str):
+            target = model[target]
+        if not isinstance(target, default_reference_class):
+            raise ValueError('Unknown target node class')
+        return model, target.name
+
+    def _check_outputs(self, output_names):
+        checked, seen = [], set()
+        for name in output_names or []:
+            if isinstance(name, em.NodeReference):
+                name = name.name
+            if name in seen:
+                continue
+            if not isinstance(name, str):
+                raise ValueError('All output names must be strings, object {} was given'.format(
+                    name))
+            if not self.model.has_node(name):
+                raise ValueError('Node {} output was requested, but it is not in the model.'
+                                 .format(name))
+            seen.add(name)
+            checked.append(name)
+        return checked
+
+
+class Sampler(ParameterInference):
+    def sample(self, n_samples, *args, **kwargs):
+        bar = kwargs.pop('bar', True)
+        self.bar = bar
+        return self.infer(n_samples, *args, bar=bar, **kwargs)
+
+    def _extract_result_kwargs(self):
+        kwargs = super()._extract_result_kwargs()
+        for key in ['threshold', 'accept_rate']:
+            if key in self.state:
+                kwargs[key] = self.state[key]
+        if hasattr(self, 'discrepancy_name'):
+            kwargs['discrepancy_name'] = self.discrepancy_name
+        return kwargs
+
+
+# ------------------------------------------------------------------------------- rejection
+def _to_dev_f64(x):
+    return x if dev.is_device_array(x) else dev.to_device(np.asarray(x, dtype=np.float64))
+
+
+class Rejection(Sampler):
+    """Parallel ABC rejection sampler; the running best-n state lives on the device."""
+
+    def __init__(self, model, discrepancy_name=None, output_names=None, **kwargs):
+        model, discrepancy_name = self._resolve_model(model, discrepancy_name)
+        output_names = [discrepancy_name] + model.parameter_names + (output_names or [])
+        self.adaptive = isinstance(model[discrepancy_name], em.AdaptiveDistance)
+        if self.adaptive:
+            model[discrepancy_name].init_adaptation_round()
+            self.sums = [s.name for s in model[discrepancy_name].parents]
+            for k in self.sums:
+                if k not in output_names:
+                    output_names.append(k)
+        super().__init__(model, output_names, **kwargs)
+        self.discrepancy_name = discrepancy_name
+
+    def set_objective(self, n_samples, threshold=None, quantile=None, n_sim=None):
+        if quantile is None and threshold is None and n_sim is None:
+            quantile = .01
+        self.state = dict(samples=None, threshold=np.inf, n_sim=0, accept_rate=1, n_batches=0)
+        if quantile:
+            n_sim = ceil(n_samples / quantile)
+        if n_sim:
+            n_batches = ceil(n_sim / self.batch_size)
+            if self.comm.on:
+                n_batches = ceil(n_batches / self.comm.size)   # batches per rank
+        else:
+            n_batches = 1 if self.comm.on else self.max_parallel_batches
+        self.objective = dict(n_samples=n_samples, threshold=threshold, n_batches=n_batches)
+        self._next_batch_index = 0
+        self._n_acceptable = 0
+
+    # -- device-side acceptance: thresholds are handed to the distance kernel
+    def _accept_hint(self):
+        thr = self.objective.get('threshold')
+        if thr is None:
+            # quantile / n_sim mode: once the best-n buffer is full only rows at or below its
+            # current n-th distance can enter it (single-column distances only)
+            cur = self.state.get('threshold')
+            if self.state.get('samples') is not None and np.ndim(cur) == 0 and np.isfinite(cur) \
+                    and not self.adaptive:
+                return {self.discrepancy_name: float(cur)}
+            return None
+        return {self.discrepancy_name: np.atleast_1d(np.asarray(thr, dtype=np.float64))}
+
+    def update(self, batch, batch_index):
+        super().update(batch, batch_index)
+        if self.state['samples'] is None:
+            self._init_samples_lazy(batch)
+        self._merge_batch(batch)
+        self._update_state_meta()
+        self._update_objective_n_batches()
+
+    def extract_result(self):
+        if self.state['samples'] is None:
+            raise ValueError('Nothing to extract')
+        self._gather_ranks()
+        if self.adaptive:
+            self._update_distances()
+        n = self.objective['n_samples']
+        outputs = {k: dev.to_host(v[:n]) for k, v in self.state['samples'].items()}
+        return Sample(outputs=outputs, **self._extract_result_kwargs())
+
+    def _init_samples_lazy(self, batch):
+        """Best-n buffers on the device (the reference keeps n + batch_size rows on the host,
+        samplers.py:177-207; here the merge reads the batch in place)."""
+        samples = {}
+        n = self.objective['n_samples']
+        for node in self.output_names:
+            if node not in batch:
+                raise KeyError("Did not receive outputs for node {}".format(node))
+            nbatch = batch[node]
+            if not em.is_array(nbatch):
+                raise ValueError("Node {} output must be in a numpy array of length {} "
+                                 "(batch_size).".format(node, self.batch_size))
+            if len(nbatch) != self.batch_size:
+                raise ValueError("Node {} output has array length {}. It should be equal to the "
+                                 "batch size {}.".format(node, len(nbatch), self.batch_size))
+            shape = (n,) + tuple(nbatch.shape[1:])
+            if node == self.discrepancy_name:
+                samples[node] = torch.full(shape, float('inf'), dtype=torch.float64, device='cuda')
+            else:
+                samples[node] = torch.zeros(shape, dtype=torch.float64, device='cuda')
+        self.state['samples'] = samples
+
+    def _merge_batch(self, batch):
+        """samplers.py:209-237 on the device: accepted rows of the batch + current best-n ->
+        sort by the (last) distance column -> gather the n smallest for every output."""
+        samples = self.state['samples']
+        n = self.objective['n_samples']
+        dname = self.discrepancy_name
+        if self.adaptive:
+            self.model[dname].add_data(*[batch[s] for s in self.sums])
+
+        d_batch = _to_dev_f64(batch[dname])
+        acc = batch.get(('accepted', dname))
+        if self.objective.get('threshold') is None and acc is None:
+            map_b, n_cand = None, self.batch_size
+        else:
+            if acc is None:  # discrepancy node without fused acceptance (custom callable)
+                thr = self.objective.get('threshold')
+                if thr is None:
+                    thr = self.state['threshold']
+                ok = (d_batch <= torch.as_tensor(thr, dtype=torch.float64, device='cuda'))
+                if ok.dim() > 1:
+                    ok = ok.all(dim=1)
+                acc = torch.nonzero(ok).ravel().to(torch.int32)
+            map_b, n_cand = acc, int(acc.numel())
+        if self.objective.get('threshold') is not None:
+            self._n_acceptable += n_cand
+        if n_cand == 0:
+            return
+        key_state = samples[dname] if samples[dname].dim() == 1 else samples[dname][:, -1]
+        key_batch = d_batch if d_batch.dim() == 1 else d_batch[:, -1]
+        cand_keys = key_batch if map_b is None else ops.take_rows(key_batch, map_b)
+        perm = ops.argsort(torch.cat([key_state, cand_keys]))
+        for node in samples:
+            samples[node] = ops.take_rows2(samples[node], _to_dev_f64(batch[node]), perm, n, map_b)
+
+    def _update_state_meta(self):
+        o, s = self.objective, self.state
+        d = s['samples'][self.discrepancy_name]
+        last = d[o['n_samples'] - 1]
+        s['threshold'] = float(last.item()) if last.dim() == 0 else last.cpu().numpy()
+        s['accept_rate'] = min(1, o['n_samples'] / s['n_sim'])
+
+    def _update_objective_n_batches(self):
+        """samplers.py:246-277.  n_acceptable = rows of the reference's (n + batch) buffer at or
+        below the threshold = all rows accepted so far (the buffer never overflows before the
+        sampler stops), tracked as a running count."""
+        if self.objective.get('threshold') is None:
+            return
+        s = self.state
+        n_samples = self.objective['n_samples']
+        n_acceptable = self.comm.all_reduce_sum(self._n_acceptable) if self.comm.on \
+            else self._n_acceptable
+        n_sim = s['n_sim'] * self.comm.size if self.comm.on else s['n_sim']
+        if n_acceptable == 0:
+            n_batches = self.objective['n_batches'] + 1
+        else:
+            accept_rate_t = n_acceptable / n_sim
+            margin = .2 * self.batch_size * int(n_acceptable < n_samples)
+            n_batches = ceil((n_samples / accept_rate_t + margin) / self.batch_size)
+            if self.comm.on:
+                n_batches = ceil(n_batches / self.comm.size)
+        self.objective['n_batches'] = n_batches
+
+    def _update_distances(self):
+        """samplers.py:279-299: append the new weight vector, re-score the kept rows with all
+        K+1 nested distances, re-rank by the newest.  Like the reference, the distance output
+        becomes the UNSORTED newest column while every other output is re-ordered."""
+        node = self.model[self.discrepancy_name]
+        node.update_distance()
+        nums = self.objective['n_samples']
+        data = {s: self.state['samples'][s][:nums] for s in self.sums}
+        ds = node.generate(batch_size=nums, with_values=data)
+        sort_distance = ds if ds.dim() == 1 else ds[:, -1].contiguous()
+        sort_mask = ops.argsort(sort_distance)
+        self.state['samples'][self.discrepancy_name] = sort_distance
+        for k in self.state['samples'].keys():
+            if k != self.discrepancy_name:
+                self.state['samples'][k] = ops.take_rows(self.state['samples'][k], sort_mask)
+        self._update_state_meta()
+
+    def _gather_ranks(self):
+        """Multi-GPU: one all-gather of the fixed-capacity local best-n buffers, then the same
+        sort + gather on every rank, so all ranks hold the identical global best-n."""
+        if not self.comm.on:
+            return
+        samples = self.state['samples']
+        n = self.objective['n_samples']
+        gathered = {k: self.comm.all_gather_rows(v) for k, v in samples.items()}
+        d = gathered[self.discrepancy_name]
+        perm = ops.argsort(d if d.dim() == 1 else d[:, -1].contiguous())[:n]
+        for k in samples:
+            samples[k] = ops.take_rows(gathered[k], perm)
+        self.state['n_sim'] = int(self.comm.all_reduce_sum(self.state['n_sim']))
+        self.state['n_batches'] = int(self.comm.all_reduce_sum(self.state['n_batches']))
+        if self.adaptive:
+            self._merge_adaptive_moments()
+        self._update_state_meta()
+
+    def _merge_adaptive_moments(self):
+        """Chan-merge the per-rank (n, mean, M2) column moments (3 x D doubles per rank)."""
+        st = self.model[self.discrepancy_name]._s
+        n_r, m_r, s_r = st['store']
+        D = np.size(m_r) if np.ndim(m_r) else 1
+        pack = torch.zeros(1, 1 + 2 * D, dtype=torch.float64, device='cuda')
+        pack[0, 0] = float(n_r)
+        pack[0, 1:1 + D] = torch.as_tensor(np.broadcast_to(m_r, (D,)).copy(), device='cuda')
+        pack[0, 1 + D:] = torch.as_tensor(np.broadcast_to(s_r, (D,)).copy(), device='cuda')
+        allp = self.comm.all_gather_rows(pack).cpu().numpy()
+        n0, m0, s0 = 0.0, np.zeros(D), np.zeros(D)
+        for row in allp:
+            nb, mb, sb = row[0], row[1:1 + D], row[1 + D:]
+            if nb == 0:
+                continue
+            n1 = n0 + nb
+            delta = mb - m0
+            m0 = m0 + delta * (nb / n1)
+            s0 = s0 + sb + delta ** 2 * (n0 * nb / n1)
+            n0 = n1
+        st['store'] = [n0, m0, s0]
+        st['scale'] = np.sqrt(s0 / n0)
+
+    def iterate(self):
+        """Batch index b is computed by rank b % world (each rank advances by world_size)."""
+        if not self.comm.on:
+            return super().iterate()
+        batch_index = self._next_batch_index * self.comm.size + self.comm.rank
+        values = self.prepare_new_batch(batch_index)
+        self._next_batch_index += 1
+        batch = self._run_batch(batch_index, values)
+        self.update(batch, batch_index)
+
+
+# ------------------------------------------------------------------------------------- SMC
+class SMC(Sampler):
+    """Sequential Monte Carlo ABC sampler (samplers.py:320-559)."""
+
+    def __init__(self, model, discrepancy_name=None, output_names=None, **kwargs):
+        model, discrepancy_name = self._resolve_model(model, discrepancy_name)
+        output_names = [discrepancy_name] + model.parameter_names + (output_names or [])
+        super().__init__(model, output_names, **kwargs)
+        self._prior = ModelPrior(self.model)
+        self.discrepancy_name = discrepancy_name
+        self.state['round'] = 0
+        self._populations = []
+        self._rejection = None
+        self._round_random_state = None
+        self._quantiles = None
+        self.bar = False
+
+    def set_objective(self, n_samples, thresholds=None, quantiles=None):
+        if thresholds is None and quantiles is None:
+            raise ValueError("Either thresholds or quantiles is required to run ABC-SMC.")
+        rounds = (len(quantiles) if thresholds is None else len(thresholds)) - 1
+        self.state['round'] = len(self._populations)
+        rounds = rounds + self.state['round']
+        if thresholds is None:
+            thresholds = np.full((rounds + 1), None)
+            self._quantiles = np.concatenate((np.full((self.state['round']), None), quantiles))
+        else:
+            thresholds = np.concatenate((np.full((self.state['round']), None), thresholds))
+        self.objective.update(dict(n_samples=n_samples, n_batches=self.max_parallel_batches,
+                                   round=rounds, thresholds=thresholds))
+        self._init_new_round()
+        self._update_objective()
+
+    def extract_result(self):
+        pop = self._extract_population()
+        self._populations.append(pop)
+        return SmcSample(outputs=pop.outputs, populations=self._populations.copy(),
+                         weights=pop.weights, threshold=pop.threshold,
+                         **self._extract_result_kwargs())
+
+    def _accept_hint(self):
+        return self._rejection._accept_hint()
+
+    def update(self, batch, batch_index):
+        super().update(batch, batch_index)
+        self._rejection.update(batch, batch_index)
+        if self._rejection.finished:
+            if self.state['round'] < self.objective['round']:
+                self._populations.append(self._extract_population())
+                self.state['round'] += 1
+                self._init_new_round()
+        self._update_objective()
+
+    def iterate(self):
+        if not self.comm.on:
+            return super().iterate()
+        batch_index = self._next_batch_index * self.comm.size + self.comm.rank
+        values = self.prepare_new_batch(batch_index)
+        self._next_batch_index += 1
+        batch = self._run_batch(batch_index, values)
+        self.update(batch, batch_index)
+
+    def prepare_new_batch(self, batch_index):
+        if self.state['round'] == 0:
+            return
+        means, cov, weights = self._gm_params_host
+        params = GMDistribution.rvs(means, cov, weights, size=self.batch_size,
+                                    prior_logpdf=self._prior.logpdf,
+                                    random_state=self._round_random_state)
+        params = params.reshape((-1, len(self.parameter_names)))
+        return {p: params[:, i] for i, p in enumerate(self.parameter_names)}
+
+    def _init_new_round(self):
+        self._set_rejection_round(self.state['round'])
+        if self.state['round'] == 0 and self._quantiles is not None:
+            self._rejection.set_objective(self.objective['n_samples'], quantile=self._quantiles[0])
+        else:
+            if self._quantiles is not None:
+                self._set_threshold()
+            self._rejection.set_objective(self.objective['n_samples'],
+                                          threshold=self.current_population_threshold)
+
+    def _set_rejection_round(self, round):
+        seed = self.seed if round == 0 else em.get_sub_seed(self.seed, round)
+        if self.comm.on and round > 0:
+            # each rank draws its own proposals: decorrelate the per-round streams by rank
+            seed = em.get_sub_seed(int(seed), self.comm.rank)
+        self._round_random_state = np.random.RandomState(seed)
+        self._rejection = Rejection(self.model, discrepancy_name=self.discrepancy_name,
+                                    output_names=self.output_names, batch_size=self.batch_size,
+                                    seed=seed, max_parallel_batches=self.max_parallel_batches)
+
+    def _extract_population(self):
+        sample = self._rejection.extract_result()
+        sample.method_name = "Rejection within SMC-ABC"
+        means, w, cov = self._compute_weights_means_and_cov(sample)
+        sample.means = means
+        sample.weights = w
+        sample.meta['cov'] = cov
+        return sample
+
+    def _compute_weights_means_and_cov(self, pop):
+        """samplers.py:508-534 with the O(N_new x N_prev) mixture density on the device (and
+        sharded over ranks when distributed)."""
+        params = np.column_stack(tuple([pop.outputs[p] for p in self.parameter_names]))
+        params_dev = dev.to_device(params)
+        if self._populations:
+            means, cov, weights = self._gm_params_host
+            N = len(params)
+            if self.comm.on:
+                per = ceil(N / self.comm.size)
+                lo = min(N, self.comm.rank * per)
+                hi = min(N, lo + per)
+                q_part = torch.full((per,), float('nan'), dtype=torch.float64, device='cuda')
+                if hi > lo:
+                    q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], means, cov, weights)
+                q_logpdf = self.comm.all_gather_rows(q_part)
+                q_logpdf = torch.cat([q_logpdf[r * per:r * per + max(0, min(N, (r + 1) * per) - r * per)]
+                                      for r in range(self.comm.size)])
+            else:
+                q_logpdf = ops.gm_logpdf(params_dev, means, cov, weights)
+            p_logpdf = self._prior.logpdf(params)
+            w_dev = ops.smc_weights(p_logpdf, q_logpdf)
+            w = w_dev.cpu().numpy()
+        else:
+            w = np.ones(pop.n_samples)
+            w_dev = None
+        means = params.copy()
+        if np.count_nonzero(w) == 0:
+            raise RuntimeError("All sample weights are zero. If you are using a prior "
+                               "with a bounded support, this may be caused by specifying "
+                               "a too small sample size.")
+        cov = 2 * np.diag(ops.weighted_var(params_dev, w_dev))
+        if not np.all(np.isfinite(cov)):
+            logger.warning("Could not estimate the sample covariance. This is often "
+                           "caused by majority of the sample weights becoming zero."
+                           "Falling back to using unit covariance.")
+            cov = np.diag(np.ones(params.shape[1]))
+        return means, w, cov
+
+    def _update_objective(self):
+        n_batches = sum([pop.n_batches for pop in self._populations])
+        if self.comm.on:
+            n_batches = ceil(n_batches / self.comm.size)
+        self.objective['n_batches'] = n_batches + self._rejection.objective['n_batches']
+
+    def _set_threshold(self):
+        previous_population = self._populations[self.state['round'] - 1]
+        threshold = ops.weighted_sample_quantile(previous_population.discrepancies,
+                                                 self._quantiles[self.state['round']],
+                                                 previous_population.weights)
+        self.objective['thresholds'][self.state['round']] = threshold
+
+    @property
+    def _gm_params_host(self):
+        sample = self._populations[-1]
+        return sample.means, sample.cov, sample.weights
+
+    @property
+    def current_population_threshold(self):
+        return self.objective['thresholds'][self.state['round']]
+
+
+class AdaptiveDistanceSMC(SMC):
+    """SMC-ABC with adaptive threshold and distance (Prangle 2017 Alg. 5); samplers.py:562-659."""
+
+    def __init__(self, model, discrepancy_name=None, output_names=None, **kwargs):
+        model, discrepancy_name = self._resolve_model(model, discrepancy_name)
+        if not isinstance(model[discrepancy_name], em.AdaptiveDistance):
+            raise TypeError('This method requires an adaptive distance node.')
+        model[discrepancy_name].init_state()
+        sums = [s.name for s in model[discrepancy_name].parents]
+        if output_names is None:
+            output_names = sums
+        else:
+            for k in sums:
+                if k not in output_names:
+                    output_names.append(k)
+        super().__init__(model, discrepancy_name, output_names=output_names, **kwargs)
+
+    def set_objective(self, n_samples, rounds, quantile=0.5):
+        super().set_objective(ceil(n_samples / quantile), quantiles=[1] * rounds)
+        self.population_size = n_samples
+        self.quantile = quantile
+
+    def _extract_population(self):
+        rejection_sample = self._rejection.extract_result()
+        outputs = dict()
+        for k in self.output_names:
+            outputs[k] = rejection_sample.outputs[k][:self.population_size]
+        meta = rejection_sample.meta
+        meta['adaptive_distance_w'] = self.model[self.discrepancy_name]._s['w'][-1]
+        meta['threshold'] = max(outputs[self.discrepancy_name])
+        meta['accept_rate'] = self.population_size / meta['n_sim']
+        sample = Sample("Rejection within adaptive distance SMC-ABC", outputs,
+                        self.parameter_names, **{k: v for k, v in meta.items()
+                                                 if k not in ('method_name', 'parameter_names')})
+        means, w, cov = self._compute_weights_means_and_cov(sample)
+        sample.means = means
+        sample.weights = w
+        sample.meta['cov'] = cov
+        return sample
+
+    def _extract_result_kwargs(self):
+        kwargs = super()._extract_result_kwargs()
+        kwargs['adaptive_distance_w'] = [pop.adaptive_distance_w for pop in self._populations]
+        return kwargs
+
+    def _set_threshold(self):
+        round = self.state['round']
+        self.objective['thresholds'][round] = self._populations[round - 1].threshold
+
+    @property
+    def current_population_threshold(self):
+        return [np.inf] + [pop.threshold for pop in self._populations]

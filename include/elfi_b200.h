@@ -133,8 +133,9 @@ int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA,
 /* elfi_b200_wquantile_f64: weighted_sample_quantile (elfi/methods/utils.py:379-411).
  *   x (n), w (n) or NULL (equal weights), 0 <= alpha <= 1.
  *   out[0] = alpha-quantile (an element of x), out[1] = its rank in sorted order (as double).
- * The cumulative weights are accumulated by a blocked parallel scan (the reference's
- * np.cumsum is sequential): identical unless alpha lies within ~1e-13 of a cumulative weight. */
+ * np.sum (pairwise) and np.cumsum (sequential) are reproduced in the reference's order, so
+ * the selected element is identical even when alpha falls exactly on a cumulative weight
+ * (equal weights + round alpha, the normal case in SMC round 0). */
 int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w, int64_t n,
                             double alpha, double* out, void* stream);
 

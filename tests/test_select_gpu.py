@@ -25,7 +25,7 @@ def test_argsort_special_values_and_stability():
     perm = ops.argsort(x).cpu().numpy()
     xs = x[perm]
     assert np.isnan(xs[-1])
-    assert np.all(np.diff(xs[:-1]) >= 0)
+    assert np.array_equal(xs[:-1], np.sort(x)[:-1])
     ties = [i for i in perm if x[i] == 1.5]
     assert ties == sorted(ties)                      # stable
     x = np.repeat(np.arange(50.0), 400)[np.random.RandomState(0).permutation(20000)]
@@ -66,7 +66,21 @@ def test_weighted_quantile_golden():
         assert ops.weighted_sample_quantile(g['x'], a) == qu
 
 
-@pytest.mark.parametrize('n', [1, 2, 100, 4096, 4097, 250000])
+@pytest.mark.parametrize('n', [2, 10, 200, 1000, 5000, 100000])
+def test_weighted_quantile_equal_weights_knife_edge(n):
+    """alpha exactly on a cumulative weight: the sequential rounding decides (SMC round 0)."""
+    from elfi_b200 import ops
+    rs = np.random.RandomState(n)
+    x = rs.rand(n)
+    for a in (0.1, 0.2, 0.25, 0.3, 0.5, 0.7, 0.75, 0.9):
+        assert ops.weighted_sample_quantile(x, a) == o.weighted_sample_quantile(x, a)
+        assert ops.weighted_sample_quantile(x, a, np.ones(n)) == o.weighted_sample_quantile(
+            x, a, np.ones(n))
+        w3 = np.full(n, 3.0)
+        assert ops.weighted_sample_quantile(x, a, w3) == o.weighted_sample_quantile(x, a, w3)
+
+
+@pytest.mark.parametrize('n', [1, 2, 100, 4096, 4097, 250000, 1000003])
 def test_weighted_quantile_vs_oracle(n):
     from elfi_b200 import ops
     rs = np.random.RandomState(n)
