@@ -12,3 +12,4 @@ from .model import (AdaptiveDistance, Constant, Discrepancy, Distance, ElfiModel
                     NodeReference, Operation, Prior, RandomVariable, Simulator, Summary,
                     get_default_model, new_model, set_default_model)
 from .samplers import SMC, AdaptiveDistanceSMC, GMDistribution, ModelPrior, Rejection  # noqa: F401
+from .bo import BOLFI, LCBSC, BayesianOptimization, BolfiPosterior, GPyRegression  # noqa: F401

@@ -1,0 +1,576 @@
+// gp.cu -- Gaussian-process surrogate of BOLFI, fp64:
+//   K10  RBF + bias Gram matrix, Ky = K + (noise + jitter) I    (gpy_regression.py:132-133, 159)
+//   K11  Cholesky Ky = L L^T, W = L^-1, alpha = Ky^-1 y          (GPy posterior woodbury_*; read
+//        back at gpy_regression.py:152-158)
+//   K12  mean / variance at m query points + LCBSC               (gpy_regression.py:132-138,
+//        acquisition.py:276-280)
+//   K13  predictive gradients + LCBSC gradient                   (gpy_regression.py:206-218,
+//        acquisition.py:296-301)
+//
+// Precision: the north_star asks for 1e-5 relative agreement of posterior mean / variance in
+// fp64; Ky has condition numbers ~1e6, so the factorisation stays in fp64.  tcgen05.mma has no
+// f64 kind, so the tensor-core path for this work is the DMMA instruction
+// mma.sync.aligned.m8n8k4.f64 (one NT GEMM kernel below does every O(n^3) / O(n^2 m) product:
+// the trailing updates of the blocked Cholesky, the recursive triangular inverse and the
+// n^2 m / 2 variance product  V = K* W^T).
+//
+// Variance uses the explicit inverse factor W = L^-1 instead of a triangular solve per query
+// chunk:  v_i = k** - || W k_i ||^2.  The product is a GEMM with a triangular K-range (row a
+// of W is zero beyond column a), i.e. n^2 m / 2 FMAs = 0.4 TFLOP at n = 2000, m = 1e5.
+#include "common.cuh"
+
+namespace elfi {
+
+constexpr int GP_NB = 64;          // Cholesky panel width / base block of the inverse
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16;
+constexpr int GM_LDS = 20;         // padded row stride (doubles) of the smem tiles
+constexpr int GM_THREADS = 256;
+constexpr size_t GM_SMEM = size_t(2) * 2 * GM_BM * GM_LDS * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    const uint32_t d = smem_u32(smem_dst);
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct GemmArgs {
+    const double* A; int64_t lda; int64_t strideA;   // (M, K) row-major
+    const double* B; int64_t ldb; int64_t strideB;   // (N, K) row-major  -> C = A * B^T
+    double* C; int64_t ldc; int64_t strideC;         // (M, N)
+    double* Ct; int64_t ldct; int64_t strideCt;      // optional transposed copy (N, M)
+    int64_t M, N, K;
+    double alpha, beta;
+    int mode;   // 0 full; 1 lower tiles only (SYRK-style); 2 K limited to col0 + BN (B lower-tri)
+};
+
+// C = alpha * A * B^T + beta * C on the fp64 tensor path.  CTA tile 128x128x16, 8 warps as
+// 2 (M) x 4 (N), warp tile 64x32 = 8x4 DMMA tiles; cp.async double buffering; batch = grid.z.
+__global__ void __launch_bounds__(GM_THREADS)
+gemm_nt_dmma_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double smem_d[];
+    double* As = smem_d;                                  // [2][BM][LDS]
+    double* Bs = smem_d + size_t(2) * GM_BM * GM_LDS;     // [2][BN][LDS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int grp = lane >> 2, tig = lane & 3;
+    const int64_t row0 = int64_t(blockIdx.y) * GM_BM, col0 = int64_t(blockIdx.x) * GM_BN;
+    if (g.mode == 1 && col0 > row0 + GM_BM - 1) return;
+    const int64_t bz = blockIdx.z;
+    const double* A = g.A + bz * g.strideA;
+    const double* B = g.B + bz * g.strideB;
+    double* C = g.C + bz * g.strideC;
+    int64_t Kend = g.K;
+    if (g.mode == 2 && col0 + GM_BN < Kend) Kend = col0 + GM_BN;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto load_stage = [&](int stage, int64_t k0) {
+        // 128 rows x 8 chunks of 16 bytes per matrix; 4 chunks per thread per matrix
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int idx = tid + it * GM_THREADS;       // 0..1023
+            const int r = idx >> 3, ch = idx & 7;
+            const int64_t k = k0 + ch * 2;
+            const bool pa = (row0 + r < g.M) && (k < Kend);
+            const bool pb = (col0 + r < g.N) && (k < Kend);
+            cp_async16(As + (size_t(stage) * GM_BM + r) * GM_LDS + ch * 2,
+                       pa ? A + (row0 + r) * g.lda + k : A, pa);
+            cp_async16(Bs + (size_t(stage) * GM_BN + r) * GM_LDS + ch * 2,
+                       pb ? B + (col0 + r) * g.ldb + k : B, pb);
+        }
+        cp_async_commit();
+    };
+
+    const int64_t nk = (Kend + GM_BK - 1) / GM_BK;
+    if (nk > 0) load_stage(0, 0);
+    for (int64_t kt = 0; kt < nk; ++kt) {
+        const int cur = int(kt & 1);
+        if (kt + 1 < nk) {
+            load_stage(cur ^ 1, (kt + 1) * GM_BK);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* as = As + size_t(cur) * GM_BM * GM_LDS + size_t(wm * 64) * GM_LDS;
+        const double* bs = Bs + size_t(cur) * GM_BN * GM_LDS + size_t(wn * 32) * GM_LDS;
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = as[(i * 8 + grp) * GM_LDS + kk + tig];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = bs[(j * 8 + grp) * GM_LDS + kk + tig];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    double* Ct = g.Ct ? g.Ct + bz * g.strideCt : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = row0 + wm * 64 + i * 8 + grp;
+        if (r >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t c = col0 + wn * 32 + j * 8 + tig * 2 + e;
+                if (c >= g.N) continue;
+                double v = g.alpha * acc[i][j][e];
+                if (g.beta != 0.0) v += g.beta * C[r * g.ldc + c];
+                C[r * g.ldc + c] = v;
+                if (Ct) Ct[c * g.ldct + r] = v;
+            }
+        }
+    }
+}
+
+static int launch_gemm(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return ELFI_B200_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ELFI_CUDA_OK(cudaFuncSetAttribute(gemm_nt_dmma_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(GM_SMEM)));
+        attr_set = true;
+    }
+    dim3 grid(unsigned((g.N + GM_BN - 1) / GM_BN), unsigned((g.M + GM_BM - 1) / GM_BM), unsigned(batch));
+    gemm_nt_dmma_kernel<<<grid, GM_THREADS, GM_SMEM, stream>>>(g);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+// ---- K10: Gram / cross-covariance ----------------------------------------------------------
+// out[i, j] = s2 * exp(-0.5 |a_i - b_j|^2 / l^2) + bias (+ diag_add when i == j and symmetric).
+// Rows >= na or cols >= nb of the padded output are written as identity / zero padding.
+__global__ void __launch_bounds__(256)
+gp_cov_kernel(const double* __restrict__ Aq, int64_t lda, int64_t na, const double* __restrict__ Bq,
+              int64_t ldb, int64_t nb, int p, double s2, double neg_half_inv_l2, double bias,
+              double diag_add, int pad_identity, double* __restrict__ out, int64_t ldo,
+              int64_t rows_out, int64_t cols_out) {
+    const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= cols_out || i >= rows_out) return;
+    double v;
+    if (i < na && j < nb) {
+        double r2 = 0.0;
+        for (int a = 0; a < p; ++a) {
+            const double d = Aq[i * lda + a] - Bq[j * ldb + a];
+            r2 = fma(d, d, r2);
+        }
+        v = s2 * exp(r2 * neg_half_inv_l2) + bias;
+        if (i == j) v += diag_add;
+    } else {
+        v = (pad_identity && i == j) ? 1.0 : 0.0;
+    }
+    out[i * ldo + j] = v;
+}
+
+// ---- K11: blocked Cholesky (right-looking, panel width 64) ------------------------------------
+// Factor the diagonal block A[k:k+64, k:k+64] in place (lower); info != 0 on a bad pivot.
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k, int* __restrict__ info) {
+    __shared__ double s[GP_NB][GP_NB + 1];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < GP_NB * GP_NB; idx += 256) {
+        const int r = idx / GP_NB, c = idx % GP_NB;
+        s[r][c] = A[(k + r) * lda + k + c];
+    }
+    __syncthreads();
+    const int r = tid >> 2, q = tid & 3;
+    for (int j = 0; j < GP_NB; ++j) {
+        if (tid == 0) {
+            const double d = s[j][j];
+            if (!(d > 0.0)) atomicExch(info, int(k + j + 1));
+            s[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        if (tid > j && tid < GP_NB) s[tid][j] /= s[j][j];
+        __syncthreads();
+        if (r > j) {
+            const double lrj = s[r][j];
+            for (int c = j + 1 + q; c <= r; c += 4) s[r][c] = fma(-lrj, s[c][j], s[r][c]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < GP_NB * GP_NB; idx += 256) {
+        const int rr = idx / GP_NB, c = idx % GP_NB;
+        A[(k + rr) * lda + k + c] = (c <= rr) ? s[rr][c] : 0.0;
+    }
+}
+
+// Panel below the diagonal block: X L_kk^T = A_panel, one thread per row.
+__global__ void __launch_bounds__(128)
+potrf_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n) {
+    __shared__ double l[GP_NB][GP_NB + 1];
+    for (int idx = threadIdx.x; idx < GP_NB * GP_NB; idx += 128) {
+        const int r = idx / GP_NB, c = idx % GP_NB;
+        l[r][c] = A[(k + r) * lda + k + c];
+    }
+    __syncthreads();
+    const int64_t row = k + GP_NB + int64_t(blockIdx.x) * 128 + threadIdx.x;
+    if (row >= n) return;
+    double x[GP_NB];
+    double* a = A + row * lda + k;
+#pragma unroll
+    for (int c = 0; c < GP_NB; ++c) x[c] = a[c];
+#pragma unroll
+    for (int c = 0; c < GP_NB; ++c) {
+        double v = x[c];
+#pragma unroll
+        for (int j = 0; j < c; ++j) v = fma(-x[j], l[c][j], v);
+        x[c] = v / l[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < GP_NB; ++c) a[c] = x[c];
+}
+
+// Inverse of every 64x64 diagonal block of L: W_bb = L_bb^-1 (lower), also U_bb = W_bb^T.
+__global__ void __launch_bounds__(64)
+trtri_diag_kernel(const double* __restrict__ L, double* __restrict__ W, double* __restrict__ U,
+                  int64_t ld) {
+    __shared__ double l[GP_NB][GP_NB + 1];
+    const int64_t k = int64_t(blockIdx.x) * GP_NB;
+    for (int idx = threadIdx.x; idx < GP_NB * GP_NB; idx += 64) {
+        const int r = idx / GP_NB, c = idx % GP_NB;
+        l[r][c] = L[(k + r) * ld + k + c];
+    }
+    __syncthreads();
+    // thread c solves L x = e_c  (column c of the inverse)
+    const int c = threadIdx.x;
+    double x[GP_NB];
+#pragma unroll
+    for (int r = 0; r < GP_NB; ++r) {
+        double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < r; ++j) v = fma(-l[r][j], x[j], v);
+        x[r] = (r >= c) ? v / l[r][r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < GP_NB; ++r) {
+        W[(k + r) * ld + k + c] = x[r];
+        U[(k + c) * ld + k + r] = x[r];
+    }
+}
+
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// out[r] = sum_c M[r, c] * v[c]  (c < ncols(r): lower-triangular when tri = 1, else all n)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const double* __restrict__ M, int64_t ld, int64_t nrows, int64_t n,
+              const double* __restrict__ v, int tri, int upper, double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = int64_t(blockIdx.x) * 8 + warp;
+    if (r >= nrows) return;
+    int64_t lo = 0, hi = n;
+    if (tri) { if (upper) lo = r; else hi = r + 1; }
+    double acc = 0.0;
+    for (int64_t c = lo + lane; c < hi; c += 32) acc = fma(M[r * ld + c], v[c], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = acc;
+}
+
+// ---- K12: prediction epilogues -----------------------------------------------------------------
+// mean_i = sum_j Ks[i, j] alpha_j ; var_i = kss - sum_a V[i, a]^2 (+ noise) ; LCBSC optional
+__global__ void __launch_bounds__(256)
+predict_rows_kernel(const double* __restrict__ Ks, const double* __restrict__ V, int64_t ld,
+                    int64_t mrows, int64_t n, const double* __restrict__ alpha, double kss,
+                    double noise_add, double beta, double* __restrict__ mean,
+                    double* __restrict__ var, double* __restrict__ acq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = int64_t(blockIdx.x) * 8 + warp;
+    if (i >= mrows) return;
+    double mu = 0.0, q = 0.0;
+    for (int64_t j = lane; j < n; j += 32) {
+        mu = fma(Ks[i * ld + j], alpha[j], mu);
+        const double v = V[i * ld + j];
+        q = fma(v, v, q);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mu += __shfl_xor_sync(0xffffffffu, mu, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+        const double vr = kss - q;
+        if (mean) mean[i] = mu;
+        if (var) var[i] = vr + noise_add;
+        if (acq) acq[i] = mu - sqrt(beta * vr);      // LCBSC uses the noiseless variance
+    }
+}
+
+// ---- K13: gradients for a few query points (one CTA per point) ----------------------------------
+// kx_j = s2 exp(f r2_j); t = W (kx + b); u = W^T t = Ky^-1 (kx + b);
+// mean = (kx + b) . alpha ; var = s2 + b - |t|^2 ; grad_mu_d = sum_j dk_jd alpha_j ;
+// grad_var_d = -2 sum_j dk_jd u_j with dk_jd = 2 f (x_d - X_jd) kx_j      (gpy_regression.py:211-218)
+__global__ void __launch_bounds__(256)
+predict_grad_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __restrict__ X,
+                    int64_t ldx, int64_t n, int p, const double* __restrict__ W,
+                    const double* __restrict__ U, int64_t ldw, const double* __restrict__ alpha,
+                    double s2, double f, double bias, double* __restrict__ mean,
+                    double* __restrict__ var, double* __restrict__ gmean, double* __restrict__ gvar) {
+    extern __shared__ double sh[];
+    double* kx = sh;            // n
+    double* t = sh + n;         // n
+    double* u = sh + 2 * n;     // n
+    __shared__ double red[32];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t j = tid; j < n; j += 256) {
+        double r2 = 0.0;
+        for (int a = 0; a < p; ++a) {
+            const double d = Xq[q * ldq + a] - X[j * ldx + a];
+            r2 = fma(d, d, r2);
+        }
+        kx[j] = s2 * exp(r2 * f);
+    }
+    __syncthreads();
+    for (int64_t r = warp; r < n; r += 8) {
+        double acc = 0.0;
+        for (int64_t c = lane; c <= r; c += 32) acc = fma(W[r * ldw + c], kx[c] + bias, acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) t[r] = acc;
+    }
+    __syncthreads();
+    for (int64_t r = warp; r < n; r += 8) {
+        double acc = 0.0;
+        for (int64_t c = r + lane; c < n; c += 32) acc = fma(U[r * ldw + c], t[c], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) u[r] = acc;
+    }
+    __syncthreads();
+    auto block_sum = [&](double v) -> double {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += red[k];
+        return s;
+    };
+    double pm = 0.0, pq = 0.0;
+    for (int64_t j = tid; j < n; j += 256) {
+        pm = fma(kx[j] + bias, alpha[j], pm);
+        pq = fma(t[j], t[j], pq);
+    }
+    const double mu = block_sum(pm);
+    const double qq = block_sum(pq);
+    if (tid == 0) {
+        if (mean) mean[q] = mu;
+        if (var) var[q] = s2 + bias - qq;
+    }
+    for (int d = 0; d < p; ++d) {
+        double gm = 0.0, gv = 0.0;
+        const double xd = Xq[q * ldq + d];
+        for (int64_t j = tid; j < n; j += 256) {
+            const double dk = 2.0 * f * (xd - X[j * ldx + d]) * kx[j];
+            gm = fma(dk, alpha[j], gm);
+            gv = fma(dk, u[j], gv);
+        }
+        gm = block_sum(gm);
+        gv = block_sum(gv);
+        if (tid == 0) {
+            if (gmean) gmean[q * p + d] = gm;
+            if (gvar) gvar[q * p + d] = -2.0 * gv;
+        }
+    }
+}
+
+__global__ void lcbsc_kernel(const double* __restrict__ mean, const double* __restrict__ var,
+                             const double* __restrict__ gmean, const double* __restrict__ gvar,
+                             int64_t m, int p, double beta, double* __restrict__ acq,
+                             double* __restrict__ gacq) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (acq) acq[i] = mean[i] - sqrt(beta * var[i]);
+    if (gacq)
+        for (int d = 0; d < p; ++d)
+            gacq[i * p + d] = gmean[i * p + d] - 0.5 * gvar[i * p + d] * sqrt(beta / var[i]);
+}
+
+}  // namespace elfi
+
+extern "C" {
+
+int64_t elfi_b200_gp_padded_size(int64_t n) { return ((n + 127) / 128) * 128; }
+
+int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const double* y,
+                         int64_t n, int64_t p, double kernel_var, double lengthscale,
+                         double bias_var, double noise_var, double* L, double* W, double* U,
+                         int64_t n_pad, double* alpha, int32_t* info, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && X && y && L && W && U && alpha && info, "gp_fit: NULL argument");
+    ELFI_REQUIRE(n >= 1 && p >= 1 && ldX >= p, "gp_fit: bad shape");
+    ELFI_REQUIRE(n_pad == elfi_b200_gp_padded_size(n), "gp_fit: n_pad must be %lld",
+                 (long long)elfi_b200_gp_padded_size(n));
+    ELFI_REQUIRE(lengthscale > 0 && kernel_var > 0, "gp_fit: kernel parameters must be positive");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    ELFI_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
+    const double f = -0.5 / (lengthscale * lengthscale);
+    // Ky (padded with the identity so that the padded factor / inverse are the identity there)
+    {
+        dim3 grid(unsigned((n_pad + 255) / 256), unsigned(n_pad));
+        gp_cov_kernel<<<grid, 256, 0, stream>>>(X, ldX, n, X, ldX, n, int(p), kernel_var, f, bias_var,
+                                                noise_var, 1, L, n_pad, n_pad, n_pad);
+    }
+    // blocked Cholesky, lower, in place
+    for (int64_t k = 0; k < n_pad; k += GP_NB) {
+        potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
+        const int64_t below = n_pad - (k + GP_NB);
+        if (below > 0) {
+            potrf_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(L, n_pad, k, n_pad);
+            GemmArgs g;
+            memset(&g, 0, sizeof(g));
+            g.A = L + (k + GP_NB) * n_pad + k; g.lda = n_pad;
+            g.B = g.A; g.ldb = n_pad;
+            g.C = L + (k + GP_NB) * n_pad + (k + GP_NB); g.ldc = n_pad;
+            g.M = below; g.N = below; g.K = GP_NB;
+            g.alpha = -1.0; g.beta = 1.0; g.mode = 1;
+            int rc = launch_gemm(g, 1, stream);
+            if (rc) return rc;
+        }
+    }
+    // W = L^-1 (and U = W^T) by recursive doubling over diagonal blocks:
+    //   [[L11, 0], [L21, L22]]^-1 = [[W11, 0], [-W22 L21 W11, W22]]
+    ELFI_CUDA_OK(cudaMemsetAsync(W, 0, size_t(n_pad) * n_pad * 8, stream));
+    ELFI_CUDA_OK(cudaMemsetAsync(U, 0, size_t(n_pad) * n_pad * 8, stream));
+    trtri_diag_kernel<<<unsigned(n_pad / GP_NB), 64, 0, stream>>>(L, W, U, n_pad);
+    double* T = static_cast<double*>(ctx_scratch(ctx, size_t(n_pad) * n_pad * 8 + 256));
+    if (!T) return ELFI_B200_ERR_NOMEM;
+    for (int64_t s = GP_NB; s < n_pad; s *= 2) {
+        // pairs (top block [o, o+s), bottom block [o+s, min(o+2s, n_pad)))
+        const int64_t npairs = (n_pad + 2 * s - 1) / (2 * s);
+        for (int64_t pi = 0; pi < npairs; ++pi) {
+            const int64_t o = pi * 2 * s;
+            const int64_t s2 = (o + 2 * s <= n_pad) ? s : (n_pad - o - s);
+            if (s2 <= 0) continue;
+            // Tt (s x s2) = U11 (s x s) * L21^T          [Tt[c, r] = sum_k U11[c, k] L21[r, k]]
+            GemmArgs g;
+            memset(&g, 0, sizeof(g));
+            g.A = U + o * n_pad + o; g.lda = n_pad;
+            g.B = L + (o + s) * n_pad + o; g.ldb = n_pad;
+            g.C = T; g.ldc = n_pad;
+            g.M = s; g.N = s2; g.K = s; g.alpha = 1.0; g.beta = 0.0; g.mode = 0;
+            int rc = launch_gemm(g, 1, stream);
+            if (rc) return rc;
+            // W21 (s2 x s) = -W22 (s2 x s2) * Tt^T        [W21[r, c] = -sum_k W22[r, k] Tt[c, k]]
+            memset(&g, 0, sizeof(g));
+            g.A = W + (o + s) * n_pad + (o + s); g.lda = n_pad;
+            g.B = T; g.ldb = n_pad;
+            g.C = W + (o + s) * n_pad + o; g.ldc = n_pad;
+            g.Ct = U + o * n_pad + (o + s); g.ldct = n_pad;
+            g.M = s2; g.N = s; g.K = s2; g.alpha = -1.0; g.beta = 0.0; g.mode = 0;
+            rc = launch_gemm(g, 1, stream);
+            if (rc) return rc;
+        }
+    }
+    // alpha = Ky^-1 y = U (W y)
+    double* z = T;  // reuse scratch: zpad (n_pad), ypad (n_pad)
+    double* ypad = T + n_pad;
+    fill_kernel<<<8, 256, 0, stream>>>(ypad, n_pad, 0.0);
+    ELFI_CUDA_OK(cudaMemcpyAsync(ypad, y, size_t(n) * 8, cudaMemcpyDeviceToDevice, stream));
+    rowdot_kernel<<<unsigned((n_pad + 7) / 8), 256, 0, stream>>>(W, n_pad, n_pad, n_pad, ypad, 1, 0, z);
+    rowdot_kernel<<<unsigned((n + 7) / 8), 256, 0, stream>>>(U, n_pad, n, n_pad, z, 1, 1, alpha);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, int64_t m,
+                             const double* X, int64_t ldX, int64_t n, int64_t p, const double* W,
+                             int64_t n_pad, const double* alpha, double kernel_var,
+                             double lengthscale, double bias_var, double noise_add, double beta,
+                             double* mean, double* var, double* acq, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && Xq && X && W && alpha, "gp_predict: NULL argument");
+    ELFI_REQUIRE(m >= 0 && n >= 1 && p >= 1 && ldq >= p && ldX >= p, "gp_predict: bad shape");
+    ELFI_REQUIRE(n_pad == elfi_b200_gp_padded_size(n), "gp_predict: bad n_pad");
+    if (m == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const double f = -0.5 / (lengthscale * lengthscale);
+    // query chunks: Ks (mc x n_pad) and V (mc x n_pad) live in scratch
+    int64_t mc = 8192;
+    if (mc > m) mc = ((m + 127) / 128) * 128;
+    const size_t bytes = size_t(2) * mc * n_pad * 8 + 256;
+    double* Ks = static_cast<double*>(ctx_scratch(ctx, bytes));
+    if (!Ks) return ELFI_B200_ERR_NOMEM;
+    double* V = Ks + size_t(mc) * n_pad;
+    for (int64_t q0 = 0; q0 < m; q0 += mc) {
+        const int64_t rows = (m - q0) < mc ? (m - q0) : mc;
+        dim3 grid(unsigned((n_pad + 255) / 256), unsigned(rows));
+        gp_cov_kernel<<<grid, 256, 0, stream>>>(Xq + q0 * ldq, ldq, rows, X, ldX, n, int(p), kernel_var,
+                                                f, bias_var, 0.0, 0, Ks, n_pad, rows, n_pad);
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.A = Ks; g.lda = n_pad;
+        g.B = W; g.ldb = n_pad;
+        g.C = V; g.ldc = n_pad;
+        g.M = rows; g.N = n_pad; g.K = n_pad; g.alpha = 1.0; g.beta = 0.0; g.mode = 2;
+        int rc = launch_gemm(g, 1, stream);
+        if (rc) return rc;
+        predict_rows_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
+            Ks, V, n_pad, rows, n, alpha, kernel_var + bias_var, noise_add, beta,
+            mean ? mean + q0 : nullptr, var ? var + q0 : nullptr, acq ? acq + q0 : nullptr);
+    }
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gp_predict_grad_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, int64_t m,
+                                  const double* X, int64_t ldX, int64_t n, int64_t p,
+                                  const double* W, const double* U, int64_t n_pad,
+                                  const double* alpha, double kernel_var, double lengthscale,
+                                  double bias_var, double* mean, double* var, double* grad_mean,
+                                  double* grad_var, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && Xq && X && W && U && alpha, "gp_predict_grad: NULL argument");
+    ELFI_REQUIRE(m >= 0 && n >= 1 && p >= 1 && ldq >= p && ldX >= p, "gp_predict_grad: bad shape");
+    ELFI_REQUIRE(size_t(3) * n * 8 <= 200 * 1024, "gp_predict_grad: n=%lld too large (<= 8533)",
+                 (long long)n);
+    if (m == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t smem = size_t(3) * n * 8;
+    ELFI_CUDA_OK(cudaFuncSetAttribute(predict_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem)));
+    predict_grad_kernel<<<unsigned(m), 256, smem, stream>>>(
+        Xq, ldq, X, ldX, n, int(p), W, U, n_pad, alpha, kernel_var,
+        -0.5 / (lengthscale * lengthscale), bias_var, mean, var, grad_mean, grad_var);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* var,
+                        const double* grad_mean, const double* grad_var, int64_t m, int64_t p,
+                        double beta, double* acq, double* grad_acq, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && mean && var, "lcbsc: NULL argument");
+    ELFI_REQUIRE(grad_acq == nullptr || (grad_mean && grad_var), "lcbsc: gradients missing");
+    if (m == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    lcbsc_kernel<<<unsigned((m + 255) / 256), 256, 0, stream>>>(mean, var, grad_mean, grad_var, m,
+                                                               int(p), beta, acq, grad_acq);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+}  // extern "C"

@@ -551,9 +551,22 @@ class Constant(NodeReference):
         super().__init__(state=dict(_output=value), **kwargs)
 
 
+class _HostOperation:
+    """User-supplied Operation callables expect NumPy: device inputs are copied to the host
+    first (explicit D2H; generic Operations are host logic, not part of the CUDA hot path)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, *args, **kwargs):
+        args = [dev.to_host(a) if dev.is_device_array(a) else a for a in args]
+        kwargs = {k: (dev.to_host(v) if dev.is_device_array(v) else v) for k, v in kwargs.items()}
+        return self.fn(*args, **kwargs)
+
+
 class Operation(NodeReference):
     def __init__(self, fn, *parents, **kwargs):
-        super().__init__(*parents, state=dict(_operation=fn), **kwargs)
+        super().__init__(*parents, state=dict(_operation=_HostOperation(fn)), **kwargs)
 
 
 def rvs_from_distribution(*params, batch_size, distribution, size=None, random_state=None):

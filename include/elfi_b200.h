@@ -168,6 +168,43 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
 int elfi_b200_smc_weights_f64(elfi_b200_ctx* ctx, const double* logprior, const double* logq,
                               int64_t n, double* w, void* stream);
 
+/* ---- BOLFI Gaussian-process surrogate (fp64) -------------------------------------------------
+ * RBF + bias kernel k(a, b) = kernel_var * exp(-|a-b|^2 / (2 lengthscale^2)) + bias_var, Gaussian
+ * noise.  These replace the GPy calls behind elfi/methods/bo/gpy_regression.py:
+ *   update()/_init_gp() (242-315): Gram + Cholesky of Ky = K + noise_var I  -> elfi_b200_gp_fit_f64
+ *   predict()/predict_mean() (98-163), incl. the cached-RBF restatement (127-140)
+ *                                                                   -> elfi_b200_gp_predict_f64
+ *   predictive_gradients() (186-223, restatement 206-218)           -> elfi_b200_gp_predict_grad_f64
+ * and LCBSC.evaluate / evaluate_gradient (elfi/methods/bo/acquisition.py:262-301)
+ *                                                                   -> `acq` outputs / elfi_b200_lcbsc_f64
+ *
+ * Factor storage (caller-allocated, n_pad x n_pad row-major, n_pad = elfi_b200_gp_padded_size(n)):
+ *   L lower Cholesky factor (padded with the identity), W = L^-1, U = W^T;  alpha = Ky^-1 y (n).
+ * noise_var must already include any jitter (GPy adds 1e-8).  info (device int32) is 0 on
+ * success or 1 + the index of the first non-positive pivot.
+ * gp_predict: mean/var/acq may each be NULL; var = k** - |W k|^2 + noise_add; acq = mean -
+ * sqrt(beta * (noiseless var)).  Queries are processed in chunks through context scratch.
+ */
+int64_t elfi_b200_gp_padded_size(int64_t n);
+int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const double* y,
+                         int64_t n, int64_t p, double kernel_var, double lengthscale,
+                         double bias_var, double noise_var, double* L, double* W, double* U,
+                         int64_t n_pad, double* alpha, int32_t* info, void* stream);
+int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, int64_t m,
+                             const double* X, int64_t ldX, int64_t n, int64_t p, const double* W,
+                             int64_t n_pad, const double* alpha, double kernel_var,
+                             double lengthscale, double bias_var, double noise_add, double beta,
+                             double* mean, double* var, double* acq, void* stream);
+int elfi_b200_gp_predict_grad_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, int64_t m,
+                                  const double* X, int64_t ldX, int64_t n, int64_t p,
+                                  const double* W, const double* U, int64_t n_pad,
+                                  const double* alpha, double kernel_var, double lengthscale,
+                                  double bias_var, double* mean, double* var, double* grad_mean,
+                                  double* grad_var, void* stream);
+int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* var,
+                        const double* grad_mean, const double* grad_var, int64_t m, int64_t p,
+                        double beta, double* acq, double* grad_acq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
