@@ -216,21 +216,26 @@ class GPyRegression:
         x0 = np.log([self._hyper[k] for k in names])
 
         def objective(logh):
-            h = dict(zip(names, np.exp(logh)))
-            try:
-                val = self.log_marginal_likelihood(h)
-            except np.linalg.LinAlgError:
-                return 1e25
-            for k, (a, b) in self._priors.items():
-                val += ss.gamma.logpdf(h[k], a=a, scale=1.0 / b)
-            return -val if np.isfinite(val) else 1e25
-        try:
-            res = scipy.optimize.minimize(objective, x0, method='L-BFGS-B',
-                                          options={'maxiter': self.max_opt_iters})
+            return -self.log_posterior_hyper(dict(zip(names, np.exp(logh))))
+        f0 = objective(x0)
+        res = scipy.optimize.minimize(objective, x0, method='L-BFGS-B',
+                                      options={'maxiter': self.max_opt_iters})
+        if np.isfinite(res.fun) and res.fun <= f0:
             self._hyper = dict(zip(names, np.exp(res.x).tolist()))
-        except np.linalg.LinAlgError:
+        else:
             logger.warning("Numerical error in GP optimization. Stopping optimization")
         self._fit()
+
+    def log_posterior_hyper(self, hyper=None):
+        """log marginal likelihood + Gamma log-priors (the quantity `optimize` maximises)."""
+        h = hyper or self._hyper
+        try:
+            val = self.log_marginal_likelihood(dict(h))
+        except np.linalg.LinAlgError:
+            return -1e25
+        for k, (a, b) in self._priors.items():
+            val += ss.gamma.logpdf(h[k], a=a, scale=1.0 / b)
+        return val if np.isfinite(val) else -1e25
 
     def copy(self):
         kopy = copy.copy(self)

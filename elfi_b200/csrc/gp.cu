@@ -574,3 +574,70 @@ int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* va
 }
 
 }  // extern "C"
+
+// ---- FP64 peak probes (roofline denominators for the compute-bound kernels) -------------------
+namespace elfi {
+
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double* out, int iters) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + threadIdx.x * 1e-9 + k;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 12345.678) out[0] = s;   // keep the loop alive
+}
+
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0000001;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dmma_m8n8k4(c[k][0], c[k][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace elfi
+
+extern "C" int elfi_b200_probe_fp64_f64(elfi_b200_ctx* ctx, double* tflops_host) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && tflops_host, "probe: NULL argument");
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    double* d = static_cast<double*>(ctx_scratch(ctx, 256));
+    if (!d) return ELFI_B200_ERR_NOMEM;
+    cudaEvent_t e0, e1;
+    ELFI_CUDA_OK(cudaEventCreate(&e0));
+    ELFI_CUDA_OK(cudaEventCreate(&e1));
+    const int iters = 20000, blocks = ctx->sm_count * 8;
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            ELFI_CUDA_OK(cudaEventRecord(e0, 0));
+            if (which == 0) probe_dfma_kernel<<<blocks, 256>>>(d, iters);
+            else probe_dmma_kernel<<<blocks, 256>>>(d, iters);
+            ELFI_CUDA_OK(cudaEventRecord(e1, 0));
+            ELFI_CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            ELFI_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        // DFMA: 8 fma per thread-iteration = 16 flop; DMMA: 8 mma per warp-iteration x 512 flop
+        const double flops = which == 0 ? double(blocks) * 256 * iters * 16.0
+                                        : double(blocks) * 8 * iters * 8 * 512.0;
+        tflops_host[which] = flops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ELFI_B200_OK;
+}

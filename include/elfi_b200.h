@@ -205,6 +205,11 @@ int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* va
                         const double* grad_mean, const double* grad_var, int64_t m, int64_t p,
                         double beta, double* acq, double* grad_acq, void* stream);
 
+/* Measures the sustained fp64 throughput of this device: tflops_host[0] = DFMA (vector pipe),
+ * tflops_host[1] = DMMA (mma.sync m8n8k4.f64).  Roofline denominators for the compute-bound
+ * kernels (mixture density, GP products); blocks the host for a few milliseconds. */
+int elfi_b200_probe_fp64_f64(elfi_b200_ctx* ctx, double* tflops_host);
+
 #ifdef __cplusplus
 }
 #endif
