@@ -40,14 +40,20 @@ __device__ __forceinline__ void dist_setup_shared(uint8_t* aux, const DistParams
     }
 }
 
-__device__ __forceinline__ void dist_finish(const DistParams& p, const double* acc, int K,
+// Epilogue shared by all consumers.  KMAX is a compile-time bound so that acc[] and thr[] are
+// indexed by constants (a runtime-indexed acc[] would be demoted to local memory).
+template <int KMAX>
+__device__ __forceinline__ void dist_finish(const DistParams& p, const double (&acc)[KMAX], int K,
                                             int64_t row, int64_t B, int lane) {
     bool ok = row < B;
     if (ok) {
-        for (int k = 0; k < K; ++k) {
-            const double d = sqrt(acc[k]);
-            p.d_out[row * K + k] = d;
-            if (p.has_thr) ok = ok && (d <= p.thr[k]);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const double d = sqrt(acc[k]);
+                p.d_out[row * K + k] = d;
+                if (p.has_thr) ok = ok && (d <= p.thr[k]);
+            }
         }
     }
     if (p.mask != nullptr) {
@@ -83,7 +89,45 @@ struct EuclidConsumer {
         }
     }
     __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
-        dist_finish(p, &acc, 1, row, B, lane);
+        const double a1[1] = {acc};
+        dist_finish<1>(p, a1, 1, row, B, lane);
+    }
+};
+
+// K = 1 with weights (cdist's `w`): acc += w_j * (diff * diff).
+struct WeightedConsumer {
+    typedef DistParams Params;
+    static constexpr int PASSES = 1;
+    const Params& p;
+    const double* obs_s;
+    const double* w_s;
+    double acc;
+
+    static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
+        dist_setup_shared(aux, p, D, true);
+    }
+    __device__ WeightedConsumer(const Params& p_, const uint8_t* aux, int D, int)
+        : p(p_), obs_s(reinterpret_cast<const double*>(aux)), acc(0.0) {
+        w_s = obs_s + ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    }
+    __device__ __forceinline__ void begin_row() { acc = 0.0; }
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
+        const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
+        const double2* wv = reinterpret_cast<const double2*>(w_s + cg * RS_BOX_COLS);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = *reinterpret_cast<const double2*>(box_row + ((c ^ sw) << 4));
+            const double2 ob = o[c];
+            const double2 w = wv[c];
+            const double d0 = __dsub_rn(v.x, ob.x);
+            const double d1 = __dsub_rn(v.y, ob.y);
+            acc = __dadd_rn(acc, __dmul_rn(w.x, __dmul_rn(d0, d0)));
+            acc = __dadd_rn(acc, __dmul_rn(w.y, __dmul_rn(d1, d1)));
+        }
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
+        const double a1[1] = {acc};
+        dist_finish<1>(p, a1, 1, row, B, lane);
     }
 };
 
@@ -136,7 +180,7 @@ struct NestedConsumer {
         }
     }
     __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
-        dist_finish(p, acc, p.K, row, B, lane);
+        dist_finish<KMAX>(p, acc, p.K, row, B, lane);
     }
 };
 
@@ -269,8 +313,12 @@ int launch_dist(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int
         const size_t aux = size_t(Dp) * 8 * (W ? (1 + K) : 1);
         if (rs_pick_stages(ctx->smem_optin, aux) >= 2) {
             if (W == nullptr) return rowstream_launch<EuclidConsumer>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K == 1) return rowstream_launch<WeightedConsumer>(ctx, S, ldS, B, D, aux, p, stream);
             if (K <= 2) return rowstream_launch<NestedConsumer<2>>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 3) return rowstream_launch<NestedConsumer<3>>(ctx, S, ldS, B, D, aux, p, stream);
             if (K <= 4) return rowstream_launch<NestedConsumer<4>>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 5) return rowstream_launch<NestedConsumer<5>>(ctx, S, ldS, B, D, aux, p, stream);
+            if (K <= 6) return rowstream_launch<NestedConsumer<6>>(ctx, S, ldS, B, D, aux, p, stream);
             if (K <= 8) return rowstream_launch<NestedConsumer<8>>(ctx, S, ldS, B, D, aux, p, stream);
             if (K <= 16) return rowstream_launch<NestedConsumer<16>>(ctx, S, ldS, B, D, aux, p, stream);
             return rowstream_launch<NestedConsumer<32>>(ctx, S, ldS, B, D, aux, p, stream);

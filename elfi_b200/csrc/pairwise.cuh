@@ -6,36 +6,59 @@
 // of 8 long, so every leaf starts at an index that is a multiple of 8 and only the last leaf has
 // a tail.  PairwiseStream consumes the terms strictly in order, 8 at a time, and reproduces that
 // tree bit for bit.
+//
+// The recursion stack (pending right-part lengths and finished left sums) has MAXD levels and
+// is kept as a register SHIFT stack: the top is always element 0, push/pop move every level by
+// one with compile-time indices.  (A runtime-indexed array - or a compare-and-select loop, which
+// the compiler folds back into an indexed access - would demote the whole object to local
+// memory, an order of magnitude slower on the bandwidth-bound summary kernels.)  Pushes and pops
+// happen once per <=128-term leaf.  MAXD = 8 covers runs of up to 128 * 2^8 = 32768 terms; the
+// one-thread-per-row fallback uses a deeper stack.
 #pragma once
 
 #include "common.cuh"
 
 namespace elfi {
 
-constexpr int PW_MAX_DEPTH = 26;  // recursion depth bound: rows up to 128 * 2^26 elements
-
-// Streaming evaluation of NumPy's pairwise sum over m terms fed one aligned group of 8 at a
-// time (the last group may be partial).  All lanes of a warp run identical control flow
-// because every row has the same length.
+template <int MAXD>
 struct PairwiseStream {
     double r[8];
     double res;
-    int64_t leaf_end;     // first term index after the current leaf
-    int64_t tail_start;   // first term index of the sequential tail of the current leaf
-    int64_t leaf_start;
+    double left_val[MAXD];     // [0] = top of stack
+    int pending_right[MAXD];   // [0] = top of stack
+    uint32_t has_left;         // bit 0 = top frame already holds its left sum
+    int leaf_start, leaf_end, tail_start;
     int depth;
     bool in_tail;
-    int64_t pending_right[PW_MAX_DEPTH];
-    double left_val[PW_MAX_DEPTH];
-    bool has_left[PW_MAX_DEPTH];
 
-    __device__ __forceinline__ void descend(int64_t start, int64_t n) {
+    static __host__ __device__ constexpr int64_t max_terms() { return int64_t(128) << MAXD; }
+
+    __device__ __forceinline__ void push_frame(int right) {
+#pragma unroll
+        for (int d = MAXD - 1; d > 0; --d) {
+            pending_right[d] = pending_right[d - 1];
+            left_val[d] = left_val[d - 1];
+        }
+        pending_right[0] = right;
+        left_val[0] = 0.0;
+        has_left <<= 1;
+        ++depth;
+    }
+    __device__ __forceinline__ void pop_frame() {
+#pragma unroll
+        for (int d = 0; d < MAXD - 1; ++d) {
+            pending_right[d] = pending_right[d + 1];
+            left_val[d] = left_val[d + 1];
+        }
+        has_left >>= 1;
+        --depth;
+    }
+
+    __device__ __forceinline__ void descend(int start, int n) {
         while (n > 128) {
-            int64_t n2 = n / 2;
+            int n2 = n / 2;
             n2 -= n2 % 8;
-            pending_right[depth] = n - n2;
-            has_left[depth] = false;
-            ++depth;
+            push_frame(n - n2);
             n = n2;
         }
         leaf_start = start;
@@ -44,40 +67,38 @@ struct PairwiseStream {
         in_tail = n < 8;
         res = 0.0;
     }
-    __device__ __forceinline__ void begin(int64_t m) {
+    __device__ __forceinline__ void begin(int m) {
         depth = 0;
+        has_left = 0;
         descend(0, m);
     }
-    __device__ __forceinline__ double leaf_value() const {
-        if (leaf_end - leaf_start < 8) return res;
-        if (in_tail) return res;
+    __device__ __forceinline__ double fold() const {
         return __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                          __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
     }
+    __device__ __forceinline__ double leaf_value() const { return in_tail ? res : fold(); }
+
     // Called when term index j0 (a multiple of 8) is about to be fed and j0 == leaf_end.
     __device__ __forceinline__ void close_leaf_and_open_next() {
         double v = leaf_value();
-        const int64_t next = leaf_end;
+        const int next = leaf_end;
         while (depth > 0) {
-            if (!has_left[depth - 1]) {
-                left_val[depth - 1] = v;
-                has_left[depth - 1] = true;
-                const int64_t n = pending_right[depth - 1];
-                descend(next, n);
+            if (!(has_left & 1u)) {
+                left_val[0] = v;
+                has_left |= 1u;
+                descend(next, pending_right[0]);
                 return;
             }
-            v = __dadd_rn(left_val[depth - 1], v);
-            --depth;
+            v = __dadd_rn(left_val[0], v);
+            pop_frame();
         }
         res = v;  // not reached while terms remain
     }
     // Feed up to 8 terms t[0..cnt) with global indices j0..j0+cnt-1, j0 % 8 == 0.
-    __device__ __forceinline__ void feed8(int64_t j0, const double* t, int cnt) {
+    __device__ __forceinline__ void feed8(int j0, const double (&t)[8], int cnt) {
         if (j0 == leaf_end) close_leaf_and_open_next();
         if (!in_tail && j0 == tail_start && tail_start != leaf_start) {
-            // leaf has a tail: fold the strided accumulators first, then go sequential
-            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            res = fold();     // the leaf has a tail: fold the strided accumulators, go sequential
             in_tail = true;
         }
         if (in_tail) {
@@ -95,8 +116,8 @@ struct PairwiseStream {
     __device__ __forceinline__ double finish() {
         double v = leaf_value();
         while (depth > 0) {
-            v = __dadd_rn(left_val[depth - 1], v);
-            --depth;
+            v = __dadd_rn(left_val[0], v);
+            pop_frame();
         }
         return v;
     }

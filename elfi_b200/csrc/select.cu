@@ -269,32 +269,92 @@ __device__ __forceinline__ void wq_stage(const double* __restrict__ src, int64_t
     }
 }
 
-// out[0] = np.sum(w) in NumPy's pairwise order (w == NULL: n, exactly)
+// out[0] = np.sum(w) in NumPy's pairwise order (w == NULL: n, exactly).  One warp: the control
+// state of the pairwise tree is uniform, lane k < 8 owns the strided accumulator r[k] of the
+// current <=128-term leaf, the fold ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three shuffle steps.
 __global__ void __launch_bounds__(32)
-wq_total_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ out) {
+wq_total_kernel(const double* __restrict__ w, int64_t n64, double* __restrict__ out) {
     __shared__ double buf[2][WQ_CHUNK];
+    __shared__ double left_val[32];
+    __shared__ int pending_right[32];
     const int lane = threadIdx.x;
+    const int n = int(n64);
     if (w == nullptr) {
         if (lane == 0) out[0] = double(n);
         return;
     }
-    PairwiseStream pw;
-    if (lane == 0) pw.begin(n);
-    wq_stage(w, n, 0, buf[0], lane);
+    uint32_t has_left = 0;
+    int depth = 0, leaf_start = 0, leaf_end = 0, tail_start = 0;
+    bool in_tail = false;
+    double r = 0.0, res = 0.0;   // r: lanes 0..7; res: meaningful in every lane (kept uniform)
+    auto descend = [&](int start, int len) {
+        while (len > 128) {
+            int n2 = len / 2;
+            n2 -= n2 % 8;
+            if (lane == 0) pending_right[depth] = len - n2;
+            has_left &= ~(1u << depth);
+            ++depth;
+            len = n2;
+        }
+        __syncwarp();
+        leaf_start = start;
+        leaf_end = start + len;
+        tail_start = len < 8 ? start : start + (len - len % 8);
+        in_tail = len < 8;
+        res = 0.0;
+    };
+    auto fold = [&]() -> double {
+        double t = r + __shfl_down_sync(0xffffffffu, r, 1);      // lanes 0,2,4,6: r_k + r_{k+1}
+        t = t + __shfl_down_sync(0xffffffffu, t, 2);             // lanes 0,4
+        t = t + __shfl_down_sync(0xffffffffu, t, 4);             // lane 0
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    auto leaf_value = [&]() -> double { return in_tail ? res : fold(); };
+    descend(0, n);
+    wq_stage(w, n64, 0, buf[0], lane);
     __syncwarp();
     int cur = 0;
-    for (int64_t base = 0; base < n; base += WQ_CHUNK, cur ^= 1) {
-        if (base + WQ_CHUNK < n) wq_stage(w, n, base + WQ_CHUNK, buf[cur ^ 1], lane);
-        if (lane == 0) {
-            const int64_t lim = (n - base) < WQ_CHUNK ? (n - base) : WQ_CHUNK;
-            for (int64_t j = 0; j < lim; j += 8) {
-                const int cnt = (lim - j) < 8 ? int(lim - j) : 8;
-                pw.feed8(base + j, &buf[cur][j], cnt);
+    for (int base = 0; base < n; base += WQ_CHUNK, cur ^= 1) {
+        if (int64_t(base) + WQ_CHUNK < n64) wq_stage(w, n64, int64_t(base) + WQ_CHUNK, buf[cur ^ 1], lane);
+        const int lim = (n - base) < WQ_CHUNK ? (n - base) : WQ_CHUNK;
+        for (int j = 0; j < lim; j += 8) {
+            const int j0 = base + j;
+            const int cnt = (lim - j) < 8 ? (lim - j) : 8;
+            if (j0 == leaf_end) {                       // close the leaf, open the next one
+                double v = leaf_value();
+                bool opened = false;
+                while (depth > 0 && !opened) {
+                    if (!((has_left >> (depth - 1)) & 1u)) {
+                        if (lane == 0) left_val[depth - 1] = v;
+                        has_left |= 1u << (depth - 1);
+                        __syncwarp();
+                        descend(j0, pending_right[depth - 1]);
+                        opened = true;
+                    } else {
+                        v = left_val[depth - 1] + v;
+                        --depth;
+                    }
+                }
+            }
+            if (!in_tail && j0 == tail_start && tail_start != leaf_start) {
+                res = fold();
+                in_tail = true;
+            }
+            if (in_tail) {
+                for (int k = 0; k < cnt; ++k) res = res + buf[cur][j + k];   // uniform, sequential
+            } else if (lane < 8) {
+                const double t = buf[cur][j + lane];
+                r = (j0 == leaf_start) ? t : r + t;
             }
         }
         __syncwarp();
     }
-    if (lane == 0) out[0] = pw.finish();
+    double v = leaf_value();
+    while (depth > 0) {
+        v = left_val[depth - 1] + v;
+        --depth;
+    }
+    if (lane == 0) out[0] = v;
 }
 
 // ws[i] = w[perm[i]] / total   (weights[index] of utils.py:401-402; exact IEEE division)
@@ -309,6 +369,8 @@ __global__ void wq_normalise_kernel(const double* __restrict__ w, const int32_t*
 
 // index_alpha = #{ k in [0, n-2] : cumsum(ws)[k] < alpha }, cumsum strictly sequential
 // (utils.py:403-406; the last cumulative weight is forced to 1.0 there, hence n-2).
+// Lane 0 carries the running sum; terms are fetched eight at a time so the shared-memory
+// latency is paid once per eight dependent adds.
 __global__ void __launch_bounds__(32)
 wq_seqscan_kernel(const double* __restrict__ ws, int64_t n, double alpha,
                   const uint64_t* __restrict__ ukeys, double* __restrict__ out) {
@@ -325,14 +387,25 @@ wq_seqscan_kernel(const double* __restrict__ ws, int64_t n, double alpha,
         if (done_s) break;
         if (base + WQ_CHUNK < n - 1) wq_stage(ws, n, base + WQ_CHUNK, buf[cur ^ 1], lane);
         if (lane == 0) {
-            const int64_t lim = (n - 1 - base) < WQ_CHUNK ? (n - 1 - base) : WQ_CHUNK;
-            for (int64_t j = 0; j < lim; ++j) {
-                c = __dadd_rn(c, buf[cur][j]);
-                if (c < alpha) {
-                    ++count;
-                } else {
-                    done_s = 1;   // cumulative weights are non-decreasing
-                    break;
+            const int lim = int((n - 1 - base) < WQ_CHUNK ? (n - 1 - base) : WQ_CHUNK);
+            int j = 0;
+            for (; j + 8 <= lim; j += 8) {
+                double t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = buf[cur][j + k];
+                int below = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    c = __dadd_rn(c, t[k]);
+                    below += (c < alpha) ? 1 : 0;   // non-decreasing: a prefix of the 8 is below
+                }
+                count += below;
+                if (below < 8) { done_s = 1; break; }
+            }
+            if (!done_s) {
+                for (; j < lim; ++j) {
+                    c = __dadd_rn(c, buf[cur][j]);
+                    if (c < alpha) ++count; else { done_s = 1; break; }
                 }
             }
         }

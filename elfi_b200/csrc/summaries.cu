@@ -18,12 +18,14 @@
 namespace elfi {
 
 // Collects terms into aligned groups of 8 and forwards them to a PairwiseStream.
+constexpr int RS_PW_DEPTH = 6;   // rows of up to 8192 terms on the row-stream path
+
 struct TermGrouper {
-    PairwiseStream pw;
+    PairwiseStream<RS_PW_DEPTH> pw;
     double buf[8];
-    int64_t j0;
+    int j0;
     int fill;
-    __device__ __forceinline__ void begin(int64_t m) {
+    __device__ __forceinline__ void begin(int m) {
         pw.begin(m);
         j0 = 0;
         fill = 0;
@@ -162,24 +164,25 @@ summary_direct_kernel(const double* __restrict__ X, int64_t ld, int64_t B, int n
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (row >= B) return;
     const double* x = X + row * ld;
-    PairwiseStream pw;
+    PairwiseStream<24> pw;
     double buf[8];
-    auto run = [&](int64_t m, auto term) -> double {
+    auto run = [&](int m, auto term) -> double {
         pw.begin(m);
-        for (int64_t j0 = 0; j0 < m; j0 += 8) {
-            const int cnt = (m - j0) < 8 ? int(m - j0) : 8;
+        for (int j0 = 0; j0 < m; j0 += 8) {
+            const int cnt = (m - j0) < 8 ? (m - j0) : 8;
+#pragma unroll
             for (int k = 0; k < 8; ++k) buf[k] = k < cnt ? term(j0 + k) : 0.0;
             pw.feed8(j0, buf, cnt);
         }
         return pw.finish();
     };
     if (mode == 0) {
-        const int64_t m = n - lag;
-        const double s = run(m, [&](int64_t j) { return __dmul_rn(__ldg(x + j + lag), __ldg(x + j)); });
+        const int m = n - lag;
+        const double s = run(m, [&](int j) { return __dmul_rn(__ldg(x + j + lag), __ldg(x + j)); });
         p.out[row * p.ld_out + p.col_a] = s / double(m);
     } else {
-        const double mean = run(n, [&](int64_t j) { return __ldg(x + j); }) / double(n);
-        const double ss = run(n, [&](int64_t j) {
+        const double mean = run(n, [&](int j) { return __ldg(x + j); }) / double(n);
+        const double ss = run(n, [&](int j) {
             const double c = __dsub_rn(__ldg(x + j), mean);
             return __dmul_rn(c, c);
         });
@@ -189,7 +192,8 @@ summary_direct_kernel(const double* __restrict__ X, int64_t ld, int64_t B, int n
 }
 
 static bool rowstream_ok(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t n) {
-    return n >= RS_BOX_COLS && tma_compatible(X, ld) && rs_pick_stages(ctx->smem_optin, 0) >= 2;
+    return n >= RS_BOX_COLS && n <= PairwiseStream<RS_PW_DEPTH>::max_terms() &&
+           tma_compatible(X, ld) && rs_pick_stages(ctx->smem_optin, 0) >= 2;
 }
 
 }  // namespace elfi
