@@ -136,7 +136,7 @@ def test_bolfi_ma2_smoke():
     m = ma2.get_model(seed_obs=4)
     log_d = elfi.Operation(np.log, m['d'], name='log_d')
     bolfi = elfi.BOLFI(log_d, batch_size=5, initial_evidence=20, update_interval=10,
-                       bounds={'t1': (-2, 2), 't2': (-1, 1)}, acq_noise_var=[0.1, 0.1], seed=1)
+                       bounds={'t1': (-2, 2), 't2': (-1, 1)}, acq_noise_var=0.1, seed=1)
     post = bolfi.fit(n_evidence=60, bar=False)
     assert bolfi.target_model.n_evidence == 60
     res = bolfi.extract_result()
