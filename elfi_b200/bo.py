@@ -219,6 +219,7 @@ class GPyRegression:
             return -self.log_posterior_hyper(dict(zip(names, np.exp(logh))))
         f0 = objective(x0)
         res = scipy.optimize.minimize(objective, x0, method='L-BFGS-B',
+                                      bounds=[(v - 12.0, v + 12.0) for v in x0],
                                       options={'maxiter': self.max_opt_iters})
         if np.isfinite(res.fun) and res.fun <= f0:
             self._hyper = dict(zip(names, np.exp(res.x).tolist()))
@@ -231,7 +232,7 @@ class GPyRegression:
         h = hyper or self._hyper
         try:
             val = self.log_marginal_likelihood(dict(h))
-        except np.linalg.LinAlgError:
+        except (np.linalg.LinAlgError, _lib.ElfiB200Error):
             return -1e25
         for k, (a, b) in self._priors.items():
             val += ss.gamma.logpdf(h[k], a=a, scale=1.0 / b)

@@ -127,28 +127,30 @@ __global__ void wstats_final_kernel(const double* __restrict__ partial, int nblo
 
 // ---------------------------------------------------------------------------------------------
 // K9: Gaussian mixture density.
-// exp(a) for a <= 0: t = a*log2(e); k = rint(t) (2^52 trick); f = t - k in [-.5, .5];
-// 2^f by a degree-7 Taylor polynomial in f*ln2 (|f ln2| <= 0.347 -> rel. error < 6e-9);
-// scaled by 2^k through the exponent field.  t < -1020 flushes to 0.
-__device__ __forceinline__ double fast_exp_neg(double a) {
-    const double t = a * 1.4426950408889634;
+// The whitened coordinates are pre-scaled by sqrt(log2(e)/2), so that for a pair
+//   exp(-maha/2) = 2^(-nt),  nt = |y_i - m_j|^2 >= 0.
+// 2^(-nt): k = rint(-nt) through the 2^52 trick (no 64-bit conversions, which run on the slow
+// XU pipe), f = -nt - k in [-.5, .5], 2^f by a degree-7 polynomial (coefficients ln2^i / i!,
+// relative error < 6e-9), scaled by 2^k through the exponent field; nt > 1020 flushes to 0.
+// fp64-pipe instructions per pair: 2P (distance) + 3 (range reduction) + 7 (polynomial)
+// + 1 (compare) + 1 (accumulate) = 2P + 12.
+__device__ __forceinline__ double exp2_neg(double nt) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    const double tm = t + magic;
-    const double kd = tm - magic;
-    const double f = t - kd;
-    const double z = f * 0.6931471805599453;
-    double pz = 1.0 / 5040.0;
-    pz = fma(pz, z, 1.0 / 720.0);
-    pz = fma(pz, z, 1.0 / 120.0);
-    pz = fma(pz, z, 1.0 / 24.0);
-    pz = fma(pz, z, 1.0 / 6.0);
-    pz = fma(pz, z, 0.5);
-    pz = fma(pz, z, 1.0);
-    pz = fma(pz, z, 1.0);
-    const int k = __double2loint(tm);  // low word of (t + magic) holds rint(t) as int32
-    int hi = __double2hiint(pz) + (k << 20);
+    const double tm = magic - nt;
+    const double kd = tm - magic;             // rint(-nt)
+    const double f = -nt - kd;
+    double pz = 1.5252733804059841e-05;       // ln2^7 / 7!
+    pz = fma(pz, f, 1.5403530393381609e-04);  // ln2^6 / 6!
+    pz = fma(pz, f, 1.3333558146428443e-03);  // ln2^5 / 5!
+    pz = fma(pz, f, 9.6181291076284772e-03);  // ln2^4 / 4!
+    pz = fma(pz, f, 5.5504108664821580e-02);  // ln2^3 / 3!
+    pz = fma(pz, f, 2.4022650695910071e-01);  // ln2^2 / 2!
+    pz = fma(pz, f, 6.9314718055994531e-01);  // ln2
+    pz = fma(pz, f, 1.0);
+    const int k = __double2loint(tm);         // low word of (magic - nt) holds rint(-nt)
+    const int hi = __double2hiint(pz) + (k << 20);
     const double r = __hiloint2double(hi, __double2loint(pz));
-    return (t >= -1020.0) ? r : ((t != t) ? t : 0.0);
+    return (nt <= 1020.0) ? r : 0.0;
 }
 
 // whitened coordinates: y = Linv * x (Linv lower triangular, row-major p x p); for the
@@ -159,18 +161,23 @@ __global__ void gm_whiten_kernel(const double* __restrict__ x, int64_t ld, int64
                                  int out_ld) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double scale = 0.8493218002880191;   // sqrt(log2(e) / 2)
     for (int a = 0; a < p; ++a) {
         double s = 0.0;
         for (int b = 0; b <= a; ++b) s = fma(Linv[a * p + b], x[i * ld + b], s);
-        out[i * out_ld + a] = s;
+        out[i * out_ld + a] = s * scale;
     }
     if (out_ld > p) out[i * out_ld + p] = w ? w[i] / wsum[0] : 1.0 / double(n);
 }
 
+// grid = (point blocks, component chunks).  Each CTA accumulates its chunk of the mixture for
+// 128 * R points and writes one partial sum per point; gm_finish_kernel adds the chunks in a
+// fixed order (deterministic) and takes the log.  The 2-D grid keeps >= 8 CTAs per SM even when a
+// rank owns only ~1e5 points, which the dependent polynomial chains need to fill the fp64 pipe.
 template <int P, int R>
 __global__ void __launch_bounds__(128)
 gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict__ mw, int64_t M,
-              double lognorm, double* __restrict__ logq) {
+              int64_t chunk_len, double* __restrict__ partial) {
     constexpr int TILE = 512;
     __shared__ double sm[TILE * (P + 1)];
     double x[R][P];
@@ -182,12 +189,15 @@ gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict
 #pragma unroll
         for (int a = 0; a < P; ++a) x[r][a] = (i0 + r < N) ? xw[(i0 + r) * P + a] : 0.0;
     }
-    for (int64_t j0 = 0; j0 < M; j0 += TILE) {
-        const int64_t cnt = (M - j0) < TILE ? (M - j0) : TILE;
+    const int64_t jbeg = int64_t(blockIdx.y) * chunk_len;
+    const int64_t jend = (jbeg + chunk_len < M) ? jbeg + chunk_len : M;
+    for (int64_t j0 = jbeg; j0 < jend; j0 += TILE) {
+        const int cnt = int((jend - j0) < TILE ? (jend - j0) : TILE);
         __syncthreads();
-        for (int64_t t = threadIdx.x; t < cnt * (P + 1); t += blockDim.x)
+        for (int t = threadIdx.x; t < cnt * (P + 1); t += blockDim.x)
             sm[t] = mw[j0 * (P + 1) + t];
         __syncthreads();
+#pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
             double m[P];
 #pragma unroll
@@ -195,19 +205,28 @@ gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict
             const double wj = sm[j * (P + 1) + P];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                double maha = 0.0;
+                double nt = 0.0;
 #pragma unroll
                 for (int a = 0; a < P; ++a) {
                     const double d = x[r][a] - m[a];
-                    maha = fma(d, d, maha);
+                    nt = fma(d, d, nt);
                 }
-                acc[r] = fma(wj, fast_exp_neg(-0.5 * maha), acc[r]);
+                acc[r] = fma(wj, exp2_neg(nt), acc[r]);
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-        if (i0 + r < N) logq[i0 + r] = log(acc[r]) + lognorm;
+        if (i0 + r < N) partial[int64_t(blockIdx.y) * N + i0 + r] = acc[r];
+}
+
+__global__ void gm_finish_kernel(const double* __restrict__ partial, int64_t N, int chunks,
+                                 double lognorm, double* __restrict__ logq) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += partial[int64_t(c) * N + i];
+    logq[i] = log(s) + lognorm;
 }
 
 // generic p (<= 16), one point per thread
@@ -220,12 +239,12 @@ gm_pdf_generic_kernel(const double* __restrict__ xw, int64_t N, const double* __
     for (int a = 0; a < p; ++a) x[a] = xw[i * p + a];
     double acc = 0.0;
     for (int64_t j = 0; j < M; ++j) {
-        double maha = 0.0;
+        double nt = 0.0;
         for (int a = 0; a < p; ++a) {
             const double d = x[a] - __ldg(mw + j * (p + 1) + a);
-            maha = fma(d, d, maha);
+            nt = fma(d, d, nt);
         }
-        acc = fma(__ldg(mw + j * (p + 1) + p), fast_exp_neg(-0.5 * maha), acc);
+        acc = fma(__ldg(mw + j * (p + 1) + p), exp2_neg(nt), acc);
     }
     logq[i] = log(acc) + lognorm;
 }
@@ -307,15 +326,31 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    // component chunks: enough CTAs (>= 8 per SM) even when N is only ~1e5 per rank
+    constexpr int R = 4;
+    const int64_t xblocks = (N + 128 * R - 1) / (128 * R);
+    int64_t chunks = 1, chunk_len = M;
+    if (p <= 4) {
+        chunks = (int64_t(ctx->sm_count) * 8 + xblocks - 1) / xblocks;
+        const int64_t max_chunks = (M + 511) / 512;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks > 65535) chunks = 65535;
+        if (chunks < 1) chunks = 1;
+        chunk_len = (M + chunks - 1) / chunks;
+        chunk_len = ((chunk_len + 511) / 512) * 512;
+        chunks = (M + chunk_len - 1) / chunk_len;
+    }
     const size_t off_xw = align(size_t(p) * p * 8);
     const size_t off_mw = off_xw + align(size_t(N) * p * 8);
     const size_t off_ws = off_mw + align(size_t(M) * (p + 1) * 8);
-    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, off_ws + 256));
+    const size_t off_part = off_ws + 256;
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, off_part + size_t(chunks) * N * 8 + 256));
     if (!base) return ELFI_B200_ERR_NOMEM;
     double* Linv = reinterpret_cast<double*>(base);
     double* xw = reinterpret_cast<double*>(base + off_xw);
     double* mw = reinterpret_cast<double*>(base + off_mw);
     double* wsum = reinterpret_cast<double*>(base + off_ws);
+    double* partial = reinterpret_cast<double*>(base + off_part);
     ELFI_CUDA_OK(cudaMemcpyAsync(Linv, Linv_host, size_t(p) * p * 8, cudaMemcpyHostToDevice, stream));
     if (w) sum_kernel<<<1, 1024, 0, stream>>>(w, M, wsum);
     gm_whiten_kernel<<<unsigned((N + 255) / 256), 256, 0, stream>>>(x, ldx, N, int(p), Linv, nullptr,
@@ -323,16 +358,18 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     gm_whiten_kernel<<<unsigned((M + 255) / 256), 256, 0, stream>>>(means, ldm, M, int(p), Linv, w,
                                                                    wsum, mw, int(p + 1));
     const double lognorm = -0.5 * (double(p) * 1.8378770664093453 + logdet);  // log(2 pi)
-    constexpr int R = 4;
-    const unsigned blocks = unsigned((N + 128 * R - 1) / (128 * R));
-    switch (p) {
-        case 1: gm_pdf_kernel<1, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
-        case 2: gm_pdf_kernel<2, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
-        case 3: gm_pdf_kernel<3, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
-        case 4: gm_pdf_kernel<4, R><<<blocks, 128, 0, stream>>>(xw, N, mw, M, lognorm, logq); break;
-        default:
-            gm_pdf_generic_kernel<<<unsigned((N + 127) / 128), 128, 0, stream>>>(xw, N, mw, M, int(p),
-                                                                              lognorm, logq);
+    if (p <= 4) {
+        dim3 grid(static_cast<unsigned>(xblocks), static_cast<unsigned>(chunks));
+        switch (p) {
+            case 1: gm_pdf_kernel<1, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+            case 2: gm_pdf_kernel<2, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+            case 3: gm_pdf_kernel<3, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+            default: gm_pdf_kernel<4, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+        }
+        gm_finish_kernel<<<unsigned((N + 255) / 256), 256, 0, stream>>>(partial, N, int(chunks), lognorm, logq);
+    } else {
+        gm_pdf_generic_kernel<<<unsigned((N + 127) / 128), 128, 0, stream>>>(xw, N, mw, M, int(p),
+                                                                          lognorm, logq);
     }
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
