@@ -28,6 +28,7 @@ import torch
 from . import device as dev
 from . import model as em
 from . import ops
+from . import sharding
 from .results import Sample, SmcSample
 
 logger = logging.getLogger(__name__)
@@ -347,7 +348,7 @@ class Rejection(Sampler):
         if n_sim:
             n_batches = ceil(n_sim / self.batch_size)
             if self.comm.on:
-                n_batches = ceil(n_batches / self.comm.size)   # batches per rank
+                n_batches = sharding.batches_per_rank(n_batches, self.comm.size)
         else:
             n_batches = 1 if self.comm.on else self.max_parallel_batches
         self.objective = dict(n_samples=n_samples, threshold=threshold, n_batches=n_batches)
@@ -514,16 +515,7 @@ class Rejection(Sampler):
         pack[0, 1:1 + D] = torch.as_tensor(np.broadcast_to(m_r, (D,)).copy(), device='cuda')
         pack[0, 1 + D:] = torch.as_tensor(np.broadcast_to(s_r, (D,)).copy(), device='cuda')
         allp = self.comm.all_gather_rows(pack).cpu().numpy()
-        n0, m0, s0 = 0.0, np.zeros(D), np.zeros(D)
-        for row in allp:
-            nb, mb, sb = row[0], row[1:1 + D], row[1 + D:]
-            if nb == 0:
-                continue
-            n1 = n0 + nb
-            delta = mb - m0
-            m0 = m0 + delta * (nb / n1)
-            s0 = s0 + sb + delta ** 2 * (n0 * nb / n1)
-            n0 = n1
+        n0, m0, s0 = sharding.chan_merge([(row[0], row[1:1 + D], row[1 + D:]) for row in allp])
         st['store'] = [n0, m0, s0]
         st['scale'] = np.sqrt(s0 / n0)
 
@@ -531,7 +523,7 @@ class Rejection(Sampler):
         """Batch index b is computed by rank b % world (each rank advances by world_size)."""
         if not self.comm.on:
             return super().iterate()
-        batch_index = self._next_batch_index * self.comm.size + self.comm.rank
+        batch_index = sharding.batch_index(self._next_batch_index, self.comm.rank, self.comm.size)
         values = self.prepare_new_batch(batch_index)
         self._next_batch_index += 1
         batch = self._run_batch(batch_index, values)
@@ -594,7 +586,7 @@ class SMC(Sampler):
     def iterate(self):
         if not self.comm.on:
             return super().iterate()
-        batch_index = self._next_batch_index * self.comm.size + self.comm.rank
+        batch_index = sharding.batch_index(self._next_batch_index, self.comm.rank, self.comm.size)
         values = self.prepare_new_batch(batch_index)
         self._next_batch_index += 1
         batch = self._run_batch(batch_index, values)
@@ -648,15 +640,12 @@ class SMC(Sampler):
             means, cov, weights = self._gm_params_host
             N = len(params)
             if self.comm.on:
-                per = ceil(N / self.comm.size)
-                lo = min(N, self.comm.rank * per)
-                hi = min(N, lo + per)
+                lo, hi, per = sharding.shard_bounds(N, self.comm.rank, self.comm.size)
                 q_part = torch.full((per,), float('nan'), dtype=torch.float64, device='cuda')
                 if hi > lo:
                     q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], means, cov, weights)
                 q_logpdf = self.comm.all_gather_rows(q_part)
-                q_logpdf = torch.cat([q_logpdf[r * per:r * per + max(0, min(N, (r + 1) * per) - r * per)]
-                                      for r in range(self.comm.size)])
+                q_logpdf = q_logpdf[:N]   # equal-capacity shards: only the tail is padding
             else:
                 q_logpdf = ops.gm_logpdf(params_dev, means, cov, weights)
             p_logpdf = self._prior.logpdf(params)

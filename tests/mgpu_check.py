@@ -1,0 +1,68 @@
+"""Multi-GPU parity check, launched by torchrun (one process per GPU, NCCL):
+  * Rejection in quantile mode over W ranks == the single-process golden (same batches);
+  * SMC over W ranks: round 0 identical to the golden, later rounds statistically sane;
+  * AdaptiveDistanceSMC: moments merged across ranks.
+Prints MGPU_OK on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def main():
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import elfi_b200 as elfi
+    from elfi_b200.examples import ma2
+    gold = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'ma2_rejection_quantile.npz')))
+
+    m = ma2.get_model(seed_obs=4)
+    res = elfi.Rejection(m['d'], batch_size=1000, seed=123).sample(100, quantile=0.01, bar=False)
+    assert res.n_sim == 10000, res.n_sim
+    assert res.threshold == float(gold['threshold'])
+    assert np.array_equal(res.discrepancies, gold['out_d'])
+    assert np.array_equal(res.samples['t1'], gold['out_t1'])
+    assert np.array_equal(res.samples['t2'], gold['out_t2'])
+
+    # every rank must hold the identical result
+    chk = torch.tensor([float(res.discrepancies.sum())], dtype=torch.float64, device='cuda')
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    assert all(float(c) == float(chk) for c in allc)
+
+    gs = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'ma2_smc_quantiles.npz')))
+    smc = elfi.SMC(m['d'], batch_size=1000, seed=123).sample(200, quantiles=[.5, .5, .5], bar=False)
+    pop0 = smc.populations[0]
+    assert np.array_equal(pop0.outputs['d'], gs['pop0_out_d'])       # round 0: same batches
+    assert np.array_equal(pop0.outputs['t1'], gs['pop0_out_t1'])
+    assert smc.populations[1].threshold == float(gs['pop1_threshold'])  # from pop0 only
+    means = smc.sample_means_array
+    assert abs(means[0] - 0.6) < 0.15 and abs(means[1] - 0.2) < 0.15, means
+    assert np.all(np.isfinite(smc.weights)) and smc.weights.min() > 0
+    thr = [p.threshold for p in smc.populations]
+    assert thr[0] > thr[1] > thr[2]
+
+    m2 = ma2.get_model(seed_obs=4)
+    m2['d'].become(elfi.AdaptiveDistance(m2['S1'], m2['S2']))
+    ad = elfi.AdaptiveDistanceSMC(m2['d'], batch_size=500, seed=11).sample(100, rounds=2,
+                                                                          quantile=0.5, bar=False)
+    ga = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'ma2_adaptive_distance_smc.npz')))
+    # round 0 simulates batches 0 and 1 (n = 200 of 1000 sims): same set as the golden run
+    np.testing.assert_allclose(ad.populations[0].adaptive_distance_w, ga['pop0_w'], rtol=1e-9)
+    np.testing.assert_allclose(ad.populations[0].outputs['t1'], ga['pop0_out_t1'], rtol=1e-9)
+    dist.barrier()
+    if rank == 0:
+        print('MGPU_OK world={}'.format(world), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
