@@ -40,10 +40,11 @@ __all__ = ['Rejection', 'SMC', 'AdaptiveDistanceSMC', 'ModelPrior', 'GMDistribut
 class Comm:
     """torch.distributed plumbing (NCCL on GPUs, gloo in CPU tests); identity when single."""
 
-    def __init__(self):
+    def __init__(self, enabled=True):
         import torch.distributed as dist
         self.dist = dist
-        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.on = bool(enabled) and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size() > 1
         self.rank = dist.get_rank() if self.on else 0
         self.size = dist.get_world_size() if self.on else 1
 
@@ -187,7 +188,9 @@ class ParameterInference:
     """Batch loop of elfi's ParameterInference for a single in-order device client."""
 
     def __init__(self, model, output_names, batch_size=1, seed=None, pool=None,
-                 max_parallel_batches=None):
+                 max_parallel_batches=None, distributed=True):
+        """`distributed=False` keeps the inference on this rank only even when a
+        torch.distributed process group is initialised."""
         model = model.model if isinstance(model, em.NodeReference) else model
         if not model.parameter_names:
             raise ValueError('Model {} defines no parameters'.format(model))
@@ -196,7 +199,8 @@ class ParameterInference:
         self.computation_context = em.ComputationContext(batch_size=batch_size, seed=seed,
                                                          pool=pool)
         self._compiled = em.compile_net(self.model.source_net, self.output_names)
-        self.comm = Comm()
+        self._distributed = distributed
+        self.comm = Comm(distributed)
         self.max_parallel_batches = max_parallel_batches or self.comm.size
         if self.max_parallel_batches <= 0:
             raise ValueError('Value for max_parallel_batches ({}) must be at least one.'.format(
@@ -620,7 +624,8 @@ class SMC(Sampler):
         self._round_random_state = np.random.RandomState(seed)
         self._rejection = Rejection(self.model, discrepancy_name=self.discrepancy_name,
                                     output_names=self.output_names, batch_size=self.batch_size,
-                                    seed=seed, max_parallel_batches=self.max_parallel_batches)
+                                    seed=seed, max_parallel_batches=self.max_parallel_batches,
+                                    distributed=self._distributed)
 
     def _extract_population(self):
         sample = self._rejection.extract_result()

@@ -38,17 +38,23 @@ def main():
     dist.all_gather(allc, chk)
     assert all(float(c) == float(chk) for c in allc)
 
-    gs = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'ma2_smc_quantiles.npz')))
-    smc = elfi.SMC(m['d'], batch_size=1000, seed=123).sample(200, quantiles=[.5, .5, .5], bar=False)
-    pop0 = smc.populations[0]
-    assert np.array_equal(pop0.outputs['d'], gs['pop0_out_d'])       # round 0: same batches
-    assert np.array_equal(pop0.outputs['t1'], gs['pop0_out_t1'])
-    assert smc.populations[1].threshold == float(gs['pop1_threshold'])  # from pop0 only
+    # SMC: 2 batches in round 0 (rank 0 -> batch 0, rank 1 -> batch 1) == single-process run
+    single = elfi.SMC(m['d'], batch_size=200, seed=123, distributed=False).sample(
+        200, quantiles=[.5, .5, .5], bar=False)
+    smc = elfi.SMC(m['d'], batch_size=200, seed=123).sample(200, quantiles=[.5, .5, .5], bar=False)
+    if world == 2:
+        for k in ('d', 't1', 't2'):
+            assert np.array_equal(smc.populations[0].outputs[k], single.populations[0].outputs[k]), k
+        assert smc.populations[1].threshold == single.populations[1].threshold   # from pop 0 only
     means = smc.sample_means_array
-    assert abs(means[0] - 0.6) < 0.15 and abs(means[1] - 0.2) < 0.15, means
+    assert abs(means[0] - 0.6) < 0.2 and abs(means[1] - 0.2) < 0.2, means
     assert np.all(np.isfinite(smc.weights)) and smc.weights.min() > 0
     thr = [p.threshold for p in smc.populations]
     assert thr[0] > thr[1] > thr[2]
+    w_chk = torch.tensor([float(smc.weights.sum())], dtype=torch.float64, device='cuda')
+    allw = [torch.zeros_like(w_chk) for _ in range(world)]
+    dist.all_gather(allw, w_chk)
+    assert all(float(c) == float(w_chk) for c in allw), 'ranks disagree on the SMC population'
 
     m2 = ma2.get_model(seed_obs=4)
     m2['d'].become(elfi.AdaptiveDistance(m2['S1'], m2['S2']))
