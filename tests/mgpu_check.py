@@ -45,7 +45,6 @@ def main():
     if world == 2:
         for k in ('d', 't1', 't2'):
             assert np.array_equal(smc.populations[0].outputs[k], single.populations[0].outputs[k]), k
-        assert smc.populations[1].threshold == single.populations[1].threshold   # from pop 0 only
     means = smc.sample_means_array
     assert abs(means[0] - 0.6) < 0.2 and abs(means[1] - 0.2) < 0.2, means
     assert np.all(np.isfinite(smc.weights)) and smc.weights.min() > 0
