@@ -55,14 +55,21 @@ def main():
     dist.all_gather(allw, w_chk)
     assert all(float(c) == float(w_chk) for c in allw), 'ranks disagree on the SMC population'
 
-    m2 = ma2.get_model(seed_obs=4)
-    m2['d'].become(elfi.AdaptiveDistance(m2['S1'], m2['S2']))
-    ad = elfi.AdaptiveDistanceSMC(m2['d'], batch_size=500, seed=11).sample(100, rounds=2,
-                                                                          quantile=0.5, bar=False)
-    ga = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'ma2_adaptive_distance_smc.npz')))
-    # round 0 simulates batches 0 and 1 (n = 200 of 1000 sims): same set as the golden run
-    np.testing.assert_allclose(ad.populations[0].adaptive_distance_w, ga['pop0_w'], rtol=1e-9)
-    np.testing.assert_allclose(ad.populations[0].outputs['t1'], ga['pop0_out_t1'], rtol=1e-9)
+    # adaptive distance: 2 batches in round 0; column moments Chan-merged across ranks
+    def adaptive(distributed):
+        m2 = ma2.get_model(seed_obs=4)
+        m2['d'].become(elfi.AdaptiveDistance(m2['S1'], m2['S2']))
+        return elfi.AdaptiveDistanceSMC(m2['d'], batch_size=100, seed=11,
+                                        distributed=distributed).sample(100, rounds=2, quantile=0.5,
+                                                                        bar=False)
+    ad1, ad = adaptive(False), adaptive(True)
+    if world == 2:
+        np.testing.assert_allclose(ad.populations[0].adaptive_distance_w,
+                                   ad1.populations[0].adaptive_distance_w, rtol=1e-10)
+        for k in ('t1', 't2', 'S1', 'S2'):
+            np.testing.assert_allclose(ad.populations[0].outputs[k], ad1.populations[0].outputs[k],
+                                       rtol=1e-9)
+    assert np.all(np.isfinite(ad.weights)) and len(ad.populations) == 2
     dist.barrier()
     if rank == 0:
         print('MGPU_OK world={}'.format(world), flush=True)
