@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get(
     os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libelfi_b200.so'))
 
 c_i64 = ctypes.c_int64
+c_u64 = ctypes.c_uint64
 c_int = ctypes.c_int
 c_dbl = ctypes.c_double
 c_ptr = ctypes.c_void_p
@@ -41,6 +42,12 @@ SIGNATURES = {
                                 c_ptr, c_dbl, c_ptr, c_ptr],
     'elfi_b200_smc_weights_f64': [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr],
     'elfi_b200_probe_fp64_f64': [c_ptr, c_ptr],
+    'elfi_b200_prior_ma2_f64': [c_ptr, c_i64, c_u64, c_u64, ctypes.c_int32, c_ptr, c_ptr, c_ptr],
+    'elfi_b200_logprior_ma2_f64': [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr],
+    'elfi_b200_sim_ma2_f64': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_u64, c_u64, c_ptr, c_i64, c_ptr,
+                              c_i64, c_ptr],
+    'elfi_b200_gm_rvs_f64': [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_u64, c_u64,
+                             ctypes.c_int32, c_ptr, c_i64, c_ptr],
     'elfi_b200_gp_padded_size': [c_i64],
     'elfi_b200_gp_fit_f64': [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl,
                              c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],

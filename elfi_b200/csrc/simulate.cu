@@ -1,0 +1,308 @@
+// simulate.cu -- device-side generation for the throughput mode:
+// MA2 prior draws, the MA2 simulator fused with its autocovariance summaries, and Gaussian-mixture
+// proposals with the MA2 prior support, so that a whole SMC-ABC batch is born in HBM and only
+// accepted particles ever leave the device.
+//
+// Reference functions mirrored (statistically, not bit-wise: the reference draws from a host
+// MT19937 RandomState, here a counter-based Philox4x32-10 stream keyed by (seed, batch, row)):
+//   elfi/examples/ma2.py:11-37    MA2(t1, t2)              x_i = w_i + t1 w_{i-1} + t2 w_{i-2}
+//   elfi/examples/ma2.py:40-59    autocov (lags 1, 2), NumPy pairwise summation order kept
+//   elfi/examples/ma2.py:96-186   CustomPrior1 (triangular t1), CustomPrior2 (uniform t2 | t1)
+//   elfi/methods/utils.py:200-261 GMDistribution.rvs (choice by weights + MVN perturbation +
+//                                 rejection of draws outside the prior support)
+// The random numbers are a pure function of (seed, stream, row, index): the simulator can be
+// replayed (e.g. to materialise X for a test) and any sharding of rows gives the same particles.
+#include "pairwise.cuh"
+
+namespace elfi {
+
+struct Philox {
+    uint32_t key0, key1;
+    __device__ __forceinline__ Philox(uint64_t seed) : key0(uint32_t(seed)), key1(uint32_t(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // (0, 1], 53 bits
+    const uint64_t v = (uint64_t(a) << 21) ^ uint64_t(b >> 11);
+    return (double(v & ((uint64_t(1) << 53) - 1)) + 1.0) * (1.0 / 9007199254740992.0);
+}
+
+// two standard normals from one Philox block (Box-Muller)
+__device__ __forceinline__ void normal2(const uint4& r, double& n0, double& n1) {
+    const double u = u01(r.x, r.y), v = u01(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u));
+    double s, c;
+    sincospi(2.0 * v, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+// ---- MA2 prior ------------------------------------------------------------------------------
+// mode 0: joint draw (t1, t2); mode 1: t1 only; mode 2: t2 given the t1 passed in.
+__global__ void prior_ma2_kernel(int64_t B, uint64_t seed, uint64_t offset, int mode,
+                                 double* __restrict__ t1, double* __restrict__ t2) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const Philox ph(seed);
+    const uint64_t row = offset + uint64_t(i);
+    const uint4 r = ph(uint32_t(row), uint32_t(row >> 32), 0u, 0x50524931u);
+    const double u = u01(r.x, r.y), v = u01(r.z, r.w);
+    const double b = 2.0, a = 1.0;
+    double x1;
+    if (mode == 2) {
+        x1 = t1[i];
+    } else {
+        x1 = u < 0.5 ? sqrt(2.0 * u) * b - b : -sqrt(2.0 * (1.0 - u)) * b + b;
+        t1[i] = x1;
+    }
+    if (mode != 1) {
+        const double loc = fmax(-a - x1, -a + x1);
+        t2[i] = loc + (a - loc) * v;
+    }
+}
+
+__device__ __forceinline__ bool ma2_in_support(double x1, double x2) {
+    const double ax = fabs(x1);
+    return ax < 2.0 && x2 >= -1.0 + ax && x2 <= 1.0;
+}
+
+// log p(t1) + log p(t2 | t1) of the MA2 priors (b = 2, a = 1); -inf outside the support
+__global__ void logprior_ma2_kernel(const double* __restrict__ x, int64_t ld, int64_t B,
+                                    double* __restrict__ out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double x1 = x[i * ld], x2 = x[i * ld + 1];
+    const double ax = fabs(x1);
+    double lp = -INFINITY;
+    if (ma2_in_support(x1, x2)) lp = log(0.5 - ax * 0.25) - log(2.0 - ax);
+    out[i] = lp;
+}
+
+// ---- MA2 simulator (+ fused autocovariance) ---------------------------------------------------
+// One thread per row; normals are generated eight at a time (4 Philox blocks).
+template <bool WRITE_X, bool SUMMARIES>
+__global__ void __launch_bounds__(128)
+sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int64_t B, int n_obs,
+               uint64_t seed, uint64_t offset, double* __restrict__ X, int64_t ldX,
+               double* __restrict__ S, int64_t ldS) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const Philox ph(seed);
+    const uint64_t row = offset + uint64_t(i);
+    const uint32_t r0 = uint32_t(row), r1 = uint32_t(row >> 32);
+    const double a1 = t1[i], a2 = t2[i];
+    PairwiseStream<6> p1, p2;      // lag-1 and lag-2 product sums (rows up to 8192 terms)
+    if (SUMMARIES) {
+        p1.begin(n_obs - 1);
+        p2.begin(n_obs - 2);
+    }
+    // w has n_obs + 2 entries; x_k = w_{k+2} + a1 w_{k+1} + a2 w_k
+    double wm2, wm1;   // w_{k}, w_{k+1} before the current group
+    {
+        double n0, n1;
+        normal2(ph(r0, r1, 0u, 0x4d413257u), n0, n1);
+        wm2 = n0;
+        wm1 = n1;
+    }
+    double xm1 = 0.0, xm2 = 0.0;   // x_{k-1}, x_{k-2}
+    double b1[8], b2[8];
+    for (int k0 = 0; k0 < n_obs; k0 += 8) {
+        double w[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            normal2(ph(r0, r1, uint32_t(1 + (k0 >> 1) + q), 0x4d413257u), w[2 * q], w[2 * q + 1]);
+        double x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const double wk = (e == 0) ? wm2 : (e == 1 ? wm1 : w[e >= 2 ? e - 2 : 0]);
+            const double wk1 = (e == 0) ? wm1 : w[e >= 1 ? e - 1 : 0];
+            // (w2 + t1*w1) + t2*w0 with separate roundings, like the NumPy expression in ma2.py:36
+            x[e] = __dadd_rn(__dadd_rn(w[e], __dmul_rn(a1, wk1)), __dmul_rn(a2, wk));
+        }
+        wm2 = w[6];
+        wm1 = w[7];
+        const int cnt = (n_obs - k0) < 8 ? (n_obs - k0) : 8;
+        if (WRITE_X) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < cnt) X[i * ldX + k0 + e] = x[e];
+        }
+        if (SUMMARIES) {
+            // lag-1 products p[j] = x[j+1] x[j], j = k - 1 for element k; lag-2: j = k - 2.
+            // Feed aligned groups of 8 products: group g of lag 1 needs x[8g .. 8g+8].
+            // b1[] holds products with indices 8(g) .. 8g+7 once x[8g+8] is known, so products are
+            // emitted one group late: element k contributes product index k-1 (lag 1), k-2 (lag 2).
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + e;
+                if (e < cnt) {
+                    const double prev1 = (e == 0) ? xm1 : x[e >= 1 ? e - 1 : 0];
+                    const double prev2 = (e == 0) ? xm2 : (e == 1 ? xm1 : x[e >= 2 ? e - 2 : 0]);
+                    // product index for lag 1 is k-1: slot (k-1) & 7 == (e + 7) & 7
+                    if (k >= 1) {
+                        b1[(e + 7) & 7] = __dmul_rn(x[e], prev1);
+                        if (((e + 7) & 7) == 7) p1.feed8(k - 8, b1, 8);
+                    }
+                    if (k >= 2) {
+                        b2[(e + 6) & 7] = __dmul_rn(x[e], prev2);
+                        if (((e + 6) & 7) == 7) p2.feed8(k - 9, b2, 8);
+                    }
+                }
+            }
+        }
+        xm2 = x[6];
+        xm1 = x[7];
+    }
+    if (SUMMARIES) {
+        const int m1 = n_obs - 1, m2 = n_obs - 2;
+        if (m1 % 8) p1.feed8(m1 - m1 % 8, b1, m1 % 8);
+        if (m2 % 8) p2.feed8(m2 - m2 % 8, b2, m2 % 8);
+        S[i * ldS + 0] = p1.finish() / double(m1);
+        S[i * ldS + 1] = p2.finish() / double(m2);
+    }
+}
+
+// ---- Gaussian-mixture proposals ------------------------------------------------------------------
+// cumw: inclusive cumulative sum of the normalised weights (N); Lc: lower Cholesky factor of the
+// shared covariance (p x p, row-major, p <= 4).  support: 0 none, 1 MA2 prior support.
+__global__ void gm_rvs_kernel(const double* __restrict__ means, int64_t ldm, const double* __restrict__ cumw,
+                              int64_t N, int p, const double* __restrict__ Lc, int64_t B,
+                              uint64_t seed, uint64_t offset, int support, double* __restrict__ out,
+                              int64_t ldo) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const Philox ph(seed);
+    const uint64_t row = offset + uint64_t(i);
+    const double total = cumw[N - 1];
+    double x[4];
+    for (uint32_t trial = 0; trial < 1000u; ++trial) {
+        const uint4 r = ph(uint32_t(row), uint32_t(row >> 32), trial * 4u, 0x474d5256u);
+        const double u = u01(r.x, r.y) * total;
+        int64_t lo = 0, hi = N - 1;               // first index with cumw >= u
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (cumw[mid] < u) lo = mid + 1; else hi = mid;
+        }
+        double z[4];
+        normal2(ph(uint32_t(row), uint32_t(row >> 32), trial * 4u + 1u, 0x474d5256u), z[0], z[1]);
+        if (p > 2) normal2(ph(uint32_t(row), uint32_t(row >> 32), trial * 4u + 2u, 0x474d5256u), z[2], z[3]);
+        for (int a = 0; a < p; ++a) {
+            double s = means[lo * ldm + a];
+            for (int b = 0; b <= a; ++b) s = fma(Lc[a * p + b], z[b], s);
+            x[a] = s;
+        }
+        if (support == 0 || (support == 1 && ma2_in_support(x[0], x[1]))) break;
+    }
+    for (int a = 0; a < p; ++a) out[i * ldo + a] = x[a];
+}
+
+// inclusive scan of w / sum(w) (single block; N up to a few million is fine: one pass each)
+__global__ void __launch_bounds__(1024)
+cumsum_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ out) {
+    __shared__ double ws[32];
+    __shared__ double carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0.0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + tid;
+        const double v = i < n ? (w ? w[i] : 1.0) : 0.0;
+        double incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) ws[wid] = incl;
+        __syncthreads();
+        double woff = 0.0;
+        for (int k = 0; k < wid; ++k) woff += ws[k];
+        const double carry = carry_s;
+        if (i < n) out[i] = carry + woff + incl;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+}
+
+}  // namespace elfi
+
+extern "C" {
+
+int elfi_b200_prior_ma2_f64(elfi_b200_ctx* ctx, int64_t B, uint64_t seed, uint64_t offset,
+                            int32_t mode, double* t1, double* t2, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && mode >= 0 && mode <= 2, "prior_ma2: bad argument");
+    ELFI_REQUIRE(B == 0 || (t1 && (mode == 1 || t2)), "prior_ma2: NULL argument");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    prior_ma2_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(B, seed, offset, mode, t1, t2);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_logprior_ma2_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t B,
+                               double* out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (x && out)) && ldx >= 2, "logprior_ma2: bad argument");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    logprior_ma2_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(x, ldx, B, out);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2, int64_t B,
+                          int64_t n_obs, uint64_t seed, uint64_t offset, double* X, int64_t ldX,
+                          double* S, int64_t ldS, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (t1 && t2)), "sim_ma2: NULL argument");
+    ELFI_REQUIRE(n_obs >= 3 && n_obs <= 8192, "sim_ma2: n_obs=%lld outside [3, 8192]", (long long)n_obs);
+    ELFI_REQUIRE(X || S, "sim_ma2: nothing to produce (X and S are both NULL)");
+    ELFI_REQUIRE((!X || ldX >= n_obs) && (!S || ldS >= 2), "sim_ma2: bad leading dimension");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const unsigned blocks = unsigned((B + 127) / 128);
+    if (X && S) sim_ma2_kernel<true, true><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS);
+    else if (X) sim_ma2_kernel<true, false><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS);
+    else sim_ma2_kernel<false, true><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* weights,
+                         int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
+                         uint64_t offset, int32_t support, double* out, int64_t ldo, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && means && Lchol_host && (B == 0 || out), "gm_rvs: NULL argument");
+    ELFI_REQUIRE(N >= 1 && p >= 1 && p <= 4 && ldm >= p && ldo >= p, "gm_rvs: bad shape (p <= 4)");
+    ELFI_REQUIRE(support == 0 || (support == 1 && p == 2), "gm_rvs: unknown support %d", support);
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, size_t(N) * 8 + 512));
+    if (!base) return ELFI_B200_ERR_NOMEM;
+    double* Lc = reinterpret_cast<double*>(base);
+    double* cumw = reinterpret_cast<double*>(base + 256);
+    ELFI_CUDA_OK(cudaMemcpyAsync(Lc, Lchol_host, size_t(p) * p * 8, cudaMemcpyHostToDevice, stream));
+    cumsum_kernel<<<1, 1024, 0, stream>>>(weights, N, cumw);
+    gm_rvs_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(means, ldm, cumw, N, int(p), Lc, B,
+                                                                seed, offset, support, out, ldo);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+}  // extern "C"

@@ -659,7 +659,18 @@ def _stack_summaries(summaries):
                              'summary (XA) and observed (XB) output data dimensions. They '
                              'have to be at most 2d.')
         cols.append(t if t.dim() == 2 else t[:, None])
-    return cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
+    if len(cols) == 1:
+        return cols[0]
+    # columns that are adjacent views of one row-major matrix (e.g. the (B, 2) output of the fused
+    # MA2 summaries) are re-assembled without a copy
+    width = sum(c.shape[1] for c in cols)
+    first = cols[0]
+    if first.stride(0) == width and all(
+            c.stride(0) == width and (c.shape[1] == 1 or c.stride(1) == 1) and
+            c.data_ptr() == first.data_ptr() + 8 * sum(x.shape[1] for x in cols[:k]) and
+            c.shape[0] == first.shape[0] for k, c in enumerate(cols)):
+        return torch.as_strided(first, (first.shape[0], width), (width, 1))
+    return torch.cat(cols, dim=1)
 
 
 def _stack_observed(observed):

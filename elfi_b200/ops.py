@@ -287,3 +287,59 @@ def smc_weights(logprior, logq):
     _lib.call('elfi_b200_smc_weights_f64', dev.context(), dev.ptr(lp), dev.ptr(lq), lp.numel(),
               dev.ptr(w), dev.stream_ptr())
     return w
+
+
+# ------------------------------------------------------------------ throughput mode (device RNG)
+def prior_ma2(batch_size, seed, offset=0, t1=None, which='both'):
+    """MA2 prior draws on the device (elfi/examples/ma2.py:96-186).
+
+    which='both' -> (t1, t2); 't1' -> t1; 't2' -> t2 conditional on the given t1."""
+    mode = {'both': 0, 't1': 1, 't2': 2}[which]
+    if mode == 2:
+        t1 = dev.to_device(t1).reshape(-1).contiguous()
+        batch_size = t1.numel()
+    else:
+        t1 = dev.empty((batch_size,))
+    t2 = dev.empty((batch_size,)) if mode != 1 else None
+    _lib.call('elfi_b200_prior_ma2_f64', dev.context(), batch_size, int(seed), int(offset), mode,
+              dev.ptr(t1), dev.ptr(t2), dev.stream_ptr())
+    return (t1, t2) if mode == 0 else (t1 if mode == 1 else t2)
+
+
+def logprior_ma2(params):
+    """Joint log prior density of MA2's (t1, t2); -inf outside the support."""
+    x = _matrix(params)
+    out = dev.empty((x.shape[0],))
+    _lib.call('elfi_b200_logprior_ma2_f64', dev.context(), dev.ptr(x), _ld(x), x.shape[0],
+              dev.ptr(out), dev.stream_ptr())
+    return out
+
+
+def sim_ma2(t1, t2, n_obs=100, seed=0, offset=0, want_data=False, want_summaries=True):
+    """MA2 simulator on the device; returns (X or None, S or None) with S = autocov lags (1, 2)
+    computed in the same kernel (X never touches HBM unless asked for)."""
+    t1 = dev.to_device(t1).reshape(-1)
+    t2 = dev.to_device(t2).reshape(-1)
+    B = t1.numel()
+    X = dev.empty((B, n_obs)) if want_data else None
+    S = dev.empty((B, 2)) if want_summaries else None
+    _lib.call('elfi_b200_sim_ma2_f64', dev.context(), dev.ptr(t1), dev.ptr(t2), B, n_obs,
+              int(seed), int(offset), dev.ptr(X), n_obs, dev.ptr(S), 2, dev.stream_ptr())
+    return X, S
+
+
+def gm_rvs(means, cov, weights, size, seed, offset=0, support=0):
+    """GMDistribution.rvs on the device (elfi/methods/utils.py:200-261); support=1 keeps only
+    draws inside the MA2 prior support (redrawn per particle)."""
+    means = _matrix(means)
+    N, p = means.shape
+    cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    if cov.shape == (1, 1) and p > 1:
+        cov = np.eye(p) * cov[0, 0]
+    L = np.ascontiguousarray(np.linalg.cholesky(cov))
+    w = None if weights is None else dev.to_device(weights).reshape(-1)
+    out = dev.empty((size, p))
+    _lib.call('elfi_b200_gm_rvs_f64', dev.context(), dev.ptr(means), _ld(means), dev.ptr(w), N, p,
+              dev.ptr(L), size, int(seed), int(offset), int(support), dev.ptr(out), p,
+              dev.stream_ptr())
+    return out

@@ -538,11 +538,17 @@ class Rejection(Sampler):
 class SMC(Sampler):
     """Sequential Monte Carlo ABC sampler (samplers.py:320-559)."""
 
-    def __init__(self, model, discrepancy_name=None, output_names=None, **kwargs):
+    def __init__(self, model, discrepancy_name=None, output_names=None, device_proposal=None,
+                 **kwargs):
+        """`device_proposal` (optional, throughput mode): an object with
+        ``rvs(means, cov, weights, size, key) -> (size, p) device tensor`` restricted to the prior
+        support and ``logpdf(params) -> device tensor`` (e.g. examples.ma2.DeviceProposal); the
+        default draws proposals from the host RandomState exactly like the reference."""
         model, discrepancy_name = self._resolve_model(model, discrepancy_name)
         output_names = [discrepancy_name] + model.parameter_names + (output_names or [])
         super().__init__(model, output_names, **kwargs)
         self._prior = ModelPrior(self.model)
+        self._device_proposal = device_proposal
         self.discrepancy_name = discrepancy_name
         self.state['round'] = 0
         self._populations = []
@@ -600,6 +606,11 @@ class SMC(Sampler):
         if self.state['round'] == 0:
             return
         means, cov, weights = self._gm_params_host
+        if self._device_proposal is not None:
+            key = int(self._round_random_state.randint(2 ** 31 - 1))
+            params = self._device_proposal.rvs(self._gm_means_dev(), cov, weights, self.batch_size,
+                                               key)
+            return {p: params[:, i] for i, p in enumerate(self.parameter_names)}
         params = GMDistribution.rvs(means, cov, weights, size=self.batch_size,
                                     prior_logpdf=self._prior.logpdf,
                                     random_state=self._round_random_state)
@@ -653,7 +664,10 @@ class SMC(Sampler):
                 q_logpdf = q_logpdf[:N]   # equal-capacity shards: only the tail is padding
             else:
                 q_logpdf = ops.gm_logpdf(params_dev, means, cov, weights)
-            p_logpdf = self._prior.logpdf(params)
+            if self._device_proposal is not None:
+                p_logpdf = self._device_proposal.logpdf(params_dev)
+            else:
+                p_logpdf = self._prior.logpdf(params)
             w_dev = ops.smc_weights(p_logpdf, q_logpdf)
             w = w_dev.cpu().numpy()
         else:
@@ -689,6 +703,12 @@ class SMC(Sampler):
     def _gm_params_host(self):
         sample = self._populations[-1]
         return sample.means, sample.cov, sample.weights
+
+    def _gm_means_dev(self):
+        sample = self._populations[-1]
+        if getattr(sample, '_means_dev', None) is None:
+            sample._means_dev = dev.to_device(sample.means)
+        return sample._means_dev
 
     @property
     def current_population_threshold(self):

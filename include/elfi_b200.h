@@ -210,6 +210,32 @@ int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* va
  * kernels (mixture density, GP products); blocks the host for a few milliseconds. */
 int elfi_b200_probe_fp64_f64(elfi_b200_ctx* ctx, double* tflops_host);
 
+/* ---- throughput mode: device-side generation --------------------
+ * Counter-based Philox4x32-10 streams keyed by (seed, offset + row): statistically equivalent to,
+ * not bit-identical with, the reference's host RandomState.  `offset` = global index of the first
+ * row of this call (e.g. batch_index * batch_size), so that any row sharding yields the same
+ * particles.
+ *   elfi_b200_prior_ma2_f64     CustomPrior1 / CustomPrior2 draws (elfi/examples/ma2.py:96-186);
+ *                               mode 0 = (t1, t2) jointly, 1 = t1 only, 2 = t2 given the t1 passed in
+ *   elfi_b200_logprior_ma2_f64  their joint log density (what ModelPrior.logpdf returns for MA2)
+ *   elfi_b200_sim_ma2_f64       MA2 simulator (ma2.py:11-37); writes X (B, n_obs) and/or, fused,
+ *                               the lag-1 / lag-2 autocovariances S (B, 2) (ma2.py:40-59, NumPy
+ *                               pairwise order) so that X never has to touch HBM
+ *   elfi_b200_gm_rvs_f64        GMDistribution.rvs (elfi/methods/utils.py:200-261): component by
+ *                               weight, + MVN(0, Sigma) with Sigma = L L^T (Lchol_host, p <= 4),
+ *                               redrawn until inside the support (0 = none, 1 = MA2 prior support)
+ */
+int elfi_b200_prior_ma2_f64(elfi_b200_ctx* ctx, int64_t B, uint64_t seed, uint64_t offset,
+                            int32_t mode, double* t1, double* t2, void* stream);
+int elfi_b200_logprior_ma2_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t B,
+                               double* out, void* stream);
+int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2, int64_t B,
+                          int64_t n_obs, uint64_t seed, uint64_t offset, double* X, int64_t ldX,
+                          double* S, int64_t ldS, void* stream);
+int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* weights,
+                         int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
+                         uint64_t offset, int32_t support, double* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
