@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""SMC-ABC on MA2 in throughput mode (device priors / simulator / proposals) at scale:
+accepted particles per second through the public sampler API, 1..N GPUs (torchrun).
+
+    python scripts/bench_smc.py --n 1000000 --batch 1000000 --pops 5 --quantile 0.5
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_smc.py ...
+
+`--batch` is the per-rank batch size.  Prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=1_000_000)
+    ap.add_argument('--batch', type=int, default=1_000_000)
+    ap.add_argument('--pops', type=int, default=5)
+    ap.add_argument('--quantile', type=float, default=0.5)
+    ap.add_argument('--seed', type=int, default=1)
+    ap.add_argument('--warm', type=int, default=1)
+    args = ap.parse_args()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import elfi_b200 as elfi
+    from elfi_b200.examples import ma2
+
+    m = ma2.get_device_model(seed_obs=4)
+
+    def run(n, batch, pops):
+        smc = elfi.SMC(m['d'], batch_size=batch, seed=args.seed, device_proposal=ma2.DeviceProposal)
+        return smc.sample(n, quantiles=[args.quantile] * pops, bar=False)
+
+    for _ in range(args.warm):
+        run(min(args.n, 20000), min(args.batch, 20000), 2)      # warm-up: contexts, scratch, NCCL
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = run(args.n, args.batch, args.pops)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if int(os.environ.get('RANK', '0')) == 0:
+        accepted = args.n * args.pops
+        out = {'bench': 'smc_abc_ma2_throughput_mode', 'n_gpus': world, 'population': args.n,
+               'populations': args.pops, 'quantile': args.quantile, 'batch_per_rank': args.batch,
+               'seconds': dt, 'accepted_particles_per_s': accepted / dt,
+               'simulated': int(res.n_sim), 'simulated_per_s': res.n_sim / dt,
+               'pair_terms': float(args.n) ** 2 * (args.pops - 1),
+               'pair_terms_per_s': float(args.n) ** 2 * (args.pops - 1) / dt,
+               'posterior_means': [float(v) for v in res.sample_means_array],
+               'thresholds': [float(p.threshold) for p in res.populations]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
