@@ -2,7 +2,7 @@
 """SMC-ABC on MA2 in throughput mode (device priors / simulator / proposals) at scale:
 accepted particles per second through the public sampler API, 1..N GPUs (torchrun).
 
-    python scripts/bench_smc.py --n 1000000 --batch 1000000 --pops 5 --quantile 0.5
+    python scripts/bench_smc.py --population 1000000 --batch 1000000 --pops 5 --quantile 0.5
     python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_smc.py ...
 
 `--batch` is the per-rank batch size.  Prints one JSON line on rank 0."""
@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=1_000_000)
+    ap.add_argument('--population', dest='n', type=int, default=1_000_000)
     ap.add_argument('--batch', type=int, default=1_000_000)
     ap.add_argument('--pops', type=int, default=5)
     ap.add_argument('--quantile', type=float, default=0.5)

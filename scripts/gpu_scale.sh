@@ -9,10 +9,10 @@ for g in 1 2 4 8; do
   if [ $g -le $N ]; then
     if [ $g -eq 1 ]; then
       timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/scale_bench_g$g.json 2> gpurun_out/scale_bench_g$g.err
-      timeout 600 python scripts/bench_smc.py --n 1000000 --batch 1000000 --pops 3 > gpurun_out/scale_smc_g$g.json 2> gpurun_out/scale_smc_g$g.err
+      timeout 600 python scripts/bench_smc.py --population 1000000 --batch 1000000 --pops 3 > gpurun_out/scale_smc_g$g.json 2> gpurun_out/scale_smc_g$g.err
     else
       timeout 600 $TR --nproc-per-node $g --master-port 2962$g bench.py --gpus $g --steps 20 --warmup 3 > gpurun_out/scale_bench_g$g.json 2> gpurun_out/scale_bench_g$g.err
-      timeout 600 $TR --nproc-per-node $g --master-port 2963$g scripts/bench_smc.py --n 1000000 --batch $((1000000 / g)) --pops 3 > gpurun_out/scale_smc_g$g.json 2> gpurun_out/scale_smc_g$g.err
+      timeout 600 $TR --nproc-per-node $g --master-port 2963$g scripts/bench_smc.py --population 1000000 --batch $((1000000 / g)) --pops 3 > gpurun_out/scale_smc_g$g.json 2> gpurun_out/scale_smc_g$g.err
     fi
     tail -1 gpurun_out/scale_bench_g$g.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench g=%d value=%.4g ms=%.4f e2e=%.4g frac=%.3f'%(d['n_gpus'],d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['frac']))"
     tail -1 gpurun_out/scale_smc_g$g.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('smc g=%d s=%.3f acc/s=%.4g pairs/s=%.4g'%(d['n_gpus'],d['seconds'],d['accepted_particles_per_s'],d['pair_terms_per_s']))"

@@ -26,11 +26,18 @@ def main():
 
     m = ma2.get_model(seed_obs=4)
     res = elfi.Rejection(m['d'], batch_size=1000, seed=123).sample(100, quantile=0.01, bar=False)
-    assert res.n_sim == 10000, res.n_sim
-    assert res.threshold == float(gold['threshold'])
-    assert np.array_equal(res.discrepancies, gold['out_d'])
-    assert np.array_equal(res.samples['t1'], gold['out_t1'])
-    assert np.array_equal(res.samples['t2'], gold['out_t2'])
+    per_rank = -(-10 // world)                      # ceil(10 batches / world)
+    assert res.n_sim == per_rank * world * 1000, res.n_sim
+    if per_rank * world == 10:                      # same batches as the golden single-process run
+        assert res.threshold == float(gold['threshold'])
+        assert np.array_equal(res.discrepancies, gold['out_d'])
+        assert np.array_equal(res.samples['t1'], gold['out_t1'])
+        assert np.array_equal(res.samples['t2'], gold['out_t2'])
+    # always: identical to ONE rank simulating the same batch indices 0 .. per_rank*world-1
+    one = elfi.Rejection(m['d'], batch_size=1000, seed=123, distributed=False).sample(
+        100, n_sim=per_rank * world * 1000, bar=False)
+    assert np.array_equal(res.discrepancies, one.discrepancies)
+    assert np.array_equal(res.samples_array, one.samples_array)
 
     # every rank must hold the identical result
     chk = torch.tensor([float(res.discrepancies.sum())], dtype=torch.float64, device='cuda')
