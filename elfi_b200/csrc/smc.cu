@@ -331,8 +331,10 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     const int64_t xblocks = (N + 128 * R - 1) / (128 * R);
     int64_t chunks = 1, chunk_len = M;
     if (p <= 4) {
-        chunks = (int64_t(ctx->sm_count) * 8 + xblocks - 1) / xblocks;
-        const int64_t max_chunks = (M + 511) / 512;
+        // ~16 waves of CTAs (8 resident per SM) keep the tail of the last wave below a few
+        // percent; a CTA still sweeps >= 2048 components so its prologue stays negligible
+        chunks = (int64_t(ctx->sm_count) * 8 * 16 + xblocks - 1) / xblocks;
+        const int64_t max_chunks = (M + 2047) / 2048;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks > 65535) chunks = 65535;
         if (chunks < 1) chunks = 1;

@@ -33,6 +33,39 @@ from .results import Sample, SmcSample
 
 logger = logging.getLogger(__name__)
 
+
+class _PhaseTimer:
+    """Optional wall-clock phase accounting (ELFI_B200_TIMING=1): synchronises the device at
+    phase boundaries, so it is off by default."""
+
+    def __init__(self):
+        import os
+        self.on = os.environ.get('ELFI_B200_TIMING') == '1'
+        self.tot = {}
+
+    def __call__(self, name):
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                if timer.on:
+                    torch.cuda.synchronize()
+                    import time
+                    self_inner.t0 = time.perf_counter()
+
+            def __exit__(self_inner, *a):
+                if timer.on:
+                    torch.cuda.synchronize()
+                    import time
+                    timer.tot[name] = timer.tot.get(name, 0.0) + time.perf_counter() - self_inner.t0
+        return _Ctx()
+
+    def report(self):
+        return {k: round(v, 4) for k, v in sorted(self.tot.items(), key=lambda kv: -kv[1])}
+
+
+PHASES = _PhaseTimer()
+
 __all__ = ['Rejection', 'SMC', 'AdaptiveDistanceSMC', 'ModelPrior', 'GMDistribution']
 
 
@@ -253,10 +286,13 @@ class ParameterInference:
     def iterate(self):
         """One batch: prepare -> execute on the device -> update (in batch_index order)."""
         batch_index = self._next_batch_index
-        values = self.prepare_new_batch(batch_index)
+        with PHASES('prepare_new_batch'):
+            values = self.prepare_new_batch(batch_index)
         self._next_batch_index += 1
-        batch = self._run_batch(batch_index, values)
-        self.update(batch, batch_index)
+        with PHASES('run_batch'):
+            batch = self._run_batch(batch_index, values)
+        with PHASES('update'):
+            self.update(batch, batch_index)
 
     @property
     def finished(self):
@@ -597,10 +633,13 @@ class SMC(Sampler):
         if not self.comm.on:
             return super().iterate()
         batch_index = sharding.batch_index(self._next_batch_index, self.comm.rank, self.comm.size)
-        values = self.prepare_new_batch(batch_index)
+        with PHASES('prepare_new_batch'):
+            values = self.prepare_new_batch(batch_index)
         self._next_batch_index += 1
-        batch = self._run_batch(batch_index, values)
-        self.update(batch, batch_index)
+        with PHASES('run_batch'):
+            batch = self._run_batch(batch_index, values)
+        with PHASES('update'):
+            self.update(batch, batch_index)
 
     def prepare_new_batch(self, batch_index):
         if self.state['round'] == 0:
@@ -639,9 +678,11 @@ class SMC(Sampler):
                                     distributed=self._distributed)
 
     def _extract_population(self):
-        sample = self._rejection.extract_result()
+        with PHASES('extract_result(gather+to_host)'):
+            sample = self._rejection.extract_result()
         sample.method_name = "Rejection within SMC-ABC"
-        means, w, cov = self._compute_weights_means_and_cov(sample)
+        with PHASES('weights_means_cov'):
+            means, w, cov = self._compute_weights_means_and_cov(sample)
         sample.means = means
         sample.weights = w
         sample.meta['cov'] = cov
@@ -694,9 +735,10 @@ class SMC(Sampler):
 
     def _set_threshold(self):
         previous_population = self._populations[self.state['round'] - 1]
-        threshold = ops.weighted_sample_quantile(previous_population.discrepancies,
-                                                 self._quantiles[self.state['round']],
-                                                 previous_population.weights)
+        with PHASES('weighted_quantile'):
+            threshold = ops.weighted_sample_quantile(previous_population.discrepancies,
+                                                     self._quantiles[self.state['round']],
+                                                     previous_population.weights)
         self.objective['thresholds'][self.state['round']] = threshold
 
     @property

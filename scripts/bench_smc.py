@@ -48,6 +48,8 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    from elfi_b200.samplers import PHASES
+    PHASES.tot.clear()
     t0 = time.perf_counter()
     res = run(args.n, args.batch, args.pops)
     torch.cuda.synchronize()
@@ -64,6 +66,9 @@ def main():
                'pair_terms_per_s': float(args.n) ** 2 * (args.pops - 1) / dt,
                'posterior_means': [float(v) for v in res.sample_means_array],
                'thresholds': [float(p.threshold) for p in res.populations]}
+        from elfi_b200.samplers import PHASES
+        if PHASES.on:
+            out['phases_s'] = PHASES.report()
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
