@@ -417,6 +417,111 @@ wq_seqscan_kernel(const double* __restrict__ ws, int64_t n, double alpha,
     }
 }
 
+// ---- fast path of the weighted quantile -----------------------------------------------------------
+// A blocked parallel scan gives cumulative weights c~_k whose distance to the reference's
+// sequential np.cumsum values is bounded by eps = 4 n 2^-53 (both are within ~n u of the exact
+// real sums).  If no c~_k falls within eps of alpha the selected order statistic is provably the
+// same as the reference's and the sequential kernel above is skipped; otherwise (alpha sitting on
+// a cumulative weight: equal weights + round alpha) the exact path decides.
+__global__ void __launch_bounds__(1024)
+wq_par_block_sums_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm, int64_t n,
+                         double* __restrict__ partial) {
+    __shared__ double ws[32];
+    const int64_t lo = int64_t(blockIdx.x) * 4096;
+    double acc = 0.0;
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = lo + k * 1024 + threadIdx.x;
+        if (i < n) acc += w ? w[perm[i]] : 1.0;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = ws[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
+// exclusive scan of the block sums (single block); total in partial[nb]; zeroes the two counters
+__global__ void __launch_bounds__(1024)
+wq_par_scan_kernel(double* __restrict__ partial, int64_t nb, int32_t* __restrict__ counts) {
+    __shared__ double ws[32];
+    __shared__ double carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { carry_s = 0.0; counts[0] = 0; counts[1] = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += 1024) {
+        const int64_t i = base + tid;
+        const double v = i < nb ? partial[i] : 0.0;
+        double incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) ws[wid] = incl;
+        __syncthreads();
+        double woff = 0.0;
+        for (int k = 0; k < wid; ++k) woff += ws[k];
+        const double carry = carry_s;
+        if (i < nb) partial[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) partial[nb] = carry_s;
+}
+
+// counts[0] = #{k <= n-2 : c~_k < alpha - eps}, counts[1] = #{k <= n-2 : c~_k < alpha + eps}
+__global__ void __launch_bounds__(1024)
+wq_par_count_kernel(const double* __restrict__ w, const int32_t* __restrict__ perm, int64_t n,
+                    const double* __restrict__ partial, int64_t nb, double alpha, double eps,
+                    int32_t* __restrict__ counts) {
+    __shared__ double ws[32];
+    __shared__ double carry_s;
+    __shared__ int c0_s, c1_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double total = partial[nb];
+    if (tid == 0) { carry_s = partial[blockIdx.x]; c0_s = 0; c1_s = 0; }
+    __syncthreads();
+    int l0 = 0, l1 = 0;
+    const int64_t lo = int64_t(blockIdx.x) * 4096;
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = lo + k * 1024 + tid;
+        const double v = i < n ? (w ? w[perm[i]] : 1.0) : 0.0;
+        double incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) ws[wid] = incl;
+        __syncthreads();
+        double woff = 0.0;
+        for (int q = 0; q < wid; ++q) woff += ws[q];
+        const double carry = carry_s;
+        const double c = (carry + woff + incl) / total;
+        if (i < n - 1) {
+            l0 += (c < alpha - eps) ? 1 : 0;
+            l1 += (c < alpha + eps) ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    }
+    if (lane == 0) { atomicAdd(&c0_s, l0); atomicAdd(&c1_s, l1); }
+    __syncthreads();
+    if (tid == 0) { atomicAdd(&counts[0], c0_s); atomicAdd(&counts[1], c1_s); }
+}
+
+__global__ void wq_pick_kernel(const uint64_t* __restrict__ ukeys, int64_t idx, double* __restrict__ out) {
+    out[0] = u64_to_key(ukeys[idx]);
+    out[1] = double(idx);
+}
+
 }  // namespace elfi
 
 extern "C" {
@@ -487,7 +592,7 @@ int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     const size_t sort_bytes = sort_scratch_bytes(n);
-    const size_t extra = align256(size_t(n) * 8) + 256;
+    const size_t extra = align256(size_t(n + 2) * 8) + 256;
     uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, sort_bytes + extra));
     if (!base) return ELFI_B200_ERR_NOMEM;
     SortScratch s = carve_sort(base, n);
@@ -495,6 +600,25 @@ int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w
     double* total = reinterpret_cast<double*>(base + sort_bytes + align256(size_t(n) * 8));
     int rc = sort_pairs_device(x, n, s, ctx->sm_count, stream);
     if (rc) return rc;
+    if (alpha > 0.0 && n > 1) {
+        // fast path: parallel scan + error bound; falls through to the exact kernels only when
+        // alpha is within eps of a cumulative weight
+        const int64_t nb = (n + 4095) / 4096;
+        double* partial = ws;                               // reuse: nb + 1 doubles (<= n)
+        int32_t* counts = reinterpret_cast<int32_t*>(total) + 4;
+        const double eps = (4.0 * double(n) + 64.0) * 1.1102230246251565e-16;
+        wq_par_block_sums_kernel<<<unsigned(nb), 1024, 0, stream>>>(w, s.v[0], n, partial);
+        wq_par_scan_kernel<<<1, 1024, 0, stream>>>(partial, nb, counts);
+        wq_par_count_kernel<<<unsigned(nb), 1024, 0, stream>>>(w, s.v[0], n, partial, nb, alpha, eps, counts);
+        int32_t hc[2] = {0, -1};
+        ELFI_CUDA_OK(cudaMemcpyAsync(hc, counts, 8, cudaMemcpyDeviceToHost, stream));
+        ELFI_CUDA_OK(cudaStreamSynchronize(stream));
+        if (hc[0] == hc[1]) {
+            wq_pick_kernel<<<1, 1, 0, stream>>>(s.k[0], int64_t(hc[0]), out);
+            ELFI_CUDA_OK(cudaGetLastError());
+            return ELFI_B200_OK;
+        }
+    }
     wq_total_kernel<<<1, 32, 0, stream>>>(w, n, total);
     int blocks = int((n + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;

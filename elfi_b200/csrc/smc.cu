@@ -11,6 +11,8 @@
 // exp(-maha/2) by range reduction (round via the 2^52 trick, no 64-bit conversions, which run
 // at quarter rate) and a degree-7 polynomial: relative error < 1e-8 per term, far inside the
 // 1e-5 relative tolerance on the weights.  Accumulation is fp64.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace elfi {
@@ -333,7 +335,9 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     if (p <= 4) {
         // ~16 waves of CTAs (8 resident per SM) keep the tail of the last wave below a few
         // percent; a CTA still sweeps >= 2048 components so its prologue stays negligible
-        chunks = (int64_t(ctx->sm_count) * 8 * 16 + xblocks - 1) / xblocks;
+        int waves = 16;
+        if (const char* e = getenv("ELFI_B200_GM_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;
+        chunks = (int64_t(ctx->sm_count) * 8 * waves + xblocks - 1) / xblocks;
         const int64_t max_chunks = (M + 2047) / 2048;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks > 65535) chunks = 65535;

@@ -135,7 +135,9 @@ int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA,
  *   out[0] = alpha-quantile (an element of x), out[1] = its rank in sorted order (as double).
  * np.sum (pairwise) and np.cumsum (sequential) are reproduced in the reference's order, so
  * the selected element is identical even when alpha falls exactly on a cumulative weight
- * (equal weights + round alpha, the normal case in SMC round 0). */
+ * (equal weights + round alpha, the normal case in SMC round 0).  A parallel scan with a rigorous
+ * error bound answers first; the sequential kernel only runs when alpha is within that bound of a
+ * cumulative weight.  The call synchronises `stream`. */
 int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w, int64_t n,
                             double alpha, double* out, void* stream);
 
