@@ -91,6 +91,14 @@ class Comm:
         self.dist.all_gather_into_tensor(out, t)
         return out
 
+    def all_reduce_max(self, value):
+        if not self.on:
+            return value
+        devname = 'cuda' if self.dist.get_backend() == 'nccl' else 'cpu'
+        t = torch.tensor([float(value)], dtype=torch.float64, device=devname)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
     def all_reduce_sum(self, value):
         if not self.on:
             return value
@@ -424,7 +432,9 @@ class Rejection(Sampler):
             self._update_distances()
         n = self.objective['n_samples']
         outputs = {k: dev.to_host(v[:n]) for k, v in self.state['samples'].items()}
-        return Sample(outputs=outputs, **self._extract_result_kwargs())
+        sample = Sample(outputs=outputs, **self._extract_result_kwargs())
+        sample._dev = {k: v[:n] for k, v in self.state['samples'].items()}   # device twins
+        return sample
 
     def _init_samples_lazy(self, batch):
         """Best-n buffers on the device (the reference keeps n + batch_size rows on the host,
@@ -534,11 +544,29 @@ class Rejection(Sampler):
             return
         samples = self.state['samples']
         n = self.objective['n_samples']
-        gathered = {k: self.comm.all_gather_rows(v) for k, v in samples.items()}
+        # ranks hold n-row buffers padded with +inf; only the common capacity that covers every
+        # rank's finite rows is exchanged (one scalar MAX all-reduce, then the all-gather)
+        dloc = samples[self.discrepancy_name]
+        key = dloc if dloc.dim() == 1 else dloc[:, -1]
+        valid = int(torch.isfinite(key).sum().item())
+        cap = int(self.comm.all_reduce_max(valid))
+        cap = max(1, min(n, ((cap + 31) // 32) * 32))
+        gathered = {k: self.comm.all_gather_rows(v[:cap]) for k, v in samples.items()}
         d = gathered[self.discrepancy_name]
-        perm = ops.argsort(d if d.dim() == 1 else d[:, -1].contiguous())[:n]
-        for k in samples:
-            samples[k] = ops.take_rows(gathered[k], perm)
+        perm = ops.argsort(d if d.dim() == 1 else d[:, -1].contiguous())
+        total = perm.numel()
+        if total >= n:
+            for k in samples:
+                samples[k] = ops.take_rows(gathered[k], perm[:n])
+        else:   # fewer than n rows exist globally: keep the padding semantics of the local buffers
+            for k in samples:
+                top = ops.take_rows(gathered[k], perm)
+                pad = samples[k][:n - total].clone()
+                if k == self.discrepancy_name:
+                    pad.fill_(float('inf'))
+                else:
+                    pad.zero_()
+                samples[k] = torch.cat([top, pad])
         self.state['n_sim'] = int(self.comm.all_reduce_sum(self.state['n_sim']))
         self.state['n_batches'] = int(self.comm.all_reduce_sum(self.state['n_batches']))
         if self.adaptive:
@@ -647,8 +675,11 @@ class SMC(Sampler):
         means, cov, weights = self._gm_params_host
         if self._device_proposal is not None:
             key = int(self._round_random_state.randint(2 ** 31 - 1))
-            params = self._device_proposal.rvs(self._gm_means_dev(), cov, weights, self.batch_size,
-                                               key)
+            prev = self._populations[-1]
+            w_dev = getattr(prev, '_w_dev', None)
+            params = self._device_proposal.rvs(self._gm_means_dev(), cov,
+                                               w_dev if w_dev is not None else weights,
+                                               self.batch_size, key)
             return {p: params[:, i] for i, p in enumerate(self.parameter_names)}
         params = GMDistribution.rvs(means, cov, weights, size=self.batch_size,
                                     prior_logpdf=self._prior.logpdf,
@@ -692,7 +723,12 @@ class SMC(Sampler):
         """samplers.py:508-534 with the O(N_new x N_prev) mixture density on the device (and
         sharded over ranks when distributed)."""
         params = np.column_stack(tuple([pop.outputs[p] for p in self.parameter_names]))
-        params_dev = dev.to_device(params)
+        twins = getattr(pop, '_dev', None)
+        if twins is not None and all(p in twins for p in self.parameter_names):
+            params_dev = torch.stack([twins[p][:len(params)].reshape(-1)
+                                      for p in self.parameter_names], dim=1)
+        else:
+            params_dev = dev.to_device(params)
         if self._populations:
             means, cov, weights = self._gm_params_host
             N = len(params)
@@ -714,7 +750,10 @@ class SMC(Sampler):
         else:
             w = np.ones(pop.n_samples)
             w_dev = None
-        means = params.copy()
+        means = params
+        pop._means_dev = params_dev
+        pop._w_dev = w_dev if w_dev is not None else torch.ones(len(params), dtype=torch.float64,
+                                                                device='cuda')
         if np.count_nonzero(w) == 0:
             raise RuntimeError("All sample weights are zero. If you are using a prior "
                                "with a bounded support, this may be caused by specifying "
