@@ -32,6 +32,9 @@ B_PER_GPU = 1_000_000
 D = 128
 ACCEPT_Q = 0.01
 WORKLOAD = 'rejection_dist_thr_B1e6_D128_f64'
+# dram__bytes_read.sum + dram__bytes_write.sum of the distance kernel at this shape, from the
+# committed ncu --set full capture (1.024039 GB + 11.09 MB); algorithmic bytes are 1.032 GB
+NCU_DRAM_BYTES_PER_LAUNCH = 1.0351e9
 
 
 def peaks():
@@ -309,7 +312,10 @@ def run_ours(args):
                     'note': 'pinned host S -> chunked H2D overlapped with the kernel; '
                             'PCIe-bound'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': how,
+                         'frac': achieved / peak, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
+                         'traffic_source': 'profiles/r1_dist_first_ncu_full.md (dram__bytes_read + '
+                                           'dram__bytes_write of one ncu --set full capture)',
+                         'peak_source': how,
                          'kernel': 'rowstream_kernel<EuclidConsumer>',
                          'kernel_ms': kernel_ms, 'algorithmic_bytes': alg_bytes,
                          'frac_of_nominal_8TBs': achieved / 8000.0},
