@@ -146,6 +146,46 @@ def main():
         lp = gprior.logpdf(theta)
     save('gauss_prior_logpdf', theta=theta, logpdf=lp)
 
+
+    # --- deterministic topological order (elfi/executor.py:162-246) on random DAGs
+    import networkx as nx
+    from elfi.executor import nx_constant_topological_sort
+    cases = []
+    rs2 = np.random.RandomState(5)
+    names = ['a', 'B', '_c', 'd1', 'd10', 'd2', 'E', '_f_observed', 'g', 'h', '_i', 'J', 'k', 'l0']
+    for trial in range(12):
+        n = rs2.randint(4, len(names) + 1)
+        nodes = list(rs2.permutation(names)[:n])
+        edges = [(nodes[i], nodes[j]) for i in range(n) for j in range(i + 1, n)
+                 if rs2.rand() < 0.3]
+        G = nx.DiGraph()
+        G.add_nodes_from(nodes)
+        G.add_edges_from(edges)
+        cases.append({'nodes': [str(x) for x in nodes], 'edges': [[str(a), str(b)] for a, b in edges],
+                      'order': [str(x) for x in nx_constant_topological_sort(G)]})
+    mc = elfi.get_client().compile(m.source_net, ['d'])
+    named = {n: ('c%d' % i if n.startswith('_t') else n) for i, n in enumerate(sorted(mc.nodes()))}
+    cases.append({'nodes': [named[n] for n in mc.nodes()],
+                  'edges': [[named[a], named[b]] for a, b in mc.edges()],
+                  'order': None})
+    H = nx.DiGraph()
+    H.add_nodes_from(cases[-1]['nodes'])
+    H.add_edges_from(cases[-1]['edges'])
+    cases[-1]['order'] = [str(x) for x in nx_constant_topological_sort(H)]
+    with open(os.path.join(HERE, 'topo_orders.json'), 'w') as f:
+        json.dump(cases, f)
+
+    # --- GMDistribution.rvs host RNG stream (elfi/methods/utils.py:200-261)
+    gm_means = rs.randn(50, 2) * 0.3 + [0.5, 0.1]
+    gm_w = rs.rand(50)
+    gm_cov = np.array([[0.02, 0.004], [0.004, 0.01]])
+    gm_cov_wide = np.array([[1.5, 0.0], [0.0, 0.8]])
+    draws = GMDistribution.rvs(gm_means, gm_cov, gm_w, size=333, random_state=np.random.RandomState(7))
+    draws2 = GMDistribution.rvs(gm_means, gm_cov_wide, gm_w, size=333, prior_logpdf=prior.logpdf,
+                                random_state=np.random.RandomState(8))
+    save('gm_rvs', means=gm_means, weights=gm_w, cov=gm_cov, cov_wide=gm_cov_wide, size=np.int64(333),
+         draws=draws, draws_with_prior=draws2)
+
     with open(os.path.join(HERE, 'meta.json'), 'w') as f:
         json.dump(meta, f, indent=1)
     print(meta)

@@ -1,0 +1,159 @@
+"""CPU tests of the host-side mirror of the ELFI node / sampler API (no GPU needed): graph
+compilation, the reference's deterministic execution order and sub-seeding, host RNG parity of
+priors + simulators against goldens produced by the reference, ModelPrior, GMDistribution.rvs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+
+def test_sub_seeds_match_reference():
+    from elfi_b200.model import get_sub_seed
+    meta = json.load(open(os.path.join(GOLDEN, 'meta.json')))
+    assert [int(get_sub_seed(123, i)) for i in range(8)] == meta['sub_seeds_123']
+    assert [int(get_sub_seed(1, i)) for i in (10, 100, 1000)] == meta['sub_seeds_1_hi']
+    cache = {}
+    assert [int(get_sub_seed(123, i, cache=cache)) for i in range(8)] == meta['sub_seeds_123']
+    with pytest.raises(ValueError):
+        get_sub_seed(np.random.RandomState(0), 0)
+
+
+def test_host_rng_stream_matches_reference_ma2():
+    """priors + simulator consume the per-batch RandomState exactly like elfi/executor.py."""
+    from elfi_b200.examples import ma2
+    g = load_golden('ma2_generate')
+    m = ma2.get_model(seed_obs=4)
+    out = m.generate(1000, ['t1', 't2', 'MA2'], seed=123)
+    for k in ('t1', 't2', 'MA2'):
+        assert np.array_equal(out[k], g[k]), k
+    assert np.array_equal(m.observed['MA2'], g['observed_MA2'])
+
+
+def test_host_rng_stream_matches_reference_gauss():
+    from elfi_b200.examples import gauss
+    g = load_golden('gauss_generate')
+    m = gauss.get_model(n_obs=50, seed_obs=3)
+    out = m.generate(500, ['mu', 'sigma', 'gauss'], seed=5)
+    for k in ('mu', 'sigma', 'gauss'):
+        assert np.array_equal(out[k], g[k]), k
+
+
+def test_model_prior_logpdf_matches_reference():
+    from elfi_b200.examples import gauss, ma2
+    from elfi_b200.samplers import ModelPrior
+    for name, model in (('ma2_prior_logpdf', ma2.get_model(seed_obs=4)),
+                        ('gauss_prior_logpdf', gauss.get_model(n_obs=50, seed_obs=3))):
+        g = load_golden(name)
+        with np.errstate(divide='ignore'):
+            lp = ModelPrior(model).logpdf(g['theta'])
+        assert np.array_equal(lp, g['logpdf']), name
+    prior = ModelPrior(ma2.get_model(seed_obs=4))
+    assert prior.dim == 2 and prior.parameter_names == ['t1', 't2']
+    x = prior.rvs(7, random_state=np.random.RandomState(0))
+    assert x.shape == (7, 2) and np.all(np.isfinite(prior.logpdf(x)))
+
+
+def test_compile_adds_observed_twins_and_feeders():
+    from elfi_b200 import model as em
+    from elfi_b200.examples import ma2
+    m = ma2.get_model(seed_obs=1)
+    net = em.compile_net(m.source_net, ['d'])
+    for n in ('_MA2_observed', '_S1_observed', '_S2_observed', '_d_observed', '_batch_size',
+              '_random_state', 't1', 't2', 'MA2', 'S1', 'S2', 'd'):
+        assert net.has_node(n), n
+    assert net['_d_observed']['d']['param'] == 'observed'
+    assert net['_random_state']['MA2']['param'] == 'random_state'
+    assert net['_MA2_observed']['_S1_observed']['param'] == 0
+    order = net.graph['order']
+    assert order.index('t1') < order.index('t2') < order.index('MA2') < order.index('S1') < \
+        order.index('d')
+    # pruning: only ancestors of the requested outputs survive
+    net2 = em.compile_net(m.source_net, ['t1'])
+    assert not net2.has_node('MA2') and not net2.has_node('d')
+
+
+def test_execution_order_is_reference_order():
+    """Same order as elfi/executor.py:nx_constant_topological_sort (golden from the reference)."""
+    from elfi_b200.model import _constant_topological_order
+    import networkx as nx
+    g = json.load(open(os.path.join(GOLDEN, 'topo_orders.json')))
+    for case in g:
+        G = nx.DiGraph()
+        G.add_nodes_from(case['nodes'])
+        G.add_edges_from(case['edges'])
+        assert _constant_topological_order(G) == case['order']
+
+
+def test_node_api_errors_and_become():
+    import elfi_b200 as elfi
+    m = elfi.ElfiModel()
+    with pytest.raises(ValueError):
+        elfi.Summary(lambda x: x, model=m, name='s')              # needs a parent
+    elfi.Prior('uniform', 0, 1, model=m, name='p')
+    with pytest.raises(ValueError):
+        elfi.Prior('uniform', 0, 1, model=m, name='p')            # duplicate name
+    elfi.Simulator(lambda p, batch_size=1, random_state=None: np.zeros((batch_size, 3)), m['p'],
+                   observed=np.zeros((1, 3)), name='sim')
+    elfi.Summary(lambda x: x.mean(axis=1), m['sim'], name='s')
+    elfi.Distance('euclidean', m['s'], name='d')
+    assert m.parameter_names == ['p']
+    assert isinstance(m['d'], elfi.Distance) and m['d'].parents[0].name == 's'
+    with pytest.raises(ValueError):
+        elfi.Distance('seuclidean', m['s'], model=m, name='d2')   # V required
+    m0 = elfi.ElfiModel()
+    elfi.Constant(1.0, model=m0, name='c')
+    elfi.Operation(lambda c: c, m0['c'], name='op')
+    with pytest.raises(ValueError):
+        elfi.Rejection(m0['op'])                                  # model without parameters
+    m['d'].become(elfi.AdaptiveDistance(m['s']))
+    assert isinstance(m['d'], elfi.AdaptiveDistance)
+    kopy = m.copy()
+    assert kopy.name != m.name and kopy.has_node('d')
+    assert kopy.get_node('d')['attr_dict'] is m.get_node('d')['attr_dict']   # shared node state
+
+
+def test_unsupported_metric_fails_loudly():
+    import elfi_b200 as elfi
+    m = elfi.ElfiModel()
+    elfi.Prior('uniform', 0, 1, model=m, name='p')
+    elfi.Simulator(lambda p, batch_size=1, random_state=None: np.zeros((batch_size, 1)), m['p'],
+                   observed=np.zeros((1, 1)), name='sim')
+    elfi.Summary(lambda x: x[:, 0], m['sim'], name='s')
+    elfi.Distance('cityblock', m['s'], name='d')
+    with pytest.raises(NotImplementedError):
+        m.generate(4, ['d'], seed=1)
+
+
+def test_gm_rvs_matches_reference_stream():
+    """GMDistribution.rvs consumes the RandomState like elfi/methods/utils.py:200-261."""
+    from elfi_b200.samplers import GMDistribution
+    g = load_golden('gm_rvs')
+    out = GMDistribution.rvs(g['means'], g['cov'], g['weights'], size=int(g['size']),
+                             prior_logpdf=None, random_state=np.random.RandomState(7))
+    assert np.array_equal(out, g['draws'])
+    from elfi_b200.examples import ma2
+    from elfi_b200.samplers import ModelPrior
+    prior = ModelPrior(ma2.get_model(seed_obs=4))
+    out = GMDistribution.rvs(g['means'], g['cov_wide'], g['weights'], size=int(g['size']),
+                             prior_logpdf=prior.logpdf, random_state=np.random.RandomState(8))
+    assert np.array_equal(out, g['draws_with_prior'])
+
+
+def test_rejection_objective_bookkeeping():
+    """set_objective arithmetic of samplers.py:100-135 (no batches are run)."""
+    import elfi_b200 as elfi
+    from elfi_b200.examples import ma2
+    m = ma2.get_model(seed_obs=4)
+    rej = elfi.Rejection(m['d'], batch_size=1000, seed=1)
+    rej.set_objective(100)                       # default quantile 0.01
+    assert rej.objective['n_batches'] == 10 and rej.objective['threshold'] is None
+    rej.set_objective(100, n_sim=2500)
+    assert rej.objective['n_batches'] == 3
+    rej.set_objective(100, threshold=0.3)
+    assert rej.objective['threshold'] == 0.3 and rej.objective['n_batches'] == 1
+    smc = elfi.SMC(m['d'], batch_size=1000, seed=1)
+    with pytest.raises(ValueError):
+        smc.set_objective(10)
