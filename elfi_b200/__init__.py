@@ -11,5 +11,6 @@ from . import _lib  # noqa: F401
 from .model import (AdaptiveDistance, Constant, Discrepancy, Distance, ElfiModel,  # noqa: F401
                     NodeReference, Operation, Prior, RandomVariable, Simulator, Summary,
                     get_default_model, new_model, set_default_model)
-from .samplers import SMC, AdaptiveDistanceSMC, GMDistribution, ModelPrior, Rejection  # noqa: F401
+from .samplers import (SMC, AdaptiveDistanceSMC, AdaptiveThresholdSMC,  # noqa: F401
+                       DensityRatioEstimation, GMDistribution, ModelPrior, Rejection)
 from .bo import BOLFI, LCBSC, BayesianOptimization, BolfiPosterior, GPyRegression  # noqa: F401

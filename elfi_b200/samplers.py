@@ -66,7 +66,8 @@ class _PhaseTimer:
 
 PHASES = _PhaseTimer()
 
-__all__ = ['Rejection', 'SMC', 'AdaptiveDistanceSMC', 'ModelPrior', 'GMDistribution']
+__all__ = ['Rejection', 'SMC', 'AdaptiveDistanceSMC', 'AdaptiveThresholdSMC', 'ModelPrior',
+           'GMDistribution', 'DensityRatioEstimation']
 
 
 # ----------------------------------------------------------------------------- communication
@@ -848,3 +849,114 @@ class AdaptiveDistanceSMC(SMC):
     @property
     def current_population_threshold(self):
         return [np.inf] + [pop.threshold for pop in self._populations]
+
+
+# --------------------------------------------------------------------- adaptive threshold SMC
+def calculate_densratio_basis_sigma(sigma_1, sigma_2):
+    """elfi/methods/density_ratio_estimation.py:11-31."""
+    return sigma_1 * sigma_2 / np.sqrt(np.abs(sigma_1 ** 2 - sigma_2 ** 2))
+
+
+class DensityRatioEstimation:
+    """KLIEP density-ratio estimation on the device (density_ratio_estimation.py:34-207).
+    Only the fixed-sigma path (optimize=False) that AdaptiveThresholdSMC uses is implemented."""
+
+    def __init__(self, n=100, epsilon=0.1, max_iter=500, abs_tol=0.01, conv_check_interval=20,
+                 fold=5, optimize=False):
+        if optimize:
+            raise NotImplementedError('likelihood cross-validation of the RBF scale is not '
+                                      'implemented on the device')
+        self.n = n
+        self.epsilon = epsilon
+        self.max_iter = max_iter
+        self.abs_tol = abs_tol
+        self.fold = fold
+        self.sigma = None
+        self.conv_check_interval = conv_check_interval
+        self.optimize = False
+        self._max_ratio = None
+        self.alpha = None
+
+    def fit(self, x, y, weights_x=None, weights_y=None, sigma=None):
+        if isinstance(sigma, (float, np.floating)):
+            self.sigma = float(sigma)
+        if self.sigma is None:
+            raise ValueError("RBF width (sigma) has to provided in first call.")
+        x = np.asarray(dev.to_host(x), dtype=np.float64)
+        y = np.asarray(dev.to_host(y), dtype=np.float64)
+        x = x.reshape(x.shape[0], -1)
+        y = y.reshape(y.shape[0], -1)
+        self.alpha, self._max_ratio, self.n_iter = ops.kliep_fit(
+            x, y, weights_x, weights_y, sigma=self.sigma, n_basis=self.n, epsilon=self.epsilon,
+            max_iter=self.max_iter, abs_tol=self.abs_tol,
+            conv_check_interval=self.conv_check_interval)
+
+    def max_ratio(self):
+        return self._max_ratio
+
+
+class AdaptiveThresholdSMC(SMC):
+    """ABC-SMC with adaptive threshold selection (Simola et al. 2021); samplers.py:662-840."""
+
+    def __init__(self, model, discrepancy_name=None, output_names=None, initial_quantile=0.20,
+                 q_threshold=0.99, densratio_estimation=None, **kwargs):
+        super().__init__(model, discrepancy_name, output_names, **kwargs)
+        self.q_threshold = q_threshold
+        self.initial_quantile = initial_quantile
+        self.densratio = densratio_estimation or DensityRatioEstimation(
+            n=100, epsilon=0.001, max_iter=200, abs_tol=0.01, fold=5, optimize=False)
+
+    def set_objective(self, n_samples, max_iter=10):
+        rounds = max_iter - 1
+        self.state['round'] = len(self._populations)
+        rounds = rounds + self.state['round']
+        thresholds = np.full((rounds + 1), None)
+        self._quantiles = np.full((rounds + 1), None)
+        self._quantiles[0] = self.initial_quantile
+        self.objective.update(dict(n_samples=n_samples, n_batches=self.max_parallel_batches,
+                                   round=rounds, thresholds=thresholds))
+        self._init_new_round()
+        self._update_objective()
+
+    def update(self, batch, batch_index):
+        ParameterInference.update(self, batch, batch_index)
+        self._rejection.update(batch, batch_index)
+        if self._rejection.finished:
+            self._new_population = self._extract_population()
+            if self.state['round'] < self.objective['round']:
+                self._set_adaptive_quantile()
+                if self._quantiles[self.state['round'] + 1] < self.q_threshold:
+                    self._populations.append(self._new_population)
+                    self.state['round'] += 1
+                    self._init_new_round()
+        self._update_objective()
+
+    def extract_result(self):
+        # the reference extracts the last population again through SMC.extract_result
+        return super().extract_result()
+
+    def _set_adaptive_quantile(self):
+        cur = self._resolve_sample(backwards_index=0)
+        prev = self._resolve_sample(backwards_index=-1)
+        sigma = calculate_densratio_basis_sigma(cur['sigma_max'], prev['sigma_max'])
+        self.densratio.fit(x=cur['samples'], y=prev['samples'], weights_x=cur['weights'],
+                           weights_y=prev['weights'], sigma=float(sigma))
+        max_value = self.densratio.max_ratio()
+        max_value = 1.0 if max_value < 1.0 else max_value
+        self._quantiles[self.state['round'] + 1] = max(1 / max_value, 0.05)
+
+    def _resolve_sample(self, backwards_index):
+        if self.state['round'] + backwards_index < 0:
+            return self._densityratio_initial_sample()
+        sample = self._new_population if backwards_index == 0 else self._populations[backwards_index]
+        sample_sigma = np.sqrt(np.diag(sample.cov))
+        return dict(samples=sample.samples_array, weights=sample.weights,
+                    sigma_max=np.min(sample_sigma))
+
+    def _densityratio_initial_sample(self):
+        n_samples = self._new_population.weights.shape[0]
+        samples = self._prior.rvs(size=n_samples, random_state=self._round_random_state)
+        weights = np.ones(n_samples)
+        sample_cov = np.atleast_2d(np.cov(samples.reshape(n_samples, -1), rowvar=False))
+        return dict(samples=samples, weights=weights,
+                    sigma_max=np.min(np.sqrt(np.diag(sample_cov))))

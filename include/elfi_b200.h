@@ -238,6 +238,19 @@ int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, c
                          int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
                          uint64_t offset, int32_t support, double* out, int64_t ldo, void* stream);
 
+/* ---- KLIEP density-ratio estimation (AdaptiveThresholdSMC) -------------------------------------
+ * DensityRatioEstimation.fit + max_ratio (elfi/methods/density_ratio_estimation.py:71-207):
+ * basis centres = first n_basis rows of x, A = RBF(x, centres), b = weighted RBF mean over y,
+ * <= max_iter projected-gradient steps with a convergence check every conv_check_interval
+ * steps.  wx (unnormalised, as the reference passes it) and wy may be NULL (ones).
+ * alpha_out: device (n_basis);  result_host[0] = max_i r(x_i), result_host[1] = steps taken.
+ * Blocks until done (the convergence test needs the host). */
+int elfi_b200_kliep_fit_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t Nx,
+                            const double* y, int64_t ldy, int64_t Ny, int64_t p, const double* wx,
+                            const double* wy, double sigma, int64_t n_basis, double epsilon,
+                            int64_t max_iter, double abs_tol, int64_t conv_check_interval,
+                            double* alpha_out, double* result_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -361,3 +361,38 @@ def lcbsc(mean, var, beta):
 def lcbsc_gradient(var, grad_mean, grad_var, beta):
     """LCBSC.evaluate_gradient (elfi/methods/bo/acquisition.py:296-301)."""
     return grad_mean - 0.5 * grad_var * np.sqrt(beta / var)
+
+
+# ------------------------------------------------------------------------------ KLIEP
+def kliep_fit(x, y, weights_x=None, weights_y=None, sigma=1.0, n=100, epsilon=0.001, max_iter=200,
+              abs_tol=0.01, conv_check_interval=20):
+    """Vectorised restatement of DensityRatioEstimation.fit / _KLIEP / max_ratio
+    (elfi/methods/density_ratio_estimation.py:71-207).  Returns (alpha, max_ratio)."""
+    x = _c64(x).reshape(len(x), -1)
+    y = _c64(y).reshape(len(y), -1)
+    theta = x[:n]
+    wx = np.ones(len(x)) if weights_x is None else _c64(weights_x)
+    wy = np.ones(len(y)) if weights_y is None else _c64(weights_y)
+    wy_n = wy / np.sum(wy)
+
+    def basis(a, c):
+        d2 = ((a[:, None, :] - c[None, :, :]) ** 2).sum(-1)
+        return np.exp(-0.5 * d2 / sigma / sigma)
+    A = basis(x, theta)
+    b = basis(theta, y) @ wy_n
+    b_normalized = b / np.dot(b, b)
+    alpha = 1 / n * np.ones(n)
+    target_prev = A @ alpha
+    non_null = np.any(A > 1e-64, axis=1)
+    A_full, w_full = A[non_null], wx[non_null]
+    for i in range(max_iter):
+        dA = A_full.T @ (w_full / (A_full @ alpha))
+        alpha = alpha + epsilon * dA
+        alpha = np.maximum(0, alpha + (1 - np.dot(b, alpha)) * b_normalized)
+        alpha = alpha / np.dot(b, alpha)
+        if i % conv_check_interval == 0:
+            target = A @ alpha
+            if np.linalg.norm(target - target_prev) < abs_tol:
+                break
+            target_prev = target
+    return alpha, float(np.max(A @ alpha))

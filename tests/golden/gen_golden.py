@@ -186,6 +186,32 @@ def main():
     save('gm_rvs', means=gm_means, weights=gm_w, cov=gm_cov, cov_wide=gm_cov_wide, size=np.int64(333),
          draws=draws, draws_with_prior=draws2)
 
+
+
+    # --- AdaptiveThresholdSMC on MA2 (samplers.py:662-840)
+    ats = elfi.AdaptiveThresholdSMC(m['d'], batch_size=500, seed=2)
+    s = ats.sample(200, max_iter=4, bar=False)
+    arrs = sample_arrays(s)
+    for i, pop in enumerate(s.populations):
+        arrs.update(sample_arrays(pop, 'pop{}_'.format(i)))
+        arrs['pop{}_cov'.format(i)] = np.asarray(pop.cov)
+    arrs['n_pops'] = np.int64(len(s.populations))
+    arrs['quantiles'] = np.array([np.nan if q is None else q for q in ats._quantiles], dtype=float)
+    save('ma2_adaptive_threshold_smc', **arrs)
+
+    # --- KLIEP (elfi/methods/density_ratio_estimation.py) at a size the Python loops can do
+    from elfi.methods.density_ratio_estimation import DensityRatioEstimation
+    kx = rs.randn(400, 2) * 0.5
+    ky = rs.randn(500, 2) * 0.8 + 0.1
+    kwx = rs.rand(400) + 0.5
+    kwy = rs.rand(500) + 0.5
+    dre = DensityRatioEstimation(n=100, epsilon=0.001, max_iter=200, abs_tol=0.01, fold=5,
+                                 optimize=False)
+    dre.fit(x=kx, y=ky, weights_x=kwx, weights_y=kwy, sigma=0.7)
+    ratios = dre.w(kx)
+    save('kliep', x=kx, y=ky, wx=kwx, wy=kwy, sigma=np.float64(0.7), ratios=ratios,
+         max_ratio=np.float64(dre.max_ratio()))
+
     with open(os.path.join(HERE, 'meta.json'), 'w') as f:
         json.dump(meta, f, indent=1)
     print(meta)

@@ -141,3 +141,14 @@ def test_gp_gradients_finite_difference():
         mm, vm = o.gp_predict(x0 - e, X, L, alpha, s2, ell, b)
         np.testing.assert_allclose(gm[:, j], ((mp - mm) / (2 * h)).ravel(), rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(gv[:, j], ((vp - vm) / (2 * h)).ravel(), rtol=1e-4, atol=1e-7)
+
+
+def test_golden_kliep():
+    """oracle KLIEP restatement vs the reference's DensityRatioEstimation (fixed sigma)."""
+    g = load_golden('kliep')
+    alpha, max_ratio = o.kliep_fit(g['x'], g['y'], g['wx'], g['wy'], sigma=float(g['sigma']))
+    np.testing.assert_allclose(max_ratio, float(g['max_ratio']), rtol=1e-12)
+    theta = g['x'][:100]
+    d2 = ((g['x'][:, None, :] - theta[None, :, :]) ** 2).sum(-1)
+    ratios = np.exp(-0.5 * d2 / float(g['sigma']) ** 2) @ alpha
+    np.testing.assert_allclose(ratios, g['ratios'], rtol=1e-11)
