@@ -49,7 +49,11 @@ SIGNATURES = {
     'elfi_b200_sim_ma2_f64': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_u64, c_u64, c_ptr, c_i64, c_ptr,
                               c_i64, c_ptr],
     'elfi_b200_gm_rvs_f64': [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_u64, c_u64,
-                             ctypes.c_int32, c_ptr, c_i64, c_ptr],
+                             ctypes.c_int32, c_ptr, c_ptr, c_i64, c_ptr],
+    'elfi_b200_prior_gauss_f64': [c_ptr, c_i64, c_u64, c_u64, c_ptr, c_ptr, c_ptr, c_ptr],
+    'elfi_b200_logprior_gauss_f64': [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    'elfi_b200_sim_gauss_f64': [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_u64, c_u64, c_ptr, c_i64, c_ptr,
+                                c_i64, c_ptr],
     'elfi_b200_gp_padded_size': [c_i64],
     'elfi_b200_gp_fit_f64': [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl,
                              c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],

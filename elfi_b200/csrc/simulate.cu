@@ -176,10 +176,12 @@ sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int
 // ---- Gaussian-mixture proposals ------------------------------------------------------------------
 // cumw: inclusive cumulative sum of the normalised weights (N); Lc: lower Cholesky factor of the
 // shared covariance (p x p, row-major, p <= 4).  support: 0 none, 1 MA2 prior support.
+struct BoxSupport { double lo[4], hi[4]; };
+
 __global__ void gm_rvs_kernel(const double* __restrict__ means, int64_t ldm, const double* __restrict__ cumw,
                               int64_t N, int p, const double* __restrict__ Lc, int64_t B,
-                              uint64_t seed, uint64_t offset, int support, double* __restrict__ out,
-                              int64_t ldo) {
+                              uint64_t seed, uint64_t offset, int support, BoxSupport box,
+                              double* __restrict__ out, int64_t ldo) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const Philox ph(seed);
@@ -202,9 +204,97 @@ __global__ void gm_rvs_kernel(const double* __restrict__ means, int64_t ldm, con
             for (int b = 0; b <= a; ++b) s = fma(Lc[a * p + b], z[b], s);
             x[a] = s;
         }
-        if (support == 0 || (support == 1 && ma2_in_support(x[0], x[1]))) break;
+        bool ok = support == 0 || (support == 1 && ma2_in_support(x[0], x[1]));
+        if (support == 2) {
+            ok = true;
+            for (int a = 0; a < p; ++a) ok = ok && x[a] >= box.lo[a] && x[a] <= box.hi[a];
+        }
+        if (ok) break;
     }
     for (int a = 0; a < p; ++a) out[i * ldo + a] = x[a];
+}
+
+// ---- Gaussian noise model (elfi/examples/gauss.py) --------------------------------------------------
+// priors of get_model(): mu ~ U(mu_lo, mu_lo + mu_w); sigma ~ truncnorm(a, b) (standard normal
+// truncated to [a, b], scipy convention with loc 0, scale 1).
+struct GaussPrior { double mu_lo, mu_w, a, b, cdf_a, cdf_w; };
+
+__global__ void prior_gauss_kernel(int64_t B, uint64_t seed, uint64_t offset, GaussPrior g,
+                                   double* __restrict__ mu, double* __restrict__ sigma) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const Philox ph(seed);
+    const uint64_t row = offset + uint64_t(i);
+    const uint4 r = ph(uint32_t(row), uint32_t(row >> 32), 0u, 0x47415553u);
+    const double u = u01(r.x, r.y), v = u01(r.z, r.w);
+    mu[i] = g.mu_lo + g.mu_w * u;
+    double sgm = normcdfinv(g.cdf_a + v * g.cdf_w);     // inverse-CDF sampling of the truncation
+    sigma[i] = fmin(fmax(sgm, g.a), g.b);
+}
+
+__global__ void logprior_gauss_kernel(const double* __restrict__ x, int64_t ld, int64_t B, GaussPrior g,
+                                      double* __restrict__ out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double m = x[i * ld], s = x[i * ld + 1];
+    double lp = -INFINITY;
+    if (m >= g.mu_lo && m <= g.mu_lo + g.mu_w && s >= g.a && s <= g.b)
+        lp = -log(g.mu_w) - 0.5 * s * s - 0.9189385332046727 - log(g.cdf_w);
+    out[i] = lp;
+}
+
+// y_ij = mu_i + sigma_i z_ij (gauss.py:11-35) with np.mean / np.var summaries (gauss.py:142-173,
+// NumPy pairwise order).  The variance needs the mean first: the counter-based normals are simply
+// generated a second time instead of being stored.
+template <bool WRITE_Y>
+__global__ void __launch_bounds__(128)
+sim_gauss_kernel(const double* __restrict__ mu, const double* __restrict__ sigma, int64_t B, int n_obs,
+                 uint64_t seed, uint64_t offset, double* __restrict__ Y, int64_t ldY,
+                 double* __restrict__ S, int64_t ldS) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const Philox ph(seed);
+    const uint64_t row = offset + uint64_t(i);
+    const uint32_t r0 = uint32_t(row), r1 = uint32_t(row >> 32);
+    const double m = mu[i], sg = sigma[i];
+    PairwiseStream<6> pw;
+    double mean = 0.0;
+    for (int pass = 0; pass < (S ? 2 : 1); ++pass) {
+        if (S) pw.begin(n_obs);
+        double t[8];
+        for (int k0 = 0; k0 < n_obs; k0 += 8) {
+            double y[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double z0, z1;
+                normal2(ph(r0, r1, uint32_t((k0 >> 1) + q), 0x47534d55u), z0, z1);
+                y[2 * q] = __dadd_rn(m, __dmul_rn(sg, z0));
+                y[2 * q + 1] = __dadd_rn(m, __dmul_rn(sg, z1));
+            }
+            const int cnt = (n_obs - k0) < 8 ? (n_obs - k0) : 8;
+            if (WRITE_Y && pass == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (e < cnt) Y[i * ldY + k0 + e] = y[e];
+            }
+            if (S) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (pass == 0) {
+                        t[e] = y[e];
+                    } else {
+                        const double c = __dsub_rn(y[e], mean);
+                        t[e] = __dmul_rn(c, c);
+                    }
+                }
+                pw.feed8(k0, t, cnt);
+            }
+        }
+        if (S) {
+            const double v = pw.finish() / double(n_obs);
+            if (pass == 0) { mean = v; S[i * ldS] = v; } else { S[i * ldS + 1] = v; }
+        }
+    }
 }
 
 // inclusive scan of w / sum(w) (single block; N up to a few million is fine: one pass each)
@@ -285,11 +375,17 @@ int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2
 
 int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* weights,
                          int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
-                         uint64_t offset, int32_t support, double* out, int64_t ldo, void* stream_) {
+                         uint64_t offset, int32_t support, const double* box_host, double* out,
+                         int64_t ldo, void* stream_) {
     using namespace elfi;
     ELFI_REQUIRE(ctx && means && Lchol_host && (B == 0 || out), "gm_rvs: NULL argument");
     ELFI_REQUIRE(N >= 1 && p >= 1 && p <= 4 && ldm >= p && ldo >= p, "gm_rvs: bad shape (p <= 4)");
-    ELFI_REQUIRE(support == 0 || (support == 1 && p == 2), "gm_rvs: unknown support %d", support);
+    ELFI_REQUIRE(support == 0 || (support == 1 && p == 2) || (support == 2 && box_host),
+                 "gm_rvs: unknown support %d", support);
+    BoxSupport box;
+    memset(&box, 0, sizeof(box));
+    if (support == 2)
+        for (int a = 0; a < p; ++a) { box.lo[a] = box_host[a]; box.hi[a] = box_host[p + a]; }
     if (B == 0) return ELFI_B200_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
@@ -300,7 +396,61 @@ int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, c
     ELFI_CUDA_OK(cudaMemcpyAsync(Lc, Lchol_host, size_t(p) * p * 8, cudaMemcpyHostToDevice, stream));
     cumsum_kernel<<<1, 1024, 0, stream>>>(weights, N, cumw);
     gm_rvs_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(means, ldm, cumw, N, int(p), Lc, B,
-                                                                seed, offset, support, out, ldo);
+                                                                seed, offset, support, box, out, ldo);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+static elfi::GaussPrior make_gauss_prior(const double* prm) {
+    elfi::GaussPrior g;
+    g.mu_lo = prm[0]; g.mu_w = prm[1]; g.a = prm[2]; g.b = prm[3];
+    g.cdf_a = 0.5 * erfc(-g.a * 0.7071067811865476);
+    g.cdf_w = 0.5 * erfc(-g.b * 0.7071067811865476) - g.cdf_a;
+    return g;
+}
+
+/* prm_host = [mu_lo, mu_width, a, b] of mu ~ U(mu_lo, mu_lo + mu_width), sigma ~ truncnorm(a, b) */
+int elfi_b200_prior_gauss_f64(elfi_b200_ctx* ctx, int64_t B, uint64_t seed, uint64_t offset,
+                              const double* prm_host, double* mu, double* sigma, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && prm_host && (B == 0 || (mu && sigma)), "prior_gauss: NULL argument");
+    ELFI_REQUIRE(prm_host[1] > 0 && prm_host[3] > prm_host[2], "prior_gauss: bad prior parameters");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    prior_gauss_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(B, seed, offset,
+                                                                     make_gauss_prior(prm_host), mu, sigma);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_logprior_gauss_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t B,
+                                 const double* prm_host, double* out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && prm_host && (B == 0 || (x && out)) && ldx >= 2, "logprior_gauss: bad argument");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    logprior_gauss_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(x, ldx, B,
+                                                                        make_gauss_prior(prm_host), out);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_sim_gauss_f64(elfi_b200_ctx* ctx, const double* mu, const double* sigma, int64_t B,
+                            int64_t n_obs, uint64_t seed, uint64_t offset, double* Y, int64_t ldY,
+                            double* S, int64_t ldS, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (mu && sigma)), "sim_gauss: NULL argument");
+    ELFI_REQUIRE(n_obs >= 1 && n_obs <= 8192, "sim_gauss: n_obs=%lld outside [1, 8192]", (long long)n_obs);
+    ELFI_REQUIRE(Y || S, "sim_gauss: nothing to produce (Y and S are both NULL)");
+    ELFI_REQUIRE((!Y || ldY >= n_obs) && (!S || ldS >= 2), "sim_gauss: bad leading dimension");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const unsigned blocks = unsigned((B + 127) / 128);
+    if (Y) sim_gauss_kernel<true><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS);
+    else sim_gauss_kernel<false><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

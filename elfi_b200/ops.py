@@ -328,9 +328,10 @@ def sim_ma2(t1, t2, n_obs=100, seed=0, offset=0, want_data=False, want_summaries
     return X, S
 
 
-def gm_rvs(means, cov, weights, size, seed, offset=0, support=0):
+def gm_rvs(means, cov, weights, size, seed, offset=0, support=0, box=None):
     """GMDistribution.rvs on the device (elfi/methods/utils.py:200-261); support=1 keeps only
-    draws inside the MA2 prior support (redrawn per particle)."""
+    draws inside the MA2 prior support, support=2 inside ``box`` = (lo (p,), hi (p,)) (redrawn per
+    particle)."""
     means = _matrix(means)
     N, p = means.shape
     cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
@@ -338,30 +339,44 @@ def gm_rvs(means, cov, weights, size, seed, offset=0, support=0):
         cov = np.eye(p) * cov[0, 0]
     L = np.ascontiguousarray(np.linalg.cholesky(cov))
     w = None if weights is None else dev.to_device(weights).reshape(-1)
+    boxarr = None
+    if support == 2:
+        boxarr = np.ascontiguousarray(np.concatenate([np.asarray(box[0], dtype=np.float64),
+                                                      np.asarray(box[1], dtype=np.float64)]))
     out = dev.empty((size, p))
     _lib.call('elfi_b200_gm_rvs_f64', dev.context(), dev.ptr(means), _ld(means), dev.ptr(w), N, p,
-              dev.ptr(L), size, int(seed), int(offset), int(support), dev.ptr(out), p,
-              dev.stream_ptr())
+              dev.ptr(L), size, int(seed), int(offset), int(support), dev.ptr(boxarr),
+              dev.ptr(out), p, dev.stream_ptr())
     return out
 
 
-def kliep_fit(x, y, weights_x=None, weights_y=None, sigma=1.0, n_basis=100, epsilon=0.001,
-              max_iter=200, abs_tol=0.01, conv_check_interval=20):
-    """KLIEP fit on the device (elfi/methods/density_ratio_estimation.py:71-207).
+def _gauss_prm(prm):
+    return np.ascontiguousarray(prm, dtype=np.float64)
 
-    Returns (alpha device tensor (n_basis,), max_ratio float, steps int)."""
-    x = _matrix(x)
-    y = _matrix(y)
-    if x.shape[0] < n_basis:
-        raise ValueError("Number of RBFs ({}) can't be larger than number of samples ({}).".format(
-            n_basis, x.shape[0]))
-    wx = None if weights_x is None else dev.to_device(weights_x).reshape(-1)
-    wy = None if weights_y is None else dev.to_device(weights_y).reshape(-1)
-    alpha = dev.empty((n_basis,))
-    res = (ctypes.c_double * 2)()
-    torch.cuda.current_stream().synchronize()
-    _lib.call('elfi_b200_kliep_fit_f64', dev.context(), dev.ptr(x), _ld(x), x.shape[0], dev.ptr(y),
-              _ld(y), y.shape[0], x.shape[1], dev.ptr(wx), dev.ptr(wy), float(sigma), int(n_basis),
-              float(epsilon), int(max_iter), float(abs_tol), int(conv_check_interval),
-              dev.ptr(alpha), res)
-    return alpha, float(res[0]), int(res[1])
+
+def prior_gauss(batch_size, seed, prm, offset=0):
+    """Gaussian-model prior draws (elfi/examples/gauss.py:118-126): prm = [mu_lo, mu_width, a, b]."""
+    mu, sigma = dev.empty((batch_size,)), dev.empty((batch_size,))
+    _lib.call('elfi_b200_prior_gauss_f64', dev.context(), batch_size, int(seed), int(offset),
+              dev.ptr(_gauss_prm(prm)), dev.ptr(mu), dev.ptr(sigma), dev.stream_ptr())
+    return mu, sigma
+
+
+def logprior_gauss(params, prm):
+    x = _matrix(params)
+    out = dev.empty((x.shape[0],))
+    _lib.call('elfi_b200_logprior_gauss_f64', dev.context(), dev.ptr(x), _ld(x), x.shape[0],
+              dev.ptr(_gauss_prm(prm)), dev.ptr(out), dev.stream_ptr())
+    return out
+
+
+def sim_gauss(mu, sigma, n_obs=50, seed=0, offset=0, want_data=False, want_summaries=True):
+    """Gaussian simulator on the device -> (Y or None, S or None), S = [mean, var] fused."""
+    mu = dev.to_device(mu).reshape(-1).contiguous()
+    sigma = dev.to_device(sigma).reshape(-1).contiguous()
+    B = mu.numel()
+    Y = dev.empty((B, n_obs)) if want_data else None
+    S = dev.empty((B, 2)) if want_summaries else None
+    _lib.call('elfi_b200_sim_gauss_f64', dev.context(), dev.ptr(mu), dev.ptr(sigma), B, n_obs,
+              int(seed), int(offset), dev.ptr(Y), n_obs, dev.ptr(S), 2, dev.stream_ptr())
+    return Y, S

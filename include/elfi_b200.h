@@ -225,7 +225,8 @@ int elfi_b200_probe_fp64_f64(elfi_b200_ctx* ctx, double* tflops_host);
  *                               pairwise order) so that X never has to touch HBM
  *   elfi_b200_gm_rvs_f64        GMDistribution.rvs (elfi/methods/utils.py:200-261): component by
  *                               weight, + MVN(0, Sigma) with Sigma = L L^T (Lchol_host, p <= 4),
- *                               redrawn until inside the support (0 = none, 1 = MA2 prior support)
+ *                               redrawn until inside the support (0 = none, 1 = MA2 prior support,
+ *                               2 = box: box_host = [lo_0..lo_{p-1}, hi_0..hi_{p-1}])
  */
 int elfi_b200_prior_ma2_f64(elfi_b200_ctx* ctx, int64_t B, uint64_t seed, uint64_t offset,
                             int32_t mode, double* t1, double* t2, void* stream);
@@ -236,7 +237,20 @@ int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2
                           double* S, int64_t ldS, void* stream);
 int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* weights,
                          int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
-                         uint64_t offset, int32_t support, double* out, int64_t ldo, void* stream);
+                         uint64_t offset, int32_t support, const double* box_host, double* out,
+                         int64_t ldo, void* stream);
+
+/* Gaussian noise model of elfi/examples/gauss.py (1-d case): priors mu ~ U(prm[0], prm[0]+prm[1]),
+ * sigma ~ truncnorm(prm[2], prm[3]) (gauss.py:118-126); simulator y = mu + sigma z (gauss.py:11-35)
+ * with np.mean / np.var summaries (gauss.py:142-173, pairwise order) fused in the same kernel
+ * (S (B, 2) = [mean, var]); Y (B, n_obs) is written only when requested. */
+int elfi_b200_prior_gauss_f64(elfi_b200_ctx* ctx, int64_t B, uint64_t seed, uint64_t offset,
+                              const double* prm_host, double* mu, double* sigma, void* stream);
+int elfi_b200_logprior_gauss_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t B,
+                                 const double* prm_host, double* out, void* stream);
+int elfi_b200_sim_gauss_f64(elfi_b200_ctx* ctx, const double* mu, const double* sigma, int64_t B,
+                            int64_t n_obs, uint64_t seed, uint64_t offset, double* Y, int64_t ldY,
+                            double* S, int64_t ldS, void* stream);
 
 /* ---- KLIEP density-ratio estimation (AdaptiveThresholdSMC) -------------------------------------
  * DensityRatioEstimation.fit + max_ratio (elfi/methods/density_ratio_estimation.py:71-207):

@@ -123,3 +123,44 @@ def test_smc_throughput_mode_statistics():
                                                              bar=False)
     assert abs(ref.sample_means_array[0] - means[0]) < 0.03
     assert abs(ref.sample_means_array[1] - means[1]) < 0.03
+
+
+def test_gauss_fused_summaries_and_prior():
+    from elfi_b200 import ops
+    rs = np.random.RandomState(0)
+    for n_obs in (50, 1, 7, 8, 9, 129, 500):
+        B = 555
+        mu, sigma = rs.uniform(-1, 9, B), rs.uniform(0.1, 3, B)
+        Y, S = ops.sim_gauss(mu, sigma, n_obs, seed=11, offset=3, want_data=True)
+        Y = Y.cpu().numpy()
+        assert np.array_equal(S[:, 0].cpu().numpy(), np.mean(Y, axis=1)), n_obs
+        assert np.array_equal(S[:, 1].cpu().numpy(), np.var(Y, axis=1)), n_obs
+    prm = [-1.0, 10.0, 0.01, 10.0]
+    mu, sigma = ops.prior_gauss(200000, seed=5, prm=prm)
+    mu, sigma = mu.cpu().numpy(), sigma.cpu().numpy()
+    assert ss.kstest(mu, ss.uniform(-1, 10).cdf).pvalue > 1e-3
+    assert ss.kstest(sigma, ss.truncnorm(0.01, 10).cdf).pvalue > 1e-3
+    theta = np.column_stack([rs.uniform(-2, 10, 3000), rs.uniform(-1, 11, 3000)])
+    with np.errstate(divide='ignore'):
+        ref = ss.uniform.logpdf(theta[:, 0], -1, 10) + ss.truncnorm.logpdf(theta[:, 1], 0.01, 10)
+    got = ops.logprior_gauss(theta, prm).cpu().numpy()
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    np.testing.assert_allclose(got[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-11)
+    x = ops.gm_rvs(np.array([[8.9, 0.02]]), np.eye(2) * 0.3, None, 20000, seed=2, support=2,
+                   box=([-1.0, 0.01], [9.0, 10.0])).cpu().numpy()
+    assert x[:, 0].min() >= -1 and x[:, 0].max() <= 9 and x[:, 1].min() >= 0.01
+
+
+def test_gauss_smc_throughput_mode_statistics():
+    """config #3's model (Gaussian noise, SMC-ABC) on the device vs the host-RNG path."""
+    import elfi_b200 as elfi
+    from elfi_b200.examples import gauss
+    m, proposal = gauss.get_device_model(n_obs=50, seed_obs=3)
+    res = elfi.SMC(m['d'], batch_size=50000, seed=4, device_proposal=proposal).sample(
+        4000, quantiles=[0.2, 0.3, 0.3], bar=False)
+    mh = gauss.get_model(n_obs=50, seed_obs=3)
+    ref = elfi.SMC(mh['d'], batch_size=50000, seed=4).sample(4000, quantiles=[0.2, 0.3, 0.3],
+                                                            bar=False)
+    a, b = res.sample_means_array, ref.sample_means_array
+    assert abs(a[0] - b[0]) < 0.05 and abs(a[1] - b[1]) < 0.05, (a, b)
+    assert abs(a[0] - 4.0) < 0.3 and abs(a[1] - 0.4) < 0.3
