@@ -380,3 +380,25 @@ def sim_gauss(mu, sigma, n_obs=50, seed=0, offset=0, want_data=False, want_summa
     _lib.call('elfi_b200_sim_gauss_f64', dev.context(), dev.ptr(mu), dev.ptr(sigma), B, n_obs,
               int(seed), int(offset), dev.ptr(Y), n_obs, dev.ptr(S), 2, dev.stream_ptr())
     return Y, S
+
+
+def kliep_fit(x, y, weights_x=None, weights_y=None, sigma=1.0, n_basis=100, epsilon=0.001,
+              max_iter=200, abs_tol=0.01, conv_check_interval=20):
+    """KLIEP fit on the device (elfi/methods/density_ratio_estimation.py:71-207).
+
+    Returns (alpha device tensor (n_basis,), max_ratio float, steps int)."""
+    x = _matrix(x)
+    y = _matrix(y)
+    if x.shape[0] < n_basis:
+        raise ValueError("Number of RBFs ({}) can't be larger than number of samples ({}).".format(
+            n_basis, x.shape[0]))
+    wx = None if weights_x is None else dev.to_device(weights_x).reshape(-1)
+    wy = None if weights_y is None else dev.to_device(weights_y).reshape(-1)
+    alpha = dev.empty((n_basis,))
+    res = (ctypes.c_double * 2)()
+    torch.cuda.current_stream().synchronize()
+    _lib.call('elfi_b200_kliep_fit_f64', dev.context(), dev.ptr(x), _ld(x), x.shape[0], dev.ptr(y),
+              _ld(y), y.shape[0], x.shape[1], dev.ptr(wx), dev.ptr(wy), float(sigma), int(n_basis),
+              float(epsilon), int(max_iter), float(abs_tol), int(conv_check_interval),
+              dev.ptr(alpha), res)
+    return alpha, float(res[0]), int(res[1])
