@@ -143,7 +143,9 @@ template <class Consumer>
 int rowstream_launch(elfi_b200_ctx* ctx, const double* M, int64_t ld, int64_t B, int64_t D,
                      size_t aux_bytes, const typename Consumer::Params& params,
                      cudaStream_t stream) {
-    ELFI_REQUIRE(D <= (int64_t(1) << 30) && B <= (int64_t(1) << 36), "matrix too large");
+    ELFI_REQUIRE(D <= (int64_t(1) << 30) && B < (int64_t(1) << 31),
+                 "matrix too large for int32 TMA coordinates (B=%lld, D=%lld)", (long long)B,
+                 (long long)D);
     if (B == 0) return ELFI_B200_OK;
     const int ns = rs_pick_stages(ctx->smem_optin, aux_bytes);
     ELFI_REQUIRE(ns >= 2, "row too wide for the shared-memory pipeline (D=%lld)", (long long)D);

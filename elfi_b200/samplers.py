@@ -901,6 +901,10 @@ class AdaptiveThresholdSMC(SMC):
     def __init__(self, model, discrepancy_name=None, output_names=None, initial_quantile=0.20,
                  q_threshold=0.99, densratio_estimation=None, **kwargs):
         super().__init__(model, discrepancy_name, output_names, **kwargs)
+        if self.comm.on:
+            raise NotImplementedError(
+                'AdaptiveThresholdSMC runs on one rank (pass distributed=False): its density-ratio '
+                'step draws a host-side reference sample that is not synchronised across ranks')
         self.q_threshold = q_threshold
         self.initial_quantile = initial_quantile
         self.densratio = densratio_estimation or DensityRatioEstimation(

@@ -15,7 +15,8 @@
  *   - sizes are int64_t; `stream` is a cudaStream_t passed as void* (NULL = legacy default
  *     stream); kernels are asynchronous on that stream;
  *   - the context owns only scratch memory; it never takes ownership of caller buffers;
- *   - one context per device; a context may be used by one host thread at a time.
+ *   - one context per device; a context may be used by one host thread and one stream at a
+ *     time (its scratch arena is ordered by that stream; growing it synchronises the device).
  */
 #ifndef ELFI_B200_H
 #define ELFI_B200_H
