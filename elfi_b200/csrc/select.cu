@@ -417,6 +417,35 @@ wq_seqscan_kernel(const double* __restrict__ ws, int64_t n, double alpha,
     }
 }
 
+// ---- per-row sort (order-statistic summaries, e.g. the g-and-k model: np.sort(y, axis=1)) ---------
+// One warp per row: keys go to shared memory as order-preserving u64 (NaN last, like np.sort),
+// padded to a power of two, bitonic network with __syncwarp between stages.
+__global__ void __launch_bounds__(256)
+rowsort_kernel(const double* __restrict__ X, int64_t ldX, int64_t B, int n, int npow2,
+               double* __restrict__ out, int64_t ld_out) {
+    extern __shared__ uint64_t sk_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* sk = sk_all + size_t(warp) * npow2;
+    for (int64_t row = int64_t(blockIdx.x) * 8 + warp; row < B; row += int64_t(gridDim.x) * 8) {
+        for (int i = lane; i < npow2; i += 32) sk[i] = i < n ? key_to_u64(X[row * ldX + i]) : ~uint64_t(0);
+        __syncwarp();
+        for (int k = 2; k <= npow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (npow2 >> 1); t += 32) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const bool up = (i & k) == 0;
+                    const uint64_t a = sk[i], b = sk[l];
+                    if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < n; i += 32) out[row * ld_out + i] = u64_to_key(sk[i]);
+        __syncwarp();
+    }
+}
+
 // ---- fast path of the weighted quantile -----------------------------------------------------------
 // A blocked parallel scan gives cumulative weights c~_k whose distance to the reference's
 // sequential np.cumsum values is bounded by eps = 4 n 2^-53 (both are within ~n u of the exact
@@ -624,6 +653,27 @@ int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     wq_normalise_kernel<<<blocks, 256, 0, stream>>>(w, s.v[0], n, total, ws);
     wq_seqscan_kernel<<<1, 32, 0, stream>>>(ws, n, alpha, s.k[0], out);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_rowsort_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int64_t B, int64_t n,
+                          double* out, int64_t ld_out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (X && out)), "rowsort: NULL argument");
+    ELFI_REQUIRE(B >= 0 && n >= 1 && n <= 4096 && ldX >= n && ld_out >= n,
+                 "rowsort: bad shape (1 <= n <= 4096)");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    int npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
+    const size_t smem = size_t(8) * npow2 * 8;
+    ELFI_CUDA_OK(cudaFuncSetAttribute(rowsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem)));
+    int64_t blocks = (B + 7) / 8;
+    if (blocks > int64_t(ctx->sm_count) * 8) blocks = int64_t(ctx->sm_count) * 8;
+    rowsort_kernel<<<unsigned(blocks), 256, smem, stream>>>(X, ldX, B, int(n), npow2, out, ld_out);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

@@ -402,3 +402,13 @@ def kliep_fit(x, y, weights_x=None, weights_y=None, sigma=1.0, n_basis=100, epsi
               float(epsilon), int(max_iter), float(abs_tol), int(conv_check_interval),
               dev.ptr(alpha), res)
     return alpha, float(res[0]), int(res[1])
+
+
+def rowsort(x):
+    """np.sort(x, axis=1) on the device (ascending, NaN last); order-statistic summaries."""
+    x = _matrix(x)
+    B, n = x.shape
+    out = dev.empty((B, n))
+    _lib.call('elfi_b200_rowsort_f64', dev.context(), dev.ptr(x), _ld(x), B, n, dev.ptr(out), n,
+              dev.stream_ptr())
+    return out

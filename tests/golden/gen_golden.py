@@ -199,6 +199,26 @@ def main():
     arrs['quantiles'] = np.array([np.nan if q is None else q for q in ats._quantiles], dtype=float)
     save('ma2_adaptive_threshold_smc', **arrs)
 
+
+    # --- g-and-k: stock model forward pass + the 2-d order-statistic / AdaptiveDistance variant
+    from elfi.examples import gnk
+    gk = gnk.get_model(n_obs=50, seed=7)
+    gen = gk.generate(300, ['A', 'B', 'g', 'k', 'GNK', 'd'], seed=3)
+    save('gnk_generate', observed_GNK=np.asarray(gk.observed['GNK']),
+         **{k: np.asarray(v) for k, v in gen.items()})
+    gk2 = gnk.get_model(n_obs=64, seed=7)
+    elfi.Summary(lambda y: np.sort(y[:, :, 0], axis=1), gk2['GNK'], name='ss_sorted')
+    gk2['d'].become(elfi.AdaptiveDistance(gk2['ss_sorted']))
+    s = elfi.AdaptiveDistanceSMC(gk2['d'], batch_size=400, seed=13).sample(100, rounds=2,
+                                                                           quantile=0.5, bar=False)
+    arrs = sample_arrays(s)
+    for i, pop in enumerate(s.populations):
+        arrs.update(sample_arrays(pop, 'pop{}_'.format(i)))
+        arrs['pop{}_w'.format(i)] = np.asarray(
+            pop.adaptive_distance_w if pop.adaptive_distance_w is not None else np.nan)
+    arrs['n_pops'] = np.int64(len(s.populations))
+    save('gnk_adaptive_distance_smc', **arrs)
+
     # --- KLIEP (elfi/methods/density_ratio_estimation.py) at a size the Python loops can do
     from elfi.methods.density_ratio_estimation import DensityRatioEstimation
     kx = rs.randn(400, 2) * 0.5

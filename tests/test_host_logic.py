@@ -157,3 +157,15 @@ def test_rejection_objective_bookkeeping():
     smc = elfi.SMC(m['d'], batch_size=1000, seed=1)
     with pytest.raises(ValueError):
         smc.set_objective(10)
+
+
+def test_gnk_stock_model_matches_reference():
+    """g-and-k stock graph (host simulator, identity ss_order, euclidean_multiss): no GPU needed."""
+    from elfi_b200.examples import gnk
+    g = load_golden('gnk_generate')
+    m = gnk.get_model(n_obs=50, seed=7)
+    out = m.generate(300, ['A', 'B', 'g', 'k', 'GNK', 'd'], seed=3)
+    for k in ('A', 'B', 'g', 'k', 'GNK'):
+        assert np.array_equal(out[k], g[k]), k
+    assert np.array_equal(np.asarray(out['d']), g['d'])
+    assert np.array_equal(m.observed['GNK'], g['observed_GNK'])

@@ -148,3 +148,24 @@ def test_statistical_posterior_means():
     assert abs(res.sample_means['t1'] - 0.6) < 0.05
     assert abs(res.sample_means['t2'] - 0.2) < 0.05
     assert res.n_sim == 100000
+
+
+def test_adaptive_distance_smc_gnk_config5_model():
+    """BASELINE config #5's model at a size the reference can run: g-and-k, (B, n_obs) order
+    statistics on the device, AdaptiveDistance, AdaptiveDistanceSMC."""
+    import elfi_b200 as elfi
+    from elfi_b200.examples import gnk
+    g = load_golden('gnk_adaptive_distance_smc')
+    m = gnk.get_adaptive_model(n_obs=64, seed=7)
+    res = elfi.AdaptiveDistanceSMC(m['d'], batch_size=400, seed=13).sample(100, rounds=2,
+                                                                          quantile=0.5, bar=False)
+    assert res.n_sim == int(g['n_sim'])
+    assert len(res.populations) == int(g['n_pops'])
+    for i, pop in enumerate(res.populations):
+        pre = 'pop{}_'.format(i)
+        assert pop.n_sim == int(g[pre + 'n_sim'])
+        np.testing.assert_allclose(pop.adaptive_distance_w, g[pre + 'w'], rtol=1e-9)
+        for k in ('d', 'A', 'B', 'g', 'k', 'ss_sorted'):
+            np.testing.assert_allclose(pop.outputs[k], g[pre + 'out_' + k], rtol=1e-6, atol=1e-9,
+                                       err_msg='pop {} output {}'.format(i, k))
+        np.testing.assert_allclose(pop.weights, g[pre + 'weights'], rtol=1e-5)

@@ -88,3 +88,18 @@ def test_weighted_quantile_vs_oracle(n):
     w = rs.rand(n) ** 3
     for a in (0.0, 0.05, 0.3333, 0.5, 0.99, 1.0):
         assert ops.weighted_sample_quantile(x, a, w) == o.weighted_sample_quantile(x, a, w)
+
+
+@pytest.mark.parametrize('B,n', [(1000, 256), (37, 1), (500, 2), (333, 50), (100, 257), (64, 1000),
+                                 (9, 4096)])
+def test_rowsort_matches_numpy(B, n):
+    from elfi_b200 import ops
+    rs = np.random.RandomState(B + n)
+    x = rs.randn(B, n) * 10 ** rs.uniform(-2, 2, (B, 1))
+    if n >= 8:
+        x[::5, 3] = np.nan
+        x[::7, 1] = np.inf
+        x[::11, 0] = -np.inf
+        x[::3, 2] = x[::3, 4]                 # ties
+    got = ops.rowsort(x).cpu().numpy()
+    assert np.array_equal(got, np.sort(x, axis=1), equal_nan=True)
