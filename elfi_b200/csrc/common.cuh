@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...);
         if (_e != cudaSuccess) {                                                        \
             ::elfi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
                               __FILE__, __LINE__);                                      \
+            cudaGetLastError(); /* clear the (non-sticky) error for later calls */      \
             return ELFI_B200_ERR_CUDA;                                                  \
         }                                                                               \
     } while (0)

@@ -661,8 +661,8 @@ int elfi_b200_rowsort_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int6
                           double* out, int64_t ld_out, void* stream_) {
     using namespace elfi;
     ELFI_REQUIRE(ctx && (B == 0 || (X && out)), "rowsort: NULL argument");
-    ELFI_REQUIRE(B >= 0 && n >= 1 && n <= 4096 && ldX >= n && ld_out >= n,
-                 "rowsort: bad shape (1 <= n <= 4096)");
+    ELFI_REQUIRE(B >= 0 && n >= 1 && n <= 2048 && ldX >= n && ld_out >= n,
+                 "rowsort: bad shape (1 <= n <= 2048)");
     if (B == 0) return ELFI_B200_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));

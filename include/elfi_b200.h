@@ -266,7 +266,7 @@ int elfi_b200_kliep_fit_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
                             int64_t max_iter, double abs_tol, int64_t conv_check_interval,
                             double* alpha_out, double* result_host);
 
-/* elfi_b200_rowsort_f64: out[i, :] = np.sort(X[i, :]) (ascending, NaN last), 1 <= n <= 4096.
+/* elfi_b200_rowsort_f64: out[i, :] = np.sort(X[i, :]) (ascending, NaN last), 1 <= n <= 2048.
  * Order-statistic summaries such as the g-and-k model's (elfi/examples/gnk.py:145-161; the
  * 2-d form np.sort(y[:, :, 0], axis=1) that an (B, n_obs) summary matrix needs). */
 int elfi_b200_rowsort_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int64_t B, int64_t n,

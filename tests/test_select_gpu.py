@@ -91,7 +91,7 @@ def test_weighted_quantile_vs_oracle(n):
 
 
 @pytest.mark.parametrize('B,n', [(1000, 256), (37, 1), (500, 2), (333, 50), (100, 257), (64, 1000),
-                                 (9, 4096)])
+                                 (9, 2048)])
 def test_rowsort_matches_numpy(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B + n)
@@ -103,3 +103,10 @@ def test_rowsort_matches_numpy(B, n):
         x[::3, 2] = x[::3, 4]                 # ties
     got = ops.rowsort(x).cpu().numpy()
     assert np.array_equal(got, np.sort(x, axis=1), equal_nan=True)
+
+
+def test_rowsort_rejects_too_wide_rows_without_poisoning_the_context():
+    from elfi_b200 import _lib, ops
+    with pytest.raises(_lib.ElfiB200Error):
+        ops.rowsort(np.zeros((4, 4096)))
+    assert np.array_equal(ops.rowsort(np.array([[3.0, 1.0, 2.0]])).cpu().numpy(), [[1.0, 2.0, 3.0]])
