@@ -360,6 +360,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     args = ap.parse_args()
+    # make sure the in-tree CUDA library and the oracle are built (no-op when up to date); with
+    # torchrun only local rank 0 builds, the others wait for the files
+    import __graft_entry__ as entry
+    if int(os.environ.get('LOCAL_RANK', '0')) == 0:
+        entry.build_cuda()
+        entry.build_oracle()
+    else:
+        t_wait = time.time() + 600
+        while not os.path.exists(entry.LIB) and time.time() < t_wait:
+            time.sleep(1.0)
     if args.impl == 'reference':
         run_reference(args)
     else:
