@@ -17,7 +17,6 @@ with Gamma priors) is not available to pin against -> `optimize()` maximises the
 (log marginal likelihood + Gamma log-priors) with L-BFGS-B on log-parameters; PARITY UNPINNED.
 """
 import copy
-import ctypes
 import logging
 from math import ceil
 
@@ -28,7 +27,6 @@ import torch
 
 from . import _lib
 from . import device as dev
-from . import model as em
 from .results import OptimizationResult
 from .samplers import ModelPrior, ParameterInference
 
