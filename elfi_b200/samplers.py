@@ -723,12 +723,12 @@ class SMC(Sampler):
     def _compute_weights_means_and_cov(self, pop):
         """samplers.py:508-534 with the O(N_new x N_prev) mixture density on the device (and
         sharded over ranks when distributed)."""
-        params = np.column_stack(tuple([pop.outputs[p] for p in self.parameter_names]))
         twins = getattr(pop, '_dev', None)
         if twins is not None and all(p in twins for p in self.parameter_names):
-            params_dev = torch.stack([twins[p][:len(params)].reshape(-1)
-                                      for p in self.parameter_names], dim=1)
+            params_dev = torch.stack([twins[p].reshape(-1) for p in self.parameter_names], dim=1)
+            params = params_dev.cpu().numpy()          # one D2H instead of a host column_stack
         else:
+            params = np.column_stack(tuple([pop.outputs[p] for p in self.parameter_names]))
             params_dev = dev.to_device(params)
         if self._populations:
             means, cov, weights = self._gm_params_host
@@ -755,7 +755,8 @@ class SMC(Sampler):
         pop._means_dev = params_dev
         pop._w_dev = w_dev if w_dev is not None else torch.ones(len(params), dtype=torch.float64,
                                                                 device='cuda')
-        if np.count_nonzero(w) == 0:
+        all_zero = (not bool((w_dev != 0).any())) if w_dev is not None else np.count_nonzero(w) == 0
+        if all_zero:
             raise RuntimeError("All sample weights are zero. If you are using a prior "
                                "with a bounded support, this may be caused by specifying "
                                "a too small sample size.")
@@ -775,10 +776,14 @@ class SMC(Sampler):
 
     def _set_threshold(self):
         previous_population = self._populations[self.state['round'] - 1]
+        twins = getattr(previous_population, '_dev', None) or {}
+        d_prev = twins.get(self.discrepancy_name, previous_population.discrepancies)
+        w_prev = getattr(previous_population, '_w_dev', None)
+        if w_prev is None:
+            w_prev = previous_population.weights
         with PHASES('weighted_quantile'):
-            threshold = ops.weighted_sample_quantile(previous_population.discrepancies,
-                                                     self._quantiles[self.state['round']],
-                                                     previous_population.weights)
+            threshold = ops.weighted_sample_quantile(d_prev, self._quantiles[self.state['round']],
+                                                     w_prev)
         self.objective['thresholds'][self.state['round']] = threshold
 
     @property
