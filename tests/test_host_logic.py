@@ -169,3 +169,30 @@ def test_gnk_stock_model_matches_reference():
         assert np.array_equal(out[k], g[k]), k
     assert np.array_equal(np.asarray(out['d']), g['d'])
     assert np.array_equal(m.observed['GNK'], g['observed_GNK'])
+
+
+def test_result_containers():
+    from elfi_b200.results import OptimizationResult, Sample, SmcSample
+    outs = {'d': np.array([0.1, 0.2, 0.3]), 't1': np.array([1.0, 2.0, 3.0]),
+            't2': np.array([0.0, 1.0, 5.0])}
+    s = Sample('Rejection', outs, ['t1', 't2'], discrepancy_name='d', threshold=0.3, n_sim=300,
+               accept_rate=0.01, seed=1, n_batches=3)
+    assert s.n_samples == 3 and s.dim == 2 and s.threshold == 0.3 and s.n_sim == 300
+    assert np.array_equal(s.discrepancies, outs['d'])
+    assert s.samples_array.shape == (3, 2) and list(s.samples) == ['t1', 't2']
+    assert s.sample_means['t1'] == 2.0 and not s.is_multivariate
+    assert getattr(s, '_dev', None) is None
+    with pytest.raises(AttributeError):
+        s.not_there
+    s.weights = np.array([0.0, 0.0, 1.0])
+    s.meta['cov'] = np.eye(2)
+    assert s.sample_means_array[0] == 3.0 and s.cov.shape == (2, 2)
+    with pytest.raises(ValueError):
+        SmcSample('SMC', outs, ['t1', 't2'], populations=[s])
+    smc = SmcSample('SMC', outs, ['t1', 't2'], populations=[s, s], weights=np.ones(3), threshold=0.1)
+    assert smc.n_populations == 2 and smc.threshold == 0.1
+    opt = OptimizationResult(x_min={'t1': 0.5}, method_name='BO', outputs=outs,
+                             parameter_names=['t1', 't2'], n_sim=5)
+    assert opt.x_min['t1'] == 0.5 and opt.n_sim == 5
+    import copy
+    assert copy.copy(s).threshold == 0.3
