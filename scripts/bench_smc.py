@@ -26,6 +26,8 @@ def main():
     ap.add_argument('--quantile', type=float, default=0.5)
     ap.add_argument('--seed', type=int, default=1)
     ap.add_argument('--warm', type=int, default=1)
+    ap.add_argument('--model', default='ma2', choices=['ma2', 'gauss'],
+                    help='ma2 (scaling target) or gauss (BASELINE config #3)')
     args = ap.parse_args()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -34,12 +36,15 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import elfi_b200 as elfi
-    from elfi_b200.examples import ma2
+    from elfi_b200.examples import gauss, ma2
 
-    m = ma2.get_device_model(seed_obs=4)
+    if args.model == 'ma2':
+        m, proposal = ma2.get_device_model(seed_obs=4), ma2.DeviceProposal
+    else:
+        m, proposal = gauss.get_device_model(n_obs=50, seed_obs=3)
 
     def run(n, batch, pops):
-        smc = elfi.SMC(m['d'], batch_size=batch, seed=args.seed, device_proposal=ma2.DeviceProposal)
+        smc = elfi.SMC(m['d'], batch_size=batch, seed=args.seed, device_proposal=proposal)
         return smc.sample(n, quantiles=[args.quantile] * pops, bar=False)
 
     for _ in range(args.warm):
@@ -57,7 +62,7 @@ def main():
     dt = time.perf_counter() - t0
     if int(os.environ.get('RANK', '0')) == 0:
         accepted = args.n * args.pops
-        out = {'bench': 'smc_abc_ma2_throughput_mode', 'n_gpus': world, 'population': args.n,
+        out = {'bench': 'smc_abc_{}_throughput_mode'.format(args.model), 'n_gpus': world, 'population': args.n,
                'populations': args.pops, 'quantile': args.quantile, 'batch_per_rank': args.batch,
                'seconds': dt, 'accepted_particles_per_s': accepted / dt,
                'simulated': int(res.n_sim), 'simulated_per_s': res.n_sim / dt,
