@@ -12,6 +12,7 @@
 //
 // Traffic: n*8 bytes read per row (variance re-reads the tile from L2), 8 bytes written per
 // statistic.  Roofline: HBM.
+#include "leafsum.cuh"
 #include "pairwise.cuh"
 #include "rowstream.cuh"
 
@@ -43,7 +44,7 @@ struct TermGrouper {
     }
     __device__ __forceinline__ double finish() {
         if (fill > 0) pw.feed8(j0, buf, fill);
-        return pw.finish();
+        return __dadd_rn(0.0, pw.finish());   // np.add.reduce starts from the identity 0.0
     }
 };
 
@@ -156,6 +157,56 @@ struct MeanVarConsumer {
     }
 };
 
+// Single-leaf variants (leafsum.cuh): every reduced run has <= 128 terms, so NumPy's tree is one
+// leaf and the per-lane state is 8 accumulators per sum.  Same results as the consumers above,
+// a fraction of the integer bookkeeping (profiles/r1_summ_instruction_mix.md).
+template <int LAG_A, int LAG_B>
+struct AutocovLeafConsumer {
+    typedef SummaryParams Params;
+    static constexpr int PASSES = 1;
+    const Params& p;
+    AutocovLeaf<LAG_A, LAG_B> st;
+
+    static __device__ void setup_shared(uint8_t*, const Params&, int) {}
+    __device__ AutocovLeafConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
+    __device__ __forceinline__ void begin_row() { st.begin(p.n); }
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
+        double cur[16];
+        load_box_row(box_row, sw, cur);
+        st.box(cg * RS_BOX_COLS, cur);
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int) {
+        if (row < B) {
+            p.out[row * p.ld_out + p.col_a] = st.sum_a() / double(p.n - LAG_A);
+            if constexpr (LAG_B >= 0)
+                p.out[row * p.ld_out + p.col_b] = st.sum_b() / double(p.n - LAG_B);
+        }
+    }
+};
+
+struct MeanVarLeafConsumer {
+    typedef SummaryParams Params;
+    static constexpr int PASSES = 2;
+    const Params& p;
+    MeanVarLeaf st;
+
+    static __device__ void setup_shared(uint8_t*, const Params&, int) {}
+    __device__ MeanVarLeafConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
+    __device__ __forceinline__ void begin_row() { st.begin(p.n); }
+    __device__ __forceinline__ void consume(int pass, int cg, const uint8_t* box_row, int sw) {
+        double cur[16];
+        load_box_row(box_row, sw, cur);
+        st.box(pass, cg * RS_BOX_COLS, cur);
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int) {
+        const double var = st.variance();
+        if (row < B) {
+            if (p.col_a >= 0) p.out[row * p.ld_out + p.col_a] = st.mean;
+            if (p.col_b >= 0) p.out[row * p.ld_out + p.col_b] = var;
+        }
+    }
+};
+
 // Generic fallback (any lag, any alignment): one thread per row straight from global memory,
 // same PairwiseStream so results are identical.  mode 0 = autocov(lag), 1 = mean+var.
 __global__ void __launch_bounds__(128)
@@ -174,7 +225,7 @@ summary_direct_kernel(const double* __restrict__ X, int64_t ld, int64_t B, int n
             for (int k = 0; k < 8; ++k) buf[k] = k < cnt ? term(j0 + k) : 0.0;
             pw.feed8(j0, buf, cnt);
         }
-        return pw.finish();
+        return __dadd_rn(0.0, pw.finish());   // np.add.reduce starts from the identity 0.0
     };
     if (mode == 0) {
         const int m = n - lag;
@@ -194,6 +245,15 @@ summary_direct_kernel(const double* __restrict__ X, int64_t ld, int64_t B, int n
 static bool rowstream_ok(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t n) {
     return n >= RS_BOX_COLS && n <= PairwiseStream<RS_PW_DEPTH>::max_terms() &&
            tma_compatible(X, ld) && rs_pick_stages(ctx->smem_optin, 0) >= 2;
+}
+
+// One row-stream launch for lag pair (LA, LB): single-leaf consumer when every run fits a leaf.
+template <int LA, int LB>
+static int autocov_launch(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t B, int64_t n,
+                          const SummaryParams& p, cudaStream_t stream) {
+    if (n - LA <= LEAF_MAX_TERMS)   // LA is the smaller lag: the longer run
+        return rowstream_launch<AutocovLeafConsumer<LA, LB>>(ctx, X, ld, B, n, 0, p, stream);
+    return rowstream_launch<AutocovConsumer<LA, LB>>(ctx, X, ld, B, n, 0, p, stream);
 }
 
 }  // namespace elfi
@@ -230,19 +290,19 @@ int elfi_b200_summary_autocov_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
         if (fast) {
             if (la == 1 && lb == 2) {
                 p.col_b = int(l + 1);
-                rc = rowstream_launch<AutocovConsumer<1, 2>>(ctx, X, ldX, B, n, 0, p, stream);
+                rc = autocov_launch<1, 2>(ctx, X, ldX, B, n, p, stream);
                 if (rc == 0) l += 2;
             } else if (la == 1) {
-                rc = rowstream_launch<AutocovConsumer<1, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                rc = autocov_launch<1, -1>(ctx, X, ldX, B, n, p, stream);
                 if (rc == 0) l += 1;
             } else if (la == 2) {
-                rc = rowstream_launch<AutocovConsumer<2, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                rc = autocov_launch<2, -1>(ctx, X, ldX, B, n, p, stream);
                 if (rc == 0) l += 1;
             } else if (la == 3) {
-                rc = rowstream_launch<AutocovConsumer<3, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                rc = autocov_launch<3, -1>(ctx, X, ldX, B, n, p, stream);
                 if (rc == 0) l += 1;
             } else if (la == 4) {
-                rc = rowstream_launch<AutocovConsumer<4, -1>>(ctx, X, ldX, B, n, 0, p, stream);
+                rc = autocov_launch<4, -1>(ctx, X, ldX, B, n, p, stream);
                 if (rc == 0) l += 1;
             }
             if (rc != -100 && rc != 0) return rc;
@@ -276,8 +336,11 @@ int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
     p.n = int(n);
     p.col_a = col_mean;
     p.col_b = col_var;
-    if (rowstream_ok(ctx, X, ldX, n))
+    if (rowstream_ok(ctx, X, ldX, n)) {
+        if (n <= LEAF_MAX_TERMS)
+            return rowstream_launch<MeanVarLeafConsumer>(ctx, X, ldX, B, n, 0, p, stream);
         return rowstream_launch<MeanVarConsumer>(ctx, X, ldX, B, n, 0, p, stream);
+    }
     summary_direct_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(X, ldX, B, int(n), 0, 1, p);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;

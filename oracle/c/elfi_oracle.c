@@ -115,7 +115,11 @@ static double pairwise_sum(const double *a, int64_t n, int64_t stride)
     }
 }
 
-double oracle_pairwise_sum(const double *a, int64_t n) { return pairwise_sum(a, n, 1); }
+/* np.add.reduce starts from the identity 0.0 and adds the pairwise sum of the run to it
+ * (DOUBLE_add, IS_BINARY_REDUCE branch): only the sign of a zero sum is affected. */
+static double np_sum(const double *a, int64_t n) { return 0.0 + pairwise_sum(a, n, 1); }
+
+double oracle_pairwise_sum(const double *a, int64_t n) { return np_sum(a, n); }
 
 /* autocov (elfi/examples/ma2.py:40-59): C_i = mean_j( x[i,j+lag] * x[i,j] ), j < n-lag.
  * NumPy materialises the product row then reduces it pairwise; same here. */
@@ -127,7 +131,7 @@ void oracle_autocov(const double *X, int64_t ld, int64_t B, int64_t n, int64_t l
             const double *x = X + i * ld;
             int64_t m = n - lag;
             for (int64_t j = 0; j < m; ++j) tmp[j] = x[j + lag] * x[j];
-            out[i] = pairwise_sum(tmp, m, 1) / (double)m;
+            out[i] = np_sum(tmp, m) / (double)m;
         }
         free(tmp);
     }
@@ -141,14 +145,14 @@ void oracle_meanvar(const double *X, int64_t ld, int64_t B, int64_t n, double *m
         double *tmp = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
         for (int64_t i = 0; i < B; ++i) {
             const double *x = X + i * ld;
-            double mu = pairwise_sum(x, n, 1) / (double)n;
+            double mu = np_sum(x, n) / (double)n;
             if (mean) mean[i] = mu;
             if (var) {
                 for (int64_t j = 0; j < n; ++j) {
                     double c = x[j] - mu;
                     tmp[j] = c * c;
                 }
-                var[i] = pairwise_sum(tmp, n, 1) / (double)n;
+                var[i] = np_sum(tmp, n) / (double)n;
             }
         }
         free(tmp);

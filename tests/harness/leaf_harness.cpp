@@ -1,0 +1,65 @@
+// Host build of elfi_b200/csrc/leafsum.cuh: feeds rows to the single-leaf summary structs the
+// way the row-stream kernel does (16 columns per call, in order, one or two sweeps) so that the
+// arithmetic and control flow of the device consumers can be checked against NumPy on a CPU.
+// Columns at or beyond the row length are filled with NaN: a term that touched them would
+// poison the result.  Test infrastructure only (tests/test_leafsum_host.py builds it with g++).
+#include <cmath>
+#include <cstdint>
+#include <limits>
+
+#include "../../elfi_b200/csrc/leafsum.cuh"
+
+namespace {
+
+void load_box(const double* x, int n, int t0, double* cur) {
+    for (int c = 0; c < elfi::LEAF_BOX; ++c)
+        cur[c] = (t0 + c < n) ? x[t0 + c] : std::numeric_limits<double>::quiet_NaN();
+}
+
+template <int LA, int LB>
+void autocov_rows(const double* X, int64_t ld, int64_t B, int n, double* out) {
+    for (int64_t b = 0; b < B; ++b) {
+        elfi::AutocovLeaf<LA, LB> st;
+        st.begin(n);
+        double cur[elfi::LEAF_BOX];
+        for (int t0 = 0; t0 < n; t0 += elfi::LEAF_BOX) {
+            load_box(X + b * ld, n, t0, cur);
+            st.box(t0, cur);
+        }
+        out[2 * b] = st.sum_a() / double(n - LA);
+        out[2 * b + 1] = (LB >= 0) ? st.sum_b() / double(n - LB) : 0.0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int harness_autocov(const double* X, int64_t ld, int64_t B, int n, int lag_a, int lag_b,
+                    double* out) {
+    if (lag_a == 1 && lag_b == 2) autocov_rows<1, 2>(X, ld, B, n, out);
+    else if (lag_a == 1 && lag_b < 0) autocov_rows<1, -1>(X, ld, B, n, out);
+    else if (lag_a == 2 && lag_b < 0) autocov_rows<2, -1>(X, ld, B, n, out);
+    else if (lag_a == 3 && lag_b < 0) autocov_rows<3, -1>(X, ld, B, n, out);
+    else if (lag_a == 4 && lag_b < 0) autocov_rows<4, -1>(X, ld, B, n, out);
+    else return -1;
+    return 0;
+}
+
+int harness_meanvar(const double* X, int64_t ld, int64_t B, int n, double* out) {
+    for (int64_t b = 0; b < B; ++b) {
+        elfi::MeanVarLeaf st;
+        st.begin(n);
+        double cur[elfi::LEAF_BOX];
+        for (int pass = 0; pass < 2; ++pass)
+            for (int t0 = 0; t0 < n; t0 += elfi::LEAF_BOX) {
+                load_box(X + b * ld, n, t0, cur);
+                st.box(pass, t0, cur);
+            }
+        out[2 * b] = st.mean;
+        out[2 * b + 1] = st.variance();
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -42,6 +42,20 @@ def test_numpy_pairwise_order(n):
             assert np.array_equal(o.autocov(x, lag), np.mean(x[:, lag:] * x[:, :-lag], axis=1))
 
 
+def test_numpy_reduce_starts_from_identity():
+    """np.add.reduce = 0.0 + pairwise_sum: an all negative-zero run sums to +0.0."""
+    x = np.random.RandomState(2).randn(8, 100)
+    x[0] = -0.0
+    x[1, ::2] = -0.0
+    x[2] = 0.0
+    m, v = o.meanvar(x)
+    assert np.array_equal(m.view(np.int64), np.mean(x, axis=1).view(np.int64))
+    assert np.array_equal(v.view(np.int64), np.var(x, axis=1).view(np.int64))
+    for lag in (1, 2):
+        ref = np.mean(x[:, lag:] * x[:, :-lag], axis=1)
+        assert np.array_equal(o.autocov(x, lag).view(np.int64), ref.view(np.int64))
+
+
 def test_golden_ma2_forward():
     g = load_golden('ma2_generate')
     x = g['MA2']
