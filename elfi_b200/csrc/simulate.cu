@@ -12,6 +12,7 @@
 //                                 rejection of draws outside the prior support)
 // The random numbers are a pure function of (seed, stream, row, index): the simulator can be
 // replayed (e.g. to materialise X for a test) and any sharding of rows gives the same particles.
+#include "gnkmath.cuh"
 #include "pairwise.cuh"
 
 namespace elfi {
@@ -297,6 +298,59 @@ sim_gauss_kernel(const double* __restrict__ mu, const double* __restrict__ sigma
     }
 }
 
+// ---- g-and-k model (elfi/examples/gnk.py) -------------------------------------------------------
+// y_ij = Q(z_ij; A_i, B_i, g_i, k_i, c) with the quantile function of gnkmath.cuh (gnk.py:60-66).
+// One thread per pair of observations: Philox block (row, pair) -> two normals -> two adjacent
+// outputs, so a warp writes 512 contiguous bytes of a row.  The draws of a row do not depend on
+// n_obs or on how rows are sharded.
+__global__ void __launch_bounds__(256)
+sim_gnk_kernel(const double* __restrict__ A, const double* __restrict__ Bs, const double* __restrict__ g,
+               const double* __restrict__ k, double c, int64_t B, int n_obs, uint64_t seed,
+               uint64_t offset, double* __restrict__ Y, int64_t ldY) {
+    const int half = (n_obs + 1) >> 1;
+    const int64_t total = B * half;
+    const Philox ph(seed);
+    const bool vec = (ldY & 1) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx / half;
+        const int q = int(idx - i * half);
+        const uint64_t row = offset + uint64_t(i);
+        double z0, z1;
+        normal2(ph(uint32_t(row), uint32_t(row >> 32), uint32_t(q), 0x474e4b30u), z0, z1);
+        const double a = A[i], b = Bs[i], gg = g[i], kk = k[i];
+        const double y0 = gnk_quantile(a, b, gg, kk, c, z0);
+        double* dst = Y + i * ldY + 2 * q;
+        if (2 * q + 1 < n_obs) {
+            const double y1 = gnk_quantile(a, b, gg, kk, c, z1);
+            if (vec) {
+                *reinterpret_cast<double2*>(dst) = make_double2(y0, y1);
+            } else {
+                dst[0] = y0;
+                dst[1] = y1;
+            }
+        } else {
+            dst[0] = y0;
+        }
+    }
+}
+
+// log density of independent uniform priors U(lo_a, lo_a + width_a), a < p <= 8
+// (gnk.py:99-103: A, B, g, k ~ uniform(0, 10)); -inf outside the box like scipy's logpdf.
+struct BoxPrior { double lo[8], hi[8]; double logdens; };
+
+__global__ void logprior_box_kernel(const double* __restrict__ x, int64_t ld, int64_t B, int p,
+                                    BoxPrior box, double* __restrict__ out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    bool inside = true;
+    for (int a = 0; a < p; ++a) {
+        const double v = x[i * ld + a];
+        inside = inside && v >= box.lo[a] && v <= box.hi[a];   // NaN -> outside
+    }
+    out[i] = inside ? box.logdens : -INFINITY;
+}
+
 // inclusive scan of w / sum(w) (single block; N up to a few million is fine: one pass each)
 __global__ void __launch_bounds__(1024)
 cumsum_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ out) {
@@ -451,6 +505,48 @@ int elfi_b200_sim_gauss_f64(elfi_b200_ctx* ctx, const double* mu, const double* 
     const unsigned blocks = unsigned((B + 127) / 128);
     if (Y) sim_gauss_kernel<true><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS);
     else sim_gauss_kernel<false><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_sim_gnk_f64(elfi_b200_ctx* ctx, const double* A, const double* Bs, const double* g,
+                          const double* k, double c, int64_t B, int64_t n_obs, uint64_t seed,
+                          uint64_t offset, double* Y, int64_t ldY, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (B == 0 || (A && Bs && g && k && Y)), "sim_gnk: NULL argument");
+    ELFI_REQUIRE(B >= 0 && n_obs >= 1 && n_obs < (int64_t(1) << 30), "sim_gnk: bad shape B=%lld n_obs=%lld",
+                 (long long)B, (long long)n_obs);
+    ELFI_REQUIRE(ldY >= n_obs, "sim_gnk: bad leading dimension");
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const int64_t total = B * ((n_obs + 1) / 2);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = int64_t(ctx->sm_count) * 64;   // grid-stride beyond 8 waves of 8 CTAs/SM
+    if (blocks > cap) blocks = cap;
+    sim_gnk_kernel<<<unsigned(blocks), 256, 0, stream>>>(A, Bs, g, k, c, B, int(n_obs), seed, offset, Y, ldY);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_logprior_box_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t B, int64_t p,
+                               const double* box_host, double* out, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && box_host && (B == 0 || (x && out)), "logprior_box: NULL argument");
+    ELFI_REQUIRE(B >= 0 && p >= 1 && p <= 8 && ldx >= p, "logprior_box: bad shape (p <= 8)");
+    BoxPrior box;
+    memset(&box, 0, sizeof(box));
+    box.logdens = 0.0;
+    for (int a = 0; a < p; ++a) {
+        ELFI_REQUIRE(box_host[p + a] > 0.0, "logprior_box: width[%d] must be positive", a);
+        box.lo[a] = box_host[a];
+        box.hi[a] = box_host[a] + box_host[p + a];
+        box.logdens -= log(box_host[p + a]);
+    }
+    if (B == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    logprior_box_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(x, ldx, B, int(p), box, out);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

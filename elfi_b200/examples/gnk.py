@@ -67,3 +67,52 @@ def get_adaptive_model(n_obs=256, true_params=None, seed=None):
     s = em.Summary(ss_sorted, m['GNK'], name='ss_sorted')
     em.AdaptiveDistance(s, name='d')
     return m
+
+
+# ---------------------------------------------------------------------------- throughput mode
+# Device-side priors, simulator and proposals (Philox streams; statistical parity with the host
+# path).  The simulated (B, n_obs) matrix is born in HBM, sorted per row there (order statistics)
+# and consumed by the nested-distance kernel; only accepted particles leave the device.
+def gnk_device(A, B, g, k, c=0.8, n_obs=50, batch_size=1, random_state=None):
+    """Device twin of GNK: returns a (batch_size, n_obs) CUDA tensor."""
+    from .gauss import _key
+
+    def as_dev(v):
+        if dev.is_device_array(v):
+            return v.reshape(-1)
+        return dev.to_device(np.broadcast_to(np.asarray(v, dtype=np.float64).reshape(-1),
+                                             (batch_size,)).copy())
+    return ops.sim_gnk(as_dev(A), as_dev(B), as_dev(g), as_dev(k), n_obs=n_obs,
+                       seed=_key(random_state), c=c)
+
+
+class DeviceProposal:
+    """SMC proposals / prior density on the device for the g-and-k model
+    (pass an instance as ``device_proposal=`` to SMC / AdaptiveDistanceSMC)."""
+    parameter_names = ['A', 'B', 'g', 'k']
+
+    def __init__(self, lo=0.0, width=10.0):
+        self.lo = np.broadcast_to(np.asarray(lo, dtype=np.float64), (4,)).copy()
+        self.width = np.broadcast_to(np.asarray(width, dtype=np.float64), (4,)).copy()
+        self.box = (list(self.lo), list(self.lo + self.width))
+
+    def rvs(self, means, cov, weights, size, key):
+        return ops.gm_rvs(means, cov, weights, size, seed=key, support=2, box=self.box)
+
+    def logpdf(self, params):
+        return ops.logprior_box(params, self.lo, self.width)
+
+
+def get_device_model(n_obs=256, true_params=None, seed=None):
+    """Config #5 in throughput mode: uniform(0, 10) priors drawn on the device, `gnk_device`,
+    row-sorted order statistics and AdaptiveDistance.  Returns (model, DeviceProposal)."""
+    from .gauss import _DeviceUniform
+    if true_params is None:
+        true_params = [3, 1, 2, .5]
+    m = em.new_model()
+    priors = [em.Prior(_DeviceUniform, 0, 10, model=m, name=n) for n in ('A', 'B', 'g', 'k')]
+    y_obs = GNK(*true_params, n_obs=n_obs, random_state=np.random.RandomState(seed))
+    em.Simulator(partial(gnk_device, n_obs=n_obs), *priors, observed=y_obs, name='GNK')
+    s = em.Summary(ss_sorted, m['GNK'], name='ss_sorted')
+    em.AdaptiveDistance(s, name='d')
+    return m, DeviceProposal()

@@ -382,6 +382,32 @@ def sim_gauss(mu, sigma, n_obs=50, seed=0, offset=0, want_data=False, want_summa
     return Y, S
 
 
+def sim_gnk(A, B, g, k, n_obs=50, seed=0, offset=0, c=0.8):
+    """g-and-k simulator on the device (elfi/examples/gnk.py:11-68) -> Y (batch, n_obs)."""
+    cols = [dev.to_device(v).reshape(-1).contiguous() for v in (A, B, g, k)]
+    n = cols[0].numel()
+    if any(col.numel() != n for col in cols):
+        raise ValueError('A, B, g and k must have the same number of elements')
+    Y = dev.empty((n, n_obs))
+    _lib.call('elfi_b200_sim_gnk_f64', dev.context(), dev.ptr(cols[0]), dev.ptr(cols[1]),
+              dev.ptr(cols[2]), dev.ptr(cols[3]), float(c), n, n_obs, int(seed), int(offset),
+              dev.ptr(Y), n_obs, dev.stream_ptr())
+    return Y
+
+
+def logprior_box(params, lo, width):
+    """Sum of independent uniform(lo, width) log densities per row (scipy convention: -inf
+    outside); the joint prior of the g-and-k example (elfi/examples/gnk.py:99-103)."""
+    x = _matrix(params)
+    p = x.shape[1]
+    box = np.ascontiguousarray(np.concatenate([np.broadcast_to(np.asarray(lo, dtype=np.float64), (p,)),
+                                               np.broadcast_to(np.asarray(width, dtype=np.float64), (p,))]))
+    out = dev.empty((x.shape[0],))
+    _lib.call('elfi_b200_logprior_box_f64', dev.context(), dev.ptr(x), _ld(x), x.shape[0], p,
+              dev.ptr(box), dev.ptr(out), dev.stream_ptr())
+    return out
+
+
 def kliep_fit(x, y, weights_x=None, weights_y=None, sigma=1.0, n_basis=100, epsilon=0.001,
               max_iter=200, abs_tol=0.01, conv_check_interval=20):
     """KLIEP fit on the device (elfi/methods/density_ratio_estimation.py:71-207).

@@ -253,6 +253,18 @@ int elfi_b200_sim_gauss_f64(elfi_b200_ctx* ctx, const double* mu, const double* 
                             int64_t n_obs, uint64_t seed, uint64_t offset, double* Y, int64_t ldY,
                             double* S, int64_t ldS, void* stream);
 
+/* g-and-k model of elfi/examples/gnk.py (throughput mode, statistical parity).
+ * sim_gnk: Y[i, j] = A_i + B_i (1 + c (1 - exp(-g_i z)) / (1 + exp(-g_i z))) (1 + z^2)^k_i z with
+ * z = z_ij ~ N(0, 1) from the Philox stream (seed, offset + i, j) (gnk.py:11-68); Y is (B, n_obs)
+ * with leading dimension ldY.  The order-statistic summary is elfi_b200_rowsort_f64 on Y.
+ * logprior_box: sum of independent uniform log densities, box_host = [lo (p), width (p)], p <= 8
+ * (the priors A, B, g, k ~ uniform(0, 10) of gnk.py:99-103); -inf outside. */
+int elfi_b200_sim_gnk_f64(elfi_b200_ctx* ctx, const double* A, const double* Bs, const double* g,
+                          const double* k, double c, int64_t B, int64_t n_obs, uint64_t seed,
+                          uint64_t offset, double* Y, int64_t ldY, void* stream);
+int elfi_b200_logprior_box_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t B, int64_t p,
+                               const double* box_host, double* out, void* stream);
+
 /* ---- KLIEP density-ratio estimation (AdaptiveThresholdSMC) -------------------------------------
  * DensityRatioEstimation.fit + max_ratio (elfi/methods/density_ratio_estimation.py:71-207):
  * basis centres = first n_basis rows of x, A = RBF(x, centres), b = weighted RBF mean over y,

@@ -26,8 +26,10 @@ def main():
     ap.add_argument('--quantile', type=float, default=0.5)
     ap.add_argument('--seed', type=int, default=1)
     ap.add_argument('--warm', type=int, default=1)
-    ap.add_argument('--model', default='ma2', choices=['ma2', 'gauss'],
-                    help='ma2 (scaling target) or gauss (BASELINE config #3)')
+    ap.add_argument('--model', default='ma2', choices=['ma2', 'gauss', 'gnk'],
+                    help='ma2 (scaling target), gauss (BASELINE config #3) or gnk (config #5: '
+                         'AdaptiveDistanceSMC over n_obs order statistics, --pops rounds)')
+    ap.add_argument('--n-obs', type=int, default=256, help='observations per simulation (gnk)')
     args = ap.parse_args()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -36,14 +38,20 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import elfi_b200 as elfi
-    from elfi_b200.examples import gauss, ma2
+    from elfi_b200.examples import gauss, gnk, ma2
 
     if args.model == 'ma2':
         m, proposal = ma2.get_device_model(seed_obs=4), ma2.DeviceProposal
-    else:
+    elif args.model == 'gauss':
         m, proposal = gauss.get_device_model(n_obs=50, seed_obs=3)
+    else:
+        m, proposal = gnk.get_device_model(n_obs=args.n_obs, seed=7)
 
     def run(n, batch, pops):
+        if args.model == 'gnk':
+            smc = elfi.AdaptiveDistanceSMC(m['d'], batch_size=batch, seed=args.seed,
+                                           device_proposal=proposal)
+            return smc.sample(n, rounds=pops, quantile=args.quantile, bar=False)
         smc = elfi.SMC(m['d'], batch_size=batch, seed=args.seed, device_proposal=proposal)
         return smc.sample(n, quantiles=[args.quantile] * pops, bar=False)
 

@@ -164,3 +164,84 @@ def test_gauss_smc_throughput_mode_statistics():
     a, b = res.sample_means_array, ref.sample_means_array
     assert abs(a[0] - b[0]) < 0.05 and abs(a[1] - b[1]) < 0.05, (a, b)
     assert abs(a[0] - 4.0) < 0.3 and abs(a[1] - 0.4) < 0.3
+
+
+def _gnk_q(prm, z, c=0.8):
+    A, B, g, k = prm
+    return A + B * (1 + c * ((1 - np.exp(-g * z)) / (1 + np.exp(-g * z)))) * (1 + z**2)**k * z
+
+
+def test_gnk_simulator_distribution_and_streams():
+    """sim_gnk draws follow the g-and-k quantile function (gnk.py:60-66): the fraction of draws
+    below Q(Phi^-1(p)) is p; rows are a pure function of (seed, offset + row, column)."""
+    from elfi_b200 import ops
+    prm = (3.0, 1.0, 2.0, 0.5)
+    B, n_obs = 4000, 50
+    cols = [np.full(B, v) for v in prm]
+    Y = ops.sim_gnk(*cols, n_obs=n_obs, seed=21).cpu().numpy()
+    assert Y.shape == (B, n_obs) and np.all(np.isfinite(Y))
+    N = Y.size
+    for p in np.arange(1, 8) / 8.0:
+        frac = np.mean(Y <= _gnk_q(prm, ss.norm.ppf(p)))
+        assert abs(frac - p) < 5 * np.sqrt(p * (1 - p) / N) + 1e-9, (p, frac)
+    # every row has its own stream: row means differ, columns are uncorrelated
+    assert np.unique(Y[:, 0]).size == B
+    assert abs(np.corrcoef(Y[:, 0], Y[:, 1])[0, 1]) < 0.08
+    # sharding invariance and independence of n_obs (odd n_obs: last column written alone)
+    Y2 = ops.sim_gnk(*[c[40:100] for c in cols], n_obs=n_obs, seed=21, offset=40).cpu().numpy()
+    assert np.array_equal(Y2, Y[40:100])
+    Y3 = ops.sim_gnk(*[c[:64] for c in cols], n_obs=51, seed=21).cpu().numpy()
+    assert np.array_equal(Y3[:, :50], Y[:64])
+    Y4 = ops.sim_gnk(*[c[:64] for c in cols], n_obs=1, seed=21).cpu().numpy()
+    assert np.array_equal(Y4[:, 0], Y[:64, 0])
+    # per-row parameters are honoured: location shift by A
+    A2 = cols[0].copy()
+    A2[::2] += 100.0
+    Y5 = ops.sim_gnk(A2, *cols[1:], n_obs=n_obs, seed=21).cpu().numpy()
+    np.testing.assert_allclose(Y5[::2] - 100.0, Y[::2], rtol=0, atol=1e-10)
+    assert np.array_equal(Y5[1::2], Y[1::2])
+
+
+def test_logprior_box_matches_scipy():
+    from elfi_b200 import ops
+    rs = np.random.RandomState(4)
+    theta = rs.uniform(-1, 11, (5000, 4))
+    theta[0] = [0.0, 10.0, 5.0, 5.0]            # boundary points are inside (scipy: closed support)
+    theta[1] = [np.nan, 1.0, 1.0, 1.0]
+    with np.errstate(divide='ignore'):
+        ref = ss.uniform.logpdf(theta, 0, 10).sum(axis=1)
+    ref[1] = -np.inf                            # NaN is outside for the acceptance test
+    got = ops.logprior_box(theta, 0.0, 10.0).cpu().numpy()
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    np.testing.assert_allclose(got[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-14)
+    got2 = ops.logprior_box(theta[:, :2], [0.0, -1.0], [10.0, 2.0]).cpu().numpy()
+    with np.errstate(divide='ignore'):
+        ref2 = ss.uniform.logpdf(theta[:, 0], 0, 10) + ss.uniform.logpdf(theta[:, 1], -1, 2)
+    ref2[1] = -np.inf
+    assert np.array_equal(np.isfinite(got2), np.isfinite(ref2))
+    np.testing.assert_allclose(got2[np.isfinite(ref2)], ref2[np.isfinite(ref2)], rtol=1e-14)
+
+
+def test_gnk_adaptive_distance_smc_throughput_mode_statistics():
+    """config #5's model with priors, simulator and proposals on the device vs the host-RNG path
+    (statistical parity: the two use different random streams)."""
+    import elfi_b200 as elfi
+    from elfi_b200.examples import gnk
+    m, proposal = gnk.get_device_model(n_obs=64, seed=7)
+    res = elfi.AdaptiveDistanceSMC(m['d'], batch_size=4000, seed=13,
+                                   device_proposal=proposal).sample(500, rounds=3, quantile=0.5,
+                                                                    bar=False)
+    mh = gnk.get_adaptive_model(n_obs=64, seed=7)
+    ref = elfi.AdaptiveDistanceSMC(mh['d'], batch_size=4000, seed=13).sample(500, rounds=3,
+                                                                             quantile=0.5, bar=False)
+    assert res.n_samples == 500 and len(res.populations) == len(ref.populations) == 3
+    thr = [pop.threshold for pop in res.populations]
+    assert all(np.isfinite(thr))
+    for pop in res.populations:
+        assert np.all(np.isfinite(pop.weights)) and pop.weights.sum() > 0
+        for name in ('A', 'B', 'g', 'k'):
+            v = pop.outputs[name]
+            assert v.min() >= 0.0 and v.max() <= 10.0
+    a, b = res.sample_means_array, ref.sample_means_array
+    for i, tol in enumerate((1.0, 1.0, 1.5, 1.5)):
+        assert abs(a[i] - b[i]) < tol, (a, b)
