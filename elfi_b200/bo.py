@@ -136,7 +136,7 @@ class GPyRegression:
             f = dict(n_pad=n_pad, L=dev.empty((n_pad, n_pad)), W=dev.empty((n_pad, n_pad)),
                      U=dev.empty((n_pad, n_pad)))
         f.update(X=Xd, y=yd, n=n, alpha=dev.empty((n,)),
-                 info=torch.zeros(1, dtype=torch.int32, device='cuda'))
+                 info=dev.zeros((1,), dtype=torch.int32))
         _lib.call('elfi_b200_gp_fit_f64', dev.context(), dev.ptr(Xd), p, dev.ptr(yd), n, p,
                   h['kernel_var'], h['lengthscale'], h['bias_var'], h['noise_var'] + JITTER,
                   dev.ptr(f['L']), dev.ptr(f['W']), dev.ptr(f['U']), n_pad, dev.ptr(f['alpha']),
@@ -376,7 +376,7 @@ class LCBSC(AcquisitionBase):
     def evaluate_device(self, x, t=None):
         if self.model._factor is None:
             m = np.asarray(dev.to_host(x)).reshape(-1, self.model.input_dim).shape[0]
-            return torch.full((m,), -np.sqrt(self._beta(t)), dtype=torch.float64, device='cuda')
+            return dev.full((m,), -np.sqrt(self._beta(t)))
         return self.model.predict_device(x, noiseless=True, beta=self._beta(t))[2]
 
     def evaluate_gradient(self, x, t=None):

@@ -82,6 +82,21 @@ def empty(shape, dtype=torch.float64):
     return torch.empty(shape, dtype=dtype, device='cuda')
 
 
+def zeros(shape, dtype=torch.float64):
+    require_cuda()
+    return torch.zeros(shape, dtype=dtype, device='cuda')
+
+
+def ones(shape, dtype=torch.float64):
+    require_cuda()
+    return torch.ones(shape, dtype=dtype, device='cuda')
+
+
+def full(shape, value, dtype=torch.float64):
+    require_cuda()
+    return torch.full(shape, value, dtype=dtype, device='cuda')
+
+
 def ptr(t):
     """Device (or host) pointer of a tensor / numpy array as c_void_p; None -> NULL."""
     if t is None:

@@ -76,7 +76,7 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True):
     d = dev.empty((B, K))
     acc_idx = n_acc = None
     if thr is not None:
-        n_acc = torch.zeros(1, dtype=torch.int64, device='cuda')
+        n_acc = dev.zeros((1,), dtype=torch.int64)
         if want_indices:
             acc_idx = dev.empty((max(B, 1),), dtype=torch.int32)
     _lib.call('elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S), S.stride(0) if B > 1 else D, B, D,

@@ -454,9 +454,9 @@ class Rejection(Sampler):
                                  "batch size {}.".format(node, len(nbatch), self.batch_size))
             shape = (n,) + tuple(nbatch.shape[1:])
             if node == self.discrepancy_name:
-                samples[node] = torch.full(shape, float('inf'), dtype=torch.float64, device='cuda')
+                samples[node] = dev.full(shape, float('inf'))
             else:
-                samples[node] = torch.zeros(shape, dtype=torch.float64, device='cuda')
+                samples[node] = dev.zeros(shape)
         self.state['samples'] = samples
 
     def _merge_batch(self, batch):
@@ -477,7 +477,7 @@ class Rejection(Sampler):
                 thr = self.objective.get('threshold')
                 if thr is None:
                     thr = self.state['threshold']
-                ok = (d_batch <= torch.as_tensor(thr, dtype=torch.float64, device='cuda'))
+                ok = (d_batch <= dev.to_device(np.asarray(thr, dtype=np.float64)))
                 if ok.dim() > 1:
                     ok = ok.all(dim=1)
                 acc = torch.nonzero(ok).ravel().to(torch.int32)
@@ -579,10 +579,10 @@ class Rejection(Sampler):
         st = self.model[self.discrepancy_name]._s
         n_r, m_r, s_r = st['store']
         D = np.size(m_r) if np.ndim(m_r) else 1
-        pack = torch.zeros(1, 1 + 2 * D, dtype=torch.float64, device='cuda')
+        pack = dev.zeros((1, 1 + 2 * D))
         pack[0, 0] = float(n_r)
-        pack[0, 1:1 + D] = torch.as_tensor(np.broadcast_to(m_r, (D,)).copy(), device='cuda')
-        pack[0, 1 + D:] = torch.as_tensor(np.broadcast_to(s_r, (D,)).copy(), device='cuda')
+        pack[0, 1:1 + D] = dev.to_device(np.broadcast_to(m_r, (D,)).copy())
+        pack[0, 1 + D:] = dev.to_device(np.broadcast_to(s_r, (D,)).copy())
         allp = self.comm.all_gather_rows(pack).cpu().numpy()
         n0, m0, s0 = sharding.chan_merge([(row[0], row[1:1 + D], row[1 + D:]) for row in allp])
         st['store'] = [n0, m0, s0]
@@ -735,7 +735,7 @@ class SMC(Sampler):
             N = len(params)
             if self.comm.on:
                 lo, hi, per = sharding.shard_bounds(N, self.comm.rank, self.comm.size)
-                q_part = torch.full((per,), float('nan'), dtype=torch.float64, device='cuda')
+                q_part = dev.full((per,), float('nan'))
                 if hi > lo:
                     q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], means, cov, weights)
                 q_logpdf = self.comm.all_gather_rows(q_part)
@@ -753,8 +753,7 @@ class SMC(Sampler):
             w_dev = None
         means = params
         pop._means_dev = params_dev
-        pop._w_dev = w_dev if w_dev is not None else torch.ones(len(params), dtype=torch.float64,
-                                                                device='cuda')
+        pop._w_dev = w_dev if w_dev is not None else dev.ones((len(params),))
         all_zero = (not bool((w_dev != 0).any())) if w_dev is not None else np.count_nonzero(w) == 0
         if all_zero:
             raise RuntimeError("All sample weights are zero. If you are using a prior "

@@ -1,0 +1,261 @@
+"""CPU test double of the C ABI (include/elfi_b200.h) -- TEST INFRASTRUCTURE ONLY.
+
+The product has no CPU path: elfi_b200 raises without a CUDA device.  To test the *host logic*
+(operator wrappers in ops.py, the ElfiModel graph, Rejection / SMC state machines, the rank
+sharding) on a machine without a GPU, the `cpu_double` fixture of tests/conftest.py swaps
+
+  * elfi_b200._lib.call        -> `call` below: every entry point restated on host pointers with
+                                  NumPy + the oracle (same argument lists as the header), and
+  * the allocation helpers of elfi_b200.device -> CPU torch tensors.
+
+Nothing outside tests/ imports this module.  Entry points that the CPU tests do not need raise
+ElfiB200Error so a test can never silently pass through an unimplemented call.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+import elfi_oracle as o
+from elfi_b200 import _lib
+
+CALLS = []   # names of the entry points called (tests assert the expected kernels were reached)
+
+
+def _addr(p):
+    if p is None:
+        return 0
+    if isinstance(p, ctypes.c_void_p):
+        return p.value or 0
+    if isinstance(p, int):
+        return p
+    raise TypeError('unexpected pointer argument {!r}'.format(p))
+
+
+def _mat(p, rows, cols, ld=None, dtype=np.float64):
+    """(rows, cols) view with leading dimension ld over host memory; None for NULL."""
+    a = _addr(p)
+    if a == 0:
+        return None
+    rows, cols = int(rows), int(cols)
+    ld = cols if ld is None else int(ld)
+    item = np.dtype(dtype).itemsize
+    if rows == 0 or cols == 0:
+        return np.empty((rows, cols), dtype=dtype)
+    nbytes = ((rows - 1) * ld + cols) * item
+    buf = (ctypes.c_char * nbytes).from_address(a)
+    flat = np.frombuffer(buf, dtype=dtype)
+    return np.lib.stride_tricks.as_strided(flat, (rows, cols), (ld * item, item))
+
+
+def _vec(p, n, dtype=np.float64):
+    m = _mat(p, 1, n, dtype=dtype)
+    return None if m is None else m[0]
+
+
+def _require(cond, msg):
+    if not cond:
+        raise _lib.ElfiB200Error('cpu double: ' + msg)
+
+
+# ------------------------------------------------------------------------------ entry points
+def _distances(S, obs, W, K):
+    d = np.empty((S.shape[0], K))
+    for k in range(K):
+        d[:, k] = o.cdist_euclid(np.ascontiguousarray(S), obs, w=None if W is None else W[k])
+    return d
+
+
+def dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, acc_idx, n_acc, stream):
+    _require(K == 1 or _addr(W), 'K > 1 needs weights')
+    S = _mat(S, B, D, ldS)
+    d = _distances(S, _vec(obs, D), _mat(W, K, D), K) if B else np.empty((0, K))
+    out = _mat(d_out, B, K)
+    if B:
+        out[:] = d
+    thr = _vec(thr_host, K)
+    if thr is not None:
+        idx = o.accept_indices(d, thr) if B else np.empty(0, dtype=np.int32)
+        if _addr(acc_idx):
+            _vec(acc_idx, max(B, 1), np.int32)[:len(idx)] = idx
+        if _addr(n_acc):
+            _vec(n_acc, 1, np.int64)[0] = len(idx)
+
+
+def dist_euclid_thr_f64_host(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, acc_idx, n_acc):
+    Sm = _mat(S, B, D, ldS)
+    d = _distances(Sm, _vec(obs, D), _mat(W, K, D), K) if B else np.empty((0, K))
+    if _addr(d_out) and B:
+        _mat(d_out, B, K)[:] = d
+    thr = _vec(thr_host, K)
+    if thr is not None:
+        idx = o.accept_indices(d, thr) if B else np.empty(0, dtype=np.int32)
+        if _addr(acc_idx):
+            _vec(acc_idx, max(B, 1), np.int32)[:len(idx)] = idx
+        if n_acc is not None:
+            n_acc._obj.value = len(idx)   # ctypes.byref(c_int64)
+
+
+def summary_autocov_f64(ctx, X, ldX, B, n, lags_host, nlags, out, ld_out, stream):
+    X = _mat(X, B, n, ldX)
+    lags = _vec(lags_host, nlags, np.int32)
+    out = _mat(out, B, nlags, ld_out)
+    for c, lag in enumerate(lags):
+        _require(1 <= lag < n, 'autocov: lag {} outside [1, n)'.format(lag))
+        if B:
+            out[:, c] = o.autocov(np.ascontiguousarray(X), int(lag))
+
+
+def summary_meanvar_f64(ctx, X, ldX, B, n, out, ld_out, col_mean, col_var, stream):
+    if not B:
+        return
+    X = _mat(X, B, n, ldX)
+    mean, var = o.meanvar(np.ascontiguousarray(X))
+    width = max(col_mean, col_var) + 1
+    out = _mat(out, B, width, ld_out)
+    if col_mean >= 0:
+        out[:, col_mean] = mean
+    if col_var >= 0:
+        out[:, col_var] = var
+
+
+def sort_pairs_f64(ctx, keys, n, keys_sorted, perm, stream):
+    if not n:
+        return
+    k = _vec(keys, n)
+    order = np.argsort(k, kind='stable')     # NaN last, ties by index: the ABI's contract
+    if _addr(perm):
+        _vec(perm, n, np.int32)[:] = order
+    if _addr(keys_sorted):
+        _vec(keys_sorted, n)[:] = k[order]
+
+
+def gather_rows_f64(ctx, src, ld_src, idx, n, width, dst, ld_dst, stream):
+    if not (n and width):
+        return
+    idx = _vec(idx, n, np.int32)
+    src = _mat(src, int(idx.max()) + 1, width, ld_src)
+    _mat(dst, n, width, ld_dst)[:] = src[idx]
+
+
+def gather2_rows_f64(ctx, A, ldA, nA, B, ldB, mapB, perm, n, width, dst, ld_dst, stream):
+    if not (n and width):
+        return
+    sel = np.arange(n) if not _addr(perm) else _vec(perm, n, np.int32).astype(np.int64)
+    from_b = sel >= nA
+    rows_b = sel[from_b] - nA
+    if _addr(mapB) and rows_b.size:
+        rows_b = _vec(mapB, int(rows_b.max()) + 1, np.int32)[rows_b].astype(np.int64)
+    out = _mat(dst, n, width, ld_dst)
+    if (~from_b).any():
+        out[~from_b] = _mat(A, nA, width, ldA)[sel[~from_b]]
+    if from_b.any():
+        out[from_b] = _mat(B, int(rows_b.max()) + 1, width, ldB)[rows_b]
+
+
+def wquantile_f64(ctx, x, w, n, alpha, out, stream):
+    _require(n >= 1 and 0.0 <= alpha <= 1.0, 'wquantile: bad arguments')
+    x = _vec(x, n).copy()
+    w = _vec(w, n)
+    q = o.weighted_sample_quantile(x, alpha, None if w is None else w.copy())
+    res = _vec(out, 2)
+    res[0] = q
+    res[1] = float(np.searchsorted(np.sort(x), q))
+
+
+def colmoments_f64(ctx, S, ldS, B, D, out, stream):
+    S = _mat(S, B, D, ldS)
+    res = _mat(out, 2, D)
+    mean = S.mean(axis=0)
+    res[0] = mean
+    res[1] = ((S - mean) ** 2).sum(axis=0)
+
+
+def weighted_stats_f64(ctx, x, ldx, w, N, p, stats, stream):
+    x = np.ascontiguousarray(_mat(x, N, p, ldx))
+    w = np.ones(N) if not _addr(w) else _vec(w, N).copy()
+    s = _vec(stats, 2 + 2 * p)
+    s[0] = np.sum(w)
+    s[1] = np.sum(w ** 2)
+    with np.errstate(all='ignore'):
+        s[2:2 + p] = np.average(x, weights=w, axis=0)
+        s[2 + p:] = o.weighted_var(x, w)
+
+
+def gm_logpdf_f64(ctx, x, ldx, N, means, ldm, w, M, p, Linv_host, logdet, logq, stream):
+    x = np.ascontiguousarray(_mat(x, N, p, ldx))
+    means = np.ascontiguousarray(_mat(means, M, p, ldm))
+    Linv = _mat(Linv_host, p, p)
+    L = np.linalg.inv(Linv)
+    weights = None if not _addr(w) else _vec(w, M).copy()
+    _vec(logq, N)[:] = o.gm_logpdf(x, means, L @ L.T, weights)
+
+
+def smc_weights_f64(ctx, logprior, logq, n, w, stream):
+    with np.errstate(all='ignore'):
+        _vec(w, n)[:] = np.exp(_vec(logprior, n) - _vec(logq, n))
+
+
+def rowsort_f64(ctx, X, ldX, B, n, out, ld_out, stream):
+    _require(1 <= n <= 2048, 'rowsort: n outside [1, 2048]')
+    if B:
+        _mat(out, B, n, ld_out)[:] = np.sort(_mat(X, B, n, ldX), axis=1)
+
+
+def kliep_fit_f64(ctx, x, ldx, Nx, y, ldy, Ny, p, wx, wy, sigma, n_basis, epsilon, max_iter,
+                  abs_tol, conv_check_interval, alpha_out, result_host):
+    xm = np.ascontiguousarray(_mat(x, Nx, p, ldx))
+    ym = np.ascontiguousarray(_mat(y, Ny, p, ldy))
+    alpha, max_ratio = o.kliep_fit(
+        xm, ym, None if not _addr(wx) else _vec(wx, Nx).copy(),
+        None if not _addr(wy) else _vec(wy, Ny).copy(), sigma=sigma, n=int(n_basis),
+        epsilon=epsilon, max_iter=int(max_iter), abs_tol=abs_tol,
+        conv_check_interval=int(conv_check_interval))
+    _vec(alpha_out, n_basis)[:] = alpha
+    out = _vec(result_host, 2)
+    out[0] = max_ratio
+    out[1] = -1.0   # the oracle does not count steps
+
+
+_TABLE = {'elfi_b200_' + f.__name__: f for f in (
+    dist_euclid_thr_f64, dist_euclid_thr_f64_host, summary_autocov_f64, summary_meanvar_f64,
+    sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
+    weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64)}
+
+
+def call(name, *args):
+    """Stand-in for elfi_b200._lib.call: same names, same argument lists, host pointers."""
+    fn = _TABLE.get(name)
+    if fn is None:
+        raise _lib.ElfiB200Error('cpu double: {} is not emulated (device-only entry point)'.format(name))
+    if len(args) != len(_lib.SIGNATURES[name]):
+        raise TypeError('{} takes {} arguments, got {}'.format(name, len(_lib.SIGNATURES[name]),
+                                                               len(args)))
+    CALLS.append(name)
+    fn(*args)
+    return 0
+
+
+# ------------------------------------------------------------------------------ device.py side
+def install(monkeypatch):
+    """Patch elfi_b200._lib.call and the allocation helpers of elfi_b200.device (CPU tensors)."""
+    from elfi_b200 import device as dev
+
+    def to_device(x, dtype=torch.float64):
+        if isinstance(x, torch.Tensor):
+            t = x if x.dtype == dtype else x.to(dtype)
+            return t.contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=dev._np_dtype(dtype)).copy())
+
+    monkeypatch.setattr(_lib, 'call', call)
+    monkeypatch.setattr(dev, 'require_cuda', lambda: None)
+    monkeypatch.setattr(dev, 'context', lambda device=None: ctypes.c_void_p(1))
+    monkeypatch.setattr(dev, 'stream_ptr', lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(dev, 'is_device_array', lambda x: isinstance(x, torch.Tensor))
+    monkeypatch.setattr(dev, 'to_device', to_device)
+    monkeypatch.setattr(dev, 'empty', lambda shape, dtype=torch.float64: torch.empty(shape, dtype=dtype))
+    monkeypatch.setattr(dev, 'zeros', lambda shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype))
+    monkeypatch.setattr(dev, 'ones', lambda shape, dtype=torch.float64: torch.ones(shape, dtype=dtype))
+    monkeypatch.setattr(dev, 'full', lambda shape, value, dtype=torch.float64:
+                        torch.full(shape, value, dtype=dtype))
+    del CALLS[:]

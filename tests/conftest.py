@@ -42,3 +42,12 @@ def load_golden(name):
 @pytest.fixture
 def golden():
     return load_golden
+
+
+@pytest.fixture
+def cpu_double(monkeypatch):
+    """Host-logic tests without a GPU: the C ABI is replaced by tests/abi_double.py (NumPy + the
+    oracle on host pointers) and device allocations by CPU tensors.  Test-only; see that module."""
+    import abi_double
+    abi_double.install(monkeypatch)
+    return abi_double

@@ -1,0 +1,93 @@
+"""The N > 1 sampler path end to end on CPU: world_size-2 gloo processes, C ABI replaced by the
+CPU test double (tests/abi_double.py).  Same assertions as tests/mgpu_check.py makes under
+torchrun + NCCL on the GPUs: batch index b runs on rank b % W, one all-gather of the best-n
+buffers per population, Chan-merged AdaptiveDistance moments, sharded mixture density --
+and the result equals a single rank simulating the same batches."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    import abi_double
+    patch = pytest.MonkeyPatch()
+    abi_double.install(patch)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import elfi_b200 as elfi
+    from elfi_b200.examples import ma2
+    gold = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'ma2_rejection_quantile.npz')))
+
+    # Rejection, quantile mode: 10 batches over 2 ranks == the reference's single-process golden
+    m = ma2.get_model(seed_obs=4)
+    res = elfi.Rejection(m['d'], batch_size=1000, seed=123).sample(100, quantile=0.01, bar=False)
+    assert res.n_sim == 10000
+    assert res.threshold == float(gold['threshold'])
+    assert np.array_equal(res.discrepancies, gold['out_d'])
+    assert np.array_equal(res.samples['t1'], gold['out_t1'])
+    assert np.array_equal(res.samples['t2'], gold['out_t2'])
+    # threshold mode stops on a global accepted count; every rank ends with the same sample
+    thr = elfi.Rejection(m['d'], batch_size=500, seed=7).sample(50, threshold=0.2, bar=False)
+    one = elfi.Rejection(m['d'], batch_size=500, seed=7, distributed=False).sample(
+        50, n_sim=thr.n_sim, bar=False)
+    assert np.all(thr.discrepancies <= 0.2) and thr.n_samples == 50
+    assert np.array_equal(np.sort(one.discrepancies)[:10], np.sort(thr.discrepancies)[:10])
+
+    # SMC: round 0 is rank 0 -> batch 0, rank 1 -> batch 1 == single-process round 0
+    single = elfi.SMC(m['d'], batch_size=200, seed=123, distributed=False).sample(
+        200, quantiles=[.5, .5, .5], bar=False)
+    smc = elfi.SMC(m['d'], batch_size=200, seed=123).sample(200, quantiles=[.5, .5, .5], bar=False)
+    for k in ('d', 't1', 't2'):
+        assert np.array_equal(smc.populations[0].outputs[k], single.populations[0].outputs[k]), k
+    means = smc.sample_means_array
+    assert abs(means[0] - 0.6) < 0.25 and abs(means[1] - 0.2) < 0.25, means
+    assert np.all(np.isfinite(smc.weights)) and smc.weights.min() > 0
+    t = [p.threshold for p in smc.populations]
+    assert t[0] > t[1] > t[2]
+
+    # AdaptiveDistanceSMC: per-rank column moments are Chan-merged before the weights update
+    def adaptive(distributed):
+        m2 = ma2.get_model(seed_obs=4)
+        m2['d'].become(elfi.AdaptiveDistance(m2['S1'], m2['S2']))
+        return elfi.AdaptiveDistanceSMC(m2['d'], batch_size=100, seed=11, distributed=distributed
+                                        ).sample(100, rounds=2, quantile=0.5, bar=False)
+    ad1, ad = adaptive(False), adaptive(True)
+    np.testing.assert_allclose(ad.populations[0].adaptive_distance_w,
+                               ad1.populations[0].adaptive_distance_w, rtol=1e-10)
+    for k in ('t1', 't2', 'S1', 'S2'):
+        np.testing.assert_allclose(ad.populations[0].outputs[k], ad1.populations[0].outputs[k],
+                                   rtol=1e-9)
+    assert np.all(np.isfinite(ad.weights)) and len(ad.populations) == 2
+
+    # all ranks hold identical results
+    np.save(os.path.join(out_dir, 'rank{}.npy'.format(rank)),
+            np.concatenate([res.discrepancies, smc.weights, smc.samples_array.ravel(), ad.weights]))
+    dist.barrier()
+    dist.destroy_process_group()
+    patch.undo()
+
+
+def test_world_size_2_samplers_on_cpu_double(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (np.load(os.path.join(str(tmp_path), 'rank{}.npy'.format(r))) for r in range(world))
+    assert np.array_equal(a, b)
