@@ -52,6 +52,12 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def synchronize():
+    """Wait for the work queued on the current stream."""
+    require_cuda()
+    torch.cuda.current_stream().synchronize()
+
+
 def is_device_array(x):
     return isinstance(x, torch.Tensor) and x.is_cuda
 

@@ -422,7 +422,7 @@ def kliep_fit(x, y, weights_x=None, weights_y=None, sigma=1.0, n_basis=100, epsi
     wy = None if weights_y is None else dev.to_device(weights_y).reshape(-1)
     alpha = dev.empty((n_basis,))
     res = (ctypes.c_double * 2)()
-    torch.cuda.current_stream().synchronize()
+    dev.synchronize()   # this entry point runs on its own stream order: inputs must be complete
     _lib.call('elfi_b200_kliep_fit_f64', dev.context(), dev.ptr(x), _ld(x), x.shape[0], dev.ptr(y),
               _ld(y), y.shape[0], x.shape[1], dev.ptr(wx), dev.ptr(wy), float(sigma), int(n_basis),
               float(epsilon), int(max_iter), float(abs_tol), int(conv_check_interval),

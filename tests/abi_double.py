@@ -27,6 +27,8 @@ def _addr(p):
         return 0
     if isinstance(p, ctypes.c_void_p):
         return p.value or 0
+    if isinstance(p, ctypes.Array):
+        return ctypes.addressof(p)
     if isinstance(p, int):
         return p
     raise TypeError('unexpected pointer argument {!r}'.format(p))
@@ -251,6 +253,7 @@ def install(monkeypatch):
     monkeypatch.setattr(dev, 'require_cuda', lambda: None)
     monkeypatch.setattr(dev, 'context', lambda device=None: ctypes.c_void_p(1))
     monkeypatch.setattr(dev, 'stream_ptr', lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(dev, 'synchronize', lambda: None)
     monkeypatch.setattr(dev, 'is_device_array', lambda x: isinstance(x, torch.Tensor))
     monkeypatch.setattr(dev, 'to_device', to_device)
     monkeypatch.setattr(dev, 'empty', lambda shape, dtype=torch.float64: torch.empty(shape, dtype=dtype))
