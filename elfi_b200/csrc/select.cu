@@ -10,6 +10,7 @@
 // (<= 2e6 pairs = 24 MB) are L2 resident, so the sort is latency/issue bound, not HBM bound;
 // passes whose digit is constant over all keys (typical for the high exponent bits of
 // distances) degenerate to a copy.
+#include "eqweight.h"
 #include "pairwise.cuh"
 
 namespace elfi {
@@ -629,6 +630,13 @@ int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w
     double* total = reinterpret_cast<double*>(base + sort_bytes + align256(size_t(n) * 8));
     int rc = sort_pairs_device(x, n, s, ctx->sm_count, stream);
     if (rc) return rc;
+    if (w == nullptr && alpha > 0.0) {
+        // equal weights: the position in NumPy's sequential cumulative sum is known in closed form
+        // (eqweight.h), so neither a scan nor a host round trip is needed
+        wq_pick_kernel<<<1, 1, 0, stream>>>(s.k[0], equal_weight_cum_index(n, alpha) - 1, out);
+        ELFI_CUDA_OK(cudaGetLastError());
+        return ELFI_B200_OK;
+    }
     if (alpha > 0.0 && n > 1) {
         // fast path: parallel scan + error bound; falls through to the exact kernels only when
         // alpha is within eps of a cumulative weight

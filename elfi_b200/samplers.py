@@ -753,6 +753,7 @@ class SMC(Sampler):
             w_dev = None
         means = params
         pop._means_dev = params_dev
+        pop._equal_weights = w_dev is None
         pop._w_dev = w_dev if w_dev is not None else dev.ones((len(params),))
         all_zero = (not bool((w_dev != 0).any())) if w_dev is not None else np.count_nonzero(w) == 0
         if all_zero:
@@ -780,6 +781,8 @@ class SMC(Sampler):
         w_prev = getattr(previous_population, '_w_dev', None)
         if w_prev is None:
             w_prev = previous_population.weights
+        if getattr(previous_population, '_equal_weights', False):
+            w_prev = None   # ones: same arithmetic as weights=None, which has a closed form
         with PHASES('weighted_quantile'):
             threshold = ops.weighted_sample_quantile(d_prev, self._quantiles[self.state['round']],
                                                      w_prev)

@@ -138,7 +138,9 @@ int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA,
  * the selected element is identical even when alpha falls exactly on a cumulative weight
  * (equal weights + round alpha, the normal case in SMC round 0).  A parallel scan with a rigorous
  * error bound answers first; the sequential kernel only runs when alpha is within that bound of a
- * cumulative weight.  The call synchronises `stream`. */
+ * cumulative weight.  With w == NULL the position follows in closed form from n and alpha (the
+ * sequential sum of n copies of 1/n is an arithmetic progression per binade) and nothing is
+ * scanned.  The call synchronises `stream` unless w == NULL. */
 int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w, int64_t n,
                             double alpha, double* out, void* stream);
 
