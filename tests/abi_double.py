@@ -219,10 +219,81 @@ def kliep_fit_f64(ctx, x, ldx, Nx, y, ldy, Ny, p, wx, wy, sigma, n_basis, epsilo
     out[1] = -1.0   # the oracle does not count steps
 
 
+# ---- BOLFI surrogate: SciPy restatement of the factor layout the header documents ----------
+def _gp_factors(L, n, n_pad):
+    import scipy.linalg as sl
+    Lp = np.eye(n_pad)
+    Lp[:n, :n] = L
+    Wp = sl.solve_triangular(Lp, np.eye(n_pad), lower=True)
+    return Lp, Wp
+
+
+def gp_fit_f64(ctx, X, ldX, y, n, p, kernel_var, lengthscale, bias_var, noise_var, L, W, U, n_pad,
+               alpha, info, stream):
+    Xm = np.ascontiguousarray(_mat(X, n, p, ldX))
+    yv = _vec(y, n).copy()
+    info_v = _vec(info, 1, np.int32)
+    K = o.gp_gram(Xm, kernel_var, lengthscale, bias_var) + noise_var * np.eye(n)
+    try:
+        Lc = np.linalg.cholesky(K)
+    except np.linalg.LinAlgError:
+        info_v[0] = 1            # "1 + index of the first bad pivot": any non-zero value raises
+        return
+    info_v[0] = 0
+    import scipy.linalg as sl
+    Lp, Wp = _gp_factors(Lc, n, n_pad)
+    _mat(L, n_pad, n_pad)[:] = Lp
+    _mat(W, n_pad, n_pad)[:] = Wp
+    _mat(U, n_pad, n_pad)[:] = Wp.T
+    _vec(alpha, n)[:] = sl.cho_solve((Lc, True), yv)
+
+
+def _gp_state(X, ldX, n, p, W, n_pad, alpha):
+    Xm = np.ascontiguousarray(_mat(X, n, p, ldX))
+    Wn = _mat(W, n_pad, n_pad)[:n, :n]
+    return Xm, np.linalg.inv(Wn), _vec(alpha, n).copy()[:, None]
+
+
+def gp_predict_f64(ctx, Xq, ldq, m, X, ldX, n, p, W, n_pad, alpha, kernel_var, lengthscale,
+                   bias_var, noise_add, beta, mean, var, acq, stream):
+    Xm, Lc, al = _gp_state(X, ldX, n, p, W, n_pad, alpha)
+    xq = np.ascontiguousarray(_mat(Xq, m, p, ldq))
+    mu, v = o.gp_predict(xq, Xm, Lc, al, kernel_var, lengthscale, bias_var)
+    mu, v = mu.ravel(), v.ravel()
+    if _addr(mean):
+        _vec(mean, m)[:] = mu
+    if _addr(var):
+        _vec(var, m)[:] = v + noise_add
+    if _addr(acq):
+        _vec(acq, m)[:] = o.lcbsc(mu, v, beta)
+
+
+def gp_predict_grad_f64(ctx, Xq, ldq, m, X, ldX, n, p, W, U, n_pad, alpha, kernel_var,
+                        lengthscale, bias_var, mean, var, grad_mean, grad_var, stream):
+    Xm, Lc, al = _gp_state(X, ldX, n, p, W, n_pad, alpha)
+    xq = np.ascontiguousarray(_mat(Xq, m, p, ldq))
+    mu, v = o.gp_predict(xq, Xm, Lc, al, kernel_var, lengthscale, bias_var)
+    gm, gv = o.gp_predictive_gradients(xq, Xm, Lc, al, kernel_var, lengthscale, bias_var)
+    _vec(mean, m)[:] = mu.ravel()
+    _vec(var, m)[:] = v.ravel()
+    _mat(grad_mean, m, p)[:] = gm
+    _mat(grad_var, m, p)[:] = gv
+
+
+def lcbsc_f64(ctx, mean, var, grad_mean, grad_var, m, p, beta, acq, grad_acq, stream):
+    mu, v = _vec(mean, m), _vec(var, m)
+    if _addr(acq):
+        _vec(acq, m)[:] = o.lcbsc(mu, v, beta)
+    if _addr(grad_acq):
+        _mat(grad_acq, m, p)[:] = o.lcbsc_gradient(v[:, None], _mat(grad_mean, m, p),
+                                                   _mat(grad_var, m, p), beta)
+
+
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
     dist_euclid_thr_f64, dist_euclid_thr_f64_host, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
-    weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64)}
+    weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
+    gp_predict_f64, gp_predict_grad_f64, lcbsc_f64)}
 
 
 def call(name, *args):
