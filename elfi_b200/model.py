@@ -98,20 +98,31 @@ def get_sub_seed(seed, sub_seed_index, high=2 ** 31, cache=None):
 
 
 class ComputationContext:
-    """batch_size + seed (+ caches) shared by all batches of one inference
-    (elfi/model/elfi_model.py:126-208; pools are out of scope)."""
+    """batch_size + seed + optional output pool (+ caches) shared by all batches of one inference
+    (elfi/model/elfi_model.py:126-208)."""
 
     def __init__(self, batch_size=None, seed=None, pool=None):
-        if pool is not None:
-            raise NotImplementedError('OutputPool is outside the B200 hot path')
+        if pool is not None and pool.has_context:
+            if batch_size is None:
+                batch_size = pool.batch_size
+            elif batch_size != pool.batch_size:
+                raise ValueError('Pool batch_size differs from the given batch_size!')
+            if seed is None:
+                seed = pool.seed
+            elif seed != pool.seed:
+                raise ValueError('Pool seed differs from the given seed!')
         self.batch_size = batch_size or 1
         self.seed = np.random.RandomState().get_state()[1][1] if seed is None else seed
-        self.pool = None
+        self.pool = pool
         self.caches = {'plan': {}, 'sub_seed': {}}
         self.num_submissions = 0
+        if pool is not None and not pool.has_context:
+            pool.set_context(self)
 
     def callback(self, batch, batch_index):
-        pass
+        """Store the finished batch in the pool (elfi_model.py:196-208)."""
+        if self.pool is not None:
+            self.pool.add_batch(batch, batch_index)
 
 
 # ------------------------------------------------------------------------------------ graph
@@ -396,6 +407,18 @@ def execute_batch(model, outputs, context, batch_index, with_values=None, accept
             values['_random_state'] = np.random.RandomState(sub_seed)
         else:
             raise ValueError("Seed of type {} is not supported".format(seed))
+    # pool (elfi/loader.py:95-129): stored outputs replace their nodes, missing ones are
+    # requested so that the callback can store them when the batch is done
+    outputs = set(net.graph['outputs'])
+    if context.pool is not None:
+        stored = context.pool.get_batch(batch_index)
+        for node in context.pool.stores:
+            if not net.has_node(node):
+                continue
+            if node in stored:
+                values[node] = stored[node]
+            else:
+                outputs.add(node)
     for k, v in (with_values or {}).items():
         if net.has_node(k):
             values[k] = v
@@ -404,7 +427,7 @@ def execute_batch(model, outputs, context, batch_index, with_values=None, accept
             values[node] = attr['output']
 
     # ---- which nodes must run: ancestors of the outputs not cut off by a known value
-    needed = [o for o in net.graph['outputs'] if o not in values]
+    needed = [o for o in outputs if o not in values]
     todo = set()
     stack = list(needed)
     while stack:
@@ -425,7 +448,7 @@ def execute_batch(model, outputs, context, batch_index, with_values=None, accept
             extras[('accepted', node)] = out.accepted
             out = out.value
         values[node] = out
-    result = {k: values[k] for k in net.graph['outputs']}
+    result = {k: values[k] for k in outputs}
     result.update(extras)
     return result
 

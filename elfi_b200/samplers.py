@@ -256,6 +256,11 @@ class ParameterInference:
         return self.computation_context.seed
 
     @property
+    def pool(self):
+        """The output pool of the inference (parameter_inference.py:111-114)."""
+        return self.computation_context.pool
+
+    @property
     def parameter_names(self):
         return self.model.parameter_names
 
@@ -284,6 +289,7 @@ class ParameterInference:
                                  batch_index, with_values=values, accept=self._accept_hint(),
                                  compiled=self._compiled)
         self.computation_context.num_submissions += 1
+        self.computation_context.callback(batch, batch_index)
         return batch
 
     def infer(self, *args, vis=None, bar=True, **kwargs):
