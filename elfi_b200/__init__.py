@@ -14,4 +14,5 @@ from .model import (AdaptiveDistance, Constant, Discrepancy, Distance, ElfiModel
 from .samplers import (SMC, AdaptiveDistanceSMC, AdaptiveThresholdSMC,  # noqa: F401
                        DensityRatioEstimation, GMDistribution, ModelPrior, Rejection)
 from .store import ArrayPool, OutputPool  # noqa: F401
-from .bo import BOLFI, LCBSC, BayesianOptimization, BolfiPosterior, GPyRegression  # noqa: F401
+from .bo import (BOLFI, LCBSC, BayesianOptimization, BolfiPosterior, GPyRegression,  # noqa: F401
+                 MaxVar, RandMaxVar, UniformAcquisition)

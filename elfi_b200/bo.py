@@ -27,10 +27,14 @@ import torch
 
 from . import _lib
 from . import device as dev
-from .results import OptimizationResult
-from .samplers import ModelPrior, ParameterInference
+from . import mcmc
+from .model import get_sub_seed
+from .results import BolfiSample, OptimizationResult
+from .samplers import ModelPrior, ParameterInference, resolve_sigmas
 
 logger = logging.getLogger(__name__)
+
+HYPER_LOG_RANGE = np.log(1e3)   # optimize(): search box half-width in log space
 
 JITTER = 1e-8   # GPy's exact Gaussian inference adds 1e-8 to the diagonal
 
@@ -110,6 +114,7 @@ class GPyRegression:
         # Gamma.from_EV(E, V) with E = V = value -> shape a = E^2/V = E, rate b = E/V = 1
         self._priors = {'lengthscale': (length_scale, 1.0), 'kernel_var': (kernel_var, 1.0),
                         'bias_var': (bias_var, 1.0)}
+        self._hyper_anchor = dict(self._hyper)   # centre of the optimiser's search box
 
     def update(self, x, y, optimize=False):
         """Append evidence and refit (the reference rebuilds the GP on every update, 286-315)."""
@@ -198,6 +203,20 @@ class GPyRegression:
     def predictive_gradient_mean(self, x):
         return self.predictive_gradients(x)[0]
 
+    def predict_with_gradients(self, x, noiseless=False):
+        """mean (m, 1), var (m, 1), grad_mean (m, p), grad_var (m, p) from ONE device call --
+        what predict() + predictive_gradients() return together (the posterior / MaxVar
+        gradients need all four at the same point)."""
+        x = np.asanyarray(dev.to_host(x), dtype=np.float64).reshape((-1, self.input_dim))
+        if self._factor is None:
+            zeros = np.zeros((x.shape[0], self.input_dim))
+            return np.zeros((x.shape[0], 1)), np.ones((x.shape[0], 1)), zeros, zeros.copy()
+        mean, var, gm, gv = self._predict_grad_device(x)
+        var = var.cpu().numpy()[:, None]
+        if not noiseless:
+            var = var + self._factor['hyper']['noise_var']
+        return mean.cpu().numpy()[:, None], var, gm.cpu().numpy(), gv.cpu().numpy()
+
     # ---- hyper-parameters -------------------------------------------------------------------
     def log_marginal_likelihood(self, hyper=None):
         """-1/2 y^T alpha - sum log L_ii - n/2 log 2 pi for the given (or current) hyper-parameters."""
@@ -211,13 +230,20 @@ class GPyRegression:
         """Maximise log marginal likelihood + Gamma log-priors over (kernel_var, lengthscale,
         bias_var, noise_var) in log space.  PARITY UNPINNED w.r.t. GPy's SCG."""
         names = ['kernel_var', 'lengthscale', 'bias_var', 'noise_var']
-        x0 = np.log([self._hyper[k] for k in names])
+        # Search box: three decades either side of the initial heuristics.  The Gamma priors of
+        # the reference have shape < 1 whenever the heuristic variance is < 1, i.e. an unbounded
+        # density at zero; a box tied to the current values would let repeated optimisations walk
+        # a variance down to nothing (the GP then explains all evidence as noise).
+        anchor = getattr(self, '_hyper_anchor', None) or self._hyper
+        centre = np.log([anchor[k] for k in names])
+        box = [(c - HYPER_LOG_RANGE, c + HYPER_LOG_RANGE) for c in centre]
+        x0 = np.clip(np.log([self._hyper[k] for k in names]), [b[0] for b in box],
+                     [b[1] for b in box])
 
         def objective(logh):
             return -self.log_posterior_hyper(dict(zip(names, np.exp(logh))))
         f0 = objective(x0)
-        res = scipy.optimize.minimize(objective, x0, method='L-BFGS-B',
-                                      bounds=[(v - 12.0, v + 12.0) for v in x0],
+        res = scipy.optimize.minimize(objective, x0, method='L-BFGS-B', bounds=box,
                                       options={'maxiter': self.max_opt_iters})
         if np.isfinite(res.fun) and res.fun <= f0:
             self._hyper = dict(zip(names, np.exp(res.x).tolist()))
@@ -394,6 +420,140 @@ class LCBSC(AcquisitionBase):
         return value
 
 
+class MaxVar(AcquisitionBase):
+    """Acquire where the variance of the unnormalised approximate posterior
+    prior(theta)^2 * Var[Phi((eps - f(theta)) / sigma_n)] is largest (Jarvenpaa et al. 2019;
+    elfi/methods/bo/acquisition.py:304-469).  eps is the `quantile_eps` quantile of the evidence
+    discrepancies.  The GP moments and their gradients at a point come from one device call."""
+
+    def __init__(self, model, prior, quantile_eps=.01, **opts):
+        super().__init__(model, prior=prior, **opts)
+        self.name = 'max_var'
+        self.label_fn = 'Variance of the Unnormalised Approximate Posterior'
+        self.quantile_eps = quantile_eps
+        self.eps = .1   # until the first acquire(): the GP is not fitted yet
+
+    def _update_eps(self):
+        self.eps = np.percentile(self.model.Y, self.quantile_eps * 100)
+
+    def acquire(self, n, t=None):
+        logger.debug('Acquiring the next batch of %d values', n)
+        self._update_eps()
+        theta_max, _ = minimize(lambda theta: -self.evaluate(theta), self.model.bounds,
+                                grad=lambda theta: -self.evaluate_gradient(theta),
+                                prior=self.prior, n_start_points=self.n_inits,
+                                maxiter=self.max_opt_iters, random_state=self.random_state)
+        return np.tile(theta_max, (n, 1))   # the same location for the whole batch
+
+    def _gp(self, theta):
+        theta = np.asanyarray(theta, dtype=float).reshape((-1, self.model.input_dim))
+        if hasattr(self.model, 'predict_with_gradients'):
+            return (theta,) + tuple(self.model.predict_with_gradients(theta, noiseless=True))
+        return (theta,) + tuple(self.model.predict(theta, noiseless=True)) + \
+            tuple(self.model.predictive_gradients(theta))
+
+    def evaluate(self, theta_new, t=None):
+        """Var[p_a] = Phi_skew(eps) - Phi(eps)^2: a skew-normal cdf stands in for Owen's T."""
+        theta, mean, var = self._gp(theta_new)[:3]
+        sigma2_n = self.model.noise
+        skew = np.sqrt(sigma2_n) / np.sqrt(sigma2_n + 2. * var)
+        scale = np.sqrt(sigma2_n + var)
+        var_p_a = ss.skewnorm.cdf(self.eps, skew, loc=mean, scale=scale) \
+            - ss.norm.cdf(self.eps, loc=mean, scale=scale) ** 2
+        prior = self.prior.pdf(theta_new).ravel()[:, np.newaxis]
+        return prior ** 2 * var_p_a
+
+    def evaluate_gradient(self, theta_new, t=None):
+        theta, mean, var, grad_mean, grad_var = self._gp(theta_new)
+        sigma2_n = self.model.noise
+        phi = ss.norm.cdf
+        scale = np.sqrt(sigma2_n + var)
+        a = (self.eps - mean) / scale
+        b = np.sqrt(sigma2_n) / np.sqrt(sigma2_n + 2 * var)
+        grad_a = (-1. / scale) * grad_mean \
+            - ((self.eps - mean) / (2. * (sigma2_n + var) ** 1.5)) * grad_var
+        grad_b = (-np.sqrt(sigma2_n) / (sigma2_n + 2 * var) ** 1.5) * grad_var
+        phi_a = phi(a)
+        gauss_a = np.exp(-.5 * a ** 2)
+        int_1 = phi_a - phi_a ** 2
+        int_2 = phi(self.eps, loc=mean, scale=scale) \
+            - ss.skewnorm.cdf(self.eps, b, loc=mean, scale=scale)
+        grad_int_1 = (1. - 2 * phi_a) * (gauss_a / np.sqrt(2. * np.pi)) * grad_a
+        grad_int_2 = (1. / np.pi) * (
+            (np.exp(-.5 * a ** 2 * (1. + b ** 2)) / (1. + b ** 2)) * grad_b
+            + np.sqrt(np.pi / 2.) * gauss_a * (1. - 2. * phi(a * b)) * grad_a)
+        prior = self.prior.pdf(theta_new).ravel()[:, np.newaxis]
+        grad_prior = prior * self.prior.gradient_logpdf(theta_new)   # f' = (log f)' f
+        return 2. * prior * (int_1 - int_2) * grad_prior + prior ** 2 * (grad_int_1 - grad_int_2)
+
+
+class RandMaxVar(MaxVar):
+    """Sample the next point from the MaxVar surface, treated as an unnormalised density, with a
+    short MCMC chain (acquisition.py:472-626)."""
+
+    def __init__(self, model, prior, quantile_eps=.01, sampler='nuts', n_samples=50, warmup=None,
+                 limit_faulty_init=1000, init_from_prior=False, sigma_proposals=None, **opts):
+        super().__init__(model, prior, quantile_eps, **opts)
+        self.name = 'rand_max_var'
+        self.name_sampler = sampler
+        self._n_samples = n_samples
+        self._warmup = warmup or n_samples // 2
+        self._limit_faulty_init = limit_faulty_init
+        self._init_from_prior = init_from_prior
+        if self.name_sampler == 'metropolis':
+            self._sigma_proposals = resolve_sigmas(self.model.parameter_names, sigma_proposals,
+                                                   self.model.bounds)
+
+    def _initial_point(self):
+        bounds = self.model.bounds
+        if self._init_from_prior:
+            theta = self.prior.rvs(random_state=self.random_state)
+            return np.array([np.clip(theta[i], lo, hi) for i, (lo, hi) in enumerate(bounds)])
+        return np.array([self.random_state.uniform(lo, hi) for lo, hi in bounds])
+
+    def acquire(self, n, t=None):
+        if n > self._n_samples:
+            raise ValueError(("The number of acquisitions ({0}) has to be lower than the number "
+                              "of the samples ({1}).").format(n, self._n_samples - self._warmup))
+        logger.debug('Acquiring the next batch of %d values', n)
+        self._update_eps()
+
+        def logpdf(theta):
+            value = float(np.ravel(self.evaluate(theta))[0])
+            return -np.inf if value == 0 else np.log(value)
+
+        def gradient_logpdf(theta):
+            value = float(np.ravel(self.evaluate(theta))[0])
+            return -np.inf if value == 0 else (self.evaluate_gradient(theta) / value).ravel()
+
+        for _ in range(self._limit_faulty_init):
+            theta_init = self._initial_point()
+            if not np.isinf(logpdf(theta_init)):
+                break
+        else:
+            raise SystemExit("Unable to find a suitable initial point.")
+        if self.name_sampler == 'metropolis':
+            samples = mcmc.metropolis(self._n_samples, theta_init, logpdf,
+                                      sigma_proposals=self._sigma_proposals, seed=self.seed)
+        elif self.name_sampler == 'nuts':
+            samples = mcmc.nuts(self._n_samples, theta_init, logpdf, gradient_logpdf,
+                                seed=self.seed)
+        else:
+            raise ValueError("Incompatible sampler. Please check the options in the documentation.")
+        if n > 1:
+            return self.random_state.permutation(samples[self._warmup:])[:n]
+        return samples[-1:]
+
+
+class UniformAcquisition(AcquisitionBase):
+    """Uniform draws inside the GP bounds (acquisition.py:824-845)."""
+
+    def acquire(self, n, t=None):
+        bounds = np.stack(self.model.bounds)
+        return ss.uniform(bounds[:, 0], bounds[:, 1] - bounds[:, 0]).rvs(
+            size=(n, self.model.input_dim), random_state=self.random_state)
+
+
 # ------------------------------------------------------------------------------------ BO loop
 def ceil_to_batch_size(num, batch_size):
     return int(batch_size * ceil(num / batch_size))
@@ -511,37 +671,86 @@ class BayesianOptimization(ParameterInference):
 
 
 class BolfiPosterior:
-    """Unnormalised BOLFI posterior  prior(x) * Phi((h - mu(x)) / sigma(x))
-    (elfi/methods/posteriors.py:21-189; logpdf / pdf / unnormalised likelihood only)."""
+    """Unnormalised BOLFI posterior  prior(x) * Phi((h - mu(x)) / sigma(x))  with the GP mean and
+    the noisy GP standard deviation (elfi/methods/posteriors.py:21-189).  Zero outside the GP
+    bounds.  logpdf and gradient_logpdf at the same point share one device call."""
 
     def __init__(self, model, threshold=None, prior=None, n_inits=10, max_opt_iters=1000, seed=0):
         self.model = model
         self.threshold = threshold
         self.prior = prior
         self.dim = self.model.input_dim
-        if self.threshold is None:
-            def fun_1d(x):
-                return self.model.predict_mean(x).ravel()
-            res = scipy.optimize.differential_evolution(func=fun_1d, bounds=self.model.bounds,
-                                                        maxiter=1000, polish=True,
-                                                        init='latinhypercube', seed=seed)
-            self.threshold = float(res.fun)
+        self.random_state = np.random.RandomState(seed)
+        self.n_inits = n_inits
+        self.max_opt_iters = max_opt_iters
+        self._memo = (None, None)
+        if self.threshold is None:   # minimum of the GP mean (posteriors.py:62-73)
+            _, minval = minimize(self.model.predict_mean, self.model.bounds,
+                                 grad=self.model.predictive_gradient_mean, prior=self.prior,
+                                 n_start_points=self.n_inits, maxiter=self.max_opt_iters,
+                                 random_state=self.random_state)
+            self.threshold = minval
+            logger.info("Using optimized minimum value (%.4f) of the GP discrepancy mean "
+                        "function as a threshold" % (self.threshold))
+
+    def rvs(self, size=None, random_state=None):
+        raise NotImplementedError('Currently not implemented. Please use a sampler to '
+                                  'sample from the posterior.')
+
+    # ---- GP moments at the points inside the bounds -------------------------------------------
+    def _rows(self, x):
+        x = np.asanyarray(x)
+        scalar = x.ndim == 0 or (x.ndim == 1 and self.dim > 1)
+        return x.reshape((-1, self.dim)), scalar
+
+    def _within_bounds(self, x):
+        x = x.reshape((-1, self.dim))
+        lo = np.array([b[0] for b in self.model.bounds])
+        hi = np.array([b[1] for b in self.model.bounds])
+        return np.all((x >= lo) & (x <= hi), axis=1)
+
+    def _moments(self, x):
+        key = x.tobytes()
+        if self._memo[0] != key:
+            if hasattr(self.model, 'predict_with_gradients'):
+                out = self.model.predict_with_gradients(x)
+            else:
+                out = self.model.predict(x) + self.model.predictive_gradients(x)
+            self._memo = (key, out)
+        return self._memo[1]
 
     def _unnormalized_loglikelihood(self, x):
-        x = np.asanyarray(x)
-        ndim = x.ndim
-        x = x.reshape((-1, self.dim))
-        mean, var = self.model.predict(x, noiseless=True)
-        logpdf = ss.norm.logcdf(self.threshold, mean, np.sqrt(var)).squeeze()
-        if ndim == 0 or (ndim == 1 and self.dim > 1):
-            logpdf = logpdf[0] if np.ndim(logpdf) else logpdf
-        return logpdf
+        x, scalar = self._rows(x)
+        logpdf = np.full(len(x), -np.inf)
+        inside = self._within_bounds(x)
+        if inside.any():
+            mean, var = self._moments(np.ascontiguousarray(x[inside]))[:2]
+            logpdf[inside] = ss.norm.logcdf(self.threshold, mean, np.sqrt(var)).squeeze()
+        return logpdf[0] if scalar else logpdf
+
+    def _gradient_unnormalized_loglikelihood(self, x):
+        x, scalar = self._rows(x)
+        grad = np.zeros_like(x, dtype=float)
+        inside = self._within_bounds(x)
+        if inside.any():
+            mean, var, grad_mean, grad_var = self._moments(np.ascontiguousarray(x[inside]))
+            std = np.sqrt(var)
+            z = (self.threshold - mean) / std
+            dz = (-grad_mean * std - (self.threshold - mean) * 0.5 * grad_var / std) / var
+            grad[inside, :] = dz * ss.norm.pdf(z) / ss.norm.cdf(z)
+        return grad[0] if scalar else grad
 
     def logpdf(self, x):
         return self._unnormalized_loglikelihood(x) + self.prior.logpdf(x)
 
     def pdf(self, x):
         return np.exp(self.logpdf(x))
+
+    def gradient_logpdf(self, x):
+        return self._gradient_unnormalized_loglikelihood(x) + self.prior.gradient_logpdf(x)
+
+    def _unnormalized_likelihood(self, x):
+        return np.exp(self._unnormalized_loglikelihood(x))
 
 
 class BOLFI(BayesianOptimization):
@@ -558,3 +767,52 @@ class BOLFI(BayesianOptimization):
             raise ValueError('Model is not fitted yet, please see the `fit` method.')
         prior = ModelPrior(self.model, parameter_names=self.target_model.parameter_names)
         return BolfiPosterior(self.target_model, threshold=threshold, prior=prior)
+
+    def sample(self, n_samples, warmup=None, n_chains=4, threshold=None, initials=None,
+               algorithm='nuts', sigma_proposals=None, n_evidence=None, **kwargs):
+        """Draw from the BOLFI posterior with `n_chains` NUTS (default) or Metropolis chains of
+        `n_samples` iterations each, warm-up included (bolfi.py:464-598).  Chains start from the
+        evidence points with the smallest discrepancies unless `initials` (n_chains, n_params) is
+        given; chain i is seeded with get_sub_seed(seed, i).  Returns a BolfiSample."""
+        if self.state['n_batches'] == 0:
+            self.fit(n_evidence)
+        if algorithm not in ['nuts', 'metropolis']:
+            raise ValueError("Unknown posterior sampler.")
+        posterior = self.extract_posterior(threshold)
+        warmup = warmup or n_samples // 2
+        if initials is not None:
+            if np.asarray(initials).shape != (n_chains, self.target_model.input_dim):
+                raise ValueError("The shape of initials must be (n_chains, n_params).")
+            initials = np.asarray(initials, dtype=float)
+        else:
+            initials = np.asarray(self.target_model.X[np.argsort(self.target_model.Y[:, 0])])
+        if algorithm == 'metropolis':
+            sigma_proposals = resolve_sigmas(self.target_model.parameter_names, sigma_proposals,
+                                             self.target_model.bounds)
+        chains = []
+        start = 0
+        for chain in range(n_chains):
+            seed = get_sub_seed(self.seed, chain)
+            while np.isinf(posterior.logpdf(initials[start])):   # skip zero-density starts
+                start += 1
+                if start == len(initials):
+                    raise ValueError(
+                        "BOLFI.sample: Cannot find enough acceptable initialization points!")
+            if algorithm == 'nuts':
+                chains.append(mcmc.nuts(n_samples, initials[start], posterior.logpdf,
+                                        posterior.gradient_logpdf, n_adapt=warmup, seed=seed,
+                                        **kwargs))
+            else:
+                chains.append(mcmc.metropolis(n_samples, initials[start], posterior.logpdf,
+                                              sigma_proposals, warmup, seed=seed, **kwargs))
+            start += 1
+        chains = np.asarray(chains)
+        logger.info("{} chains of {} iterations acquired. Effective sample size and Rhat for each "
+                    "parameter:".format(n_chains, n_samples))
+        for i, name in enumerate(self.target_model.parameter_names):
+            logger.info("{} {} {}".format(name, mcmc.eff_sample_size(chains[:, :, i]),
+                                          mcmc.gelman_rubin_statistic(chains[:, :, i])))
+        return BolfiSample(method_name='BOLFI', chains=chains,
+                           parameter_names=self.target_model.parameter_names, warmup=warmup,
+                           threshold=float(posterior.threshold), n_sim=self.state['n_evidence'],
+                           seed=self.seed)

@@ -97,3 +97,16 @@ class SmcSample(Sample):
     @property
     def n_populations(self):
         return len(self.populations)
+
+
+class BolfiSample(Sample):
+    """Posterior draws of BOLFI.sample: `chains` is (n_chains, n_samples, n_parameters) with the
+    warm-up iterations included; `samples` holds the post-warm-up draws of all chains
+    (elfi/methods/results.py:507-543)."""
+
+    def __init__(self, method_name, chains, parameter_names, warmup, **meta):
+        chains = np.array(chains, copy=True)
+        kept = chains[:, warmup:, :].reshape((-1,) + chains.shape[2:])
+        outputs = {name: kept[:, i] for i, name in enumerate(parameter_names)}
+        super().__init__(method_name=method_name, outputs=outputs, parameter_names=parameter_names,
+                         chains=chains, n_chains=chains.shape[0], warmup=warmup, **meta)

@@ -111,6 +111,33 @@ class Comm:
 
 
 # -------------------------------------------------------------------------------- prior, GM
+def numgrad(fn, x, h=None, replace_neg_inf=True):
+    """Central-difference gradient of a scalar function at one point
+    (elfi/methods/utils.py:275-314): the 3 * dim points x + (-1, 0, 1) h e_i go to `fn` in one
+    call; if any value is -inf (a log density outside its support) the gradient is zero."""
+    h = np.asanyarray(0.00001 if h is None else h, dtype=float).reshape(-1)
+    x = np.asanyarray(x, dtype=float).reshape(-1)
+    dim = len(x)
+    offsets = (np.arange(3) - 1.0)[:, None, None] * (np.eye(dim) * h)[None, :, :]
+    f = np.asarray(fn((x + offsets).reshape(3 * dim, dim))).reshape((3, dim))
+    if replace_neg_inf and np.any(np.isneginf(f)):
+        return np.zeros(dim)
+    return np.gradient(f, *h, axis=0)[1, :]
+
+
+def resolve_sigmas(parameter_names, sigma_proposals=None, bounds=None):
+    """Proposal standard deviations in parameter order (elfi/methods/utils.py:460-503): a dict
+    keyed by parameter name, or by default a tenth of each bound interval."""
+    if sigma_proposals is None:
+        return [(hi - lo) / 10 for lo, hi in bounds]
+    if isinstance(sigma_proposals, dict):
+        if set(sigma_proposals) != set(parameter_names):
+            raise ValueError("sigma_proposals' keys have to be identical to "
+                             "target_model.parameter_names.")
+        return [sigma_proposals[name] for name in parameter_names]
+    raise ValueError("If provided, sigma_proposals need to be input as a dict.")
+
+
 class ModelPrior:
     """Joint prior of the model parameters (elfi/model/extensions.py:120-245): logpdf is the sum
     of each parameter node's distribution.logpdf(x_node, *parent values), evaluated through the
@@ -156,6 +183,18 @@ class ModelPrior:
 
     def logpdf(self, x):
         return self._evaluate(x, True)
+
+    def gradient_logpdf(self, x, stepsize=None):
+        """Central-difference gradient of the joint log prior, row by row; zero where it is not
+        finite, e.g. outside the support (elfi/model/extensions.py:217-242)."""
+        x = np.asanyarray(x)
+        ndim = x.ndim
+        x = x.reshape((-1, self.dim))
+        grads = np.array([numgrad(self.logpdf, row, h=stepsize) for row in x]).reshape(x.shape)
+        grads[~np.isfinite(grads)] = 0
+        if ndim == 0 or (ndim == 1 and self.dim > 1):
+            grads = grads[0]
+        return grads
 
     def rvs(self, size=None, random_state=None):
         random_state = np.random if random_state is None else random_state

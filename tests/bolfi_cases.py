@@ -1,0 +1,125 @@
+"""Bodies of the BOLFI posterior / acquisition / sampling tests, shared by the CPU-double and
+GPU collections.  Goldens: tests/golden/bolfi_posterior.npz (reference formulas on a duck GP
+backed by the oracle; generator tests/golden/gen_golden_bolfi.py)."""
+import numpy as np
+
+from conftest import load_golden
+
+RTOL = 1e-5   # north_star tolerance for GP posterior quantities
+
+
+def _fixture_gp():
+    from elfi_b200.bo import GPyRegression
+    g = load_golden('bolfi_posterior')
+    names = ['t1', 't2']
+    gp = GPyRegression(names, bounds={'t1': (-2, 2), 't2': (-1, 1)})
+    gp.update(g['X'], g['y'][:, None])
+    gp._hyper = dict(zip(('kernel_var', 'lengthscale', 'bias_var', 'noise_var'),
+                         (float(v) for v in g['hyper'])))
+    gp._fit()
+    return g, gp
+
+
+def _prior():
+    from elfi_b200.examples import ma2
+    from elfi_b200.samplers import ModelPrior
+    return ModelPrior(ma2.get_model(seed_obs=4))
+
+
+def case_prior_gradient():
+    g = load_golden('bolfi_posterior')
+    prior = _prior()
+    with np.errstate(all='ignore'):
+        got = prior.gradient_logpdf(g['pts'])
+        np.testing.assert_allclose(prior.logpdf(g['pts']), g['prior_logpdf'], rtol=1e-12)
+    np.testing.assert_allclose(got, g['prior_grad'], rtol=1e-9, atol=1e-12)
+    assert prior.gradient_logpdf(g['pts'][1]).shape == (2,)
+
+
+def case_posterior_matches_reference():
+    from elfi_b200.bo import BolfiPosterior
+    g, gp = _fixture_gp()
+    post = BolfiPosterior(gp, threshold=float(g['threshold']), prior=_prior())
+    with np.errstate(all='ignore'):
+        loglik = post._unnormalized_loglikelihood(g['pts'])
+        gradlik = post._gradient_unnormalized_loglikelihood(g['pts'])
+        logpdf = post.logpdf(g['pts'])
+        grad = post.gradient_logpdf(g['pts'])
+    fin = np.isfinite(g['loglik'])
+    assert np.array_equal(np.isfinite(loglik), fin)            # -inf outside the GP bounds
+    np.testing.assert_allclose(loglik[fin], g['loglik'][fin], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(gradlik, g['gradlik'], rtol=1e-4, atol=1e-7)
+    fin = np.isfinite(g['logpdf'])
+    assert np.array_equal(np.isfinite(logpdf), fin)            # and outside the prior support
+    np.testing.assert_allclose(logpdf[fin], g['logpdf'][fin], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(grad, g['grad'], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(post.logpdf(g['pts'][1]), float(g['single_logpdf']), rtol=RTOL)
+    np.testing.assert_allclose(post.gradient_logpdf(g['pts'][1]), g['single_grad'], rtol=1e-4,
+                               atol=1e-7)
+    assert np.ndim(post.logpdf(g['pts'][1])) == 0 and post.gradient_logpdf(g['pts'][1]).shape == (2,)
+    # default threshold: minimum of the GP mean found by the multi-start minimiser
+    post_default = BolfiPosterior(gp, prior=_prior(), seed=0)
+    np.testing.assert_allclose(post_default.threshold, float(g['default_threshold']), rtol=1e-4)
+
+
+def case_maxvar_matches_reference():
+    from elfi_b200.bo import MaxVar
+    g, gp = _fixture_gp()
+    acq = MaxVar(model=gp, prior=_prior(), quantile_eps=0.05, noise_var=0.1, seed=1)
+    acq._update_eps()
+    np.testing.assert_allclose(acq.eps, float(g['maxvar_eps']), rtol=1e-12)
+    got = acq.evaluate(g['maxvar_pts'])
+    assert got.shape == g['maxvar'].shape
+    np.testing.assert_allclose(got, g['maxvar'], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(acq.evaluate_gradient(g['maxvar_pts']), g['maxvar_grad'], rtol=1e-3,
+                               atol=1e-9)
+    x = acq.acquire(3)
+    assert x.shape == (3, 2) and np.all(x[0] == x[1])
+    assert -2 <= x[0, 0] <= 2 and -1 <= x[0, 1] <= 1
+    assert acq.evaluate(x[:1])[0, 0] >= got.max() * 0.999      # a maximiser beats the probe points
+
+
+def case_other_acquisitions():
+    from elfi_b200.bo import RandMaxVar, UniformAcquisition
+    g, gp = _fixture_gp()
+    u = UniformAcquisition(model=gp, seed=3).acquire(500)
+    assert u.shape == (500, 2) and u[:, 0].min() >= -2 and u[:, 0].max() <= 2
+    assert np.abs(u[:, 1]).max() <= 1 and abs(u[:, 0].mean()) < 0.3
+    for sampler in ('nuts', 'metropolis'):
+        acq = RandMaxVar(model=gp, prior=_prior(), quantile_eps=0.05, sampler=sampler,
+                         n_samples=30, seed=2)
+        x = acq.acquire(1)
+        assert x.shape == (1, 2) and np.isfinite(x).all() and acq.evaluate(x)[0, 0] > 0
+        xs = acq.acquire(4)
+        assert xs.shape == (4, 2)
+
+
+def case_bolfi_sample():
+    """BOLFI.fit + sample on MA2 (tests/functional/test_inference.py:136-190 of the reference,
+    shortened): chains stay inside the bounds and concentrate near the true parameters."""
+    import elfi_b200 as elfi
+    from elfi_b200.examples import ma2
+    m = ma2.get_model(seed_obs=4)
+    log_d = elfi.Operation(np.log, m['d'], name='log_d')
+    bolfi = elfi.BOLFI(log_d, batch_size=5, initial_evidence=30, update_interval=10,
+                       bounds={'t1': (-2, 2), 't2': (-1, 1)}, acq_noise_var=0.1, seed=1)
+    bolfi.fit(n_evidence=80, bar=False)
+    res = bolfi.sample(200, n_chains=2, info_freq=1000)
+    assert res.chains.shape == (2, 200, 2) and res.n_chains == 2 and res.warmup == 100
+    assert res.samples_array.shape == (200, 2) and res.n_sim == 80
+    assert np.all(np.abs(res.samples['t1']) <= 2) and np.all(np.abs(res.samples['t2']) <= 1)
+    means = res.sample_means_array
+    assert abs(means[0] - 0.6) < 0.6 and abs(means[1] - 0.2) < 0.6, means
+    again = bolfi.sample(200, n_chains=2, info_freq=1000)
+    assert np.array_equal(again.chains, res.chains)            # seeded by get_sub_seed(seed, chain)
+    met = bolfi.sample(300, n_chains=2, algorithm='metropolis', sigma_proposals={'t1': 0.3, 't2': 0.2})
+    assert met.chains.shape == (2, 300, 2) and met.samples_array.shape == (300, 2)
+    init = np.array([[0.5, 0.1], [0.7, 0.3], [0.4, 0.2]])
+    custom = bolfi.sample(60, n_chains=3, initials=init, threshold=float(res.threshold))
+    assert custom.chains.shape == (3, 60, 2)
+    for bad in (dict(algorithm='gibbs'), dict(initials=init[:2], n_chains=3)):
+        try:
+            bolfi.sample(10, **bad)
+        except ValueError:
+            continue
+        raise AssertionError('expected ValueError for {}'.format(bad))
