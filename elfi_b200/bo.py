@@ -752,6 +752,14 @@ class BolfiPosterior:
     def _unnormalized_likelihood(self, x):
         return np.exp(self._unnormalized_loglikelihood(x))
 
+    def logpdf_and_gradient(self, x, with_grad=True):
+        """logpdf (k,) and gradient_logpdf (k, dim) of k points from one device call: the batched
+        evaluator of mcmc.run_lockstep (all chains of BOLFI.sample advance together)."""
+        x = np.ascontiguousarray(np.asanyarray(x, dtype=float).reshape((-1, self.dim)))
+        logpdf = np.atleast_1d(self.logpdf(x))
+        grad = np.atleast_2d(self.gradient_logpdf(x)) if with_grad else None   # moments memoised
+        return logpdf, grad
+
 
 class BOLFI(BayesianOptimization):
     """Bayesian optimisation for likelihood-free inference (bolfi.py:400-462)."""
@@ -773,7 +781,9 @@ class BOLFI(BayesianOptimization):
         """Draw from the BOLFI posterior with `n_chains` NUTS (default) or Metropolis chains of
         `n_samples` iterations each, warm-up included (bolfi.py:464-598).  Chains start from the
         evidence points with the smallest discrepancies unless `initials` (n_chains, n_params) is
-        given; chain i is seeded with get_sub_seed(seed, i).  Returns a BolfiSample."""
+        given; chain i is seeded with get_sub_seed(seed, i).  `lockstep=False` runs the chains one
+        after the other like the reference's client does; the draws are the same either way (a
+        chain owns its RandomState).  Returns a BolfiSample."""
         if self.state['n_batches'] == 0:
             self.fit(n_evidence)
         if algorithm not in ['nuts', 'metropolis']:
@@ -789,7 +799,8 @@ class BOLFI(BayesianOptimization):
         if algorithm == 'metropolis':
             sigma_proposals = resolve_sigmas(self.target_model.parameter_names, sigma_proposals,
                                              self.target_model.bounds)
-        chains = []
+        lockstep = kwargs.pop('lockstep', True)
+        coroutines = []
         start = 0
         for chain in range(n_chains):
             seed = get_sub_seed(self.seed, chain)
@@ -799,13 +810,20 @@ class BOLFI(BayesianOptimization):
                     raise ValueError(
                         "BOLFI.sample: Cannot find enough acceptable initialization points!")
             if algorithm == 'nuts':
-                chains.append(mcmc.nuts(n_samples, initials[start], posterior.logpdf,
-                                        posterior.gradient_logpdf, n_adapt=warmup, seed=seed,
-                                        **kwargs))
+                coroutines.append(mcmc.nuts_chain(n_samples, initials[start], n_adapt=warmup,
+                                                  seed=seed, **kwargs))
             else:
-                chains.append(mcmc.metropolis(n_samples, initials[start], posterior.logpdf,
-                                              sigma_proposals, warmup, seed=seed, **kwargs))
+                coroutines.append(mcmc.metropolis_chain(n_samples, initials[start],
+                                                        sigma_proposals, warmup, seed=seed,
+                                                        **kwargs))
             start += 1
+        if lockstep:
+            # all chains advance together: every round of pending density / gradient requests is
+            # answered by one batched GP call instead of one call per chain and point
+            chains = mcmc.run_lockstep(coroutines, posterior.logpdf_and_gradient)
+        else:
+            chains = [mcmc._run_single(c, posterior.logpdf, posterior.gradient_logpdf)
+                      for c in coroutines]
         chains = np.asarray(chains)
         logger.info("{} chains of {} iterations acquired. Effective sample size and Rhat for each "
                     "parameter:".format(n_chains, n_samples))

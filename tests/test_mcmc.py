@@ -83,3 +83,38 @@ def test_nuts_recovers_the_target_moments():
     kept = chain[500:]
     assert np.all(np.abs(kept.mean(axis=0) - MEAN) < 0.15)
     assert np.all(np.abs(np.cov(kept.T) - np.array([[1.0, 0.6], [0.6, 0.8]])) < 0.25)
+
+
+def test_lockstep_driver_equals_sequential_chains():
+    """run_lockstep answers the pending requests of all chains with one batched evaluation per
+    round; every chain still visits exactly the points it visits when run alone."""
+    from elfi_b200 import mcmc
+    calls = []
+
+    def evaluate(X, with_grad):
+        calls.append((len(X), with_grad))
+        return (np.array([boxed_logpdf(x) for x in X]),
+                np.array([boxed_grad(x) for x in X]) if with_grad else None)
+
+    starts = [np.array([1.5, 0.5]), np.array([0.0, 0.0]), np.array([-0.5, 0.8]), np.array([1.0, -0.5])]
+    alone = [mcmc.nuts(120, s0, boxed_logpdf, boxed_grad, n_adapt=40, seed=30 + i)
+             for i, s0 in enumerate(starts)]
+    together = mcmc.run_lockstep([mcmc.nuts_chain(120, s0, n_adapt=40, seed=30 + i)
+                                  for i, s0 in enumerate(starts)], evaluate)
+    for a, b in zip(alone, together):
+        assert np.array_equal(a, b)
+    n_points = sum(k for k, _ in calls)
+    assert max(k for k, _ in calls) == 4 and len(calls) < 0.5 * n_points    # rounds are shared
+    # Metropolis never asks for gradients
+    calls.clear()
+    alone = [mcmc.metropolis(200, s0, boxed_logpdf, np.array([0.3, 0.2]), warmup=20, seed=i)
+             for i, s0 in enumerate(starts)]
+    together = mcmc.run_lockstep([mcmc.metropolis_chain(200, s0, np.array([0.3, 0.2]), warmup=20,
+                                                        seed=i) for i, s0 in enumerate(starts)],
+                                 evaluate)
+    for a, b in zip(alone, together):
+        assert np.array_equal(a, b)
+    assert not any(g for _, g in calls) and len(calls) == 221
+    # a chain that fails raises through the driver
+    with pytest.raises(ValueError):
+        mcmc.run_lockstep([mcmc.nuts_chain(10, np.array([9.0, 9.0]))], evaluate)
