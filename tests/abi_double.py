@@ -289,11 +289,114 @@ def lcbsc_f64(ctx, mean, var, grad_mean, grad_var, m, p, beta, acq, grad_acq, st
                                                    _mat(grad_var, m, p), beta)
 
 
+# ---- throughput mode: statistical stand-ins (NumPy RandomState instead of the device's Philox
+# streams; same distributions, deterministic in (seed, offset), not sharding invariant) ---------
+def _rs(seed, offset, salt=0):
+    return np.random.RandomState((int(seed) * 1000003 + int(offset) * 7919 + salt) % (2 ** 32))
+
+
+def prior_ma2_f64(ctx, B, seed, offset, mode, t1, t2, stream):
+    from elfi_b200.examples import ma2 as ex
+    rs = _rs(seed, offset, 1)
+    if mode in (0, 1):
+        _vec(t1, B)[:] = ex.CustomPrior1.rvs(2, size=B, random_state=rs)
+    if mode in (0, 2):
+        _vec(t2, B)[:] = ex.CustomPrior2.rvs(_vec(t1, B).copy(), 1, size=B, random_state=rs)
+
+
+def logprior_ma2_f64(ctx, x, ldx, B, out, stream):
+    from elfi_b200.examples import ma2 as ex
+    xm = _mat(x, B, 2, ldx)
+    with np.errstate(all='ignore'):
+        _vec(out, B)[:] = ex.CustomPrior1.logpdf(xm[:, 0], 2) + ex.CustomPrior2.logpdf(
+            xm[:, 1], xm[:, 0], 1)
+
+
+def sim_ma2_f64(ctx, t1, t2, B, n_obs, seed, offset, X, ldX, S, ldS, stream):
+    from elfi_b200.examples import ma2 as ex
+    x = ex.MA2(_vec(t1, B).copy(), _vec(t2, B).copy(), n_obs=n_obs, batch_size=B,
+               random_state=_rs(seed, offset, 2))
+    if _addr(X):
+        _mat(X, B, n_obs, ldX)[:] = x
+    if _addr(S):
+        out = _mat(S, B, 2, ldS)
+        out[:, 0] = o.autocov(x, 1)
+        out[:, 1] = o.autocov(x, 2)
+
+
+def gm_rvs_f64(ctx, means, ldm, weights, N, p, Lchol_host, B, seed, offset, support, box_host, out,
+               ldo, stream):
+    from elfi_b200.examples import ma2 as ex
+    rs = _rs(seed, offset, 3)
+    mu = _mat(means, N, p, ldm)
+    w = np.ones(N) if not _addr(weights) else _vec(weights, N).copy()
+    L = _mat(Lchol_host, p, p)
+    box = _vec(box_host, 2 * p) if support == 2 else None
+    res = _mat(out, B, p, ldo)
+    todo = np.arange(B)
+    for _ in range(1000):
+        comp = rs.choice(N, size=len(todo), p=w / w.sum())
+        draw = mu[comp] + rs.randn(len(todo), p) @ L.T
+        if support == 1:
+            with np.errstate(all='ignore'):
+                ok = np.isfinite(ex.CustomPrior1.logpdf(draw[:, 0], 2)
+                                 + ex.CustomPrior2.logpdf(draw[:, 1], draw[:, 0], 1))
+        elif support == 2:
+            ok = np.all((draw >= box[:p]) & (draw <= box[p:]), axis=1)
+        else:
+            ok = np.ones(len(todo), dtype=bool)
+        res[todo] = draw          # the last trial stays if no trial is accepted (as on the device)
+        todo = todo[~ok]
+        if not len(todo):
+            break
+
+
+def prior_gauss_f64(ctx, B, seed, offset, prm_host, mu, sigma, stream):
+    import scipy.stats as ss
+    prm = _vec(prm_host, 4)
+    rs = _rs(seed, offset, 4)
+    _vec(mu, B)[:] = prm[0] + prm[1] * (1.0 - rs.rand(B))       # (0, 1] like the device's u01
+    _vec(sigma, B)[:] = ss.truncnorm.rvs(prm[2], prm[3], size=B, random_state=rs)
+
+
+def logprior_gauss_f64(ctx, x, ldx, B, prm_host, out, stream):
+    import scipy.stats as ss
+    prm = _vec(prm_host, 4)
+    xm = _mat(x, B, 2, ldx)
+    with np.errstate(all='ignore'):
+        _vec(out, B)[:] = ss.uniform.logpdf(xm[:, 0], prm[0], prm[1]) + ss.truncnorm.logpdf(
+            xm[:, 1], prm[2], prm[3])
+
+
+def sim_gauss_f64(ctx, mu, sigma, B, n_obs, seed, offset, Y, ldY, S, ldS, stream):
+    y = _vec(mu, B)[:, None] + _vec(sigma, B)[:, None] * _rs(seed, offset, 5).randn(B, n_obs)
+    if _addr(Y):
+        _mat(Y, B, n_obs, ldY)[:] = y
+    if _addr(S):
+        out = _mat(S, B, 2, ldS)
+        out[:, 0], out[:, 1] = o.meanvar(y)
+
+
+def sim_gnk_f64(ctx, A, Bs, g, k, c, B, n_obs, seed, offset, Y, ldY, stream):
+    z = _rs(seed, offset, 6).randn(B, n_obs)
+    a, b, gg, kk = (_vec(v, B)[:, None] for v in (A, Bs, g, k))
+    e = np.exp(-gg * z)
+    _mat(Y, B, n_obs, ldY)[:] = a + b * (1 + c * ((1 - e) / (1 + e))) * (1 + z ** 2) ** kk * z
+
+
+def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
+    box = _vec(box_host, 2 * p)
+    xm = _mat(x, B, p, ldx)
+    inside = np.all((xm >= box[:p]) & (xm <= box[:p] + box[p:]), axis=1)
+    _vec(out, B)[:] = np.where(inside, -np.sum(np.log(box[p:])), -np.inf)
+
+
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
     dist_euclid_thr_f64, dist_euclid_thr_f64_host, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
-    gp_predict_f64, gp_predict_grad_f64, lcbsc_f64)}
+    gp_predict_f64, gp_predict_grad_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
+    gm_rvs_f64, prior_gauss_f64, logprior_gauss_f64, sim_gauss_f64, sim_gnk_f64, logprior_box_f64)}
 
 
 def call(name, *args):
