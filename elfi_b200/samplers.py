@@ -960,10 +960,10 @@ class AdaptiveThresholdSMC(SMC):
     def __init__(self, model, discrepancy_name=None, output_names=None, initial_quantile=0.20,
                  q_threshold=0.99, densratio_estimation=None, **kwargs):
         super().__init__(model, discrepancy_name, output_names, **kwargs)
-        if self.comm.on:
-            raise NotImplementedError(
-                'AdaptiveThresholdSMC runs on one rank (pass distributed=False): its density-ratio '
-                'step draws a host-side reference sample that is not synchronised across ranks')
+        # Multi-rank: after the gather every rank holds the same population, the KLIEP fit is
+        # deterministic, and the prior reference sample of the first fit comes from the round-0
+        # RandomState, which is seeded identically on all ranks and not used for proposals -- so
+        # every rank derives the same quantile without a collective.
         self.q_threshold = q_threshold
         self.initial_quantile = initial_quantile
         self.densratio = densratio_estimation or DensityRatioEstimation(

@@ -78,9 +78,19 @@ def _worker(rank, world, port, out_dir):
                                    rtol=1e-9)
     assert np.all(np.isfinite(ad.weights)) and len(ad.populations) == 2
 
+    # AdaptiveThresholdSMC: every rank fits the same density ratio and picks the same quantiles
+    ats = elfi.AdaptiveThresholdSMC(m['d'], batch_size=500, seed=2)
+    at = ats.sample(200, max_iter=4, bar=False)
+    q = np.array([np.nan if v is None else v for v in ats._quantiles], dtype=float)
+    assert len(at.populations) >= 2 and np.all(np.isfinite(at.weights))
+    assert q[0] == 0.2 and np.all((q[1:len(at.populations)] >= 0.05) & (q[1:len(at.populations)] <= 1))
+    t = [p.threshold for p in at.populations]
+    assert all(a > b for a, b in zip(t, t[1:]))
+
     # all ranks hold identical results
     np.save(os.path.join(out_dir, 'rank{}.npy'.format(rank)),
-            np.concatenate([res.discrepancies, smc.weights, smc.samples_array.ravel(), ad.weights]))
+            np.concatenate([res.discrepancies, smc.weights, smc.samples_array.ravel(), ad.weights,
+                            at.weights, at.samples_array.ravel(), np.nan_to_num(q)]))
     dist.barrier()
     dist.destroy_process_group()
     patch.undo()
