@@ -208,7 +208,7 @@ class ModelPrior:
         context = em.ComputationContext(size or 1, seed='global')
         batch = em.execute_batch(self._model, list(self.parameter_names), context, 0,
                                  with_values={'_random_state': random_state})
-        rvs = np.column_stack([batch[p] for p in self.parameter_names])
+        rvs = np.column_stack([dev.to_host(batch[p]) for p in self.parameter_names])
         if self.dim == 1:
             rvs = rvs.reshape(size or 1)
         return rvs[0] if size is None else rvs

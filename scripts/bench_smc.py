@@ -30,6 +30,9 @@ def main():
                     help='ma2 (scaling target), gauss (BASELINE config #3) or gnk (config #5: '
                          'AdaptiveDistanceSMC over n_obs order statistics, --pops rounds)')
     ap.add_argument('--n-obs', type=int, default=256, help='observations per simulation (gnk)')
+    ap.add_argument('--adaptive-threshold', action='store_true',
+                    help='AdaptiveThresholdSMC (KLIEP quantile selection, BASELINE config #3) '
+                         'instead of fixed quantiles; --pops is then max_iter')
     args = ap.parse_args()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -52,6 +55,10 @@ def main():
             smc = elfi.AdaptiveDistanceSMC(m['d'], batch_size=batch, seed=args.seed,
                                            device_proposal=proposal)
             return smc.sample(n, rounds=pops, quantile=args.quantile, bar=False)
+        if args.adaptive_threshold:
+            smc = elfi.AdaptiveThresholdSMC(m['d'], batch_size=batch, seed=args.seed,
+                                            device_proposal=proposal)
+            return smc.sample(n, max_iter=pops, bar=False)
         smc = elfi.SMC(m['d'], batch_size=batch, seed=args.seed, device_proposal=proposal)
         return smc.sample(n, quantiles=[args.quantile] * pops, bar=False)
 
@@ -69,13 +76,13 @@ def main():
         dist.barrier()
     dt = time.perf_counter() - t0
     if int(os.environ.get('RANK', '0')) == 0:
-        accepted = args.n * args.pops
+        accepted = args.n * len(res.populations)
         out = {'bench': 'smc_abc_{}_throughput_mode'.format(args.model), 'n_gpus': world, 'population': args.n,
-               'populations': args.pops, 'quantile': args.quantile, 'batch_per_rank': args.batch,
+               'populations': len(res.populations), 'adaptive_threshold': bool(args.adaptive_threshold), 'quantile': args.quantile, 'batch_per_rank': args.batch,
                'seconds': dt, 'accepted_particles_per_s': accepted / dt,
                'simulated': int(res.n_sim), 'simulated_per_s': res.n_sim / dt,
-               'pair_terms': float(args.n) ** 2 * (args.pops - 1),
-               'pair_terms_per_s': float(args.n) ** 2 * (args.pops - 1) / dt,
+               'pair_terms': float(args.n) ** 2 * (len(res.populations) - 1),
+               'pair_terms_per_s': float(args.n) ** 2 * (len(res.populations) - 1) / dt,
                'posterior_means': [float(v) for v in res.sample_means_array],
                'thresholds': [float(p.threshold) for p in res.populations]}
         from elfi_b200.samplers import PHASES

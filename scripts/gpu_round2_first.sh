@@ -17,6 +17,9 @@ for model in ma2 gauss; do
   ELFI_B200_TIMING=1 timeout 600 python scripts/bench_smc.py --model $model --population 1000000 --pops 3 \
       > gpurun_out/r2_smc_${model}.json 2> gpurun_out/r2_smc_${model}.err; cut -c1-400 gpurun_out/r2_smc_${model}.json
 done
+# config #3 proper: adaptive threshold (KLIEP) on the Gaussian model, 5 populations x 1e6 particles
+ELFI_B200_TIMING=1 timeout 900 python scripts/bench_smc.py --model gauss --adaptive-threshold --population 1000000 --pops 5 \
+    > gpurun_out/r2_smc_gauss_adaptive.json 2> gpurun_out/r2_smc_gauss_adaptive.err; cut -c1-400 gpurun_out/r2_smc_gauss_adaptive.json; tail -2 gpurun_out/r2_smc_gauss_adaptive.err
 ELFI_B200_TIMING=1 timeout 600 python scripts/bench_smc.py --model gnk --population 100000 --pops 3 --n-obs 256 \
     > gpurun_out/r2_smc_gnk.json 2> gpurun_out/r2_smc_gnk.err; cut -c1-400 gpurun_out/r2_smc_gnk.json; tail -2 gpurun_out/r2_smc_gnk.err
 # 4. headline bench, both arms

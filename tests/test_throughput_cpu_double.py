@@ -48,3 +48,17 @@ def test_smc_with_device_proposals_gauss():
         1000, quantiles=[0.2, 0.3, 0.3], bar=False)
     a = res.sample_means_array
     assert abs(a[0] - 4.0) < 0.3 and abs(a[1] - 0.4) < 0.3, a
+
+
+def test_adaptive_threshold_smc_on_the_gauss_device_model():
+    """BASELINE config #3's algorithm (adaptive threshold, KLIEP) on the device Gaussian model."""
+    import elfi_b200 as elfi
+    from elfi_b200.examples import gauss
+    m, proposal = gauss.get_device_model(n_obs=50, seed_obs=3)
+    ats = elfi.AdaptiveThresholdSMC(m['d'], batch_size=5000, seed=4, device_proposal=proposal)
+    res = ats.sample(500, max_iter=4, bar=False)
+    assert 2 <= len(res.populations) <= 4
+    thr = [p.threshold for p in res.populations]
+    assert all(a > b for a, b in zip(thr, thr[1:]))
+    a = res.sample_means_array
+    assert abs(a[0] - 4.0) < 0.4 and abs(a[1] - 0.4) < 0.4, a
