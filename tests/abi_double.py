@@ -413,26 +413,94 @@ def call(name, *args):
 
 
 # ------------------------------------------------------------------------------ device.py side
+class DeviceTensor(torch.Tensor):
+    """A CPU tensor that behaves like a CUDA tensor where the two differ for host code: it cannot
+    be converted to NumPy implicitly (np.asarray / .numpy() raise, as they do for cuda tensors;
+    .cpu() gives the plain tensor back) and it cannot be mixed with plain host tensors in torch
+    operations (0-dim tensors excepted, as on the device).  This makes the CPU-double tests fail
+    where the same code would fail on the GPU."""
+
+    @staticmethod
+    def wrap(t):
+        return t if isinstance(t, DeviceTensor) else t.as_subclass(DeviceTensor)
+
+    def __array__(self, *args, **kwargs):
+        raise TypeError("can't convert cuda:0 device type tensor to numpy. Use Tensor.cpu() to "
+                        "copy the tensor to host memory first. (cpu double)")
+
+    def numpy(self, *args, **kwargs):
+        return self.__array__()
+
+    def cpu(self, *args, **kwargs):
+        return self.as_subclass(torch.Tensor)
+
+    def cuda(self, *args, **kwargs):
+        return self
+
+    @property
+    def is_cuda(self):
+        return True
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, '__name__', '')
+        if name not in _MIX_OK:
+            for a in _flatten(args) + _flatten(tuple(kwargs.values())):
+                if isinstance(a, torch.Tensor) and not isinstance(a, DeviceTensor) and a.dim() > 0:
+                    raise RuntimeError("Expected all tensors to be on the same device, but found at "
+                                       "least two devices, cuda:0 and cpu! (cpu double, in {})"
+                                       .format(name))
+        return super().__torch_function__(func, types, args, kwargs)
+
+
+_MIX_OK = {'__get__', '__set__', 'as_subclass', 'cpu', 'data_ptr', '__repr__', '__str__',
+           '__format__', '__reduce_ex__', '__deepcopy__', 'all_gather_into_tensor'}
+
+
+def _flatten(items):
+    out = []
+    for it in items:
+        if isinstance(it, (list, tuple)):
+            out += _flatten(it)
+        else:
+            out.append(it)
+    return out
+
+
 def install(monkeypatch):
-    """Patch elfi_b200._lib.call and the allocation helpers of elfi_b200.device (CPU tensors)."""
+    """Patch elfi_b200._lib.call and the allocation helpers of elfi_b200.device (CPU tensors that
+    are as strict as CUDA tensors, see DeviceTensor)."""
     from elfi_b200 import device as dev
+    from elfi_b200 import samplers
 
     def to_device(x, dtype=torch.float64):
         if isinstance(x, torch.Tensor):
             t = x if x.dtype == dtype else x.to(dtype)
-            return t.contiguous()
-        return torch.from_numpy(np.ascontiguousarray(x, dtype=dev._np_dtype(dtype)).copy())
+            return DeviceTensor.wrap(t.contiguous())
+        return DeviceTensor.wrap(
+            torch.from_numpy(np.ascontiguousarray(x, dtype=dev._np_dtype(dtype)).copy()))
+
+    gather = samplers.Comm.all_gather_rows
+
+    def all_gather_rows(self, t):   # gloo works on plain tensors; the result is on "the device"
+        out = gather(self, t.as_subclass(torch.Tensor) if isinstance(t, DeviceTensor) else t)
+        return DeviceTensor.wrap(out) if isinstance(out, torch.Tensor) else out
+    monkeypatch.setattr(samplers.Comm, 'all_gather_rows', all_gather_rows)
 
     monkeypatch.setattr(_lib, 'call', call)
     monkeypatch.setattr(dev, 'require_cuda', lambda: None)
     monkeypatch.setattr(dev, 'context', lambda device=None: ctypes.c_void_p(1))
     monkeypatch.setattr(dev, 'stream_ptr', lambda: ctypes.c_void_p(0))
     monkeypatch.setattr(dev, 'synchronize', lambda: None)
-    monkeypatch.setattr(dev, 'is_device_array', lambda x: isinstance(x, torch.Tensor))
+    monkeypatch.setattr(dev, 'is_device_array', lambda x: isinstance(x, DeviceTensor))
     monkeypatch.setattr(dev, 'to_device', to_device)
-    monkeypatch.setattr(dev, 'empty', lambda shape, dtype=torch.float64: torch.empty(shape, dtype=dtype))
-    monkeypatch.setattr(dev, 'zeros', lambda shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype))
-    monkeypatch.setattr(dev, 'ones', lambda shape, dtype=torch.float64: torch.ones(shape, dtype=dtype))
+    monkeypatch.setattr(dev, 'empty', lambda shape, dtype=torch.float64:
+                        DeviceTensor.wrap(torch.empty(shape, dtype=dtype)))
+    monkeypatch.setattr(dev, 'zeros', lambda shape, dtype=torch.float64:
+                        DeviceTensor.wrap(torch.zeros(shape, dtype=dtype)))
+    monkeypatch.setattr(dev, 'ones', lambda shape, dtype=torch.float64:
+                        DeviceTensor.wrap(torch.ones(shape, dtype=dtype)))
     monkeypatch.setattr(dev, 'full', lambda shape, value, dtype=torch.float64:
-                        torch.full(shape, value, dtype=dtype))
+                        DeviceTensor.wrap(torch.full(shape, value, dtype=dtype)))
     del CALLS[:]
