@@ -91,12 +91,15 @@ ELFI_UNROLL
     }
 };
 
+// The box feeders below are templates over the accumulator `Sum` (LeafSum here, TreeSum in
+// treesum.cuh): begin(m), push<K>(j, v), push_mid<K>(v), all_mid(j_first, j_last), finish(m).
+
 // sum_j x[j + LAG] * x[j], j = 0 .. n-LAG-1, for one or two lags, fed 16 columns at a time.
 // LAG_B = -1 disables the second lag.  Lags are at most 8 so the previous box's tail fits hist[].
-template <int LAG_A, int LAG_B>
-struct AutocovLeaf {
+template <class Sum, int LAG_A, int LAG_B>
+struct AutocovBoxes {
     static constexpr int HMAX = (LAG_A > LAG_B ? LAG_A : LAG_B);
-    LeafSum sa, sb;
+    Sum sa, sb;
     double hist[HMAX];   // last HMAX columns of the previous box
     int n;
 
@@ -114,18 +117,18 @@ ELFI_UNROLL
         return leaf_mul(cur[C], prev);
     }
     template <int LAG, int C>
-    ELFI_HD void steps(LeafSum& s, int t0, const double* cur) {
+    ELFI_HD void steps(Sum& s, int t0, const double* cur) {
         const int t = t0 + C;   // element index; product index j = t - LAG
         if (t >= LAG && t < n) s.template push<((C - LAG) % 8 + 8) % 8>(t - LAG, product<LAG, C>(cur));
         if constexpr (C + 1 < LEAF_BOX) steps<LAG, C + 1>(s, t0, cur);
     }
     template <int LAG, int C>
-    ELFI_HD void steps_mid(LeafSum& s, const double* cur) {
+    ELFI_HD void steps_mid(Sum& s, const double* cur) {
         s.template push_mid<((C - LAG) % 8 + 8) % 8>(product<LAG, C>(cur));
         if constexpr (C + 1 < LEAF_BOX) steps_mid<LAG, C + 1>(s, cur);
     }
     template <int LAG>
-    ELFI_HD void lag_box(LeafSum& s, int t0, const double* cur) {
+    ELFI_HD void lag_box(Sum& s, int t0, const double* cur) {
         if (s.all_mid(t0 - LAG, t0 + LEAF_BOX - 1 - LAG))
             steps_mid<LAG, 0>(s, cur);
         else
@@ -142,10 +145,14 @@ ELFI_UNROLL
     ELFI_HD double sum_b() const { return sb.finish(n - LAG_B); }
 };
 
+template <int LAG_A, int LAG_B>
+using AutocovLeaf = AutocovBoxes<LeafSum, LAG_A, LAG_B>;
+
 // Row mean and (population) variance in two sweeps over the same boxes:
 // sweep 0 sums x, sweep 1 sums (x - mean)^2   (numpy _mean / _var, ddof = 0).
-struct MeanVarLeaf {
-    LeafSum s;
+template <class Sum>
+struct MeanVarBoxes {
+    Sum s;
     double mean;
     int n;
 
@@ -182,5 +189,7 @@ struct MeanVarLeaf {
     }
     ELFI_HD double variance() const { return s.finish(n) / double(n); }
 };
+
+using MeanVarLeaf = MeanVarBoxes<LeafSum>;
 
 }  // namespace elfi

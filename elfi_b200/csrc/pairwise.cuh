@@ -12,7 +12,7 @@
 // one with compile-time indices.  (A runtime-indexed array - or a compare-and-select loop, which
 // the compiler folds back into an indexed access - would demote the whole object to local
 // memory, an order of magnitude slower on the bandwidth-bound summary kernels.)  Pushes and pops
-// happen once per <=128-term leaf.  MAXD = 8 covers runs of up to 128 * 2^8 = 32768 terms; the
+// happen once per <=128-term leaf.  MAXD levels cover runs of up to 120 * 2^MAXD + 8 terms; the
 // one-thread-per-row fallback uses a deeper stack.
 #pragma once
 
@@ -31,7 +31,11 @@ struct PairwiseStream {
     int depth;
     bool in_tail;
 
-    static __host__ __device__ constexpr int64_t max_terms() { return int64_t(128) << MAXD; }
+    // Longest run whose recursion never holds more than MAXD open splits.  A right part has up
+    // to n/2 + 7 terms, so the depth needed is not log2(n / 128): runs of 120 * 2^MAXD + 8 terms
+    // fit, and 7689 is the first length that needs a 7th level (found by the host harness of
+    // treesum.cuh; enumerated in tests/test_leafsum_host.py).
+    static __host__ __device__ constexpr int64_t max_terms() { return (int64_t(120) << MAXD) + 8; }
 
     __device__ __forceinline__ void push_frame(int right) {
 #pragma unroll

@@ -103,7 +103,7 @@ sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int
     const uint64_t row = offset + uint64_t(i);
     const uint32_t r0 = uint32_t(row), r1 = uint32_t(row >> 32);
     const double a1 = t1[i], a2 = t2[i];
-    PairwiseStream<6> p1, p2;      // lag-1 and lag-2 product sums (rows up to 8192 terms)
+    PairwiseStream<6> p1, p2;      // lag-1 and lag-2 product sums (rows up to 7688 terms)
     if (SUMMARIES) {
         p1.begin(n_obs - 1);
         p2.begin(n_obs - 2);
@@ -413,7 +413,8 @@ int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2
                           double* S, int64_t ldS, void* stream_) {
     using namespace elfi;
     ELFI_REQUIRE(ctx && (B == 0 || (t1 && t2)), "sim_ma2: NULL argument");
-    ELFI_REQUIRE(n_obs >= 3 && n_obs <= 8192, "sim_ma2: n_obs=%lld outside [3, 8192]", (long long)n_obs);
+    ELFI_REQUIRE(n_obs >= 3 && n_obs <= PairwiseStream<6>::max_terms(),
+                 "sim_ma2: n_obs=%lld outside [3, 7688]", (long long)n_obs);
     ELFI_REQUIRE(X || S, "sim_ma2: nothing to produce (X and S are both NULL)");
     ELFI_REQUIRE((!X || ldX >= n_obs) && (!S || ldS >= 2), "sim_ma2: bad leading dimension");
     if (B == 0) return ELFI_B200_OK;
@@ -496,7 +497,8 @@ int elfi_b200_sim_gauss_f64(elfi_b200_ctx* ctx, const double* mu, const double* 
                             double* S, int64_t ldS, void* stream_) {
     using namespace elfi;
     ELFI_REQUIRE(ctx && (B == 0 || (mu && sigma)), "sim_gauss: NULL argument");
-    ELFI_REQUIRE(n_obs >= 1 && n_obs <= 8192, "sim_gauss: n_obs=%lld outside [1, 8192]", (long long)n_obs);
+    ELFI_REQUIRE(n_obs >= 1 && n_obs <= PairwiseStream<6>::max_terms(),
+                 "sim_gauss: n_obs=%lld outside [1, 7688]", (long long)n_obs);
     ELFI_REQUIRE(Y || S, "sim_gauss: nothing to produce (Y and S are both NULL)");
     ELFI_REQUIRE((!Y || ldY >= n_obs) && (!S || ldS >= 2), "sim_gauss: bad leading dimension");
     if (B == 0) return ELFI_B200_OK;

@@ -15,11 +15,14 @@
 #include "leafsum.cuh"
 #include "pairwise.cuh"
 #include "rowstream.cuh"
+#include "treesum.cuh"
+
+#include <cstdlib>
 
 namespace elfi {
 
 // Collects terms into aligned groups of 8 and forwards them to a PairwiseStream.
-constexpr int RS_PW_DEPTH = 6;   // rows of up to 8192 terms on the row-stream path
+constexpr int RS_PW_DEPTH = 6;   // rows of up to 7688 terms on the row-stream path (max_terms())
 
 struct TermGrouper {
     PairwiseStream<RS_PW_DEPTH> pw;
@@ -157,18 +160,22 @@ struct MeanVarConsumer {
     }
 };
 
-// Single-leaf variants (leafsum.cuh): every reduced run has <= 128 terms, so NumPy's tree is one
-// leaf and the per-lane state is 8 accumulators per sum.  Same results as the consumers above,
-// a fraction of the integer bookkeeping (profiles/r1_summ_instruction_mix.md).
-template <int LAG_A, int LAG_B>
-struct AutocovLeafConsumer {
+// Term-wise variants: the per-lane state is one of the accumulators of leafsum.cuh / treesum.cuh
+// and the box logic is AutocovBoxes / MeanVarBoxes, which also compile for the host.
+//   Sum = LeafSum   every reduced run has <= 128 terms, so NumPy's tree is one leaf and the state
+//                   is 8 accumulators per sum: same results as the consumers above at a fraction
+//                   of the integer bookkeeping (profiles/r1_summ_instruction_mix.md).  Default.
+//   Sum = TreeSum   longer rows, same front end (opt-in with ELFI_B200_SUMM_TERMWISE=1 until it
+//                   has been timed on the device; the TermGrouper consumers stay the default).
+template <class Sum, int LAG_A, int LAG_B>
+struct AutocovBoxConsumer {
     typedef SummaryParams Params;
     static constexpr int PASSES = 1;
     const Params& p;
-    AutocovLeaf<LAG_A, LAG_B> st;
+    AutocovBoxes<Sum, LAG_A, LAG_B> st;
 
     static __device__ void setup_shared(uint8_t*, const Params&, int) {}
-    __device__ AutocovLeafConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
+    __device__ AutocovBoxConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
     __device__ __forceinline__ void begin_row() { st.begin(p.n); }
     __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
         double cur[16];
@@ -184,14 +191,15 @@ struct AutocovLeafConsumer {
     }
 };
 
-struct MeanVarLeafConsumer {
+template <class Sum>
+struct MeanVarBoxConsumer {
     typedef SummaryParams Params;
     static constexpr int PASSES = 2;
     const Params& p;
-    MeanVarLeaf st;
+    MeanVarBoxes<Sum> st;
 
     static __device__ void setup_shared(uint8_t*, const Params&, int) {}
-    __device__ MeanVarLeafConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
+    __device__ MeanVarBoxConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
     __device__ __forceinline__ void begin_row() { st.begin(p.n); }
     __device__ __forceinline__ void consume(int pass, int cg, const uint8_t* box_row, int sw) {
         double cur[16];
@@ -206,6 +214,16 @@ struct MeanVarLeafConsumer {
         }
     }
 };
+
+typedef TreeSum<RS_PW_DEPTH> RowTreeSum;
+
+static bool summaries_termwise() {
+    static const bool on = [] {
+        const char* v = std::getenv("ELFI_B200_SUMM_TERMWISE");
+        return v != nullptr && v[0] == '1';
+    }();
+    return on;
+}
 
 // Generic fallback (any lag, any alignment): one thread per row straight from global memory,
 // same PairwiseStream so results are identical.  mode 0 = autocov(lag), 1 = mean+var.
@@ -252,7 +270,10 @@ template <int LA, int LB>
 static int autocov_launch(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t B, int64_t n,
                           const SummaryParams& p, cudaStream_t stream) {
     if (n - LA <= LEAF_MAX_TERMS)   // LA is the smaller lag: the longer run
-        return rowstream_launch<AutocovLeafConsumer<LA, LB>>(ctx, X, ld, B, n, 0, p, stream);
+        return rowstream_launch<AutocovBoxConsumer<LeafSum, LA, LB>>(ctx, X, ld, B, n, 0, p, stream);
+    if (summaries_termwise())
+        return rowstream_launch<AutocovBoxConsumer<RowTreeSum, LA, LB>>(ctx, X, ld, B, n, 0, p,
+                                                                        stream);
     return rowstream_launch<AutocovConsumer<LA, LB>>(ctx, X, ld, B, n, 0, p, stream);
 }
 
@@ -338,7 +359,9 @@ int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
     p.col_b = col_var;
     if (rowstream_ok(ctx, X, ldX, n)) {
         if (n <= LEAF_MAX_TERMS)
-            return rowstream_launch<MeanVarLeafConsumer>(ctx, X, ldX, B, n, 0, p, stream);
+            return rowstream_launch<MeanVarBoxConsumer<LeafSum>>(ctx, X, ldX, B, n, 0, p, stream);
+        if (summaries_termwise())
+            return rowstream_launch<MeanVarBoxConsumer<RowTreeSum>>(ctx, X, ldX, B, n, 0, p, stream);
         return rowstream_launch<MeanVarConsumer>(ctx, X, ldX, B, n, 0, p, stream);
     }
     summary_direct_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(X, ldX, B, int(n), 0, 1, p);

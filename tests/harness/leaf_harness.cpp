@@ -8,6 +8,7 @@
 #include <limits>
 
 #include "../../elfi_b200/csrc/leafsum.cuh"
+#include "../../elfi_b200/csrc/treesum.cuh"
 
 namespace {
 
@@ -16,10 +17,12 @@ void load_box(const double* x, int n, int t0, double* cur) {
         cur[c] = (t0 + c < n) ? x[t0 + c] : std::numeric_limits<double>::quiet_NaN();
 }
 
-template <int LA, int LB>
+typedef elfi::TreeSum<6> Tree;   // the depth the row-stream kernels use (rows up to 8192 terms)
+
+template <class Sum, int LA, int LB>
 void autocov_rows(const double* X, int64_t ld, int64_t B, int n, double* out) {
     for (int64_t b = 0; b < B; ++b) {
-        elfi::AutocovLeaf<LA, LB> st;
+        elfi::AutocovBoxes<Sum, LA, LB> st;
         st.begin(n);
         double cur[elfi::LEAF_BOX];
         for (int t0 = 0; t0 < n; t0 += elfi::LEAF_BOX) {
@@ -31,24 +34,22 @@ void autocov_rows(const double* X, int64_t ld, int64_t B, int n, double* out) {
     }
 }
 
-}  // namespace
-
-extern "C" {
-
-int harness_autocov(const double* X, int64_t ld, int64_t B, int n, int lag_a, int lag_b,
-                    double* out) {
-    if (lag_a == 1 && lag_b == 2) autocov_rows<1, 2>(X, ld, B, n, out);
-    else if (lag_a == 1 && lag_b < 0) autocov_rows<1, -1>(X, ld, B, n, out);
-    else if (lag_a == 2 && lag_b < 0) autocov_rows<2, -1>(X, ld, B, n, out);
-    else if (lag_a == 3 && lag_b < 0) autocov_rows<3, -1>(X, ld, B, n, out);
-    else if (lag_a == 4 && lag_b < 0) autocov_rows<4, -1>(X, ld, B, n, out);
+template <class Sum>
+int autocov_dispatch(const double* X, int64_t ld, int64_t B, int n, int lag_a, int lag_b,
+                     double* out) {
+    if (lag_a == 1 && lag_b == 2) autocov_rows<Sum, 1, 2>(X, ld, B, n, out);
+    else if (lag_a == 1 && lag_b < 0) autocov_rows<Sum, 1, -1>(X, ld, B, n, out);
+    else if (lag_a == 2 && lag_b < 0) autocov_rows<Sum, 2, -1>(X, ld, B, n, out);
+    else if (lag_a == 3 && lag_b < 0) autocov_rows<Sum, 3, -1>(X, ld, B, n, out);
+    else if (lag_a == 4 && lag_b < 0) autocov_rows<Sum, 4, -1>(X, ld, B, n, out);
     else return -1;
     return 0;
 }
 
-int harness_meanvar(const double* X, int64_t ld, int64_t B, int n, double* out) {
+template <class Sum>
+int meanvar_rows(const double* X, int64_t ld, int64_t B, int n, double* out) {
     for (int64_t b = 0; b < B; ++b) {
-        elfi::MeanVarLeaf st;
+        elfi::MeanVarBoxes<Sum> st;
         st.begin(n);
         double cur[elfi::LEAF_BOX];
         for (int pass = 0; pass < 2; ++pass)
@@ -60,6 +61,26 @@ int harness_meanvar(const double* X, int64_t ld, int64_t B, int n, double* out) 
         out[2 * b + 1] = st.variance();
     }
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// tree = 0: single-leaf accumulator (rows of <= 128 terms); tree = 1: TreeSum (up to 8192 terms)
+int harness_autocov(const double* X, int64_t ld, int64_t B, int n, int lag_a, int lag_b,
+                    double* out) {
+    return autocov_dispatch<elfi::LeafSum>(X, ld, B, n, lag_a, lag_b, out);
+}
+int harness_autocov_tree(const double* X, int64_t ld, int64_t B, int n, int lag_a, int lag_b,
+                         double* out) {
+    return autocov_dispatch<Tree>(X, ld, B, n, lag_a, lag_b, out);
+}
+int harness_meanvar(const double* X, int64_t ld, int64_t B, int n, double* out) {
+    return meanvar_rows<elfi::LeafSum>(X, ld, B, n, out);
+}
+int harness_meanvar_tree(const double* X, int64_t ld, int64_t B, int n, double* out) {
+    return meanvar_rows<Tree>(X, ld, B, n, out);
 }
 
 }  // extern "C"

@@ -97,3 +97,51 @@ def test_strided_rows_and_golden(harness):
     g = load_golden('gauss_generate')
     got = _meanvar(harness, np.ascontiguousarray(g['gauss']))
     assert _same_bits(got[:, 0], g['ss_mean']) and _same_bits(got[:, 1], g['ss_var'])
+
+
+# ------------------------------------------------------------------ TreeSum (treesum.cuh)
+def _tree_call(lib, fn, x, *args):
+    out = np.empty((x.shape[0], 2))
+    rc = getattr(lib, fn)(_ptr(x), ctypes.c_int64(x.strides[0] // 8), ctypes.c_int64(x.shape[0]),
+                          x.shape[1], *args, _ptr(out))
+    assert rc == 0
+    return out
+
+
+def test_tree_accumulator_matches_numpy(harness):
+    """Rows longer than one leaf: every length up to 300, the split points around powers of two,
+    and the longest run a 6-level stack can hold (7688)."""
+    rs = np.random.RandomState(14)
+    lengths = [2, 7, 8, 9, 100, 127, 128] + list(range(129, 300)) + [383, 384, 385, 511, 512, 513, 1000, 1023, 1024, 1025, 1031,
+                                     2047, 2048, 2049, 4099, 5000, 7679, 7680, 7681, 7687, 7688]
+    for n in lengths:
+        x = _rows(rs, 8, n)
+        for la, lb in PAIRS:
+            if max(la, lb) >= n:
+                continue
+            got = _tree_call(harness, 'harness_autocov_tree', x, la, lb)
+            assert _same_bits(got[:, 0], np.mean(x[:, la:] * x[:, :-la], axis=1)), (n, la)
+            if lb > 0:
+                assert _same_bits(got[:, 1], np.mean(x[:, lb:] * x[:, :-lb], axis=1)), (n, lb)
+        got = _tree_call(harness, 'harness_meanvar_tree', x)
+        assert _same_bits(got[:, 0], np.mean(x, axis=1)), n
+        assert _same_bits(got[:, 1], np.var(x, axis=1)), n
+
+
+def test_stack_depth_bound():
+    """max_terms() of PairwiseStream / TreeSum: a run of n terms needs as many stack levels as
+    splits are open at once; right parts have up to n/2 + 7 terms, so 120 * 2^D + 8 terms is the
+    most that D levels hold for every length below it (not 128 * 2^D)."""
+    from functools import lru_cache
+
+    @lru_cache(None)
+    def levels(n):
+        if n <= 128:
+            return 0
+        left = n // 2
+        left -= left % 8
+        return 1 + max(levels(left), levels(n - left))
+    for depth in (1, 2, 6, 7, 8):
+        bound = 120 * 2 ** depth + 8
+        assert max(levels(m) for m in range(1, bound + 1)) == depth
+        assert levels(bound + 1) == depth + 1

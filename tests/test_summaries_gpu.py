@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('B,n', [(1000, 100), (333, 16), (64, 17), (2000, 128), (500, 129),
                                  (100, 255), (77, 1000), (40, 4099), (5000, 50), (31, 7), (9, 3),
-                                 (200, 130), (300, 96), (300, 97)])
+                                 (200, 130), (300, 96), (300, 97), (40, 7688), (24, 7696), (16, 8192)])
 def test_autocov_bit_exact(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B + n)
@@ -32,7 +32,7 @@ def test_autocov_lag_variants(lags):
 
 
 @pytest.mark.parametrize('B,n', [(1000, 50), (333, 16), (64, 17), (2000, 128), (500, 129),
-                                 (100, 300), (50, 5000), (31, 7), (12, 1)])
+                                 (100, 300), (50, 5000), (31, 7), (12, 1), (40, 7688), (16, 8192)])
 def test_meanvar_bit_exact(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B * 7 + n)
