@@ -10,6 +10,8 @@ timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r2_py
 cat gpurun_out/r2_pytest_gpu.log
 # 2. timings: summary kernels (leaf + tree), per-kernel table, weighted quantile with equal weights
 timeout 300 python scripts/gpu_leaf_check.py > gpurun_out/r2_leaf_check.log 2>&1; tail -2 gpurun_out/r2_leaf_check.log | cut -c1-400
+# same with the term-wise tree accumulator (treesum.cuh) switched on: parity, then the 4e5 x 256 timing
+ELFI_B200_SUMM_TERMWISE=1 timeout 300 python scripts/gpu_leaf_check.py > gpurun_out/r2_leaf_check_termwise.log 2>&1; tail -2 gpurun_out/r2_leaf_check_termwise.log | cut -c1-400
 timeout 600 python scripts/bench_kernels.py > gpurun_out/r2_bench_kernels.log 2>&1; tail -3 gpurun_out/r2_bench_kernels.log | cut -c1-300
 # 3. SMC throughput mode, 1 GPU: MA2 (round-0 quantile now closed form), Gaussian (config #3),
 #    g-and-k with AdaptiveDistanceSMC (config #5)
