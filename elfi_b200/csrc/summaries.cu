@@ -289,7 +289,7 @@ int elfi_b200_summary_autocov_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
     ELFI_REQUIRE(B >= 0 && n >= 1 && ldX >= n, "autocov: bad shape B=%lld n=%lld ld=%lld",
                  (long long)B, (long long)n, (long long)ldX);
     ELFI_REQUIRE(nlags >= 1 && lags_host != nullptr && ld_out >= nlags, "autocov: bad lags/ld_out");
-    ELFI_REQUIRE(n < (int64_t(1) << 31), "autocov: row too long");
+    ELFI_REQUIRE(n <= PairwiseStream<24>::max_terms(), "autocov: row too long");
     for (int64_t l = 0; l < nlags; ++l)
         ELFI_REQUIRE(lags_host[l] >= 1 && lags_host[l] < n, "autocov: lag %d outside [1, n)",
                      lags_host[l]);
@@ -347,7 +347,7 @@ int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
                  (long long)B, (long long)n, (long long)ldX);
     ELFI_REQUIRE(col_mean < ld_out && col_var < ld_out && (col_mean >= 0 || col_var >= 0),
                  "meanvar: bad output columns");
-    ELFI_REQUIRE(n < (int64_t(1) << 31), "meanvar: row too long");
+    ELFI_REQUIRE(n <= PairwiseStream<24>::max_terms(), "meanvar: row too long");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     if (B == 0) return ELFI_B200_OK;
