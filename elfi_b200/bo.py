@@ -78,6 +78,7 @@ class GPyRegression:
         self._hyper = None      # dict(kernel_var, lengthscale, bias_var, noise_var)
         self._priors = None     # Gamma prior (a, b) per hyper-parameter
         self._factor = None     # device tensors of the current fit
+        self.is_sampling = False   # duck-type attribute (gpy_regression.py:64); no cached path here
 
     # ---- data / state ---------------------------------------------------------------------
     @property
@@ -800,6 +801,7 @@ class BOLFI(BayesianOptimization):
             sigma_proposals = resolve_sigmas(self.target_model.parameter_names, sigma_proposals,
                                              self.target_model.bounds)
         lockstep = kwargs.pop('lockstep', True)
+        self.target_model.is_sampling = True
         coroutines = []
         start = 0
         for chain in range(n_chains):
@@ -825,6 +827,7 @@ class BOLFI(BayesianOptimization):
             chains = [mcmc._run_single(c, posterior.logpdf, posterior.gradient_logpdf)
                       for c in coroutines]
         chains = np.asarray(chains)
+        self.target_model.is_sampling = False
         logger.info("{} chains of {} iterations acquired. Effective sample size and Rhat for each "
                     "parameter:".format(n_chains, n_samples))
         for i, name in enumerate(self.target_model.parameter_names):
