@@ -482,9 +482,11 @@ class Rejection(Sampler):
             raise ValueError('Nothing to extract')
         self._gather_ranks()
         if self.adaptive:
-            self._update_distances()
+            with PHASES('extract:update_distances'):
+                self._update_distances()
         n = self.objective['n_samples']
-        outputs = {k: dev.to_host(v[:n]) for k, v in self.state['samples'].items()}
+        with PHASES('extract:to_host'):
+            outputs = {k: dev.to_host(v[:n]) for k, v in self.state['samples'].items()}
         sample = Sample(outputs=outputs, **self._extract_result_kwargs())
         sample._dev = {k: v[:n] for k, v in self.state['samples'].items()}   # device twins
         return sample
@@ -601,16 +603,20 @@ class Rejection(Sampler):
         # rank's finite rows is exchanged (one scalar MAX all-reduce, then the all-gather)
         dloc = samples[self.discrepancy_name]
         key = dloc if dloc.dim() == 1 else dloc[:, -1]
-        valid = int(torch.isfinite(key).sum().item())
-        cap = int(self.comm.all_reduce_max(valid))
+        with PHASES('gather:capacity'):
+            valid = int(torch.isfinite(key).sum().item())
+            cap = int(self.comm.all_reduce_max(valid))
         cap = max(1, min(n, ((cap + 31) // 32) * 32))
-        gathered = {k: self.comm.all_gather_rows(v[:cap]) for k, v in samples.items()}
+        with PHASES('gather:all_gather'):
+            gathered = {k: self.comm.all_gather_rows(v[:cap]) for k, v in samples.items()}
         d = gathered[self.discrepancy_name]
-        perm = ops.argsort(d if d.dim() == 1 else d[:, -1].contiguous())
+        with PHASES('gather:sort'):
+            perm = ops.argsort(d if d.dim() == 1 else d[:, -1].contiguous())
         total = perm.numel()
         if total >= n:
-            for k in samples:
-                samples[k] = ops.take_rows(gathered[k], perm[:n])
+            with PHASES('gather:select'):
+                for k in samples:
+                    samples[k] = ops.take_rows(gathered[k], perm[:n])
         else:   # fewer than n rows exist globally: keep the padding semantics of the local buffers
             for k in samples:
                 top = ops.take_rows(gathered[k], perm)
@@ -777,8 +783,10 @@ class SMC(Sampler):
         sharded over ranks when distributed)."""
         twins = getattr(pop, '_dev', None)
         if twins is not None and all(p in twins for p in self.parameter_names):
-            params_dev = torch.stack([twins[p].reshape(-1) for p in self.parameter_names], dim=1)
-            params = params_dev.cpu().numpy()          # one D2H instead of a host column_stack
+            with PHASES('weights:params_to_host'):
+                params_dev = torch.stack([twins[p].reshape(-1) for p in self.parameter_names],
+                                         dim=1)
+                params = params_dev.cpu().numpy()      # one D2H instead of a host column_stack
         else:
             params = np.column_stack(tuple([pop.outputs[p] for p in self.parameter_names]))
             params_dev = dev.to_device(params)
@@ -788,18 +796,23 @@ class SMC(Sampler):
             if self.comm.on:
                 lo, hi, per = sharding.shard_bounds(N, self.comm.rank, self.comm.size)
                 q_part = dev.full((per,), float('nan'))
-                if hi > lo:
-                    q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], means, cov, weights)
-                q_logpdf = self.comm.all_gather_rows(q_part)
+                with PHASES('weights:gm_logpdf'):
+                    if hi > lo:
+                        q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], means, cov, weights)
+                with PHASES('weights:all_gather'):
+                    q_logpdf = self.comm.all_gather_rows(q_part)
                 q_logpdf = q_logpdf[:N]   # equal-capacity shards: only the tail is padding
             else:
-                q_logpdf = ops.gm_logpdf(params_dev, means, cov, weights)
-            if self._device_proposal is not None:
-                p_logpdf = self._device_proposal.logpdf(params_dev)
-            else:
-                p_logpdf = self._prior.logpdf(params)
-            w_dev = ops.smc_weights(p_logpdf, q_logpdf)
-            w = w_dev.cpu().numpy()
+                with PHASES('weights:gm_logpdf'):
+                    q_logpdf = ops.gm_logpdf(params_dev, means, cov, weights)
+            with PHASES('weights:prior_logpdf'):
+                if self._device_proposal is not None:
+                    p_logpdf = self._device_proposal.logpdf(params_dev)
+                else:
+                    p_logpdf = self._prior.logpdf(params)
+            with PHASES('weights:exp+to_host'):
+                w_dev = ops.smc_weights(p_logpdf, q_logpdf)
+                w = w_dev.cpu().numpy()
         else:
             w = np.ones(pop.n_samples)
             w_dev = None
@@ -812,7 +825,8 @@ class SMC(Sampler):
             raise RuntimeError("All sample weights are zero. If you are using a prior "
                                "with a bounded support, this may be caused by specifying "
                                "a too small sample size.")
-        cov = 2 * np.diag(ops.weighted_var(params_dev, w_dev))
+        with PHASES('weights:weighted_var'):
+            cov = 2 * np.diag(ops.weighted_var(params_dev, w_dev))
         if not np.all(np.isfinite(cov)):
             logger.warning("Could not estimate the sample covariance. This is often "
                            "caused by majority of the sample weights becoming zero."
