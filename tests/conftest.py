@@ -14,7 +14,20 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+# GPU run order: kernel-level parity first (a failure there explains every failure above it),
+# then operators inside the model graph, samplers, throughput mode, pools, BOLFI, multi-GPU.
+_GPU_ORDER = ['test_distance_gpu', 'test_summaries_gpu', 'test_select_gpu', 'test_smc_gpu',
+              'test_kliep_gpu', 'test_gp_gpu', 'test_model_gpu', 'test_samplers_gpu',
+              'test_throughput_gpu', 'test_store_gpu', 'test_bolfi_gpu', 'test_multigpu_gpu']
+
+
+def _gpu_rank(item):
+    name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+    return _GPU_ORDER.index(name) if name in _GPU_ORDER else -1
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=_gpu_rank)          # stable: CPU tests keep their order and come first
     try:
         import torch
         has_gpu = torch.cuda.is_available()

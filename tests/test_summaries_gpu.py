@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('B,n', [(1000, 100), (333, 16), (64, 17), (2000, 128), (500, 129),
                                  (100, 255), (77, 1000), (40, 4099), (5000, 50), (31, 7), (9, 3),
-                                 (200, 130), (300, 96), (300, 97), (40, 7688), (24, 7696), (16, 8192)])
+                                 (200, 130), (300, 96), (300, 97)])
 def test_autocov_bit_exact(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B + n)
@@ -32,7 +32,7 @@ def test_autocov_lag_variants(lags):
 
 
 @pytest.mark.parametrize('B,n', [(1000, 50), (333, 16), (64, 17), (2000, 128), (500, 129),
-                                 (100, 300), (50, 5000), (31, 7), (12, 1), (40, 7688), (16, 8192)])
+                                 (100, 300), (50, 5000), (31, 7), (12, 1)])
 def test_meanvar_bit_exact(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B * 7 + n)
@@ -40,23 +40,6 @@ def test_meanvar_bit_exact(B, n):
     got = ops.meanvar(y).cpu().numpy()
     assert np.array_equal(got[:, 0], np.mean(y, axis=1))
     assert np.array_equal(got[:, 1], np.var(y, axis=1))
-
-
-def test_signed_zero_rows_match_numpy_bits():
-    """All-zero / negative-zero rows: the sign of the result follows NumPy's r[k] = a[k] start."""
-    from elfi_b200 import ops
-    x = np.random.RandomState(5).randn(64, 100)
-    x[0] = 0.0
-    x[1] = -0.0
-    x[2, ::2] = -0.0
-    got = ops.autocov(x, lags=(1, 2)).cpu().numpy()
-    ref = np.column_stack([np.mean(x[:, 1:] * x[:, :-1], axis=1),
-                           np.mean(x[:, 2:] * x[:, :-2], axis=1)])
-    assert np.array_equal(got.view(np.int64), ref.view(np.int64))
-    y = x[:, :50].copy()
-    mv = ops.meanvar(y).cpu().numpy()
-    refmv = np.column_stack([np.mean(y, axis=1), np.var(y, axis=1)])
-    assert np.array_equal(mv.view(np.int64), refmv.view(np.int64))
 
 
 def test_golden_ma2_pipeline():
@@ -96,3 +79,35 @@ def test_full_size_ma2_native():
     xs = x[rows].cpu().numpy()
     assert np.array_equal(S[rows, 0].cpu().numpy(), o.autocov(xs, 1))
     assert np.array_equal(S[rows, 1].cpu().numpy(), o.autocov(xs, 2))
+
+
+def test_signed_zero_rows_match_numpy_bits():
+    """All-zero / negative-zero rows: the sign of the result follows NumPy's r[k] = a[k] start."""
+    from elfi_b200 import ops
+    x = np.random.RandomState(5).randn(64, 100)
+    x[0] = 0.0
+    x[1] = -0.0
+    x[2, ::2] = -0.0
+    got = ops.autocov(x, lags=(1, 2)).cpu().numpy()
+    ref = np.column_stack([np.mean(x[:, 1:] * x[:, :-1], axis=1),
+                           np.mean(x[:, 2:] * x[:, :-2], axis=1)])
+    assert np.array_equal(got.view(np.int64), ref.view(np.int64))
+    y = x[:, :50].copy()
+    mv = ops.meanvar(y).cpu().numpy()
+    refmv = np.column_stack([np.mean(y, axis=1), np.var(y, axis=1)])
+    assert np.array_equal(mv.view(np.int64), refmv.view(np.int64))
+
+
+@pytest.mark.parametrize('B,n', [(40, 7688), (24, 7696), (16, 8192)])
+def test_long_rows_around_the_stack_bound(B, n):
+    """7688 terms is the longest run the 6-level pairwise stack of the row-stream kernels holds;
+    longer rows must take the thread-per-row kernel (24 levels)."""
+    from elfi_b200 import ops
+    rs = np.random.RandomState(n)
+    x = rs.randn(B, n)
+    got = ops.autocov(x, lags=(1, 2)).cpu().numpy()
+    assert np.array_equal(got[:, 0], np.mean(x[:, 1:] * x[:, :-1], axis=1))
+    assert np.array_equal(got[:, 1], np.mean(x[:, 2:] * x[:, :-2], axis=1))
+    mv = ops.meanvar(x).cpu().numpy()
+    assert np.array_equal(mv[:, 0], np.mean(x, axis=1))
+    assert np.array_equal(mv[:, 1], np.var(x, axis=1))
