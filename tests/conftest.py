@@ -12,6 +12,8 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    config.addinivalue_line('markers', 'first_device_run: written after the last GPU session; '
+                                       'ordered after the device-verified tests')
 
 
 # GPU run order: kernel-level parity first (a failure there explains every failure above it),
@@ -23,7 +25,12 @@ _GPU_ORDER = ['test_distance_gpu', 'test_summaries_gpu', 'test_select_gpu', 'tes
 
 def _gpu_rank(item):
     name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
-    return _GPU_ORDER.index(name) if name in _GPU_ORDER else -1
+    rank = _GPU_ORDER.index(name) if name in _GPU_ORDER else -1
+    # tests of code that has not run on a device yet go last, so that `-x` cannot hide a
+    # regression in verified code behind them (the marker is removed once they have passed)
+    if item.get_closest_marker('first_device_run') is not None:
+        rank += 100
+    return rank
 
 
 def pytest_collection_modifyitems(config, items):
