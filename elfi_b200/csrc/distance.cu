@@ -330,6 +330,123 @@ int launch_dist(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int
     return ELFI_B200_OK;
 }
 
+// ---- other cdist metrics (elfi/model/elfi_model.py:1037: Distance passes any metric string to
+// scipy.spatial.distance.cdist) ------------------------------------------------------------------
+// SciPy 1.18 accumulates 'sqeuclidean', 'cityblock', 'chebyshev' and 'minkowski' left to right in
+// fp64 like 'euclidean' (probed: bit-identical to a sequential loop at 2000 x 128), so they are
+// variants of EuclidConsumer with another per-term operation and another finish.  Unweighted,
+// one column (K = 1).  Zero padding (TMA fill, obs pad) adds |0|, 0^2, 0^p or max(acc, 0): no-ops.
+struct MetricParams : DistParams {
+    double pexp;       // Minkowski exponent
+};
+
+template <int METRIC>
+__device__ __forceinline__ double metric_term(double acc, double d, double pexp) {
+    if (METRIC == ELFI_B200_METRIC_SQEUCLIDEAN) return __dadd_rn(acc, __dmul_rn(d, d));
+    if (METRIC == ELFI_B200_METRIC_CITYBLOCK) return __dadd_rn(acc, fabs(d));
+    if (METRIC == ELFI_B200_METRIC_CHEBYSHEV) return fabs(d) > acc ? fabs(d) : acc;
+    return __dadd_rn(acc, pow(fabs(d), pexp));                       // Minkowski
+}
+
+template <int METRIC>
+__device__ __forceinline__ double metric_value(double acc, double pexp) {
+    return METRIC == ELFI_B200_METRIC_MINKOWSKI ? pow(acc, 1.0 / pexp) : acc;
+}
+
+template <int METRIC>
+__device__ __forceinline__ void metric_finish(const MetricParams& p, double acc, int64_t row,
+                                              int64_t B, int lane, bool whole_warp) {
+    bool ok = row < B;
+    if (ok) {
+        const double d = metric_value<METRIC>(acc, p.pexp);
+        p.d_out[row] = d;
+        if (p.has_thr) ok = d <= p.thr[0];
+    }
+    if (p.mask != nullptr) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok && p.has_thr);
+        if (lane == 0 && (whole_warp || (row - lane) < B)) p.mask[row >> 5] = bits;
+    }
+}
+
+template <int METRIC>
+struct MetricConsumer {
+    typedef MetricParams Params;
+    static constexpr int PASSES = 1;
+    const Params& p;
+    const double* obs_s;
+    double acc;
+
+    static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
+        dist_setup_shared(aux, p, D, false);
+    }
+    __device__ MetricConsumer(const Params& p_, const uint8_t* aux, int, int)
+        : p(p_), obs_s(reinterpret_cast<const double*>(aux)), acc(0.0) {}
+    __device__ __forceinline__ void begin_row() { acc = 0.0; }
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
+        const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 v = *reinterpret_cast<const double2*>(box_row + ((c ^ sw) << 4));
+            const double2 ob = o[c];
+            acc = metric_term<METRIC>(acc, __dsub_rn(v.x, ob.x), p.pexp);
+            acc = metric_term<METRIC>(acc, __dsub_rn(v.y, ob.y), p.pexp);
+        }
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
+        metric_finish<METRIC>(p, acc, row, B, lane, true);
+    }
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+metric_direct_kernel(const double* __restrict__ S, int64_t ld, int64_t B, int D, MetricParams p) {
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if (row < B) {
+        const double* r = S + row * ld;
+        for (int j = 0; j < D; ++j)
+            acc = metric_term<METRIC>(acc, __dsub_rn(__ldg(r + j), __ldg(p.obs + j)), p.pexp);
+    }
+    metric_finish<METRIC>(p, acc, row, B, threadIdx.x & 31, false);
+}
+
+template <int METRIC>
+static int launch_metric_t(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int64_t D,
+                           const MetricParams& p, cudaStream_t stream) {
+    const int64_t Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    const size_t aux = size_t(Dp) * 8;
+    if (D >= RS_BOX_COLS && tma_compatible(S, ldS) && rs_pick_stages(ctx->smem_optin, aux) >= 2)
+        return rowstream_launch<MetricConsumer<METRIC>>(ctx, S, ldS, B, D, aux, p, stream);
+    metric_direct_kernel<METRIC><<<unsigned((B + 255) / 256), 256, 0, stream>>>(S, ldS, B, int(D), p);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+static int launch_metric(elfi_b200_ctx* ctx, int metric, double pexp, const double* S, int64_t ldS,
+                         int64_t B, int64_t D, const double* obs, const double* thr_host,
+                         double* d_out, uint32_t* mask, cudaStream_t stream) {
+    MetricParams p;
+    memset(&p, 0, sizeof(p));
+    p.obs = obs;
+    p.d_out = d_out;
+    p.mask = mask;
+    p.K = 1;
+    p.has_thr = thr_host != nullptr;
+    if (thr_host) p.thr[0] = thr_host[0];
+    p.pexp = pexp;
+    if (B == 0) return ELFI_B200_OK;
+    switch (metric) {
+        case ELFI_B200_METRIC_SQEUCLIDEAN:
+            return launch_metric_t<ELFI_B200_METRIC_SQEUCLIDEAN>(ctx, S, ldS, B, D, p, stream);
+        case ELFI_B200_METRIC_CITYBLOCK:
+            return launch_metric_t<ELFI_B200_METRIC_CITYBLOCK>(ctx, S, ldS, B, D, p, stream);
+        case ELFI_B200_METRIC_CHEBYSHEV:
+            return launch_metric_t<ELFI_B200_METRIC_CHEBYSHEV>(ctx, S, ldS, B, D, p, stream);
+        default:
+            return launch_metric_t<ELFI_B200_METRIC_MINKOWSKI>(ctx, S, ldS, B, D, p, stream);
+    }
+}
+
 static int check_dist_args(const void* S, int64_t ldS, int64_t B, int64_t D, const void* obs,
                            const void* W, int64_t K, const void* thr, const void* acc_idx) {
     ELFI_REQUIRE(B >= 0 && D >= 1, "dist: bad shape B=%lld D=%lld", (long long)B, (long long)D);
@@ -460,6 +577,33 @@ int elfi_b200_dist_euclid_thr_f64_host(elfi_b200_ctx* ctx, const double* S_host,
     }
     ELFI_CUDA_OK(cudaStreamSynchronize(s0));
     ELFI_CUDA_OK(cudaStreamSynchronize(s1));
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_dist_metric_thr_f64(elfi_b200_ctx* ctx, int32_t metric, double pexp, const double* S,
+                                  int64_t ldS, int64_t B, int64_t D, const double* obs,
+                                  const double* thr_host, double* d_out, int32_t* acc_idx,
+                                  int64_t* n_acc, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "dist_metric: ctx is NULL");
+    ELFI_REQUIRE(metric >= ELFI_B200_METRIC_SQEUCLIDEAN && metric <= ELFI_B200_METRIC_MINKOWSKI,
+                 "dist_metric: unknown metric code %d", int(metric));
+    ELFI_REQUIRE(metric != ELFI_B200_METRIC_MINKOWSKI || (pexp > 0.0 && pexp < 1e308),
+                 "dist_metric: Minkowski exponent must be positive and finite");
+    int rc = check_dist_args(S, ldS, B, D, obs, nullptr, 1, thr_host, acc_idx);
+    if (rc) return rc;
+    ELFI_REQUIRE(B == 0 || d_out != nullptr, "dist_metric: d_out is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    uint32_t* mask = nullptr;
+    if (thr_host != nullptr) {
+        mask = static_cast<uint32_t*>(ctx_scratch(ctx, size_t((B + 31) / 32) * 4 + 256));
+        if (!mask) return ELFI_B200_ERR_NOMEM;
+    }
+    rc = launch_metric(ctx, int(metric), pexp, S, ldS, B, D, obs, thr_host, d_out, mask, stream);
+    if (rc) return rc;
+    if (thr_host != nullptr && (acc_idx != nullptr || n_acc != nullptr))
+        return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
     return ELFI_B200_OK;
 }
 

@@ -711,6 +711,20 @@ def device_euclidean_discrepancy(*summaries, observed, w=None, accept=None):
     return AcceptedOutput(d, idx) if accept is not None else d
 
 
+DEVICE_METRICS = ('sqeuclidean', 'cityblock', 'chebyshev', 'minkowski')
+
+
+def device_metric_discrepancy(metric, *summaries, observed, p=2.0, accept=None):
+    """distance_as_discrepancy for the other unweighted cdist metrics that have a kernel."""
+    X = _stack_summaries(summaries)
+    obs = _stack_observed(observed)
+    if obs.shape[0] != 1:
+        raise ValueError('observed summaries must form a single row')
+    thr = None if accept is None else np.atleast_1d(accept)
+    d, idx = ops.dist_metric(X, obs, metric, p=p, threshold=thr)
+    return AcceptedOutput(d, idx) if accept is not None else d
+
+
 def host_distance_as_discrepancy(dist, *summaries, observed):
     """Generic path for metrics without a CUDA kernel: explicit error, never a silent fallback."""
     raise NotImplementedError(
@@ -740,6 +754,10 @@ class Distance(Discrepancy):
             elif distance == 'seuclidean' and set(cd) == {'V'}:
                 op = partial(device_euclidean_discrepancy,
                              w=1.0 / np.asarray(cd['V'], dtype=np.float64))
+                state['_uses_accept'] = True
+            elif distance in DEVICE_METRICS and not (set(cd) - {'p'}) and \
+                    (distance == 'minkowski' or not cd):
+                op = partial(device_metric_discrepancy, distance, p=cd.get('p', 2.0))
                 state['_uses_accept'] = True
             else:
                 op = partial(host_distance_as_discrepancy, distance)

@@ -93,6 +93,51 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True):
     return d, acc_idx
 
 
+METRIC_CODES = {'sqeuclidean': 1, 'cityblock': 2, 'chebyshev': 3, 'minkowski': 4}
+
+
+def dist_metric(S, obs, metric, p=2.0, threshold=None, want_indices=True):
+    """cdist(S, obs, metric) for 'sqeuclidean', 'cityblock', 'chebyshev' and 'minkowski' (p)
+    + acceptance, on the device (elfi/model/elfi_model.py:1016-1037 passes these metric strings to
+    SciPy).  Minkowski with p = 1, 2, inf is routed to cityblock / euclidean / chebyshev as SciPy
+    does.  Returns (d (B,), acc_idx or None)."""
+    if metric == 'minkowski':
+        if p == 1:
+            metric = 'cityblock'
+        elif p == 2:
+            return dist_euclid(S, obs, thresholds=threshold, want_indices=want_indices)
+        elif np.isinf(p):
+            metric = 'chebyshev'
+        elif not p > 0:
+            raise ValueError('p must be greater than 0')
+    if metric not in METRIC_CODES:
+        raise ValueError('Unknown Distance Metric: {}'.format(metric))
+    S = _matrix(S)
+    B, D = S.shape
+    obs_t = dev.to_device(obs).reshape(-1)
+    if obs_t.numel() != D:
+        raise ValueError('XA and XB must have the same number of columns '
+                         '(i.e. feature dimension.)')
+    thr = None
+    if threshold is not None:
+        thr = np.ascontiguousarray(np.atleast_1d(threshold), dtype=np.float64)
+        if thr.shape[0] != 1:
+            raise ValueError('need one threshold per distance column ({} != 1)'.format(thr.shape[0]))
+    d = dev.empty((B,))
+    acc_idx = n_acc = None
+    if thr is not None:
+        n_acc = dev.zeros((1,), dtype=torch.int64)
+        if want_indices:
+            acc_idx = dev.empty((max(B, 1),), dtype=torch.int32)
+    _lib.call('elfi_b200_dist_metric_thr_f64', dev.context(), METRIC_CODES[metric], float(p),
+              dev.ptr(S), S.stride(0) if B > 1 else D, B, D, dev.ptr(obs_t), dev.ptr(thr),
+              dev.ptr(d), dev.ptr(acc_idx), dev.ptr(n_acc), dev.stream_ptr())
+    if thr is not None:
+        n = int(n_acc.item())
+        acc_idx = acc_idx[:n] if want_indices else n
+    return d, acc_idx
+
+
 def dist_euclid_host(S, obs, w=None, thresholds=None, return_distances=True):
     """Host-buffer variant (elfi_b200_dist_euclid_thr_f64_host): numpy in, numpy out."""
     S = np.asarray(S, dtype=np.float64)

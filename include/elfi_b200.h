@@ -86,6 +86,21 @@ int elfi_b200_dist_euclid_thr_f64_host(elfi_b200_ctx* ctx, const double* S_host,
                                        double* d_out_host, int32_t* acc_idx_host,
                                        int64_t* n_acc_host);
 
+/* Other cdist metrics that elfi.Distance forwards to SciPy (elfi/model/elfi_model.py:1016-1037):
+ *   SQEUCLIDEAN  sum_j (S_ij - obs_j)^2          CITYBLOCK  sum_j |S_ij - obs_j|
+ *   CHEBYSHEV    max_j |S_ij - obs_j|            MINKOWSKI  (sum_j |S_ij - obs_j|^pexp)^(1/pexp)
+ * accumulated left to right in fp64 like SciPy does (the first three are bit-identical to cdist,
+ * Minkowski to the accuracy of pow).  Unweighted, one distance column; otherwise the arguments and
+ * the acceptance outputs are those of elfi_b200_dist_euclid_thr_f64 (d_out has B entries). */
+#define ELFI_B200_METRIC_SQEUCLIDEAN 1
+#define ELFI_B200_METRIC_CITYBLOCK 2
+#define ELFI_B200_METRIC_CHEBYSHEV 3
+#define ELFI_B200_METRIC_MINKOWSKI 4
+int elfi_b200_dist_metric_thr_f64(elfi_b200_ctx* ctx, int32_t metric, double pexp, const double* S,
+                                  int64_t ldS, int64_t B, int64_t D, const double* obs,
+                                  const double* thr_host, double* d_out, int32_t* acc_idx,
+                                  int64_t* n_acc, void* stream);
+
 /* ---- summary statistics ----------------------------------------------------------------
  * Row-wise summaries with NumPy's pairwise summation order (bit-identical results).
  *

@@ -87,6 +87,27 @@ int64_t oracle_accept(const double *d, int64_t B, int64_t K, const double *thr, 
     return n;
 }
 
+/* Other metrics that elfi.Distance hands to scipy.spatial.distance.cdist
+ * (elfi/model/elfi_model.py:1016-1037).  SciPy 1.18 accumulates them left to right in fp64 like
+ * 'euclidean' (pinned by tests/test_oracle.py against the installed SciPy).
+ * metric: 1 sqeuclidean, 2 cityblock, 3 chebyshev, 4 minkowski(p). */
+void oracle_cdist_metric(const double *S, int64_t ld, int64_t B, int64_t D, const double *obs,
+                         int32_t metric, double p, double *out)
+{
+    for (int64_t i = 0; i < B; ++i) {
+        const double *x = S + i * ld;
+        double acc = 0.0;
+        for (int64_t j = 0; j < D; ++j) {
+            double d = x[j] - obs[j];
+            if (metric == 1) acc += d * d;
+            else if (metric == 2) acc += fabs(d);
+            else if (metric == 3) { if (fabs(d) > acc) acc = fabs(d); }
+            else acc += pow(fabs(d), p);
+        }
+        out[i] = (metric == 4) ? pow(acc, 1.0 / p) : acc;
+    }
+}
+
 /* --------------------------------------------------------------------------
  * NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
  * DOUBLE_pairwise_sum), used by every np.sum/np.mean/np.var along a contiguous

@@ -86,6 +86,23 @@ def cdist_euclid(S, obs, w=None, threads=1):
     return out
 
 
+METRIC_CODES = {'sqeuclidean': 1, 'cityblock': 2, 'chebyshev': 3, 'minkowski': 4}
+
+
+def cdist_metric(S, obs, metric, p=2.0):
+    """scipy.spatial.distance.cdist(S, obs(1,D), metric[, p=p]) flattened to (B,) for the other
+    metrics elfi.Distance accepts (elfi/model/elfi_model.py:1016-1037), sequential fp64."""
+    S = _c64(S)
+    if S.ndim == 1:
+        S = S[:, None]
+    obs = _c64(obs).reshape(-1)
+    out = np.empty(len(S), dtype=np.float64)
+    _lib().oracle_cdist_metric(_p(S), ctypes.c_int64(S.shape[1]), ctypes.c_int64(len(S)),
+                               ctypes.c_int64(S.shape[1]), _p(obs),
+                               ctypes.c_int32(METRIC_CODES[metric]), ctypes.c_double(p), _p(out))
+    return out
+
+
 def nested_distance(S, obs, weights, threads=1):
     """AdaptiveDistance.nested_distance (elfi/model/elfi_model.py:1135-1151).
 

@@ -166,3 +166,22 @@ def test_golden_kliep():
     d2 = ((g['x'][:, None, :] - theta[None, :, :]) ** 2).sum(-1)
     ratios = np.exp(-0.5 * d2 / float(g['sigma']) ** 2) @ alpha
     np.testing.assert_allclose(ratios, g['ratios'], rtol=1e-11)
+
+
+@pytest.mark.parametrize('metric,kw', [('sqeuclidean', {}), ('cityblock', {}), ('chebyshev', {}),
+                                       ('minkowski', {'p': 3.0}), ('minkowski', {'p': 0.5}),
+                                       ('minkowski', {'p': 1.5})])
+def test_other_cdist_metrics_are_sequential(metric, kw):
+    """SciPy accumulates these metrics left to right like 'euclidean': the sequential C
+    restatement is bit-identical (Minkowski: same libm pow), which is what the device kernels
+    of elfi_b200_dist_metric_thr_f64 reproduce."""
+    from scipy.spatial.distance import cdist
+    rs = np.random.RandomState(3)
+    for B, D in [(500, 128), (64, 3), (200, 17), (1, 1)]:
+        S, obs = rs.randn(B, D), rs.randn(1, D)
+        ref = cdist(S, obs, metric, **kw).ravel()
+        got = o.cdist_metric(S, obs, metric, kw.get('p', 2.0))
+        if metric == 'minkowski':
+            np.testing.assert_allclose(got, ref, rtol=2e-16 * 8)
+        else:
+            assert np.array_equal(got, ref), (metric, B, D)
