@@ -122,7 +122,7 @@ def test_unsupported_metric_fails_loudly():
     elfi.Simulator(lambda p, batch_size=1, random_state=None: np.zeros((batch_size, 1)), m['p'],
                    observed=np.zeros((1, 1)), name='sim')
     elfi.Summary(lambda x: x[:, 0], m['sim'], name='s')
-    elfi.Distance('cityblock', m['s'], name='d')
+    elfi.Distance('cosine', m['s'], name='d')
     with pytest.raises(NotImplementedError):
         m.generate(4, ['d'], seed=1)
 
