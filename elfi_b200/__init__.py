@@ -15,4 +15,4 @@ from .samplers import (SMC, AdaptiveDistanceSMC, AdaptiveThresholdSMC,  # noqa: 
                        DensityRatioEstimation, GMDistribution, ModelPrior, Rejection)
 from .store import ArrayPool, OutputPool  # noqa: F401
 from .bo import (BOLFI, LCBSC, BayesianOptimization, BolfiPosterior, GPyRegression,  # noqa: F401
-                 MaxVar, RandMaxVar, UniformAcquisition)
+                 ExpIntVar, MaxVar, RandMaxVar, UniformAcquisition)

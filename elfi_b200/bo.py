@@ -218,6 +218,30 @@ class GPyRegression:
             var = var + self._factor['hyper']['noise_var']
         return mean.cpu().numpy()[:, None], var, gm.cpu().numpy(), gv.cpu().numpy()
 
+    # ---- posterior covariance between points (ExpIntVar) ---------------------------------------
+    def whiten(self, x):
+        """T (m, n) device tensor with rows W k(x_q, X): cov(a, b) = k(a, b) - T_a . T_b."""
+        f, h = self._factor, self._factor['hyper']
+        xq = dev.to_device(x).reshape(-1, self.input_dim)
+        T = dev.empty((xq.shape[0], f['n']))
+        _lib.call('elfi_b200_gp_whiten_f64', dev.context(), dev.ptr(xq), self.input_dim,
+                  xq.shape[0], dev.ptr(f['X']), self.input_dim, f['n'], self.input_dim,
+                  dev.ptr(f['W']), f['n_pad'], h['kernel_var'], h['lengthscale'], h['bias_var'],
+                  dev.ptr(T), f['n'], dev.stream_ptr())
+        return xq, T
+
+    def cross_covariance(self, a, b):
+        """Noiseless posterior covariance (len(b), len(a)) between two point sets, each given as
+        the (points, whitened) pair returned by `whiten` (so a fixed set is whitened once)."""
+        (xa, Ta), (xb, Tb) = a, b
+        h = self._factor['hyper']
+        cov = dev.empty((xb.shape[0], xa.shape[0]))
+        _lib.call('elfi_b200_gp_cross_cov_f64', dev.context(), dev.ptr(xa), self.input_dim,
+                  xa.shape[0], dev.ptr(Ta), Ta.shape[1], dev.ptr(xb), self.input_dim, xb.shape[0],
+                  dev.ptr(Tb), Tb.shape[1], self._factor['n'], self.input_dim, h['kernel_var'],
+                  h['lengthscale'], h['bias_var'], dev.ptr(cov), dev.stream_ptr())
+        return cov
+
     # ---- hyper-parameters -------------------------------------------------------------------
     def log_marginal_likelihood(self, hyper=None):
         """-1/2 y^T alpha - sum log L_ii - n/2 log 2 pi for the given (or current) hyper-parameters."""
@@ -544,6 +568,74 @@ class RandMaxVar(MaxVar):
         if n > 1:
             return self.random_state.permutation(samples[self._warmup:])[:n]
         return samples[-1:]
+
+
+class ExpIntVar(MaxVar):
+    """Expected integrated variance (Jarvenpaa et al. 2019; acquisition.py:629-821): choose the
+    point whose simulation is expected to reduce the variance of the unnormalised posterior most,
+    integrated over a grid of the parameter space or over importance samples drawn from the MaxVar
+    surface.  The posterior covariance between the integration points and a candidate is
+    k(i, c) - (W k_i) . (W k_c) on the device, with the integration points whitened once per
+    acquisition (the reference re-factorises Ky in every evaluation)."""
+
+    def __init__(self, model, prior, quantile_eps=.01, integration='grid', d_grid=.2,
+                 n_samples_imp=100, iter_imp=2, sampler='nuts', n_samples=2000,
+                 sigma_proposals=None, **opts):
+        super().__init__(model, prior, quantile_eps, **opts)
+        self.name = 'exp_int_var'
+        self.label_fn = 'Expected Loss'
+        self._integration = integration
+        self._n_samples_imp = n_samples_imp
+        self._iter_imp = iter_imp
+        if self._integration == 'importance':
+            self.density_is = RandMaxVar(model=self.model, prior=self.prior, n_inits=self.n_inits,
+                                         seed=self.seed, quantile_eps=self.quantile_eps,
+                                         sampler=sampler, n_samples=n_samples,
+                                         sigma_proposals=sigma_proposals)
+        elif self._integration == 'grid':
+            axes = [slice(b[0], b[1], d_grid) for b in self.model.bounds]
+            self.points_int = np.mgrid[axes].reshape(len(self.model.bounds), -1).T
+
+    def _prepare(self, t):
+        """Everything of the expected loss that does not depend on the candidate point."""
+        gp = self.model
+        self.sigma2_n = gp.noise
+        self._update_eps()
+        resample = self._integration == 'importance' and t % self._iter_imp == 0
+        if resample:
+            self.points_int = self.density_is.acquire(self._n_samples_imp)
+        self.mean_int, self.var_int = gp.predict(self.points_int, noiseless=True)
+        self.priors_int = (self.prior.pdf(self.points_int) ** 2)[np.newaxis, :]
+        if resample:
+            omegas = (1 / MaxVar.evaluate(self, self.points_int)).T
+            self.omegas_int = omegas / np.sum(omegas, axis=1)[:, np.newaxis]
+        elif self._integration == 'grid':
+            self.omegas_int = np.full(len(self.points_int), 1 / len(self.points_int))
+        self._whitened_int = gp.whiten(self.points_int)
+        self.phi_int = ss.norm.cdf(self.eps, loc=self.mean_int.T,
+                                   scale=np.sqrt(self.sigma2_n + self.var_int.T))
+
+    def acquire(self, n, t):
+        logger.debug('Acquiring the next batch of %d values', n)
+        self._prepare(t)
+        theta_min, _ = minimize(self.evaluate, self.model.bounds, grad=None, prior=self.prior,
+                                n_start_points=self.n_inits, maxiter=self.max_opt_iters,
+                                random_state=self.random_state)
+        return np.tile(theta_min, (n, 1))
+
+    def evaluate(self, theta_new, t=None):
+        """The candidate-dependent term of the expected loss (to be minimised)."""
+        gp = self.model
+        theta_new = np.asanyarray(theta_new, dtype=float).reshape((-1, gp.input_dim))
+        _, var_new = gp.predict(theta_new, noiseless=True)
+        cov_int = dev.to_host(gp.cross_covariance(self._whitened_int, gp.whiten(theta_new)))
+        delta_var_int = cov_int ** 2 / (self.sigma2_n + var_new)
+        spread = self.sigma2_n + self.var_int.T
+        a = np.sqrt((spread - delta_var_int) / (spread + delta_var_int))
+        phi_skew = ss.skewnorm.cdf(self.eps, a, loc=self.mean_int.T, scale=np.sqrt(spread))
+        w = (self.phi_int - phi_skew) / 2
+        loss = 2 * np.sum(self.omegas_int * self.priors_int * w, axis=1)
+        return np.where(self.prior.pdf(theta_new) == 0, np.finfo(float).max, loss)
 
 
 class UniformAcquisition(AcquisitionBase):

@@ -393,6 +393,60 @@ predict_grad_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __
     }
 }
 
+// ---- posterior cross-covariance pieces (ExpIntVar, acquisition.py:776-821) ----------------------
+// The reference evaluates cov(x_a, x_b | evidence) = k(x_a, x_b) - k_a^T Ky^-1 k_b with a fresh
+// cho_factor of Ky per call (acquisition.py:807).  With W = L^-1 from the fit, Ky^-1 = W^T W, so
+// the covariance is k(x_a, x_b) - (W k_a) . (W k_b): whiten each point once (one CTA per point, the
+// first two phases of predict_grad_kernel), then every covariance is a dot product of length n.
+__global__ void __launch_bounds__(256)
+gp_whiten_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __restrict__ X,
+                 int64_t ldx, int64_t n, int p, const double* __restrict__ W, int64_t ldw,
+                 double s2, double f, double bias, double* __restrict__ T, int64_t ldT) {
+    extern __shared__ double kq[];   // n: k(x_q, X_j) of the RBF + bias kernel
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t j = tid; j < n; j += 256) {
+        double r2 = 0.0;
+        for (int a = 0; a < p; ++a) {
+            const double d = Xq[q * ldq + a] - X[j * ldx + a];
+            r2 = fma(d, d, r2);
+        }
+        kq[j] = s2 * exp(r2 * f) + bias;
+    }
+    __syncthreads();
+    for (int64_t r = warp; r < n; r += 8) {
+        double acc = 0.0;
+        for (int64_t c = lane; c <= r; c += 32) acc = fma(W[r * ldw + c], kq[c], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) T[q * ldT + r] = acc;
+    }
+}
+
+// cov[b * ma + a] = k(x_a, x_b) - T_a . T_b, one warp per pair (a, b)
+__global__ void __launch_bounds__(256)
+gp_cross_cov_kernel(const double* __restrict__ Xa, int64_t lda, int64_t ma,
+                    const double* __restrict__ Ta, int64_t ldTa, const double* __restrict__ Xb,
+                    int64_t ldb, const double* __restrict__ Tb, int64_t ldTb, int64_t n, int p,
+                    double s2, double f, double bias, double* __restrict__ cov) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t a = int64_t(blockIdx.x) * 8 + warp;
+    const int64_t b = blockIdx.y;
+    if (a >= ma) return;             // whole warps leave together
+    const double* ta = Ta + a * ldTa;
+    const double* tb = Tb + b * ldTb;
+    double acc = 0.0;
+    for (int64_t c = lane; c < n; c += 32) acc = fma(ta[c], tb[c], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        double r2 = 0.0;
+        for (int d = 0; d < p; ++d) {
+            const double diff = Xa[a * lda + d] - Xb[b * ldb + d];
+            r2 = fma(diff, diff, r2);
+        }
+        cov[b * ma + a] = s2 * exp(r2 * f) + bias - acc;
+    }
+}
+
 __global__ void lcbsc_kernel(const double* __restrict__ mean, const double* __restrict__ var,
                              const double* __restrict__ gmean, const double* __restrict__ gvar,
                              int64_t m, int p, double beta, double* __restrict__ acq,
@@ -569,6 +623,50 @@ int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* va
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     lcbsc_kernel<<<unsigned((m + 255) / 256), 256, 0, stream>>>(mean, var, grad_mean, grad_var, m,
                                                                int(p), beta, acq, grad_acq);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gp_whiten_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, int64_t m,
+                            const double* X, int64_t ldX, int64_t n, int64_t p, const double* W,
+                            int64_t n_pad, double kernel_var, double lengthscale, double bias_var,
+                            double* T, int64_t ldT, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && X && W && (m == 0 || (Xq && T)), "gp_whiten: NULL argument");
+    ELFI_REQUIRE(m >= 0 && n >= 1 && p >= 1 && ldq >= p && ldX >= p && ldT >= n,
+                 "gp_whiten: bad shape");
+    ELFI_REQUIRE(n_pad == elfi_b200_gp_padded_size(n), "gp_whiten: bad n_pad");
+    ELFI_REQUIRE(size_t(n) * 8 <= 200 * 1024, "gp_whiten: n=%lld too large (<= 25600)", (long long)n);
+    if (m == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t smem = size_t(n) * 8;
+    ELFI_CUDA_OK(cudaFuncSetAttribute(gp_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem)));
+    gp_whiten_kernel<<<unsigned(m), 256, smem, stream>>>(Xq, ldq, X, ldX, n, int(p), W, n_pad, kernel_var,
+                                                         -0.5 / (lengthscale * lengthscale), bias_var,
+                                                         T, ldT);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gp_cross_cov_f64(elfi_b200_ctx* ctx, const double* Xa, int64_t lda, int64_t ma,
+                               const double* Ta, int64_t ldTa, const double* Xb, int64_t ldb,
+                               int64_t mb, const double* Tb, int64_t ldTb, int64_t n, int64_t p,
+                               double kernel_var, double lengthscale, double bias_var, double* cov,
+                               void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && (ma == 0 || mb == 0 || (Xa && Ta && Xb && Tb && cov)),
+                 "gp_cross_cov: NULL argument");
+    ELFI_REQUIRE(ma >= 0 && mb >= 0 && mb < 65536 && n >= 1 && p >= 1 && lda >= p && ldb >= p &&
+                 ldTa >= n && ldTb >= n, "gp_cross_cov: bad shape");
+    if (ma == 0 || mb == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    dim3 grid(unsigned((ma + 7) / 8), unsigned(mb));
+    gp_cross_cov_kernel<<<grid, 256, 0, stream>>>(Xa, lda, ma, Ta, ldTa, Xb, ldb, Tb, ldTb, n, int(p),
+                                                  kernel_var, -0.5 / (lengthscale * lengthscale),
+                                                  bias_var, cov);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

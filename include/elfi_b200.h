@@ -225,6 +225,21 @@ int elfi_b200_lcbsc_f64(elfi_b200_ctx* ctx, const double* mean, const double* va
                         const double* grad_mean, const double* grad_var, int64_t m, int64_t p,
                         double beta, double* acq, double* grad_acq, void* stream);
 
+/* Posterior cross-covariance of the GP between two sets of points, as ExpIntVar needs it
+ * (elfi/methods/bo/acquisition.py:776-821; the reference re-factorises Ky on every evaluation,
+ * :807).  With W from gp_fit, cov(x_a, x_b) = k(x_a, x_b) - (W k_a) . (W k_b):
+ *   gp_whiten:    T[q, 0:n] = W k_q,  k_q[j] = k(Xq[q], X[j])  (RBF + bias);  T is (m, ldT), ldT >= n
+ *   gp_cross_cov: cov[b * ma + a] = k(Xa[a], Xb[b]) - Ta[a, :] . Tb[b, :]     (mb x ma, row-major) */
+int elfi_b200_gp_whiten_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, int64_t m,
+                            const double* X, int64_t ldX, int64_t n, int64_t p, const double* W,
+                            int64_t n_pad, double kernel_var, double lengthscale, double bias_var,
+                            double* T, int64_t ldT, void* stream);
+int elfi_b200_gp_cross_cov_f64(elfi_b200_ctx* ctx, const double* Xa, int64_t lda, int64_t ma,
+                               const double* Ta, int64_t ldTa, const double* Xb, int64_t ldb,
+                               int64_t mb, const double* Tb, int64_t ldTb, int64_t n, int64_t p,
+                               double kernel_var, double lengthscale, double bias_var, double* cov,
+                               void* stream);
+
 /* Measures the sustained fp64 throughput of this device: tflops_host[0] = DFMA (vector pipe),
  * tflops_host[1] = DMMA (mma.sync m8n8k4.f64).  Roofline denominators for the compute-bound
  * kernels (mixture density, GP products); blocks the host for a few milliseconds. */

@@ -296,6 +296,25 @@ def gp_predict_grad_f64(ctx, Xq, ldq, m, X, ldX, n, p, W, U, n_pad, alpha, kerne
     _mat(grad_var, m, p)[:] = gv
 
 
+def gp_whiten_f64(ctx, Xq, ldq, m, X, ldX, n, p, W, n_pad, kernel_var, lengthscale, bias_var, T,
+                  ldT, stream):
+    Xm = np.ascontiguousarray(_mat(X, n, p, ldX))
+    xq = np.ascontiguousarray(_mat(Xq, m, p, ldq))
+    Wn = _mat(W, n_pad, n_pad)[:n, :n]
+    r2 = np.sum(xq ** 2, 1)[:, None] + np.sum(Xm ** 2, 1)[None, :] - 2. * xq.dot(Xm.T)
+    k = kernel_var * np.exp(np.maximum(r2, 0.0) * (-0.5 / lengthscale ** 2)) + bias_var
+    _mat(T, m, n, ldT)[:] = k.dot(Wn.T)
+
+
+def gp_cross_cov_f64(ctx, Xa, lda, ma, Ta, ldTa, Xb, ldb, mb, Tb, ldTb, n, p, kernel_var,
+                     lengthscale, bias_var, cov, stream):
+    xa = np.ascontiguousarray(_mat(Xa, ma, p, lda))
+    xb = np.ascontiguousarray(_mat(Xb, mb, p, ldb))
+    r2 = np.sum(xb ** 2, 1)[:, None] + np.sum(xa ** 2, 1)[None, :] - 2. * xb.dot(xa.T)
+    k = kernel_var * np.exp(np.maximum(r2, 0.0) * (-0.5 / lengthscale ** 2)) + bias_var
+    _mat(cov, mb, ma)[:] = k - _mat(Tb, mb, n, ldTb).dot(_mat(Ta, ma, n, ldTa).T)
+
+
 def lcbsc_f64(ctx, mean, var, grad_mean, grad_var, m, p, beta, acq, grad_acq, stream):
     mu, v = _vec(mean, m), _vec(var, m)
     if _addr(acq):
@@ -411,7 +430,7 @@ _TABLE = {'elfi_b200_' + f.__name__: f for f in (
     dist_euclid_thr_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
-    gp_predict_f64, gp_predict_grad_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
+    gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
     gm_rvs_f64, prior_gauss_f64, logprior_gauss_f64, sim_gauss_f64, sim_gnk_f64, logprior_box_f64)}
 
 

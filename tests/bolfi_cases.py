@@ -79,6 +79,44 @@ def case_maxvar_matches_reference():
     assert acq.evaluate(x[:1])[0, 0] >= got.max() * 0.999      # a maximiser beats the probe points
 
 
+def case_expintvar_matches_reference():
+    """ExpIntVar on a grid: the candidate-dependent loss equals the reference's (which factorises
+    Ky per evaluation) at probe points; the acquired point is at least as good as the reference's."""
+    from elfi_b200.bo import ExpIntVar, GPyRegression
+    g = load_golden('expintvar')
+    gp = GPyRegression(['t1', 't2'], bounds={'t1': (-2, 2), 't2': (-1, 1)})
+    gp.update(g['X'], g['y'][:, None])
+    gp._hyper = dict(zip(('kernel_var', 'lengthscale', 'bias_var', 'noise_var'),
+                         (float(v) for v in g['hyper'])))
+    gp._fit()
+    acq = ExpIntVar(model=gp, prior=_prior(), quantile_eps=0.05, integration='grid', d_grid=0.4,
+                    noise_var=0.1, seed=1, n_inits=5, max_opt_iters=100)
+    assert np.array_equal(acq.points_int, g['grid'])
+    acq._prepare(0)
+    np.testing.assert_allclose(acq.eps, float(g['eps']), rtol=1e-12)
+    np.testing.assert_allclose(acq.omegas_int, g['omegas'], rtol=1e-12)
+    np.testing.assert_allclose(acq.phi_int, g['phi_int'], rtol=1e-5, atol=1e-12)
+    loss = acq.evaluate(g['pts'])
+    np.testing.assert_allclose(loss, g['loss'], rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(acq.evaluate(g['pts'][1]), g['single'], rtol=1e-4, atol=1e-12)
+    x = acq.acquire(2, t=0)
+    assert x.shape == (2, 2) and np.all(x[0] == x[1])
+    assert acq.evaluate(x[:1])[0] <= float(g['loss'][-1]) * (1 + 1e-3) + 1e-12
+    # the covariance pieces themselves: symmetric, and the self-covariance is the variance
+    pts = g['pts'][:4]
+    wh = gp.whiten(pts)
+    cov = gp.cross_covariance(wh, wh).cpu().numpy()
+    np.testing.assert_allclose(cov, cov.T, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.diag(cov), gp.predict(pts, noiseless=True)[1].ravel(),
+                               rtol=1e-7, atol=1e-10)
+    # importance-sampling variant runs end to end
+    imp = ExpIntVar(model=gp, prior=_prior(), quantile_eps=0.05, integration='importance',
+                    n_samples_imp=20, n_samples=60, sampler='metropolis', noise_var=0.1, seed=2,
+                    n_inits=2, max_opt_iters=20)
+    xi = imp.acquire(1, t=0)
+    assert xi.shape == (1, 2) and np.isfinite(xi).all()
+
+
 def case_other_acquisitions():
     from elfi_b200.bo import RandMaxVar, UniformAcquisition
     g, gp = _fixture_gp()

@@ -26,7 +26,7 @@ elfi = import_reference()
 import elfi_oracle as o  # noqa: E402
 from elfi.examples import ma2  # noqa: E402
 from elfi.methods import mcmc  # noqa: E402
-from elfi.methods.bo.acquisition import MaxVar  # noqa: E402
+from elfi.methods.bo.acquisition import ExpIntVar, MaxVar  # noqa: E402
 from elfi.methods.posteriors import BolfiPosterior  # noqa: E402
 from elfi.model.extensions import ModelPrior  # noqa: E402
 
@@ -78,6 +78,16 @@ class DuckGP:
         self.input_dim = X.shape[1]
         self.L, self.alpha = o.gp_fit(X, y, hyper['kernel_var'], hyper['lengthscale'],
                                       hyper['bias_var'], hyper['noise_var'], jitter=1e-8)
+
+        # ExpIntVar reaches into GPy for the prior covariance function (acquisition.py:754)
+        from types import SimpleNamespace
+        self._gp = SimpleNamespace(kern=SimpleNamespace(K=self._prior_cov))
+
+    def _prior_cov(self, a, b):
+        a, b = np.atleast_2d(a), np.atleast_2d(b)
+        r2 = np.sum(a ** 2., 1)[:, None] + np.sum(b ** 2., 1)[None, :] - 2. * a.dot(b.T)
+        return self.h['kernel_var'] * np.exp(np.maximum(r2, 0.) * (-0.5 / self.h['lengthscale'] ** 2)) \
+            + self.h['bias_var']
 
     @property
     def noise(self):
@@ -155,6 +165,19 @@ def main():
     with np.errstate(all='ignore'):
         mv = acq.evaluate(inside)
         mv_grad = acq.evaluate_gradient(inside)
+    eiv = ExpIntVar(model=gp, prior=prior, quantile_eps=0.05, integration='grid', d_grid=0.4,
+                    noise_var=0.1, seed=1, n_inits=5, max_opt_iters=100)
+    with np.errstate(all='ignore'):
+        eiv_x = eiv.acquire(1, t=0)
+        eiv_pts = np.vstack([inside, eiv_x])
+        eiv_loss = eiv.evaluate(eiv_pts)
+        eiv_single = eiv.evaluate(inside[1])
+    save('expintvar', X=X, y=y, hyper=np.array([hyper[k] for k in
+                                                ('kernel_var', 'lengthscale', 'bias_var',
+                                                 'noise_var')]),
+         grid=eiv.points_int, eps=np.float64(eiv.eps), pts=eiv_pts, loss=eiv_loss,
+         single=eiv_single, acquired=eiv_x, omegas=eiv.omegas_int, phi_int=eiv.phi_int)
+
     save('bolfi_posterior', X=X, y=y, hyper=np.array([hyper[k] for k in
                                                       ('kernel_var', 'lengthscale', 'bias_var',
                                                        'noise_var')]),

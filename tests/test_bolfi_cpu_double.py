@@ -19,6 +19,10 @@ def test_maxvar_matches_reference():
     cases.case_maxvar_matches_reference()
 
 
+def test_expintvar_matches_reference():
+    cases.case_expintvar_matches_reference()
+
+
 def test_other_acquisitions():
     cases.case_other_acquisitions()
 
