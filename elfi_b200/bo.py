@@ -18,6 +18,7 @@ with Gamma priors) is not available to pin against -> `optimize()` maximises the
 """
 import copy
 import logging
+import threading
 from math import ceil
 
 import numpy as np
@@ -326,6 +327,117 @@ def minimize(fun, bounds, method='L-BFGS-B', constraints=None, grad=None, prior=
     return locs[ind_min], vals[ind_min]
 
 
+class _Rendezvous:
+    """Meeting point of several local optimisations running in worker threads and the thread
+    that owns the device: workers post the point they need and sleep; once every live worker has
+    posted, the owner evaluates all points in one batched call and wakes them."""
+
+    def __init__(self, n_workers):
+        self.cv = threading.Condition()
+        self.live = n_workers
+        self.posted = {}
+        self.answers = {}
+        self.error = None
+
+    def request(self, worker, x):
+        with self.cv:
+            self.posted[worker] = np.array(x, dtype=float, copy=True)
+            self.cv.notify_all()
+            while worker not in self.answers and self.error is None:
+                self.cv.wait()
+            if self.error is not None:
+                raise self.error
+            return self.answers.pop(worker)
+
+    def retire(self, worker):
+        with self.cv:
+            self.live -= 1
+            self.cv.notify_all()
+
+    def serve(self, batch_fun):
+        """Run on the owning thread until all workers have retired."""
+        while True:
+            with self.cv:
+                while self.live > 0 and len(self.posted) < self.live:
+                    self.cv.wait()
+                if self.live == 0:
+                    return
+                workers = sorted(self.posted)
+                X = np.array([self.posted[w] for w in workers])
+                self.posted.clear()
+            try:
+                values, grads = batch_fun(X)
+                values = np.ravel(values)
+            except BaseException as exc:        # wake the workers, then re-raise here
+                with self.cv:
+                    self.error = exc
+                    self.cv.notify_all()
+                raise
+            with self.cv:
+                for k, w in enumerate(workers):
+                    self.answers[w] = (float(values[k]),
+                                       None if grads is None else np.array(grads[k], dtype=float))
+                self.cv.notify_all()
+
+
+def minimize_lockstep(batch_fun, bounds, method='L-BFGS-B', constraints=None, prior=None,
+                      n_start_points=10, maxiter=1000, random_state=None, with_grad=True):
+    """`minimize` with all starts advancing together: batch_fun(X (k, dim)) -> (values (k,),
+    gradients (k, dim) or None) is called once per round with the points the k still-running
+    local optimisations are waiting for, i.e. ONE batched GP call on the device instead of one
+    per start and point.  Start points, local optimiser and selection are
+    those of `minimize`, so with the same function values the result is the same.  With
+    with_grad=False the optimiser differentiates numerically (batch_fun returns (values, None))."""
+    ndim = len(bounds)
+    start_points = np.empty((n_start_points, ndim))
+    if prior is None:
+        random_state = random_state or np.random
+        for i in range(ndim):
+            start_points[:, i] = random_state.uniform(*bounds[i], n_start_points)
+    else:
+        start_points = prior.rvs(n_start_points, random_state=random_state)
+        if len(start_points.shape) == 1:
+            start_points = start_points[:, None]
+        for i in range(ndim):
+            start_points[:, i] = np.clip(start_points[:, i], *bounds[i])
+
+    meet = _Rendezvous(n_start_points)
+    results = [None] * n_start_points
+
+    def local_search(i):
+        try:
+            def objective(x):
+                value, grad = meet.request(i, x)
+                return (value, grad) if with_grad else value
+            results[i] = scipy.optimize.minimize(objective, start_points[i, :], method=method,
+                                                 jac=True if with_grad else None, bounds=bounds,
+                                                 constraints=constraints,
+                                                 options={'maxiter': maxiter})
+        except BaseException as exc:
+            results[i] = exc
+        finally:
+            meet.retire(i)
+
+    threads = [threading.Thread(target=local_search, args=(i,), daemon=True)
+               for i in range(n_start_points)]
+    for th in threads:
+        th.start()
+    try:
+        meet.serve(batch_fun)
+    finally:
+        for th in threads:
+            th.join()
+    for res in results:
+        if isinstance(res, BaseException):
+            raise res
+    vals = np.array([res['fun'] for res in results], dtype=float).ravel()
+    best = int(np.argmin(vals))
+    loc = results[best]['x']
+    for i in range(ndim):
+        loc[i] = np.clip(loc[i], *bounds[i])
+    return loc, vals[best]
+
+
 class AcquisitionBase:
     """elfi/methods/bo/acquisition.py:16-191."""
 
@@ -367,13 +479,27 @@ class AcquisitionBase:
     def evaluate_gradient(self, x, t=None):
         raise NotImplementedError
 
+    lockstep = True   # advance the multi-start optimisation with one batched GP call per round
+
+    def evaluate_with_gradient(self, x, t=None):
+        """Values (m,) and gradients (m, dim) of a batch of points (default: two calls)."""
+        x = np.asanyarray(x, dtype=np.float64).reshape((-1, self.model.input_dim))
+        return np.ravel(self.evaluate(x, t)), self.evaluate_gradient(x, t)
+
     def acquire(self, n, t=None):
-        xhat, _ = minimize(lambda x: self.evaluate(x, t), self.model.bounds,
-                           method='L-BFGS-B' if self.constraints is None else 'SLSQP',
-                           constraints=self.constraints,
-                           grad=lambda x: self.evaluate_gradient(x, t), prior=self.prior,
-                           n_start_points=self.n_inits, maxiter=self.max_opt_iters,
-                           random_state=self.random_state)
+        method = 'L-BFGS-B' if self.constraints is None else 'SLSQP'
+        if self.lockstep:
+            xhat, _ = minimize_lockstep(lambda X: self.evaluate_with_gradient(X, t),
+                                        self.model.bounds, method=method,
+                                        constraints=self.constraints, prior=self.prior,
+                                        n_start_points=self.n_inits, maxiter=self.max_opt_iters,
+                                        random_state=self.random_state)
+        else:
+            xhat, _ = minimize(lambda x: self.evaluate(x, t), self.model.bounds, method=method,
+                               constraints=self.constraints,
+                               grad=lambda x: self.evaluate_gradient(x, t), prior=self.prior,
+                               n_start_points=self.n_inits, maxiter=self.max_opt_iters,
+                               random_state=self.random_state)
         x = np.tile(xhat, (n, 1))
         return self._add_noise(x)
 
@@ -431,18 +557,27 @@ class LCBSC(AcquisitionBase):
         return self.model.predict_device(x, noiseless=True, beta=self._beta(t))[2]
 
     def evaluate_gradient(self, x, t=None):
+        return self.evaluate_with_gradient(x, t, want_value=False)[1]
+
+    def evaluate_with_gradient(self, x, t=None, want_value=True):
+        """LCBSC values (m,) and gradients (m, dim) from one GP launch + one epilogue launch."""
         x = np.asanyarray(x, dtype=np.float64).reshape((-1, self.model.input_dim))
         if self.model._factor is None:
-            return np.zeros_like(x)
+            return np.full(len(x), -np.sqrt(self._beta(t))), np.zeros_like(x)
         mean, var, gm, gv = self.model._predict_grad_device(x)
         m, p = gm.shape
+        acq = dev.empty((m,)) if want_value else None
         gacq = dev.empty((m, p))
         _lib.call('elfi_b200_lcbsc_f64', dev.context(), dev.ptr(mean), dev.ptr(var), dev.ptr(gm),
-                  dev.ptr(gv), m, p, float(self._beta(t)), None, dev.ptr(gacq), dev.stream_ptr())
-        value = gacq.cpu().numpy()
+                  dev.ptr(gv), m, p, float(self._beta(t)), dev.ptr(acq), dev.ptr(gacq),
+                  dev.stream_ptr())
+        value = acq.cpu().numpy() if want_value else None
+        grad = gacq.cpu().numpy()
         if self.additive_cost is not None:
-            value += self.additive_cost.evaluate_gradient(x)
-        return value
+            if want_value:
+                value = value + np.ravel(self.additive_cost.evaluate(x))
+            grad += self.additive_cost.evaluate_gradient(x)
+        return value, grad
 
 
 class MaxVar(AcquisitionBase):
@@ -464,10 +599,16 @@ class MaxVar(AcquisitionBase):
     def acquire(self, n, t=None):
         logger.debug('Acquiring the next batch of %d values', n)
         self._update_eps()
-        theta_max, _ = minimize(lambda theta: -self.evaluate(theta), self.model.bounds,
-                                grad=lambda theta: -self.evaluate_gradient(theta),
-                                prior=self.prior, n_start_points=self.n_inits,
-                                maxiter=self.max_opt_iters, random_state=self.random_state)
+        if self.lockstep:
+            theta_max, _ = minimize_lockstep(
+                lambda X: (-np.ravel(self.evaluate(X)), -self.evaluate_gradient(X)),
+                self.model.bounds, prior=self.prior, n_start_points=self.n_inits,
+                maxiter=self.max_opt_iters, random_state=self.random_state)
+        else:
+            theta_max, _ = minimize(lambda theta: -self.evaluate(theta), self.model.bounds,
+                                    grad=lambda theta: -self.evaluate_gradient(theta),
+                                    prior=self.prior, n_start_points=self.n_inits,
+                                    maxiter=self.max_opt_iters, random_state=self.random_state)
         return np.tile(theta_max, (n, 1))   # the same location for the whole batch
 
     def _gp(self, theta):
@@ -618,9 +759,15 @@ class ExpIntVar(MaxVar):
     def acquire(self, n, t):
         logger.debug('Acquiring the next batch of %d values', n)
         self._prepare(t)
-        theta_min, _ = minimize(self.evaluate, self.model.bounds, grad=None, prior=self.prior,
-                                n_start_points=self.n_inits, maxiter=self.max_opt_iters,
-                                random_state=self.random_state)
+        if self.lockstep:
+            theta_min, _ = minimize_lockstep(lambda X: (self.evaluate(X), None), self.model.bounds,
+                                             prior=self.prior, n_start_points=self.n_inits,
+                                             maxiter=self.max_opt_iters,
+                                             random_state=self.random_state, with_grad=False)
+        else:
+            theta_min, _ = minimize(self.evaluate, self.model.bounds, grad=None, prior=self.prior,
+                                    n_start_points=self.n_inits, maxiter=self.max_opt_iters,
+                                    random_state=self.random_state)
         return np.tile(theta_min, (n, 1))
 
     def evaluate(self, theta_new, t=None):

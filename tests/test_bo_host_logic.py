@@ -146,3 +146,44 @@ def test_adaptive_threshold_smc_objective():
         DensityRatioEstimation(optimize=True)
     with pytest.raises(ValueError):
         DensityRatioEstimation().fit(np.zeros((200, 2)), np.zeros((200, 2)))   # sigma missing
+
+
+def test_lockstep_multi_start_equals_sequential_minimize():
+    """minimize_lockstep advances all local optimisations together and evaluates their pending
+    points in one batched call; start points, optimiser and selection are those of minimize."""
+    from elfi_b200.bo import minimize, minimize_lockstep
+    centre = np.array([0.3, -0.4])
+
+    def fun(x):
+        x = np.asarray(x)
+        return float(np.sum((x - centre) ** 2) + 0.3 * np.sin(5 * x[0]) * np.cos(3 * x[1]))
+
+    def grad(x):
+        x = np.asarray(x)
+        return 2 * (x - centre) + 0.3 * np.array([5 * np.cos(5 * x[0]) * np.cos(3 * x[1]),
+                                                  -3 * np.sin(5 * x[0]) * np.sin(3 * x[1])])
+    calls = []
+
+    def batch(X):
+        calls.append(len(X))
+        return np.array([fun(x) for x in X]), np.array([grad(x) for x in X])
+    bounds = [(-2, 2), (-1, 1)]
+    x_seq, v_seq = minimize(fun, bounds, grad=grad, n_start_points=7,
+                            random_state=np.random.RandomState(4))
+    x_par, v_par = minimize_lockstep(batch, bounds, n_start_points=7,
+                                     random_state=np.random.RandomState(4))
+    assert np.array_equal(x_seq, x_par) and v_seq == v_par
+    assert max(calls) == 7 and sum(calls) > 3 * len(calls)          # rounds are shared
+    # numerical differentiation inside the optimiser when no gradient is supplied
+    x_fd, v_fd = minimize_lockstep(lambda X: (np.array([fun(x) for x in X]), None), bounds,
+                                   n_start_points=4, random_state=np.random.RandomState(4),
+                                   with_grad=False)
+    x_ref, v_ref = minimize(fun, bounds, grad=None, n_start_points=4,
+                            random_state=np.random.RandomState(4))
+    assert np.array_equal(x_fd, x_ref) and v_fd == v_ref
+    # an error in the batched evaluator surfaces in the caller, no thread is left waiting
+
+    def broken(X):
+        raise RuntimeError('device lost')
+    with pytest.raises(RuntimeError):
+        minimize_lockstep(broken, bounds, n_start_points=3, random_state=np.random.RandomState(1))
