@@ -128,6 +128,39 @@ def main():
     xq = grid[:10].contiguous()
     ms, best = timeit(lambda: gp._predict_grad_device(xq), reps=5, warm=2)
     rec('K13 GP predictive gradients m=10 n=2000', ms, best)
+    try:
+        # ---- kernels added after round 1's last GPU session (first timings in round 2)
+        from elfi_b200.bo import LCBSC
+        acq = LCBSC(gp, seed=0)
+        ms, best = timeit(lambda: acq.evaluate_with_gradient(xq.cpu().numpy(), 5), reps=5, warm=2)
+        rec('LCBSC value+gradient m=10 n=2000 (one lock-step acquisition round, incl. D2H)', ms, best)
+        pts = grid[:200].contiguous()
+        ms, best = timeit(lambda: gp.whiten(pts), reps=5, warm=2)
+        rec('gp_whiten m=200 n=2000', ms, best, flops=200 * n * n)
+        wh = gp.whiten(pts)
+        one = gp.whiten(grid[777:778].contiguous())
+        ms, best = timeit(lambda: gp.cross_covariance(wh, one), reps=5, warm=2)
+        rec('gp_cross_cov 200 x 1, n=2000', ms, best)
+        S = torch.randn(B, D, dtype=torch.float64, device='cuda', generator=gen)
+        for metric, pexp in (('sqeuclidean', 2.0), ('cityblock', 2.0), ('chebyshev', 2.0),
+                             ('minkowski', 3.0)):
+            ms, best = timeit(lambda: ops.dist_metric(S, obs, metric, p=pexp))
+            rec('dist_metric {} 1e6x128'.format(metric), ms, best, bytes_=B * D * 8 + B * 8)
+        del S
+        par = [torch.rand(1_000_000, dtype=torch.float64, device='cuda', generator=gen) * 10
+               for _ in range(4)]
+        ms, best = timeit(lambda: ops.sim_gnk(*par, n_obs=256, seed=1), reps=5, warm=2)
+        rec('sim_gnk 1e6 x 256 (write only)', ms, best, bytes_=1_000_000 * 256 * 8)
+        Y = ops.sim_gnk(*par, n_obs=256, seed=1)
+        ms, best = timeit(lambda: ops.rowsort(Y), reps=5, warm=2)
+        rec('rowsort 1e6 x 256', ms, best, bytes_=2 * 1_000_000 * 256 * 8)
+        del Y, par
+        xs = torch.rand(1_000_000, dtype=torch.float64, device='cuda', generator=gen)
+        ms, best = timeit(lambda: ops.weighted_sample_quantile(xs, 0.5))
+        rec('weighted quantile 1e6, equal weights (closed-form position)', ms, best)
+    except Exception as exc:   # keep the timings gathered so far
+        out.append(dict(name='new-kernel section failed', error=repr(exc)))
+        print(json.dumps(out[-1]), flush=True)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'kernels.json'), 'w') as f:
         json.dump(out, f, indent=1)
