@@ -131,6 +131,16 @@ def main():
     out['ess'] = np.array([mcmc.eff_sample_size(chains[:, :, k]) for k in range(2)])
     out['ess_single'] = np.float64(mcmc.eff_sample_size(chains[0, :, 0]))
     out['rhat'] = np.array([mcmc.gelman_rubin_statistic(chains[:, :, k]) for k in range(2)])
+    # known-answer values held by the reference's own test (tests/unit/test_mcmc.py: chains
+    # generated in PyStan with Stan's ESS and split R-hat)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'ref_test_mcmc', '/root/reference/tests/unit/test_mcmc.py')
+    ref_test = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_test)
+    out['stan_chains'] = np.asarray(ref_test.chains_Stan)
+    out['stan_ess'] = np.float64(ref_test.ess_Stan)
+    out['stan_rhat'] = np.float64(ref_test.Rhat_Stan)
     save('mcmc', **out)
 
     # ---- BolfiPosterior / ModelPrior gradient / MaxVar on the duck GP, MA2 priors

@@ -69,6 +69,16 @@ def test_diagnostics_equal_the_reference():
                                rtol=1e-12)
 
 
+def test_diagnostics_against_stan_values():
+    """The known answers of the reference's own test (tests/unit/test_mcmc.py:48-69): chains drawn
+    in PyStan, Stan's effective sample size 4.09 and split R-hat 1.714."""
+    from elfi_b200 import mcmc
+    g = load_golden('mcmc')
+    assert np.isclose(mcmc.eff_sample_size(g['stan_chains']), float(g['stan_ess']), atol=0.01)
+    assert np.isclose(mcmc.gelman_rubin_statistic(g['stan_chains']), float(g['stan_rhat']),
+                      atol=0.01)
+
+
 def test_bad_initial_point_raises():
     from elfi_b200 import mcmc
     with pytest.raises(ValueError):
