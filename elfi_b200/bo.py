@@ -46,7 +46,10 @@ class GPyRegression:
     Named after the reference class it stands in for; no GPy involved."""
 
     def __init__(self, parameter_names=None, bounds=None, optimizer="lbfgsb", max_opt_iters=50,
-                 gp=None, **gp_params):
+                 gp=None, incremental=False, **gp_params):
+        """`incremental=True`: new evidence extends the Cholesky factor by a rank-b update
+        (O(b n^2)) instead of a refit whenever the hyper-parameters are unchanged (opt-in until it
+        has been timed on the device; the reference rebuilds the GP on every update)."""
         if parameter_names is None:
             input_dim = 1
         elif isinstance(parameter_names, (list, tuple)):
@@ -73,7 +76,7 @@ class GPyRegression:
         self.gp_params = gp_params
         self.optimizer = optimizer
         self.max_opt_iters = max_opt_iters
-        self.is_sampling = False
+        self.incremental = bool(incremental)
         self._X = None          # host (n, p)
         self._Y = None          # host (n, 1)
         self._hyper = None      # dict(kernel_var, lengthscale, bias_var, noise_var)
@@ -128,9 +131,52 @@ class GPyRegression:
         else:
             self._X = np.r_[self._X, x]
             self._Y = np.r_[self._Y, y]
-        self._fit()
+        if not (self.incremental and self._append(x, y)):
+            self._fit()
         if optimize:
             self.optimize()
+
+    def _append(self, x_new, y_new):
+        """Rank-b update of the factor for b appended points.
+        With T = W K(X, x_new) (whitened new points), S = cov(x_new, x_new) + noise I = L22 L22^T:
+            L' = [[L, 0], [T, L22]],   W' = L'^-1 = [[W, 0], [-L22^-1 T W, L22^-1]],
+            alpha' = W'^T W' y'.
+        Only T, T W and the b x b block come from the device (whiten / apply_wt / cross_cov);
+        the b x n rows are assembled on the host and written into the padded buffers.
+        Returns False when a refit is needed instead (no factor yet, other hyper-parameters, the
+        padded size would change, or the new block is not positive definite)."""
+        f = self._factor
+        if f is None or f.get('hyper') != self._hyper:
+            return False
+        n, b = f['n'], len(x_new)
+        if n + b > f['n_pad'] or n + b != len(self._X):
+            return False
+        noise = self._hyper['noise_var'] + JITTER
+        xq, T = self.whiten(x_new)
+        TW = dev.empty((b, n))
+        _lib.call('elfi_b200_gp_apply_wt_f64', dev.context(), dev.ptr(T), n, b, dev.ptr(f['U']),
+                  f['n_pad'], n, dev.ptr(TW), n, dev.stream_ptr())
+        S = dev.to_host(self.cross_covariance((xq, T), (xq, T))) + noise * np.eye(b)
+        try:
+            L22 = np.linalg.cholesky(0.5 * (S + S.T))
+        except np.linalg.LinAlgError:
+            return False
+        L22inv = np.linalg.inv(L22)
+        TW_h = dev.to_host(TW)
+        rows = -L22inv @ TW_h                                   # new rows of W (left block)
+        y_old = self._Y[:n].ravel()
+        z2 = L22inv @ (np.asarray(y_new, dtype=float).ravel() - TW_h @ y_old)
+        alpha = np.concatenate([dev.to_host(f['alpha']) + rows.T @ z2, L22inv.T @ z2])
+        end = n + b
+        f['W'][n:end, :n] = dev.to_device(rows)
+        f['W'][n:end, n:end] = dev.to_device(L22inv)
+        f['U'][:n, n:end] = dev.to_device(np.ascontiguousarray(rows.T))
+        f['U'][n:end, n:end] = dev.to_device(np.ascontiguousarray(L22inv.T))
+        f['L'][n:end, :n] = T
+        f['L'][n:end, n:end] = dev.to_device(L22)
+        f.update(X=dev.to_device(self._X), y=dev.to_device(self._Y.reshape(-1)), n=end,
+                 alpha=dev.to_device(alpha))
+        return True
 
     def _fit(self, hyper=None):
         h = hyper or self._hyper

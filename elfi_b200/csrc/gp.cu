@@ -422,6 +422,24 @@ gp_whiten_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __res
     }
 }
 
+// out[q, r] = sum_{c >= r} U[r, c] T[q, c]  (= W^T t_q; U = W^T is upper triangular): the third
+// phase of predict_grad_kernel for a batch of whitened vectors.  Used by the rank-b factor update.
+__global__ void __launch_bounds__(256)
+gp_apply_wt_kernel(const double* __restrict__ T, int64_t ldT, const double* __restrict__ U,
+                   int64_t ldw, int64_t n, double* __restrict__ out, int64_t ldo) {
+    extern __shared__ double tq[];   // n
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t j = tid; j < n; j += 256) tq[j] = T[q * ldT + j];
+    __syncthreads();
+    for (int64_t r = warp; r < n; r += 8) {
+        double acc = 0.0;
+        for (int64_t c = r + lane; c < n; c += 32) acc = fma(U[r * ldw + c], tq[c], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[q * ldo + r] = acc;
+    }
+}
+
 // cov[b * ma + a] = k(x_a, x_b) - T_a . T_b, one warp per pair (a, b)
 __global__ void __launch_bounds__(256)
 gp_cross_cov_kernel(const double* __restrict__ Xa, int64_t lda, int64_t ma,
@@ -646,6 +664,24 @@ int elfi_b200_gp_whiten_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, i
     gp_whiten_kernel<<<unsigned(m), 256, smem, stream>>>(Xq, ldq, X, ldX, n, int(p), W, n_pad, kernel_var,
                                                          -0.5 / (lengthscale * lengthscale), bias_var,
                                                          T, ldT);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gp_apply_wt_f64(elfi_b200_ctx* ctx, const double* T, int64_t ldT, int64_t m,
+                              const double* U, int64_t n_pad, int64_t n, double* out, int64_t ldo,
+                              void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && U && (m == 0 || (T && out)), "gp_apply_wt: NULL argument");
+    ELFI_REQUIRE(m >= 0 && n >= 1 && ldT >= n && ldo >= n && n_pad >= n, "gp_apply_wt: bad shape");
+    ELFI_REQUIRE(size_t(n) * 8 <= 200 * 1024, "gp_apply_wt: n=%lld too large (<= 25600)", (long long)n);
+    if (m == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t smem = size_t(n) * 8;
+    ELFI_CUDA_OK(cudaFuncSetAttribute(gp_apply_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem)));
+    gp_apply_wt_kernel<<<unsigned(m), 256, smem, stream>>>(T, ldT, U, n_pad, n, out, ldo);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

@@ -234,6 +234,11 @@ int elfi_b200_gp_whiten_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, i
                             const double* X, int64_t ldX, int64_t n, int64_t p, const double* W,
                             int64_t n_pad, double kernel_var, double lengthscale, double bias_var,
                             double* T, int64_t ldT, void* stream);
+/* out[q, 0:n] = W^T T[q, 0:n] (U = W^T from gp_fit): with T = gp_whiten(X_new) these are the rows
+ * T W that a rank-b update of the factor (b new evidence points appended, no refit) needs. */
+int elfi_b200_gp_apply_wt_f64(elfi_b200_ctx* ctx, const double* T, int64_t ldT, int64_t m,
+                              const double* U, int64_t n_pad, int64_t n, double* out, int64_t ldo,
+                              void* stream);
 int elfi_b200_gp_cross_cov_f64(elfi_b200_ctx* ctx, const double* Xa, int64_t lda, int64_t ma,
                                const double* Ta, int64_t ldTa, const double* Xb, int64_t ldb,
                                int64_t mb, const double* Tb, int64_t ldTb, int64_t n, int64_t p,

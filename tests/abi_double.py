@@ -306,6 +306,11 @@ def gp_whiten_f64(ctx, Xq, ldq, m, X, ldX, n, p, W, n_pad, kernel_var, lengthsca
     _mat(T, m, n, ldT)[:] = k.dot(Wn.T)
 
 
+def gp_apply_wt_f64(ctx, T, ldT, m, U, n_pad, n, out, ldo, stream):
+    Wn = _mat(U, n_pad, n_pad)[:n, :n].T
+    _mat(out, m, n, ldo)[:] = _mat(T, m, n, ldT).dot(Wn)
+
+
 def gp_cross_cov_f64(ctx, Xa, lda, ma, Ta, ldTa, Xb, ldb, mb, Tb, ldTb, n, p, kernel_var,
                      lengthscale, bias_var, cov, stream):
     xa = np.ascontiguousarray(_mat(Xa, ma, p, lda))
@@ -430,7 +435,7 @@ _TABLE = {'elfi_b200_' + f.__name__: f for f in (
     dist_euclid_thr_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
-    gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
+    gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
     gm_rvs_f64, prior_gauss_f64, logprior_gauss_f64, sim_gauss_f64, sim_gnk_f64, logprior_box_f64)}
 
 

@@ -161,3 +161,42 @@ def case_bolfi_sample():
         except ValueError:
             continue
         raise AssertionError('expected ValueError for {}'.format(bad))
+
+
+def case_incremental_factor_update():
+    """GPyRegression(incremental=True): appending evidence by rank-b updates gives the factor,
+    alpha and predictions of a refit; a refit happens when the padded size or the
+    hyper-parameters change."""
+    from elfi_b200.bo import GPyRegression
+    rs = np.random.RandomState(5)
+    bounds = {'t1': (-2, 2), 't2': (-1, 1)}
+    X = np.column_stack([rs.uniform(-2, 2, 200), rs.uniform(-1, 1, 200)])
+    y = np.log(0.05 + (X[:, 0] - 0.6) ** 2 + 2 * (X[:, 1] - 0.2) ** 2) + 0.1 * rs.randn(200)
+    inc = GPyRegression(['t1', 't2'], bounds=bounds, incremental=True)
+    ref = GPyRegression(['t1', 't2'], bounds=bounds)
+    inc.update(X[:100], y[:100, None])
+    ref.update(X[:100], y[:100, None])
+    grid = np.column_stack([rs.uniform(-2, 2, 50), rs.uniform(-1, 1, 50)])
+    step = [1, 5, 3, 16, 2, 1]              # crosses the 128-row padding boundary on the way
+    n = 100
+    for b in step:
+        inc.update(X[n:n + b], y[n:n + b, None])
+        ref.update(X[n:n + b], y[n:n + b, None])
+        n += b
+        assert inc.n_evidence == ref.n_evidence == n and inc._factor['n'] == n
+        np.testing.assert_allclose(inc._factor['alpha'].cpu().numpy(),
+                                   ref._factor['alpha'].cpu().numpy(), rtol=1e-6, atol=1e-8)
+        for a, r in zip(inc.predict(grid), ref.predict(grid)):
+            np.testing.assert_allclose(a, r, rtol=1e-7, atol=1e-9)
+        for a, r in zip(inc.predictive_gradients(grid[:5]), ref.predictive_gradients(grid[:5])):
+            np.testing.assert_allclose(a, r, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(inc.log_marginal_likelihood(), ref.log_marginal_likelihood(),
+                                   rtol=1e-9)
+    Wi = inc._factor['W'].cpu().numpy()[:n, :n]
+    Wr = ref._factor['W'].cpu().numpy()[:n, :n]
+    np.testing.assert_allclose(Wi, Wr, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(inc._factor['U'].cpu().numpy()[:n, :n], Wi.T, rtol=0, atol=0)
+    inc.update(X[n:n + 4], y[n:n + 4, None], optimize=True)      # new hyper-parameters: refit
+    ref.update(X[n:n + 4], y[n:n + 4, None], optimize=True)
+    for a, r in zip(inc.predict(grid), ref.predict(grid)):
+        np.testing.assert_allclose(a, r, rtol=1e-7, atol=1e-9)

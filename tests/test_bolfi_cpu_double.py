@@ -23,6 +23,10 @@ def test_expintvar_matches_reference():
     cases.case_expintvar_matches_reference()
 
 
+def test_incremental_factor_update():
+    cases.case_incremental_factor_update()
+
+
 def test_other_acquisitions():
     cases.case_other_acquisitions()
 
