@@ -141,16 +141,16 @@ def main():
         one = gp.whiten(grid[777:778].contiguous())
         ms, best = timeit(lambda: gp.cross_covariance(wh, one), reps=5, warm=2)
         rec('gp_cross_cov 200 x 1, n=2000', ms, best)
-        xn, yn = np.array([[0.31, 0.17]]), np.array([[0.2]])
+        count = [0]
 
-        def append_one():
-            gp._X, gp._Y = np.r_[gp._X, xn], np.r_[gp._Y, yn]
-            ok = gp._append(xn, yn)
-            gp._X, gp._Y, gp._factor['n'] = gp._X[:-1], gp._Y[:-1], gp._factor['n'] - (1 if ok else 0)
-            return ok
-        if append_one():
-            ms, best = timeit(append_one, reps=5, warm=2)
-            rec('GP rank-1 factor update n=2000 (vs the refit above)', ms, best)
+        def append_one():      # n = 2000 -> 2007: stays inside the padded size 2048
+            xn = np.array([[0.31 + 0.01 * count[0], 0.17]])
+            count[0] += 1
+            gp._X, gp._Y = np.r_[gp._X, xn], np.r_[gp._Y, np.array([[0.2]])]
+            if not gp._append(xn, np.array([[0.2]])):
+                raise RuntimeError('rank-1 update refused')
+        ms, best = timeit(append_one, reps=5, warm=2)
+        rec('GP rank-1 factor update n~2000 (vs the refit above)', ms, best)
         S = torch.randn(B, D, dtype=torch.float64, device='cuda', generator=gen)
         for metric, pexp in (('sqeuclidean', 2.0), ('cityblock', 2.0), ('chebyshev', 2.0),
                              ('minkowski', 3.0)):
