@@ -402,28 +402,28 @@ class _Rendezvous:
 
     def serve(self, batch_fun):
         """Run on the owning thread until all workers have retired."""
-        while True:
-            with self.cv:
-                while self.live > 0 and len(self.posted) < self.live:
-                    self.cv.wait()
-                if self.live == 0:
-                    return
-                workers = sorted(self.posted)
-                X = np.array([self.posted[w] for w in workers])
-                self.posted.clear()
-            try:
+        try:
+            while True:
+                with self.cv:
+                    while self.live > 0 and len(self.posted) < self.live:
+                        self.cv.wait()
+                    if self.live == 0:
+                        return
+                    workers = sorted(self.posted)
+                    X = np.array([self.posted[w] for w in workers])
+                    self.posted.clear()
                 values, grads = batch_fun(X)
                 values = np.ravel(values)
-            except BaseException as exc:        # wake the workers, then re-raise here
                 with self.cv:
-                    self.error = exc
+                    for k, w in enumerate(workers):
+                        self.answers[w] = (float(values[k]), None if grads is None
+                                           else np.array(grads[k], dtype=float))
                     self.cv.notify_all()
-                raise
+        except BaseException as exc:     # whatever stops the owner must release the workers
             with self.cv:
-                for k, w in enumerate(workers):
-                    self.answers[w] = (float(values[k]),
-                                       None if grads is None else np.array(grads[k], dtype=float))
+                self.error = exc
                 self.cv.notify_all()
+            raise
 
 
 def minimize_lockstep(batch_fun, bounds, method='L-BFGS-B', constraints=None, prior=None,
