@@ -178,9 +178,10 @@ sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int
 // cumw: inclusive cumulative sum of the normalised weights (N); Lc: lower Cholesky factor of the
 // shared covariance (p x p, row-major, p <= 4).  support: 0 none, 1 MA2 prior support.
 struct BoxSupport { double lo[4], hi[4]; };
+struct LowerFactor4 { double v[16]; };   // row-major p x p (p <= 4), passed by value
 
 __global__ void gm_rvs_kernel(const double* __restrict__ means, int64_t ldm, const double* __restrict__ cumw,
-                              int64_t N, int p, const double* __restrict__ Lc, int64_t B,
+                              int64_t N, int p, const LowerFactor4 Lc, int64_t B,
                               uint64_t seed, uint64_t offset, int support, BoxSupport box,
                               double* __restrict__ out, int64_t ldo) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -202,7 +203,7 @@ __global__ void gm_rvs_kernel(const double* __restrict__ means, int64_t ldm, con
         if (p > 2) normal2(ph(uint32_t(row), uint32_t(row >> 32), trial * 4u + 2u, 0x474d5256u), z[2], z[3]);
         for (int a = 0; a < p; ++a) {
             double s = means[lo * ldm + a];
-            for (int b = 0; b <= a; ++b) s = fma(Lc[a * p + b], z[b], s);
+            for (int b = 0; b <= a; ++b) s = fma(Lc.v[a * p + b], z[b], s);
             x[a] = s;
         }
         bool ok = support == 0 || (support == 1 && ma2_in_support(x[0], x[1]));
@@ -428,12 +429,23 @@ int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2
     return ELFI_B200_OK;
 }
 
-int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* weights,
-                         int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
-                         uint64_t offset, int32_t support, const double* box_host, double* out,
-                         int64_t ldo, void* stream_) {
+int elfi_b200_gm_cdf_f64(elfi_b200_ctx* ctx, const double* weights, int64_t N, double* cumw,
+                         void* stream_) {
     using namespace elfi;
-    ELFI_REQUIRE(ctx && means && Lchol_host && (B == 0 || out), "gm_rvs: NULL argument");
+    ELFI_REQUIRE(ctx && cumw && N >= 1, "gm_cdf: bad argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    cumsum_kernel<<<1, 1024, 0, stream>>>(weights, N, cumw);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_gm_rvs_cdf_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* cumw,
+                             int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
+                             uint64_t offset, int32_t support, const double* box_host, double* out,
+                             int64_t ldo, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && means && cumw && Lchol_host && (B == 0 || out), "gm_rvs: NULL argument");
     ELFI_REQUIRE(N >= 1 && p >= 1 && p <= 4 && ldm >= p && ldo >= p, "gm_rvs: bad shape (p <= 4)");
     ELFI_REQUIRE(support == 0 || (support == 1 && p == 2) || (support == 2 && box_host),
                  "gm_rvs: unknown support %d", support);
@@ -444,16 +456,30 @@ int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, c
     if (B == 0) return ELFI_B200_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
-    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, size_t(N) * 8 + 512));
-    if (!base) return ELFI_B200_ERR_NOMEM;
-    double* Lc = reinterpret_cast<double*>(base);
-    double* cumw = reinterpret_cast<double*>(base + 256);
-    ELFI_CUDA_OK(cudaMemcpyAsync(Lc, Lchol_host, size_t(p) * p * 8, cudaMemcpyHostToDevice, stream));
-    cumsum_kernel<<<1, 1024, 0, stream>>>(weights, N, cumw);
+    LowerFactor4 Lc;
+    memset(&Lc, 0, sizeof(Lc));
+    for (int a = 0; a < p; ++a)
+        for (int b = 0; b <= a; ++b) Lc.v[a * p + b] = Lchol_host[a * p + b];
     gm_rvs_kernel<<<unsigned((B + 127) / 128), 128, 0, stream>>>(means, ldm, cumw, N, int(p), Lc, B,
                                                                 seed, offset, support, box, out, ldo);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
+}
+
+int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* weights,
+                         int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
+                         uint64_t offset, int32_t support, const double* box_host, double* out,
+                         int64_t ldo, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && N >= 1, "gm_rvs: bad argument");
+    if (B == 0) return ELFI_B200_OK;
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    double* cumw = static_cast<double*>(ctx_scratch(ctx, size_t(N) * 8 + 256));
+    if (!cumw) return ELFI_B200_ERR_NOMEM;
+    int rc = elfi_b200_gm_cdf_f64(ctx, weights, N, cumw, stream_);
+    if (rc != ELFI_B200_OK) return rc;
+    return elfi_b200_gm_rvs_cdf_f64(ctx, means, ldm, cumw, N, p, Lchol_host, B, seed, offset, support,
+                                    box_host, out, ldo, stream_);
 }
 
 static elfi::GaussPrior make_gauss_prior(const double* prm) {

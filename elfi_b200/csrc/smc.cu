@@ -328,23 +328,24 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
-    // component chunks: enough CTAs (>= 8 per SM) even when N is only ~1e5 per rank
+    // Component chunks.  The chunk length depends on M ONLY, never on N: a point's partial sums are
+    // then added in the same order whether a rank evaluates all N points or a shard of them, so
+    // the sharded multi-GPU density is bit-identical to the single-GPU one.  M / 64 components per
+    // chunk (clamped to [2048, 16384], multiple of the 512-component smem tile) gives >= 8 CTAs
+    // per SM from N ~ 1e4 points per rank upwards while a CTA's prologue stays negligible.
     constexpr int R = 4;
     const int64_t xblocks = (N + 128 * R - 1) / (128 * R);
     int64_t chunks = 1, chunk_len = M;
     if (p <= 4) {
-        // ~16 waves of CTAs (8 resident per SM) keep the tail of the last wave below a few
-        // percent; a CTA still sweeps >= 2048 components so its prologue stays negligible
-        int waves = 16;
-        if (const char* e = getenv("ELFI_B200_GM_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;
-        chunks = (int64_t(ctx->sm_count) * 8 * waves + xblocks - 1) / xblocks;
-        const int64_t max_chunks = (M + 2047) / 2048;
-        if (chunks > max_chunks) chunks = max_chunks;
-        if (chunks > 65535) chunks = 65535;
-        if (chunks < 1) chunks = 1;
-        chunk_len = (M + chunks - 1) / chunks;
-        chunk_len = ((chunk_len + 511) / 512) * 512;
+        chunk_len = ((M / 64 + 511) / 512) * 512;
+        if (chunk_len < 2048) chunk_len = 2048;
+        if (chunk_len > 16384) chunk_len = 16384;
+        if (const char* e = getenv("ELFI_B200_GM_CHUNK")) {
+            const long v = atol(e);
+            if (v >= 512) chunk_len = (int64_t(v) / 512) * 512;
+        }
         chunks = (M + chunk_len - 1) / chunk_len;
+        ELFI_REQUIRE(chunks <= 65535, "gm_logpdf: too many component chunks (%lld)", (long long)chunks);
     }
     const size_t off_xw = align(size_t(p) * p * 8);
     const size_t off_mw = off_xw + align(size_t(N) * p * 8);

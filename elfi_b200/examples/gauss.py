@@ -101,8 +101,8 @@ class DeviceProposal:
         self.prm = list(prm)                      # [mu_lo, mu_width, a, b]
         self.box = ([prm[0], prm[2]], [prm[0] + prm[1], prm[3]])
 
-    def rvs(self, means, cov, weights, size, key):
-        return ops.gm_rvs(means, cov, weights, size, seed=key, support=2, box=self.box)
+    def rvs(self, means, cov, weights, size, key, cdf=None):
+        return ops.gm_rvs(means, cov, weights, size, seed=key, support=2, box=self.box, cdf=cdf)
 
     def logpdf(self, params):
         return ops.logprior_gauss(params, self.prm)

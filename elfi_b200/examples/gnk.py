@@ -96,8 +96,8 @@ class DeviceProposal:
         self.width = np.broadcast_to(np.asarray(width, dtype=np.float64), (4,)).copy()
         self.box = (list(self.lo), list(self.lo + self.width))
 
-    def rvs(self, means, cov, weights, size, key):
-        return ops.gm_rvs(means, cov, weights, size, seed=key, support=2, box=self.box)
+    def rvs(self, means, cov, weights, size, key, cdf=None):
+        return ops.gm_rvs(means, cov, weights, size, seed=key, support=2, box=self.box, cdf=cdf)
 
     def logpdf(self, params):
         return ops.logprior_box(params, self.lo, self.width)

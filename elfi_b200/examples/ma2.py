@@ -159,8 +159,8 @@ class DeviceProposal:
     parameter_names = ['t1', 't2']
 
     @staticmethod
-    def rvs(means, cov, weights, size, key):
-        return ops.gm_rvs(means, cov, weights, size, seed=key, support=1)
+    def rvs(means, cov, weights, size, key, cdf=None):
+        return ops.gm_rvs(means, cov, weights, size, seed=key, support=1, cdf=cdf)
 
     @staticmethod
     def logpdf(params):

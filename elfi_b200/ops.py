@@ -217,7 +217,12 @@ def argsort(keys, return_keys=False):
 
 
 def _as_2d(t):
-    return t if t.dim() == 2 else t.reshape(t.shape[0], -1)
+    if t.dim() == 2:
+        return t
+    width = 1
+    for extent in t.shape[1:]:
+        width *= int(extent)
+    return t.reshape(t.shape[0], width)
 
 
 def take_rows(src, idx):
@@ -296,10 +301,12 @@ def weighted_var(x, weights=None):
     return weighted_stats(x, weights)[3]
 
 
-def gm_logpdf(x, means, cov=1, weights=None):
+def gm_logpdf(x, means, cov=1, weights=None, validate=True):
     """GMDistribution.logpdf (elfi/methods/utils.py:174-197) on the device.
 
-    x (N, p) and means (M, p) may be host or device arrays; returns a device tensor (N,)."""
+    x (N, p) and means (M, p) may be host or device arrays; returns a device tensor (N,).
+    ``validate=False`` skips the two synchronising weight checks of normalize_weights
+    (utils.py:80-88) for weights the caller produced itself."""
     means = _matrix(means)
     M, p = means.shape
     x = dev.to_device(x)
@@ -313,7 +320,7 @@ def gm_logpdf(x, means, cov=1, weights=None):
     Linv = np.ascontiguousarray(np.linalg.inv(L))
     logdet = 2.0 * float(np.sum(np.log(np.diag(L))))
     w = None if weights is None else dev.to_device(weights).reshape(-1)
-    if w is not None:
+    if w is not None and validate:
         if bool((w < 0).any()):
             raise ValueError("Weights must be positive")
         if float(w.sum()) == 0:
@@ -373,24 +380,38 @@ def sim_ma2(t1, t2, n_obs=100, seed=0, offset=0, want_data=False, want_summaries
     return X, S
 
 
-def gm_rvs(means, cov, weights, size, seed, offset=0, support=0, box=None):
+def gm_cdf(weights, n=None):
+    """Inclusive running sum of the mixture weights (None -> n equal weights): the lookup table of
+    the component draw in GMDistribution.rvs (elfi/methods/utils.py:239), built once per population
+    and handed to every :func:`gm_rvs` call of that population."""
+    w = None if weights is None else dev.to_device(weights).reshape(-1)
+    n = int(w.numel()) if w is not None else int(n)
+    cumw = dev.empty((n,))
+    _lib.call('elfi_b200_gm_cdf_f64', dev.context(), dev.ptr(w), n, dev.ptr(cumw), dev.stream_ptr())
+    return cumw
+
+
+def gm_rvs(means, cov, weights, size, seed, offset=0, support=0, box=None, cdf=None):
     """GMDistribution.rvs on the device (elfi/methods/utils.py:200-261); support=1 keeps only
     draws inside the MA2 prior support, support=2 inside ``box`` = (lo (p,), hi (p,)) (redrawn per
-    particle)."""
+    particle).  ``cdf`` = :func:`gm_cdf` of the weights (then ``weights`` is not read)."""
     means = _matrix(means)
     N, p = means.shape
     cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
     if cov.shape == (1, 1) and p > 1:
         cov = np.eye(p) * cov[0, 0]
     L = np.ascontiguousarray(np.linalg.cholesky(cov))
-    w = None if weights is None else dev.to_device(weights).reshape(-1)
     boxarr = None
     if support == 2:
         boxarr = np.ascontiguousarray(np.concatenate([np.asarray(box[0], dtype=np.float64),
                                                       np.asarray(box[1], dtype=np.float64)]))
     out = dev.empty((size, p))
-    _lib.call('elfi_b200_gm_rvs_f64', dev.context(), dev.ptr(means), _ld(means), dev.ptr(w), N, p,
-              dev.ptr(L), size, int(seed), int(offset), int(support), dev.ptr(boxarr),
+    if cdf is None:
+        cdf = gm_cdf(weights, N)
+    elif cdf.numel() != N:
+        raise ValueError('cdf must have one entry per mixture component')
+    _lib.call('elfi_b200_gm_rvs_cdf_f64', dev.context(), dev.ptr(means), _ld(means), dev.ptr(cdf), N,
+              p, dev.ptr(L), size, int(seed), int(offset), int(support), dev.ptr(boxarr),
               dev.ptr(out), p, dev.stream_ptr())
     return out
 

@@ -4,8 +4,39 @@ SmcSample at 387-413, OptimizationResult at 55-70): host arrays in `outputs`, pa
 means, adaptive_distance_w, ...) readable as an attribute.  Plotting / saving are out of scope.
 """
 from collections import OrderedDict
+from collections.abc import Mapping
 
 import numpy as np
+
+
+def _host(v):
+    """Device array -> host ndarray (one synchronising D2H copy); host values pass through."""
+    return v.detach().cpu().numpy() if hasattr(v, 'is_cuda') else v
+
+
+class DeviceOutputs(Mapping):
+    """`outputs` of a sample whose arrays still live on the device: name -> host ndarray, copied
+    to the host the first time a name is read.  The samplers hand populations from one
+    generation to the next on the device, so an SMC run only pays the D2H copies of what the user
+    actually looks at (the reference's Sample holds host arrays, results.py:73-108)."""
+
+    def __init__(self, device_arrays):
+        self.device = dict(device_arrays)
+        self._host = {}
+
+    def __getitem__(self, name):
+        if name not in self._host:
+            self._host[name] = _host(self.device[name])
+        return self._host[name]
+
+    def __iter__(self):
+        return iter(self.device)
+
+    def __len__(self):
+        return len(self.device)
+
+    def rows(self, name):
+        return int(self.device[name].shape[0])
 
 
 class _Result:
@@ -13,7 +44,7 @@ class _Result:
 
     def __init__(self, method_name, outputs, parameter_names, **meta):
         self.method_name = method_name
-        self.outputs = dict(outputs)
+        self.outputs = outputs if isinstance(outputs, DeviceOutputs) else dict(outputs)
         self.parameter_names = parameter_names
         self.meta = meta
 
@@ -46,13 +77,48 @@ class Sample(_Result):
     def __init__(self, method_name, outputs, parameter_names, discrepancy_name=None, weights=None,
                  **meta):
         super().__init__(method_name, outputs, parameter_names, **meta)
-        self.samples = OrderedDict((name, self.outputs[name]) for name in parameter_names)
         self.discrepancy_name = discrepancy_name
         self.weights = weights
+
+    # `samples`, `weights` and `means` may be backed by device arrays; they become host arrays
+    # on first access and stay so
+    @property
+    def samples(self):
+        cached = self.__dict__.get('_samples')
+        if cached is None:
+            cached = OrderedDict((name, self.outputs[name]) for name in self.parameter_names)
+            self.__dict__['_samples'] = cached
+        return cached
+
+    @property
+    def weights(self):
+        w = self.__dict__.get('_weights')
+        if hasattr(w, 'is_cuda'):
+            w = self.__dict__['_weights'] = _host(w)
+        return w
+
+    @weights.setter
+    def weights(self, value):
+        self.__dict__['_weights'] = value
+
+    @property
+    def means(self):
+        m = self.__dict__.get('_means')
+        if m is None:
+            raise AttributeError("No attribute 'means' in this sample")
+        if hasattr(m, 'is_cuda'):
+            m = self.__dict__['_means'] = _host(m)
+        return m
+
+    @means.setter
+    def means(self, value):
+        self.__dict__['_means'] = value
 
     @property
     def n_samples(self):
         first = self.parameter_names[0]
+        if isinstance(self.outputs, DeviceOutputs):
+            return self.outputs.rows(first)
         return len(self.outputs[first])
 
     @property
@@ -90,7 +156,7 @@ class SmcSample(Sample):
 
     def __init__(self, method_name, outputs, parameter_names, populations, *args, **kwargs):
         super().__init__(method_name, outputs, parameter_names, *args, **kwargs)
-        if self.weights is None:
+        if self.__dict__.get('_weights') is None:
             raise ValueError("No weights provided for the sample")
         self.populations = populations
 

@@ -29,7 +29,7 @@ from . import device as dev
 from . import model as em
 from . import ops
 from . import sharding
-from .results import Sample, SmcSample
+from .results import DeviceOutputs, Sample, SmcSample
 
 logger = logging.getLogger(__name__)
 
@@ -92,13 +92,17 @@ class Comm:
         self.dist.all_gather_into_tensor(out, t)
         return out
 
-    def all_reduce_max(self, value):
+    def all_gather_ints(self, values):
+        """Every rank's list of integers as a (size, len(values)) int64 host array: ONE small
+        collective for all the per-rank counters a step needs (counts, n_sim, n_batches)."""
+        vals = np.asarray(values, dtype=np.int64).reshape(1, -1)
         if not self.on:
-            return value
+            return vals
         devname = 'cuda' if self.dist.get_backend() == 'nccl' else 'cpu'
-        t = torch.tensor([float(value)], dtype=torch.float64, device=devname)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t.item())
+        t = torch.from_numpy(vals).to(devname)
+        out = torch.empty((self.size, vals.shape[1]), dtype=torch.int64, device=devname)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
 
     def all_reduce_sum(self, value):
         if not self.on:
@@ -293,6 +297,13 @@ class ParameterInference:
         if self.max_parallel_batches <= 0:
             raise ValueError('Value for max_parallel_batches ({}) must be at least one.'.format(
                 self.max_parallel_batches))
+        # Batches are processed in groups: `world_size` batches per step across the ranks
+        # (batch b on rank b % world_size), or `max_parallel_batches` consecutive batches on a
+        # single rank -- the reference keeps that many batches in flight
+        # (parameter_inference.py:270-305).  Objectives are re-estimated and `finished` is tested
+        # at group boundaries only, so a W-rank run and a single-rank run with
+        # max_parallel_batches=W process exactly the same batches.
+        self._group = 1 if self.comm.on else int(self.max_parallel_batches)
         self.state = dict(n_sim=0, n_batches=0)
         self.objective = dict()
         self._next_batch_index = 0
@@ -357,7 +368,13 @@ class ParameterInference:
 
     @property
     def finished(self):
+        if self.state['n_batches'] % self._group:
+            return False
         return self._objective_n_batches <= self.state['n_batches']
+
+    def _round_up_to_group(self, n_batches):
+        g = self._group
+        return int(ceil(n_batches / g)) * g if g > 1 else n_batches
 
     @property
     def _objective_n_batches(self):
@@ -420,6 +437,15 @@ class Sampler(ParameterInference):
 
 
 # ------------------------------------------------------------------------------- rejection
+def _batch_key(seed, batch_index):
+    """Philox key of one batch's device proposals: splitmix64 of (round seed, batch index)."""
+    m = (1 << 64) - 1
+    z = (int(seed) * 0x9E3779B97F4A7C15 + int(batch_index) + 1) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return int((z ^ (z >> 31)) & ((1 << 63) - 1))
+
+
 def _to_dev_f64(x):
     return x if dev.is_device_array(x) else dev.to_device(np.asarray(x, dtype=np.float64))
 
@@ -450,11 +476,14 @@ class Rejection(Sampler):
             n_batches = ceil(n_sim / self.batch_size)
             if self.comm.on:
                 n_batches = sharding.batches_per_rank(n_batches, self.comm.size)
+            n_batches = self._round_up_to_group(n_batches)
         else:
             n_batches = 1 if self.comm.on else self.max_parallel_batches
         self.objective = dict(n_samples=n_samples, threshold=threshold, n_batches=n_batches)
         self._next_batch_index = 0
         self._n_acceptable = 0
+        self._n_valid = 0          # filled rows of the local best-n buffers
+        self._gathered = False     # multi-rank: the ranks' buffers have been merged
 
     # -- device-side acceptance: thresholds are handed to the distance kernel
     def _accept_hint(self):
@@ -470,25 +499,31 @@ class Rejection(Sampler):
         return {self.discrepancy_name: np.atleast_1d(np.asarray(thr, dtype=np.float64))}
 
     def update(self, batch, batch_index):
+        if self._gathered:
+            raise RuntimeError('the local best-n buffers were already merged across the ranks; '
+                               'call set_objective() before simulating further batches')
         super().update(batch, batch_index)
         if self.state['samples'] is None:
             self._init_samples_lazy(batch)
         self._merge_batch(batch)
-        self._update_state_meta()
-        self._update_objective_n_batches()
+        if self.state['n_batches'] % self._group == 0:
+            if self.objective.get('threshold') is None:
+                self._update_state_meta()     # quantile mode: the running n-th distance prunes
+            self._update_objective_n_batches()
 
     def extract_result(self):
         if self.state['samples'] is None:
             raise ValueError('Nothing to extract')
         self._gather_ranks()
+        self._update_state_meta()
         if self.adaptive:
             with PHASES('extract:update_distances'):
                 self._update_distances()
         n = self.objective['n_samples']
-        with PHASES('extract:to_host'):
-            outputs = {k: dev.to_host(v[:n]) for k, v in self.state['samples'].items()}
-        sample = Sample(outputs=outputs, **self._extract_result_kwargs())
-        sample._dev = {k: v[:n] for k, v in self.state['samples'].items()}   # device twins
+        # the arrays stay on the device; `outputs` copies a column to the host when it is read
+        twins = {k: v[:n] for k, v in self.state['samples'].items()}
+        sample = Sample(outputs=DeviceOutputs(twins), **self._extract_result_kwargs())
+        sample._dev = twins
         return sample
 
     def _init_samples_lazy(self, batch):
@@ -540,12 +575,20 @@ class Rejection(Sampler):
             self._n_acceptable += n_cand
         if n_cand == 0:
             return
+        # only the filled prefix of the best-n buffers takes part in the sort
+        nv = self._n_valid
+        n_out = min(n, nv + n_cand)
         key_state = samples[dname] if samples[dname].dim() == 1 else samples[dname][:, -1]
         key_batch = d_batch if d_batch.dim() == 1 else d_batch[:, -1]
         cand_keys = key_batch if map_b is None else ops.take_rows(key_batch, map_b)
-        perm = ops.argsort(torch.cat([key_state, cand_keys]))
+        perm = ops.argsort(torch.cat([key_state[:nv], cand_keys]))
         for node in samples:
-            samples[node] = ops.take_rows2(samples[node], _to_dev_f64(batch[node]), perm, n, map_b)
+            top = ops.take_rows2(samples[node][:nv], _to_dev_f64(batch[node]), perm, n_out, map_b)
+            if n_out == n:
+                samples[node] = top
+            else:
+                samples[node][:n_out] = top
+        self._n_valid = n_out
 
     def _update_state_meta(self):
         o, s = self.objective, self.state
@@ -566,14 +609,14 @@ class Rejection(Sampler):
             else self._n_acceptable
         n_sim = s['n_sim'] * self.comm.size if self.comm.on else s['n_sim']
         if n_acceptable == 0:
-            n_batches = self.objective['n_batches'] + 1
+            n_batches = self.objective['n_batches'] + self._group
         else:
             accept_rate_t = n_acceptable / n_sim
             margin = .2 * self.batch_size * int(n_acceptable < n_samples)
             n_batches = ceil((n_samples / accept_rate_t + margin) / self.batch_size)
             if self.comm.on:
                 n_batches = ceil(n_batches / self.comm.size)
-        self.objective['n_batches'] = n_batches
+        self.objective['n_batches'] = self._round_up_to_group(n_batches)
 
     def _update_distances(self):
         """samplers.py:279-299: append the new weight vector, re-score the kept rows with all
@@ -593,44 +636,47 @@ class Rejection(Sampler):
         self._update_state_meta()
 
     def _gather_ranks(self):
-        """Multi-GPU: one all-gather of the fixed-capacity local best-n buffers, then the same
-        sort + gather on every rank, so all ranks hold the identical global best-n."""
-        if not self.comm.on:
+        """Multi-GPU: ONE all-gather of the ranks' local best-n buffers -- every output packed into
+        one (capacity, width) matrix -- then the same sort + gather on every rank, so all ranks
+        hold the identical global best-n.  One small integer all-gather beforehand carries the
+        per-rank row counts (-> common capacity) and the n_sim / n_batches totals."""
+        if not self.comm.on or self._gathered:
             return
+        self._gathered = True
         samples = self.state['samples']
         n = self.objective['n_samples']
-        # ranks hold n-row buffers padded with +inf; only the common capacity that covers every
-        # rank's finite rows is exchanged (one scalar MAX all-reduce, then the all-gather)
-        dloc = samples[self.discrepancy_name]
-        key = dloc if dloc.dim() == 1 else dloc[:, -1]
-        with PHASES('gather:capacity'):
-            valid = int(torch.isfinite(key).sum().item())
-            cap = int(self.comm.all_reduce_max(valid))
-        cap = max(1, min(n, ((cap + 31) // 32) * 32))
+        with PHASES('gather:counts'):
+            counts = self.comm.all_gather_ints([self._n_valid, self.state['n_sim'],
+                                                self.state['n_batches']])
+        cap = max(1, min(n, ((int(counts[:, 0].max()) + 31) // 32) * 32))
+        names = list(samples)
+        shapes = {k: tuple(samples[k].shape[1:]) for k in names}
+        widths = [int(np.prod(shapes[k])) if shapes[k] else 1 for k in names]
+        offs = np.concatenate([[0], np.cumsum(widths)])
         with PHASES('gather:all_gather'):
-            gathered = {k: self.comm.all_gather_rows(v[:cap]) for k, v in samples.items()}
-        d = gathered[self.discrepancy_name]
+            # rows beyond a rank's count carry +inf distances and sort last
+            pack = torch.cat([samples[k][:cap].reshape(cap, w) for k, w in zip(names, widths)],
+                             dim=1)
+            allp = self.comm.all_gather_rows(pack)
+        kcol = int(offs[names.index(self.discrepancy_name) + 1]) - 1      # last distance column
         with PHASES('gather:sort'):
-            perm = ops.argsort(d if d.dim() == 1 else d[:, -1].contiguous())
-        total = perm.numel()
-        if total >= n:
-            with PHASES('gather:select'):
-                for k in samples:
-                    samples[k] = ops.take_rows(gathered[k], perm[:n])
-        else:   # fewer than n rows exist globally: keep the padding semantics of the local buffers
-            for k in samples:
-                top = ops.take_rows(gathered[k], perm)
-                pad = samples[k][:n - total].clone()
-                if k == self.discrepancy_name:
-                    pad.fill_(float('inf'))
-                else:
-                    pad.zero_()
-                samples[k] = torch.cat([top, pad])
-        self.state['n_sim'] = int(self.comm.all_reduce_sum(self.state['n_sim']))
-        self.state['n_batches'] = int(self.comm.all_reduce_sum(self.state['n_batches']))
+            perm = ops.argsort(allp[:, kcol].contiguous())
+        total = int(perm.numel())
+        with PHASES('gather:select'):
+            top = ops.take_rows(allp, perm[:min(n, total)])
+            for k, w, o in zip(names, widths, offs[:-1]):
+                col = top[:, o:o + w].reshape((top.shape[0],) + shapes[k])
+                if total >= n:
+                    samples[k] = col.contiguous()
+                else:   # fewer than n rows exist globally: keep the padding of the local buffers
+                    pad = samples[k][:n - total].clone()
+                    pad.fill_(float('inf')) if k == self.discrepancy_name else pad.zero_()
+                    samples[k] = torch.cat([col, pad])
+        self._n_valid = min(n, int(counts[:, 0].sum()))
+        self.state['n_sim'] = int(counts[:, 1].sum())
+        self.state['n_batches'] = int(counts[:, 2].sum())
         if self.adaptive:
             self._merge_adaptive_moments()
-        self._update_state_meta()
 
     def _merge_adaptive_moments(self):
         """Chan-merge the per-rank (n, mean, M2) column moments (3 x D doubles per rank)."""
@@ -706,6 +752,13 @@ class SMC(Sampler):
     def _accept_hint(self):
         return self._rejection._accept_hint()
 
+    def _extract_result_kwargs(self):
+        kwargs = super()._extract_result_kwargs()
+        if self.comm.on:      # the local counters cover this rank's batches only
+            kwargs['n_sim'] = sum(pop.n_sim for pop in self._populations)
+            kwargs['n_batches'] = sum(pop.n_batches for pop in self._populations)
+        return kwargs
+
     def update(self, batch, batch_index):
         super().update(batch, batch_index)
         self._rejection.update(batch, batch_index)
@@ -731,16 +784,19 @@ class SMC(Sampler):
     def prepare_new_batch(self, batch_index):
         if self.state['round'] == 0:
             return
-        means, cov, weights = self._gm_params_host
+        prev = self._populations[-1]
         if self._device_proposal is not None:
-            key = int(self._round_random_state.randint(2 ** 31 - 1))
-            prev = self._populations[-1]
-            w_dev = getattr(prev, '_w_dev', None)
-            params = self._device_proposal.rvs(self._gm_means_dev(), cov,
-                                               w_dev if w_dev is not None else weights,
-                                               self.batch_size, key)
+            # the proposal stream of a batch is a function of (round seed, global batch index)
+            # only, so every sharding of the batches over ranks draws the same particles; the
+            # component-draw table is built once per population
+            if getattr(prev, '_cdf_dev', None) is None:
+                prev._cdf_dev = ops.gm_cdf(None if prev._equal_weights else prev._w_dev,
+                                           prev.n_samples)
+            params = self._device_proposal.rvs(prev._means_dev, prev.cov, None, self.batch_size,
+                                               _batch_key(self._round_seed, batch_index),
+                                               cdf=prev._cdf_dev)
             return {p: params[:, i] for i, p in enumerate(self.parameter_names)}
-        params = GMDistribution.rvs(means, cov, weights, size=self.batch_size,
+        params = GMDistribution.rvs(prev.means, prev.cov, prev.weights, size=self.batch_size,
                                     prior_logpdf=self._prior.logpdf,
                                     random_state=self._round_random_state)
         params = params.reshape((-1, len(self.parameter_names)))
@@ -758,81 +814,86 @@ class SMC(Sampler):
 
     def _set_rejection_round(self, round):
         seed = self.seed if round == 0 else em.get_sub_seed(self.seed, round)
+        self._round_seed = int(seed)
+        host_seed = seed
         if self.comm.on and round > 0:
-            # each rank draws its own proposals: decorrelate the per-round streams by rank
-            seed = em.get_sub_seed(int(seed), self.comm.rank)
-        self._round_random_state = np.random.RandomState(seed)
+            # host proposals: each rank draws its own from the sequential host stream, so the
+            # per-round streams are decorrelated by rank (device proposals are keyed per batch)
+            host_seed = em.get_sub_seed(int(seed), self.comm.rank)
+        self._round_random_state = np.random.RandomState(host_seed)
         self._rejection = Rejection(self.model, discrepancy_name=self.discrepancy_name,
                                     output_names=self.output_names, batch_size=self.batch_size,
                                     seed=seed, max_parallel_batches=self.max_parallel_batches,
                                     distributed=self._distributed)
+        self._population_cache = None
 
     def _extract_population(self):
-        with PHASES('extract_result(gather+to_host)'):
+        # extraction is a pure function of the finished rejection round; a second request (e.g.
+        # AdaptiveThresholdSMC.extract_result after its update) gets the same object back
+        if self._population_cache is not None and self._population_cache[0] is self._rejection:
+            return self._population_cache[1]
+        with PHASES('extract_result(gather)'):
             sample = self._rejection.extract_result()
         sample.method_name = "Rejection within SMC-ABC"
         with PHASES('weights_means_cov'):
-            means, w, cov = self._compute_weights_means_and_cov(sample)
+            self._attach_weights_means_and_cov(sample)
+        self._population_cache = (self._rejection, sample)
+        return sample
+
+    def _attach_weights_means_and_cov(self, sample):
+        means, w, cov = self._compute_weights_means_and_cov(sample)
         sample.means = means
         sample.weights = w
         sample.meta['cov'] = cov
-        return sample
 
     def _compute_weights_means_and_cov(self, pop):
-        """samplers.py:508-534 with the O(N_new x N_prev) mixture density on the device (and
-        sharded over ranks when distributed)."""
-        twins = getattr(pop, '_dev', None)
-        if twins is not None and all(p in twins for p in self.parameter_names):
-            with PHASES('weights:params_to_host'):
-                params_dev = torch.stack([twins[p].reshape(-1) for p in self.parameter_names],
-                                         dim=1)
-                params = params_dev.cpu().numpy()      # one D2H instead of a host column_stack
-        else:
-            params = np.column_stack(tuple([pop.outputs[p] for p in self.parameter_names]))
-            params_dev = dev.to_device(params)
+        """samplers.py:508-534 on the device: the O(N_new x N_prev) mixture density (sharded over
+        the new particles when distributed, one all-gather of N doubles), the importance weights
+        and the weighted variance.  Returns device arrays for means and weights (the sample
+        object copies them to the host when they are read) and the host covariance matrix."""
+        twins = pop._dev
+        params_dev = torch.stack([twins[p].reshape(-1) for p in self.parameter_names], dim=1)
+        N = int(params_dev.shape[0])
         if self._populations:
-            means, cov, weights = self._gm_params_host
-            N = len(params)
+            prev = self._populations[-1]
+            w_prev = None if prev._equal_weights else prev._w_dev
             if self.comm.on:
                 lo, hi, per = sharding.shard_bounds(N, self.comm.rank, self.comm.size)
                 q_part = dev.full((per,), float('nan'))
                 with PHASES('weights:gm_logpdf'):
                     if hi > lo:
-                        q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], means, cov, weights)
+                        q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], prev._means_dev,
+                                                         prev.cov, w_prev, validate=False)
                 with PHASES('weights:all_gather'):
                     q_logpdf = self.comm.all_gather_rows(q_part)
                 q_logpdf = q_logpdf[:N]   # equal-capacity shards: only the tail is padding
             else:
                 with PHASES('weights:gm_logpdf'):
-                    q_logpdf = ops.gm_logpdf(params_dev, means, cov, weights)
+                    q_logpdf = ops.gm_logpdf(params_dev, prev._means_dev, prev.cov, w_prev,
+                                             validate=False)
             with PHASES('weights:prior_logpdf'):
                 if self._device_proposal is not None:
                     p_logpdf = self._device_proposal.logpdf(params_dev)
                 else:
-                    p_logpdf = self._prior.logpdf(params)
-            with PHASES('weights:exp+to_host'):
-                w_dev = ops.smc_weights(p_logpdf, q_logpdf)
-                w = w_dev.cpu().numpy()
+                    p_logpdf = self._prior.logpdf(dev.to_host(params_dev))
+            w_dev = ops.smc_weights(p_logpdf, q_logpdf)
+            if not bool((w_dev != 0).any()):
+                raise RuntimeError("All sample weights are zero. If you are using a prior "
+                                   "with a bounded support, this may be caused by specifying "
+                                   "a too small sample size.")
         else:
-            w = np.ones(pop.n_samples)
             w_dev = None
-        means = params
         pop._means_dev = params_dev
         pop._equal_weights = w_dev is None
-        pop._w_dev = w_dev if w_dev is not None else dev.ones((len(params),))
-        all_zero = (not bool((w_dev != 0).any())) if w_dev is not None else np.count_nonzero(w) == 0
-        if all_zero:
-            raise RuntimeError("All sample weights are zero. If you are using a prior "
-                               "with a bounded support, this may be caused by specifying "
-                               "a too small sample size.")
+        pop._w_dev = w_dev
         with PHASES('weights:weighted_var'):
             cov = 2 * np.diag(ops.weighted_var(params_dev, w_dev))
         if not np.all(np.isfinite(cov)):
             logger.warning("Could not estimate the sample covariance. This is often "
                            "caused by majority of the sample weights becoming zero."
                            "Falling back to using unit covariance.")
-            cov = np.diag(np.ones(params.shape[1]))
-        return means, w, cov
+            cov = np.diag(np.ones(params_dev.shape[1]))
+        return params_dev, (w_dev if w_dev is not None else np.ones(N)), cov
 
     def _update_objective(self):
         n_batches = sum([pop.n_batches for pop in self._populations])
@@ -841,29 +902,14 @@ class SMC(Sampler):
         self.objective['n_batches'] = n_batches + self._rejection.objective['n_batches']
 
     def _set_threshold(self):
-        previous_population = self._populations[self.state['round'] - 1]
-        twins = getattr(previous_population, '_dev', None) or {}
-        d_prev = twins.get(self.discrepancy_name, previous_population.discrepancies)
-        w_prev = getattr(previous_population, '_w_dev', None)
-        if w_prev is None:
-            w_prev = previous_population.weights
-        if getattr(previous_population, '_equal_weights', False):
-            w_prev = None   # ones: same arithmetic as weights=None, which has a closed form
+        prev = self._populations[self.state['round'] - 1]
+        d_prev = prev._dev[self.discrepancy_name]
+        # equal weights (round 0) have the same arithmetic as weights=None: closed form
+        w_prev = None if prev._equal_weights else prev._w_dev
         with PHASES('weighted_quantile'):
             threshold = ops.weighted_sample_quantile(d_prev, self._quantiles[self.state['round']],
                                                      w_prev)
         self.objective['thresholds'][self.state['round']] = threshold
-
-    @property
-    def _gm_params_host(self):
-        sample = self._populations[-1]
-        return sample.means, sample.cov, sample.weights
-
-    def _gm_means_dev(self):
-        sample = self._populations[-1]
-        if getattr(sample, '_means_dev', None) is None:
-            sample._means_dev = dev.to_device(sample.means)
-        return sample._means_dev
 
     @property
     def current_population_threshold(self):
@@ -893,21 +939,21 @@ class AdaptiveDistanceSMC(SMC):
         self.quantile = quantile
 
     def _extract_population(self):
+        if self._population_cache is not None and self._population_cache[0] is self._rejection:
+            return self._population_cache[1]
         rejection_sample = self._rejection.extract_result()
-        outputs = dict()
-        for k in self.output_names:
-            outputs[k] = rejection_sample.outputs[k][:self.population_size]
+        ps = self.population_size
+        twins = {k: rejection_sample._dev[k][:ps] for k in self.output_names}
         meta = rejection_sample.meta
         meta['adaptive_distance_w'] = self.model[self.discrepancy_name]._s['w'][-1]
-        meta['threshold'] = max(outputs[self.discrepancy_name])
+        meta['threshold'] = float(twins[self.discrepancy_name].max().item())
         meta['accept_rate'] = self.population_size / meta['n_sim']
-        sample = Sample("Rejection within adaptive distance SMC-ABC", outputs,
+        sample = Sample("Rejection within adaptive distance SMC-ABC", DeviceOutputs(twins),
                         self.parameter_names, **{k: v for k, v in meta.items()
                                                  if k not in ('method_name', 'parameter_names')})
-        means, w, cov = self._compute_weights_means_and_cov(sample)
-        sample.means = means
-        sample.weights = w
-        sample.meta['cov'] = cov
+        sample._dev = twins
+        self._attach_weights_means_and_cov(sample)
+        self._population_cache = (self._rejection, sample)
         return sample
 
     def _extract_result_kwargs(self):
@@ -955,8 +1001,7 @@ class DensityRatioEstimation:
             self.sigma = float(sigma)
         if self.sigma is None:
             raise ValueError("RBF width (sigma) has to provided in first call.")
-        x = np.asarray(dev.to_host(x), dtype=np.float64)
-        y = np.asarray(dev.to_host(y), dtype=np.float64)
+        x, y = [v if dev.is_device_array(v) else np.asarray(v, dtype=np.float64) for v in (x, y)]
         x = x.reshape(x.shape[0], -1)
         y = y.reshape(y.shape[0], -1)
         self.alpha, self._max_ratio, self.n_iter = ops.kliep_fit(
@@ -1009,7 +1054,8 @@ class AdaptiveThresholdSMC(SMC):
         self._update_objective()
 
     def extract_result(self):
-        # the reference extracts the last population again through SMC.extract_result
+        # the reference extracts the last population again through SMC.extract_result; here the
+        # population of the finished round is extracted (and, multi-rank, gathered) exactly once
         return super().extract_result()
 
     def _set_adaptive_quantile(self):
@@ -1027,7 +1073,8 @@ class AdaptiveThresholdSMC(SMC):
             return self._densityratio_initial_sample()
         sample = self._new_population if backwards_index == 0 else self._populations[backwards_index]
         sample_sigma = np.sqrt(np.diag(sample.cov))
-        return dict(samples=sample.samples_array, weights=sample.weights,
+        return dict(samples=sample._means_dev,
+                    weights=None if sample._equal_weights else sample._w_dev,
                     sigma_max=np.min(sample_sigma))
 
     def _densityratio_initial_sample(self):

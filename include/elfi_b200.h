@@ -265,6 +265,10 @@ int elfi_b200_probe_fp64_f64(elfi_b200_ctx* ctx, double* tflops_host);
  *                               weight, + MVN(0, Sigma) with Sigma = L L^T (Lchol_host, p <= 4),
  *                               redrawn until inside the support (0 = none, 1 = MA2 prior support,
  *                               2 = box: box_host = [lo_0..lo_{p-1}, hi_0..hi_{p-1}])
+ *   elfi_b200_gm_cdf_f64        inclusive running sum of the (unnormalised) component weights, the
+ *                               table np.random.choice(p=weights) builds on every call
+ *                               (utils.py:239); one per population, reused by every batch of it
+ *   elfi_b200_gm_rvs_cdf_f64    gm_rvs with that table (`cumw`, device, N) instead of the weights
  */
 int elfi_b200_prior_ma2_f64(elfi_b200_ctx* ctx, int64_t B, uint64_t seed, uint64_t offset,
                             int32_t mode, double* t1, double* t2, void* stream);
@@ -277,6 +281,12 @@ int elfi_b200_gm_rvs_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, c
                          int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
                          uint64_t offset, int32_t support, const double* box_host, double* out,
                          int64_t ldo, void* stream);
+int elfi_b200_gm_cdf_f64(elfi_b200_ctx* ctx, const double* weights, int64_t N, double* cumw,
+                         void* stream);
+int elfi_b200_gm_rvs_cdf_f64(elfi_b200_ctx* ctx, const double* means, int64_t ldm, const double* cumw,
+                             int64_t N, int64_t p, const double* Lchol_host, int64_t B, uint64_t seed,
+                             uint64_t offset, int32_t support, const double* box_host, double* out,
+                             int64_t ldo, void* stream);
 
 /* Gaussian noise model of elfi/examples/gauss.py (1-d case): priors mu ~ U(prm[0], prm[0]+prm[1]),
  * sigma ~ truncnorm(prm[2], prm[3]) (gauss.py:118-126); simulator y = mu + sigma z (gauss.py:11-35)

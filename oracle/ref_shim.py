@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference (elfi-dev/elfi at /root/reference) in this container.
+"""Import the UNMODIFIED reference (elfi-dev/elfi): from /root/reference in the build container,
+else from the mirror baseline/_ref/ that __graft_entry__.build_reference() makes for the GPU box.
 
-TEST INFRASTRUCTURE ONLY.  Used by tests/golden/gen_golden.py to produce the committed
-golden fixtures; never imported by the product (`elfi_b200/`) and never available on the
-GPU box (where /root/reference does not exist).
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by tests/golden/gen_golden*.py to produce the
+committed golden fixtures, by the reference-driven plugin tests and by ``bench.py --impl
+reference`` (the CPU arm); never imported by the product (`elfi_b200/`).
 
 The reference needs packages that are absent here (matplotlib, GPy, arviz, numdifftools,
 ipyparallel, dask, toolz) and uses NumPy-1 aliases; none of them touch the sampler hot
@@ -14,7 +15,14 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = '/root/reference'
+import os
+
+_MIRROR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+REFERENCE_ROOT = '/root/reference' if os.path.isdir('/root/reference/elfi') else _MIRROR
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'elfi'))
 
 
 def import_reference():

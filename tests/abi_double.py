@@ -364,6 +364,19 @@ def sim_ma2_f64(ctx, t1, t2, B, n_obs, seed, offset, X, ldX, S, ldS, stream):
         out[:, 1] = o.autocov(x, 2)
 
 
+def gm_cdf_f64(ctx, weights, N, cumw, stream):
+    w = np.ones(N) if not _addr(weights) else _vec(weights, N)
+    _vec(cumw, N)[:] = np.cumsum(w)
+
+
+def gm_rvs_cdf_f64(ctx, means, ldm, cumw, N, p, Lchol_host, B, seed, offset, support, box_host, out,
+                   ldo, stream):
+    c = _vec(cumw, N)
+    w = np.diff(np.concatenate([[0.0], c]))
+    gm_rvs_f64(ctx, means, ldm, ctypes.c_void_p(w.ctypes.data), N, p, Lchol_host, B, seed, offset,
+               support, box_host, out, ldo, stream)
+
+
 def gm_rvs_f64(ctx, means, ldm, weights, N, p, Lchol_host, B, seed, offset, support, box_host, out,
                ldo, stream):
     from elfi_b200.examples import ma2 as ex
@@ -436,7 +449,7 @@ _TABLE = {'elfi_b200_' + f.__name__: f for f in (
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
-    gm_rvs_f64, prior_gauss_f64, logprior_gauss_f64, sim_gauss_f64, sim_gnk_f64, logprior_box_f64)}
+    gm_rvs_f64, gm_cdf_f64, gm_rvs_cdf_f64, prior_gauss_f64, logprior_gauss_f64, sim_gauss_f64, sim_gnk_f64, logprior_box_f64)}
 
 
 def call(name, *args):

@@ -86,11 +86,41 @@ def _worker(rank, world, port, out_dir):
     assert q[0] == 0.2 and np.all((q[1:len(at.populations)] >= 0.05) & (q[1:len(at.populations)] <= 1))
     t = [p.threshold for p in at.populations]
     assert all(a > b for a, b in zip(t, t[1:]))
+    # the last population is gathered exactly once (extract_result after update used to gather
+    # the already global buffers again: duplicated rows and n_sim multiplied by the world size)
+    assert len(np.unique(at.discrepancies)) == at.n_samples
+    assert at.n_sim == sum(p.n_sim for p in at.populations)
+    assert len(np.unique(smc.discrepancies)) == smc.n_samples
+    rej = elfi.Rejection(m['d'], batch_size=500, seed=7)
+    first = rej.sample(50, quantile=0.05, bar=False)
+    again = rej.extract_result()
+    assert again.n_sim == first.n_sim == 1000
+    assert np.array_equal(again.discrepancies, first.discrepancies)
+
+    # throughput mode (device priors / simulator / proposals keyed by the global batch index):
+    # W ranks == ONE rank that processes its batches in groups of W, bit for bit, every
+    # population (thresholds, particles, weights, covariances, n_sim)
+    md = ma2.get_device_model(seed_obs=4)
+
+    def run_tp(distributed):
+        kw = dict(distributed=True) if distributed else dict(distributed=False,
+                                                            max_parallel_batches=world)
+        return elfi.SMC(md['d'], batch_size=250, seed=5, device_proposal=ma2.DeviceProposal,
+                        **kw).sample(600, quantiles=[.5, .4, .4], bar=False)
+    tp, tp1 = run_tp(True), run_tp(False)
+    assert tp.n_sim == tp1.n_sim and len(tp.populations) == 3
+    for pa, pb in zip(tp.populations, tp1.populations):
+        assert pa.threshold == pb.threshold and pa.n_sim == pb.n_sim
+        assert np.array_equal(pa.discrepancies, pb.discrepancies)
+        assert np.array_equal(pa.samples_array, pb.samples_array)
+        assert np.array_equal(pa.weights, pb.weights)
+        assert np.array_equal(pa.cov, pb.cov)
 
     # all ranks hold identical results
     np.save(os.path.join(out_dir, 'rank{}.npy'.format(rank)),
             np.concatenate([res.discrepancies, smc.weights, smc.samples_array.ravel(), ad.weights,
-                            at.weights, at.samples_array.ravel(), np.nan_to_num(q)]))
+                            at.weights, at.samples_array.ravel(), np.nan_to_num(q),
+                            tp.weights, tp.samples_array.ravel()]))
     dist.barrier()
     dist.destroy_process_group()
     patch.undo()
