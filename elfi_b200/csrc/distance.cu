@@ -21,7 +21,12 @@ struct DistParams {
     uint32_t* mask;      // ceil(B/32) words or nullptr
     int K;
     int has_thr;
+    const double* thr_dev;   // K thresholds in device memory (e.g. a quantile computed on the
+                             // device), or nullptr: then thr[] below, copied from the host
     double thr[ELFI_B200_MAX_NESTED];
+    __device__ __forceinline__ double threshold(int k) const {
+        return thr_dev ? __ldg(thr_dev + k) : thr[k];
+    }
 };
 
 // Shared consumer area: obs padded to G*16 doubles with zeros, then W rows padded likewise.
@@ -52,7 +57,7 @@ __device__ __forceinline__ void dist_finish(const DistParams& p, const double (&
             if (k < K) {
                 const double d = sqrt(acc[k]);
                 p.d_out[row * K + k] = d;
-                if (p.has_thr) ok = ok && (d <= p.thr[k]);
+                if (p.has_thr) ok = ok && (d <= p.threshold(k));
             }
         }
     }
@@ -210,7 +215,7 @@ dist_direct_kernel(const double* __restrict__ S, int64_t ld, int64_t B, int D, D
             }
             const double dist = sqrt(acc);
             p.d_out[row * K + k] = dist;
-            if (p.has_thr) ok = ok && (dist <= p.thr[k]);
+            if (p.has_thr) ok = ok && (dist <= p.threshold(k));
         }
     }
     if (p.mask != nullptr) {
@@ -294,7 +299,8 @@ int launch_compact_mask(const uint32_t* mask, int64_t B, int32_t* idx, int64_t* 
 // Distances (+ mask when thresholds are given) for a device-resident matrix.
 int launch_dist(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int64_t D,
                 const double* obs, const double* W, int64_t K, const double* thr_host,
-                double* d_out, uint32_t* mask, cudaStream_t stream) {
+                double* d_out, uint32_t* mask, cudaStream_t stream,
+                const double* thr_dev = nullptr) {
     DistParams p;
     memset(&p, 0, sizeof(p));
     p.obs = obs;
@@ -302,7 +308,8 @@ int launch_dist(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int
     p.d_out = d_out;
     p.mask = mask;
     p.K = int(K);
-    p.has_thr = thr_host != nullptr;
+    p.has_thr = thr_host != nullptr || thr_dev != nullptr;
+    p.thr_dev = thr_dev;
     if (thr_host)
         for (int k = 0; k < K; ++k) p.thr[k] = thr_host[k];
     if (B == 0) return ELFI_B200_OK;
@@ -360,7 +367,7 @@ __device__ __forceinline__ void metric_finish(const MetricParams& p, double acc,
     if (ok) {
         const double d = metric_value<METRIC>(acc, p.pexp);
         p.d_out[row] = d;
-        if (p.has_thr) ok = d <= p.thr[0];
+        if (p.has_thr) ok = d <= p.threshold(0);
     }
     if (p.mask != nullptr) {
         const uint32_t bits = __ballot_sync(0xffffffffu, ok && p.has_thr);
@@ -485,6 +492,27 @@ int elfi_b200_dist_euclid_thr_f64(elfi_b200_ctx* ctx, const double* S, int64_t l
     rc = launch_dist(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, mask, stream);
     if (rc) return rc;
     if (thr_host != nullptr && (acc_idx != nullptr || n_acc != nullptr))
+        return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_dist_euclid_thr_dev_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                      int64_t D, const double* obs, const double* W, int64_t K,
+                                      const double* thr_dev, double* d_out, int32_t* acc_idx,
+                                      int64_t* n_acc, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr && thr_dev != nullptr, "dist: ctx or thr_dev is NULL");
+    int rc = check_dist_args(S, ldS, B, D, obs, W, K, thr_dev, acc_idx);
+    if (rc) return rc;
+    ELFI_REQUIRE(B == 0 || d_out != nullptr, "dist: d_out is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t nwords = size_t((B + 31) / 32);
+    uint32_t* mask = static_cast<uint32_t*>(ctx_scratch(ctx, nwords * 4 + 256));
+    if (!mask) return ELFI_B200_ERR_NOMEM;
+    rc = launch_dist(ctx, S, ldS, B, D, obs, W, K, nullptr, d_out, mask, stream, thr_dev);
+    if (rc) return rc;
+    if (acc_idx != nullptr || n_acc != nullptr)
         return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
     return ELFI_B200_OK;
 }

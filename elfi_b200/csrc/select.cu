@@ -229,6 +229,50 @@ gather_rows_kernel(const double* __restrict__ src, int64_t ld_src, const int32_t
     }
 }
 
+// Accepted rows of a batch -> tail of a candidate buffer, with the counts read on the device.
+// Up to APPEND_MAX_SRC source arrays (each (B, width_k) with its own leading dimension) are laid
+// side by side in the packed destination row.
+constexpr int APPEND_MAX_SRC = 8;
+struct AppendSources {
+    const double* ptr[APPEND_MAX_SRC];
+    int64_t ld[APPEND_MAX_SRC];
+    int32_t width[APPEND_MAX_SRC];
+    int32_t col0[APPEND_MAX_SRC];
+    int32_t n_src, total_width;
+};
+
+__global__ void __launch_bounds__(256)
+accept_append_kernel(const int32_t* __restrict__ acc_idx, const int64_t* __restrict__ n_acc,
+                     AppendSources src, double* __restrict__ dst, int64_t ld_dst, int64_t capacity,
+                     const int64_t* __restrict__ count) {
+    const int64_t base = *count;
+    int64_t room = capacity - base;
+    if (room < 0) room = 0;
+    const int64_t rows = *n_acc < room ? *n_acc : room;
+    const int64_t total = rows * src.total_width;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t j = t / src.total_width;
+        const int c = int(t - j * src.total_width);
+        const int64_t row = acc_idx ? int64_t(acc_idx[j]) : j;
+        int k = 0;
+#pragma unroll
+        for (int q = 1; q < APPEND_MAX_SRC; ++q)
+            if (q < src.n_src && c >= src.col0[q]) k = q;
+        dst[(base + j) * ld_dst + c] = src.ptr[k][row * src.ld[k] + (c - src.col0[k])];
+    }
+}
+
+// count += rows appended; dropped[0] += rows that did not fit (runs after accept_append_kernel)
+__global__ void accept_count_kernel(const int64_t* __restrict__ n_acc, int64_t capacity,
+                                    int64_t* __restrict__ count, int64_t* __restrict__ dropped) {
+    int64_t room = capacity - *count;
+    if (room < 0) room = 0;
+    const int64_t rows = *n_acc < room ? *n_acc : room;
+    if (dropped) *dropped += *n_acc - rows;
+    *count += rows;
+}
+
 // Two-source gather for the running top-n merge: logical row r < nA is A[r], otherwise
 // B[mapB ? mapB[r - nA] : r - nA]  (B = the new batch, mapB = its accepted row indices).
 __global__ void __launch_bounds__(256)
@@ -609,6 +653,43 @@ int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA,
     if (blocks > int64_t(ctx->sm_count) * 16) blocks = int64_t(ctx->sm_count) * 16;
     gather2_rows_kernel<<<unsigned(blocks), 256, 0, stream>>>(A, ldA, nA, Bm, ldB, mapB, perm, n,
                                                              width, dst, ld_dst);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_accept_append_f64(elfi_b200_ctx* ctx, const int32_t* acc_idx, const int64_t* n_acc,
+                                int64_t max_rows, int64_t n_src, const double* const* src_host,
+                                const int64_t* ld_src_host, const int64_t* width_host, double* dst,
+                                int64_t ld_dst, int64_t capacity, int64_t* count, int64_t* dropped,
+                                void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && n_acc && src_host && ld_src_host && width_host && dst && count,
+                 "accept_append: NULL argument");
+    ELFI_REQUIRE(n_src >= 1 && n_src <= APPEND_MAX_SRC, "accept_append: 1..%d sources", APPEND_MAX_SRC);
+    ELFI_REQUIRE(max_rows >= 0 && capacity >= 0, "accept_append: bad shape");
+    AppendSources src;
+    memset(&src, 0, sizeof(src));
+    src.n_src = int32_t(n_src);
+    int64_t col = 0;
+    for (int k = 0; k < n_src; ++k) {
+        ELFI_REQUIRE(src_host[k] && width_host[k] >= 1 && ld_src_host[k] >= width_host[k],
+                     "accept_append: bad source %d", k);
+        src.ptr[k] = src_host[k];
+        src.ld[k] = ld_src_host[k];
+        src.width[k] = int32_t(width_host[k]);
+        src.col0[k] = int32_t(col);
+        col += width_host[k];
+    }
+    ELFI_REQUIRE(col <= ld_dst && col < (int64_t(1) << 30), "accept_append: ld_dst < total width");
+    src.total_width = int32_t(col);
+    if (max_rows == 0) return ELFI_B200_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    int64_t blocks = (max_rows * col + 255) / 256;
+    if (blocks > int64_t(ctx->sm_count) * 8) blocks = int64_t(ctx->sm_count) * 8;
+    accept_append_kernel<<<unsigned(blocks), 256, 0, stream>>>(acc_idx, n_acc, src, dst, ld_dst,
+                                                              capacity, count);
+    accept_count_kernel<<<1, 1, 0, stream>>>(n_acc, capacity, count, dropped);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

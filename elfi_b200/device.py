@@ -48,6 +48,54 @@ def destroy_contexts():
         del _contexts[dev]
 
 
+def gpu_numa_node(device=None):
+    """NUMA node the GPU's PCIe root hangs off (sysfs), or None when it cannot be determined."""
+    require_cuda()
+    device = torch.cuda.current_device() if device is None else int(device)
+    props = torch.cuda.get_device_properties(device)
+    try:
+        addr = '{:04x}:{:02x}:{:02x}.0'.format(props.pci_domain_id, props.pci_bus_id,
+                                               props.pci_device_id)
+        with open('/sys/bus/pci/devices/{}/numa_node'.format(addr)) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except (OSError, AttributeError, ValueError):
+        return None
+
+
+def bind_to_gpu_numa_node(device=None):
+    """Run this process on the cores of the GPU's NUMA node, so that the pinned staging buffers
+    it allocates afterwards (first touch) are local to the GPU's PCIe root: with 8 ranks on a
+    two-socket host, H2D copies from the remote socket cross the inter-socket link and slow down.
+    Returns the node (None: nothing was changed).  Call before allocating host buffers."""
+    import os
+    node = gpu_numa_node(device)
+    if node is None or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        with open('/sys/devices/system/node/node{}/cpulist'.format(node)) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Page-locked host array (numpy view of a pinned torch tensor): H2D / D2H copies of it run
+    at the PCIe rate without a staging copy."""
+    tdtype = {np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32,
+              np.int64: torch.int64}[np.dtype(dtype).type]
+    return torch.empty(shape, dtype=tdtype).pin_memory().numpy()
+
+
 def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

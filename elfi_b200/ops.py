@@ -28,7 +28,7 @@ def _matrix(S):
     return S
 
 
-def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True):
+def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True, sync=True):
     """Euclidean / nested weighted distances of the rows of S to ``obs`` + acceptance.
 
     Replaces ``cdist(S, obs, 'euclidean'[, w=w])`` reached through
@@ -40,7 +40,10 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True):
     S : (B, D) array
     obs : (D,) or (1, D) array
     w : None, (D,) or (K, D) -- cdist's ``w`` per nested column (a row of ones == unweighted)
-    thresholds : None, float or (K,) -- accept rows with all_k(d[:, k] <= thresholds[k])
+    thresholds : None, float, (K,) host values, or a (K,) DEVICE array (no host round trip)
+        -- accept rows with all_k(d[:, k] <= thresholds[k])
+    sync : False leaves the accepted count on the device: acc_idx is then the pair
+        (int32 buffer of B indices of which the first n_acc are valid, n_acc device int64[1])
 
     Returns
     -------
@@ -68,26 +71,32 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True):
         if K > MAX_NESTED:
             raise ValueError('at most {} nested distances are supported'.format(MAX_NESTED))
     thr = None
-    if thresholds is not None:
+    thr_on_device = dev.is_device_array(thresholds)
+    if thr_on_device:
+        thr = thresholds.reshape(-1)
+        if thr.dtype != torch.float64 or not thr.is_contiguous():
+            thr = thr.to(torch.float64).contiguous()
+    elif thresholds is not None:
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
-        if thr.shape[0] != K:
-            raise ValueError('need one threshold per distance column ({} != {})'.format(
-                thr.shape[0], K))
+    if thr is not None and thr.shape[0] != K:
+        raise ValueError('need one threshold per distance column ({} != {})'.format(
+            thr.shape[0], K))
     d = dev.empty((B, K))
     acc_idx = n_acc = None
     if thr is not None:
         n_acc = dev.zeros((1,), dtype=torch.int64)
         if want_indices:
             acc_idx = dev.empty((max(B, 1),), dtype=torch.int32)
-    _lib.call('elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S), S.stride(0) if B > 1 else D, B, D,
-              dev.ptr(obs_t), dev.ptr(W), K, dev.ptr(thr), dev.ptr(d), dev.ptr(acc_idx),
-              dev.ptr(n_acc), dev.stream_ptr())
+    _lib.call('elfi_b200_dist_euclid_thr_dev_f64' if thr_on_device else
+              'elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S),
+              S.stride(0) if B > 1 else D, B, D, dev.ptr(obs_t), dev.ptr(W), K, dev.ptr(thr),
+              dev.ptr(d), dev.ptr(acc_idx), dev.ptr(n_acc), dev.stream_ptr())
     if thr is not None:
-        n = int(n_acc.item())
-        if want_indices:
-            acc_idx = acc_idx[:n]
+        if not sync:
+            acc_idx = (acc_idx, n_acc)
         else:
-            acc_idx = n
+            n = int(n_acc.item())
+            acc_idx = acc_idx[:n] if want_indices else n
     if squeeze:
         d = d.reshape(B)
     return d, acc_idx
@@ -256,6 +265,45 @@ def take_rows2(a, b, perm, n_out, map_b=None):
                   _ld(b2) if b2 is not None else width, dev.ptr(map_b), dev.ptr(perm), n_out,
                   width, dev.ptr(dst), width, dev.stream_ptr())
     return dst.reshape((n_out,) + tuple(shape[1:]))
+
+
+class CandidateBuffer:
+    """Packed (capacity, width) device buffer of accepted rows + device-side row count: the tail
+    of the reference's sample buffers (samplers.py:196-230) filled without host round trips."""
+
+    def __init__(self, capacity, widths):
+        self.widths = [int(w) for w in widths]
+        self.width = sum(self.widths)
+        self.capacity = int(capacity)
+        self.rows = dev.empty((self.capacity, self.width))
+        self.count = dev.zeros((1,), dtype=torch.int64)
+        self.dropped = dev.zeros((1,), dtype=torch.int64)
+
+    def reset(self):
+        self.count.zero_()
+        self.dropped.zero_()
+
+    def append(self, sources, acc_idx, n_acc, max_rows):
+        """Append rows acc_idx[:n_acc] (device int32 / device int64 count) of `sources`."""
+        srcs = [_as_2d(t) for t in sources]
+        if [t.shape[1] for t in srcs] != self.widths:
+            raise ValueError('source widths do not match the buffer layout')
+        n = len(srcs)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+        lds = (ctypes.c_int64 * n)(*[_ld(t) for t in srcs])
+        wid = (ctypes.c_int64 * n)(*self.widths)
+        _lib.call('elfi_b200_accept_append_f64', dev.context(), dev.ptr(acc_idx), dev.ptr(n_acc),
+                  int(max_rows), n, ctypes.cast(ptrs, ctypes.c_void_p),
+                  ctypes.cast(lds, ctypes.c_void_p), ctypes.cast(wid, ctypes.c_void_p),
+                  dev.ptr(self.rows), self.width, self.capacity, dev.ptr(self.count),
+                  dev.ptr(self.dropped), dev.stream_ptr())
+
+    def best(self, n, key_col=0):
+        """(rows sorted by column key_col, first n; count, dropped) -- one D2H of the counters."""
+        count, dropped = int(self.count.item()), int(self.dropped.item())
+        keys = self.rows[:count, key_col].contiguous()
+        perm = argsort(keys)
+        return take_rows(self.rows, perm[:min(n, count)]), count, dropped
 
 
 def weighted_sample_quantile(x, alpha, weights=None):

@@ -71,6 +71,9 @@ __all__ = ['Rejection', 'SMC', 'AdaptiveDistanceSMC', 'AdaptiveThresholdSMC', 'M
 
 
 # ----------------------------------------------------------------------------- communication
+COMM_STATS = {'all_gather_calls': 0, 'all_gather_bytes': 0}   # data-path collectives (received bytes)
+
+
 class Comm:
     """torch.distributed plumbing (NCCL on GPUs, gloo in CPU tests); identity when single."""
 
@@ -90,6 +93,8 @@ class Comm:
         out = torch.empty((self.size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype,
                           device=t.device)
         self.dist.all_gather_into_tensor(out, t)
+        COMM_STATS['all_gather_calls'] += 1
+        COMM_STATS['all_gather_bytes'] += out.numel() * out.element_size()
         return out
 
     def all_gather_ints(self, values):

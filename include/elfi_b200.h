@@ -76,6 +76,15 @@ int elfi_b200_dist_euclid_thr_f64(elfi_b200_ctx* ctx, const double* S, int64_t l
                                   const double* thr_host, double* d_out, int32_t* acc_idx,
                                   int64_t* n_acc, void* stream);
 
+/* Same with the K thresholds in DEVICE memory (thr_dev, not NULL): a threshold that was itself
+ * computed on the device -- the weighted quantile of the previous population
+ * (samplers.py:542-549), the running n-th best distance of the buffer (samplers.py:243) -- feeds
+ * the next distance call without a host round trip. */
+int elfi_b200_dist_euclid_thr_dev_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                      int64_t D, const double* obs, const double* W, int64_t K,
+                                      const double* thr_dev, double* d_out, int32_t* acc_idx,
+                                      int64_t* n_acc, void* stream);
+
 /* Same computation with HOST buffers (pageable or pinned): rows are streamed to the device
  * in chunks on two copy streams overlapped with the kernel; distances, accepted indices
  * and the count are copied back.  Blocks until the results are in host memory.
@@ -135,12 +144,29 @@ int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
  * rows may be indirected through mapB (the accepted indices of the new batch): the running
  * top-n merge without materialising the (n + batch) buffers of samplers.py:196-205.
  * perm == NULL means the identity.
+ *
+ * elfi_b200_accept_append_f64: `v[-num_accepted:] = batch[node][accepted]` for every output node
+ * (samplers.py:228-230) with the counts read ON THE DEVICE, so a threshold-mode batch needs no
+ * host round trip between the distance kernel and the merge: rows acc_idx[0 .. *n_acc) (acc_idx
+ * == NULL: rows 0 .. *n_acc) of n_src <= 8 source arrays (src_host[k] = device pointer of a
+ * (B, width_host[k]) array with leading dimension ld_src_host[k]; the three descriptor arrays
+ * themselves are HOST arrays) are written side by side behind row *count of the packed candidate
+ * buffer dst (capacity rows); *count += rows appended; rows that do not fit are dropped and
+ * counted in *dropped (may be NULL).  n_acc, count, dropped are DEVICE int64.  max_rows bounds
+ * *n_acc (sizes the launch).  The best n rows are taken once, when the population is extracted
+ * (sort_pairs on the distance column + gather_rows) -- the same rows the reference's per-batch
+ * argsort over n + batch_size rows leaves in its buffer (samplers.py:232-237).
  */
 int elfi_b200_sort_pairs_f64(elfi_b200_ctx* ctx, const double* keys, int64_t n,
                              double* keys_sorted, int32_t* perm, void* stream);
 int elfi_b200_gather_rows_f64(elfi_b200_ctx* ctx, const double* src, int64_t ld_src,
                               const int32_t* idx, int64_t n, int64_t width, double* dst,
                               int64_t ld_dst, void* stream);
+int elfi_b200_accept_append_f64(elfi_b200_ctx* ctx, const int32_t* acc_idx, const int64_t* n_acc,
+                                int64_t max_rows, int64_t n_src, const double* const* src_host,
+                                const int64_t* ld_src_host, const int64_t* width_host, double* dst,
+                                int64_t ld_dst, int64_t capacity, int64_t* count, int64_t* dropped,
+                                void* stream);
 int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA, int64_t nA,
                                const double* B, int64_t ldB, const int32_t* mapB,
                                const int32_t* perm, int64_t n, int64_t width, double* dst,

@@ -84,6 +84,32 @@ def dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, acc_idx, 
             _vec(n_acc, 1, np.int64)[0] = len(idx)
 
 
+def dist_euclid_thr_dev_f64(ctx, S, ldS, B, D, obs, W, K, thr_dev, d_out, acc_idx, n_acc, stream):
+    dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr_dev, d_out, acc_idx, n_acc, stream)
+
+
+def accept_append_f64(ctx, acc_idx, n_acc, max_rows, n_src, src_host, ld_src_host, width_host, dst,
+                      ld_dst, capacity, count, dropped, stream):
+    n = int(_vec(n_acc, 1, np.int64)[0])
+    cnt = _vec(count, 1, np.int64)
+    ptrs = _vec(src_host, n_src, np.uint64)
+    lds = _vec(ld_src_host, n_src, np.int64)
+    wid = _vec(width_host, n_src, np.int64)
+    rows = min(n, max(0, capacity - int(cnt[0])))
+    idx = _vec(acc_idx, max(n, 1), np.int32)[:rows] if _addr(acc_idx) else np.arange(rows)
+    out = _mat(dst, capacity, ld_dst)
+    col = 0
+    for k in range(n_src):
+        if rows:
+            nrows_src = int(idx.max()) + 1
+            src = _mat(int(ptrs[k]), nrows_src, int(wid[k]), int(lds[k]))
+            out[int(cnt[0]):int(cnt[0]) + rows, col:col + int(wid[k])] = src[idx]
+        col += int(wid[k])
+    if _addr(dropped):
+        _vec(dropped, 1, np.int64)[0] += n - rows
+    cnt[0] += rows
+
+
 def dist_euclid_thr_f64_host(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, acc_idx, n_acc):
     Sm = _mat(S, B, D, ldS)
     d = _distances(Sm, _vec(obs, D), _mat(W, K, D), K) if B else np.empty((0, K))
@@ -445,7 +471,7 @@ def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
 
 
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
-    dist_euclid_thr_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
+    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, accept_append_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,

@@ -1,0 +1,73 @@
+"""Bodies of the tests of the sync-free batch -> candidate-buffer path (shared by the CPU-double
+and GPU collections): device-resident thresholds (elfi_b200_dist_euclid_thr_dev_f64), the append
+of accepted rows with device-side counts (elfi_b200_accept_append_f64) and the final best-n, all
+against the reference's own merge arithmetic (elfi/methods/inference/samplers.py:209-237)."""
+import numpy as np
+
+import elfi_oracle as o
+
+
+def reference_merge(batches, thr, n):
+    """samplers.py:209-237 restated on the host: mask, copy to the tail, argsort over n + B."""
+    B = len(batches[0]['d'])
+    state = {k: np.zeros(n + B) for k in batches[0]}
+    state['d'][:] = np.inf
+    for b in batches:
+        acc = b['d'] <= thr
+        k = int(acc.sum())
+        if k:
+            for name in state:
+                state[name][-k:] = b[name][acc]
+        order = np.argsort(state['d'], kind='stable')
+        for name in state:
+            state[name][:] = state[name][order]
+    return {k: v[:n] for k, v in state.items()}
+
+
+def case_device_thresholds_and_append():
+    from elfi_b200 import device as dev
+    from elfi_b200 import ops
+    rs = np.random.RandomState(3)
+    B, D, n = 5000, 24, 300
+    obs = rs.randn(1, D)
+    batches_host, buf = [], ops.CandidateBuffer(n + 2 * B, [1, 1, 1])
+    thr = None
+    for step in range(4):
+        S = rs.randn(B, D)
+        t1, t2 = rs.rand(B), rs.rand(B)
+        ref_d = o.cdist_euclid(S, obs)
+        if thr is None:
+            thr = float(np.quantile(ref_d, 0.04))
+            thr_dev = dev.to_device(np.array([thr]))
+        d, (idx, n_acc) = ops.dist_euclid(S, obs, thresholds=thr_dev, sync=False)
+        assert np.array_equal(d.cpu().numpy(), ref_d)
+        k = int(n_acc.item())
+        assert np.array_equal(idx[:k].cpu().numpy(), o.accept_indices(ref_d, thr))
+        buf.append([d, dev.to_device(t1), dev.to_device(t2)], idx, n_acc, B)
+        batches_host.append({'d': ref_d, 't1': t1, 't2': t2})
+    top, count, dropped = buf.best(n)
+    want = reference_merge(batches_host, thr, n)
+    total = sum(int((b['d'] <= thr).sum()) for b in batches_host)
+    assert count == total and dropped == 0
+    top = top.cpu().numpy()
+    m = min(n, total)
+    assert np.array_equal(top[:, 0], want['d'][:m])
+    assert np.array_equal(top[:, 1], want['t1'][:m])
+    assert np.array_equal(top[:, 2], want['t2'][:m])
+    # a full buffer drops the overflow and says so
+    small = ops.CandidateBuffer(10, [1])
+    dd, (idx, n_acc) = ops.dist_euclid(S, obs, thresholds=dev.to_device(np.array([np.inf])),
+                                       sync=False)
+    small.append([dd], idx, n_acc, B)
+    rows, count, dropped = small.best(10)
+    assert count == 10 and dropped == B - 10
+    assert np.array_equal(np.sort(rows.cpu().numpy()[:, 0]), np.sort(ref_d[:10]))
+    # 2-d source (nested distances keep all their columns) and identity indices
+    wide = ops.CandidateBuffer(64, [2, 1])
+    a = dev.to_device(rs.randn(40, 2))
+    bcol = dev.to_device(rs.randn(40))
+    cnt = dev.to_device(np.array([40]), dtype=__import__('torch').int64)
+    wide.append([a, bcol], None, cnt, 40)
+    assert int(wide.count.item()) == 40
+    got = wide.rows[:40].cpu().numpy()
+    assert np.array_equal(got[:, :2], a.cpu().numpy()) and np.array_equal(got[:, 2], bcol.cpu().numpy())

@@ -1,7 +1,9 @@
 """Multi-GPU parity check, launched by torchrun (one process per GPU, NCCL):
   * Rejection in quantile mode over W ranks == the single-process golden (same batches);
   * SMC over W ranks: round 0 identical to the golden, later rounds statistically sane;
-  * AdaptiveDistanceSMC: moments merged across ranks.
+  * AdaptiveDistanceSMC: moments merged across ranks;
+  * throughput mode SMC over W ranks == one rank in groups of W batches, bit for bit;
+  * populations are gathered exactly once.
 Prints MGPU_OK on rank 0."""
 import os
 import sys
@@ -77,6 +79,36 @@ def main():
             np.testing.assert_allclose(ad.populations[0].outputs[k], ad1.populations[0].outputs[k],
                                        rtol=1e-9)
     assert np.all(np.isfinite(ad.weights)) and len(ad.populations) == 2
+
+    # throughput mode (device priors / simulator / proposals keyed by the global batch index):
+    # W ranks == ONE rank processing the same batches in groups of W, BIT FOR BIT, every
+    # population: thresholds, particles, weights (sharded O(N^2) density), covariances, n_sim
+    md = ma2.get_device_model(seed_obs=4)
+
+    def run_tp(distributed, n=30000, batch=2500):
+        kw = dict(distributed=True) if distributed else dict(distributed=False,
+                                                            max_parallel_batches=world)
+        return elfi.SMC(md['d'], batch_size=batch, seed=5, device_proposal=ma2.DeviceProposal,
+                        **kw).sample(n, quantiles=[.5, .4, .4], bar=False)
+    tp, tp1 = run_tp(True), run_tp(False)
+    assert tp.n_sim == tp1.n_sim and len(tp.populations) == 3, (tp.n_sim, tp1.n_sim)
+    for pa, pb in zip(tp.populations, tp1.populations):
+        assert pa.threshold == pb.threshold and pa.n_sim == pb.n_sim
+        assert np.array_equal(pa.discrepancies, pb.discrepancies)
+        assert np.array_equal(pa.samples_array, pb.samples_array)
+        assert np.array_equal(pa.weights, pb.weights), np.abs(pa.weights / pb.weights - 1).max()
+        assert np.array_equal(pa.cov, pb.cov)
+    assert len(np.unique(tp.discrepancies)) == tp.n_samples
+    assert tp.n_sim == sum(p.n_sim for p in tp.populations)
+
+    # a population is gathered once: a second extraction returns the same rows and counters
+    rej = elfi.Rejection(m['d'], batch_size=500, seed=7)
+    first = rej.sample(50, quantile=0.05, bar=False)
+    again = rej.extract_result()
+    assert again.n_sim == first.n_sim and np.array_equal(again.discrepancies, first.discrepancies)
+    at = elfi.AdaptiveThresholdSMC(m['d'], batch_size=500, seed=2).sample(200, max_iter=3, bar=False)
+    assert len(np.unique(at.discrepancies)) == at.n_samples
+    assert at.n_sim == sum(p.n_sim for p in at.populations)
     dist.barrier()
     if rank == 0:
         print('MGPU_OK world={}'.format(world), flush=True)
