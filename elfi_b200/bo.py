@@ -106,20 +106,27 @@ class GPyRegression:
         return dict(self._hyper)
 
     def _default_hyper(self, x, y):
-        """gpy_regression.py:255-280: heuristics from the bounds and the first data."""
+        """gpy_regression.py:242-284.  The reference's default kernel is GPy's RBF + Bias with
+        GPy's own initial values (variance = lengthscale = bias variance = 1); the heuristics from
+        the bounds and the first data only parameterise the Gamma priors (and the noise variance,
+        :254), so until the first `optimize()` the GP runs on the unit values.  The `gp_params`
+        entries 'kernel_var' / 'lengthscale' / 'bias_var' stand in for the reference's
+        ``gp_params['kernel']`` (a GPy object, not constructible here)."""
         length_scale = (np.max(self.bounds) - np.min(self.bounds)) / 3.
         kernel_var = (np.max(y) / 3.) ** 2.
         bias_var = kernel_var / 4.
         noise_var = self.gp_params.get('noise_var') or np.max(y) ** 2. / 100.
-        self._hyper = dict(kernel_var=float(kernel_var), lengthscale=float(length_scale),
-                           bias_var=float(bias_var), noise_var=float(noise_var))
+        self._hyper = dict(kernel_var=1.0, lengthscale=1.0, bias_var=1.0,
+                           noise_var=float(noise_var))
         for k in ('kernel_var', 'lengthscale', 'bias_var'):
             if k in self.gp_params and self.gp_params[k] is not None:
                 self._hyper[k] = float(self.gp_params[k])
         # Gamma.from_EV(E, V) with E = V = value -> shape a = E^2/V = E, rate b = E/V = 1
         self._priors = {'lengthscale': (length_scale, 1.0), 'kernel_var': (kernel_var, 1.0),
                         'bias_var': (bias_var, 1.0)}
-        self._hyper_anchor = dict(self._hyper)   # centre of the optimiser's search box
+        # centre of the optimiser's search box: the prior means
+        self._hyper_anchor = dict(kernel_var=float(kernel_var), lengthscale=float(length_scale),
+                                  bias_var=float(bias_var), noise_var=float(noise_var))
 
     def update(self, x, y, optimize=False):
         """Append evidence and refit (the reference rebuilds the GP on every update, 286-315)."""

@@ -283,8 +283,13 @@ class CandidateBuffer:
         self.count.zero_()
         self.dropped.zero_()
 
-    def append(self, sources, acc_idx, n_acc, max_rows):
-        """Append rows acc_idx[:n_acc] (device int32 / device int64 count) of `sources`."""
+    def _descriptors(self, sources):
+        """ctypes descriptor arrays of a source list, cached while the same buffers come back
+        (a sampler appends from the same output tensors batch after batch)."""
+        key = tuple((t.data_ptr(), tuple(t.shape), t.stride(0)) for t in sources)
+        cached = getattr(self, '_desc', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         srcs = [_as_2d(t) for t in sources]
         if [t.shape[1] for t in srcs] != self.widths:
             raise ValueError('source widths do not match the buffer layout')
@@ -292,11 +297,18 @@ class CandidateBuffer:
         ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
         lds = (ctypes.c_int64 * n)(*[_ld(t) for t in srcs])
         wid = (ctypes.c_int64 * n)(*self.widths)
+        desc = (n, ptrs, lds, wid, ctypes.cast(ptrs, ctypes.c_void_p),
+                ctypes.cast(lds, ctypes.c_void_p), ctypes.cast(wid, ctypes.c_void_p),
+                dev.ptr(self.rows), dev.ptr(self.count), dev.ptr(self.dropped))
+        self._desc = (key, desc)
+        return desc
+
+    def append(self, sources, acc_idx, n_acc, max_rows):
+        """Append rows acc_idx[:n_acc] (device int32 / device int64 count) of `sources`."""
+        n, _, _, _, pp, pl, pw, prow, pcount, pdrop = self._descriptors(sources)
         _lib.call('elfi_b200_accept_append_f64', dev.context(), dev.ptr(acc_idx), dev.ptr(n_acc),
-                  int(max_rows), n, ctypes.cast(ptrs, ctypes.c_void_p),
-                  ctypes.cast(lds, ctypes.c_void_p), ctypes.cast(wid, ctypes.c_void_p),
-                  dev.ptr(self.rows), self.width, self.capacity, dev.ptr(self.count),
-                  dev.ptr(self.dropped), dev.stream_ptr())
+                  int(max_rows), n, pp, pl, pw, prow, self.width, self.capacity, pcount, pdrop,
+                  dev.stream_ptr())
 
     def best(self, n, key_col=0):
         """(rows sorted by column key_col, first n; count, dropped) -- one D2H of the counters."""

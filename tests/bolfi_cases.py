@@ -79,6 +79,70 @@ def case_maxvar_matches_reference():
     assert acq.evaluate(x[:1])[0, 0] >= got.max() * 0.999      # a maximiser beats the probe points
 
 
+def case_lcbsc_acquire_matches_reference():
+    """LCBSC.evaluate / evaluate_gradient / acquire / _add_noise and bo.utils.minimize against the
+    reference's own classes run on a duck GP (tests/golden/lcbsc_acquire.npz; acquisition.py:129-301,
+    bo/utils.py:40-111): same start points, same optimiser, same RandomState consumption, so the
+    acquired points agree to the accuracy of the GP posterior itself."""
+    from elfi_b200.bo import LCBSC, GPyRegression, minimize, minimize_lockstep
+    g = load_golden('lcbsc_acquire')
+    gp = GPyRegression(['t1', 't2'], bounds={'t1': (-2, 2), 't2': (-1, 1)})
+    gp.update(g['X'], g['y'][:, None])
+    gp._hyper = dict(zip(('kernel_var', 'lengthscale', 'bias_var', 'noise_var'),
+                         (float(v) for v in g['hyper'])))
+    gp._fit()
+    prior = _prior()
+    lc = LCBSC(model=gp, prior=prior, noise_var=0.1, exploration_rate=10, seed=1, n_inits=10,
+               max_opt_iters=1000)
+    for t in (0, 4, 40):
+        np.testing.assert_allclose(lc._beta(t), float(g['beta_t{}'.format(t)]), rtol=1e-14)
+        val = lc.evaluate(g['pts'], t)
+        assert val.shape == g['value_t{}'.format(t)].shape
+        np.testing.assert_allclose(val, g['value_t{}'.format(t)], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(lc.evaluate_gradient(g['pts'], t), g['grad_t{}'.format(t)],
+                                   rtol=1e-4, atol=1e-7)
+    # acquire: multi-start L-BFGS-B from prior draws, n copies, truncated-normal noise; two calls in
+    # a row continue the same RandomState exactly as the reference does
+    for lockstep in (True, False):
+        lc = LCBSC(model=gp, prior=prior, noise_var=0.1, exploration_rate=10, seed=1, n_inits=10,
+                   max_opt_iters=1000)
+        lc.lockstep = lockstep
+        np.testing.assert_allclose(lc.acquire(3, t=4), g['acquired_t4'], rtol=2e-4, atol=2e-4)
+        np.testing.assert_allclose(lc.acquire(2, t=5), g['acquired_t5'], rtol=2e-4, atol=2e-4)
+    quiet = LCBSC(model=gp, prior=prior, noise_var=0, exploration_rate=10, seed=3, n_inits=6)
+    xq = quiet.acquire(2, t=2)
+    np.testing.assert_allclose(xq, g['acquired_quiet'], rtol=2e-4, atol=2e-4)
+    assert np.array_equal(xq[0], xq[1])                     # zero noise: n copies of the minimiser
+    by_name = LCBSC(model=gp, prior=None, noise_var={'t1': 0.2, 't2': 0.0}, delta=0.2, seed=5)
+    assert by_name.exploration_rate == 5.0
+    xd = by_name.acquire(4, t=1)
+    np.testing.assert_allclose(xd, g['acquired_dict'], rtol=2e-4, atol=2e-4)
+    assert np.all(xd[:, 1] == xd[0, 1]) and len(np.unique(xd[:, 0])) == 4   # noise on t1 only
+    noisy = LCBSC(model=gp, prior=prior, noise_var=0.5, seed=9)
+    out = noisy._add_noise(g['noise_in'].copy())
+    assert np.array_equal(out, g['noise_out'])              # pure host RNG: bit-identical
+    assert np.all((out[:, 0] >= -2) & (out[:, 0] <= 2) & (out[:, 1] >= -1) & (out[:, 1] <= 1))
+
+    # bo.utils.minimize on an analytic function: prior and uniform start points
+    def quad(x):
+        x = np.atleast_2d(x)
+        return (x[:, 0] - 0.3) ** 2 + 3 * (x[:, 1] + 0.4) ** 2 + 0.5 * np.sin(5 * x[:, 0])
+
+    def quad_grad(x):
+        x = np.atleast_2d(x)
+        return np.column_stack([2 * (x[:, 0] - 0.3) + 2.5 * np.cos(5 * x[:, 0]), 6 * (x[:, 1] + 0.4)])
+    bounds = [(-2, 2), (-1, 1)]
+    loc, val = minimize(quad, bounds, grad=quad_grad, prior=prior, n_start_points=7,
+                        random_state=np.random.RandomState(4))
+    assert np.array_equal(loc, g['min_loc']) and val == float(g['min_val'])
+    loc, val = minimize(quad, bounds, grad=quad_grad, prior=None, n_start_points=5,
+                        random_state=np.random.RandomState(6))
+    assert np.array_equal(loc, g['min_loc_uniform']) and val == float(g['min_val_uniform'])
+    loc, val = minimize_lockstep(lambda X: (quad(X), quad_grad(X)), bounds, prior=prior,
+                                 n_start_points=7, random_state=np.random.RandomState(4))
+    assert np.array_equal(loc, g['min_loc']) and val == float(g['min_val'])
+
+
 def case_expintvar_matches_reference():
     """ExpIntVar on a grid: the candidate-dependent loss equals the reference's (which factorises
     Ky per evaluation) at probe points; the acquired point is at least as good as the reference's."""

@@ -26,7 +26,8 @@ elfi = import_reference()
 import elfi_oracle as o  # noqa: E402
 from elfi.examples import ma2  # noqa: E402
 from elfi.methods import mcmc  # noqa: E402
-from elfi.methods.bo.acquisition import ExpIntVar, MaxVar  # noqa: E402
+from elfi.methods.bo.acquisition import LCBSC, ExpIntVar, MaxVar  # noqa: E402
+from elfi.methods.bo.utils import minimize as ref_minimize  # noqa: E402
 from elfi.methods.posteriors import BolfiPosterior  # noqa: E402
 from elfi.model.extensions import ModelPrior  # noqa: E402
 
@@ -187,6 +188,44 @@ def main():
                                                  'noise_var')]),
          grid=eiv.points_int, eps=np.float64(eiv.eps), pts=eiv_pts, loss=eiv_loss,
          single=eiv_single, acquired=eiv_x, omegas=eiv.omegas_int, phi_int=eiv.phi_int)
+
+    # ---- LCBSC.evaluate / evaluate_gradient / acquire / _add_noise (acquisition.py:129-301) and
+    # bo.utils.minimize (utils.py:40-111) of the reference classes on the same duck GP
+    lc = LCBSC(model=gp, prior=prior, noise_var=0.1, exploration_rate=10, seed=1, n_inits=10,
+               max_opt_iters=1000)
+    lc_pts = pts[[0, 1, 2, 3, 4, 5, 9]]
+    lc_out = {'pts': lc_pts}
+    for t in (0, 4, 40):
+        lc_out['value_t{}'.format(t)] = lc.evaluate(lc_pts, t)
+        lc_out['grad_t{}'.format(t)] = lc.evaluate_gradient(lc_pts, t)
+        lc_out['beta_t{}'.format(t)] = np.float64(lc._beta(t))
+    lc_out['acquired_t4'] = lc.acquire(3, t=4)              # consumes lc.random_state
+    lc_out['acquired_t5'] = lc.acquire(2, t=5)              # ... further
+    lc_quiet = LCBSC(model=gp, prior=prior, noise_var=0, exploration_rate=10, seed=3, n_inits=6)
+    lc_out['acquired_quiet'] = lc_quiet.acquire(2, t=2)     # no noise: the minimiser itself
+    lc_dict = LCBSC(model=gp, prior=None, noise_var={'t1': 0.2, 't2': 0.0}, delta=0.2, seed=5)
+    lc_out['acquired_dict'] = lc_dict.acquire(4, t=1)       # uniform starts, per-parameter noise
+    lc_noise = LCBSC(model=gp, prior=prior, noise_var=0.5, seed=9)
+    edge = np.array([[1.99, -0.99], [-1.99, 0.99], [0.0, 0.0], [0.6, 0.2]])
+    lc_out['noise_in'] = edge.copy()
+    lc_out['noise_out'] = lc_noise._add_noise(edge.copy())
+
+    def quad(x):
+        x = np.atleast_2d(x)
+        return (x[:, 0] - 0.3) ** 2 + 3 * (x[:, 1] + 0.4) ** 2 + 0.5 * np.sin(5 * x[:, 0])
+
+    def quad_grad(x):
+        x = np.atleast_2d(x)
+        return np.column_stack([2 * (x[:, 0] - 0.3) + 2.5 * np.cos(5 * x[:, 0]), 6 * (x[:, 1] + 0.4)])
+    loc, val = ref_minimize(quad, bounds, grad=quad_grad, prior=prior, n_start_points=7,
+                            random_state=np.random.RandomState(4))
+    loc_u, val_u = ref_minimize(quad, bounds, grad=quad_grad, prior=None, n_start_points=5,
+                                random_state=np.random.RandomState(6))
+    lc_out.update(min_loc=loc, min_val=np.float64(val), min_loc_uniform=loc_u,
+                  min_val_uniform=np.float64(val_u))
+    save('lcbsc_acquire', X=X, y=y, hyper=np.array([hyper[k] for k in
+                                                    ('kernel_var', 'lengthscale', 'bias_var',
+                                                     'noise_var')]), **lc_out)
 
     save('bolfi_posterior', X=X, y=y, hyper=np.array([hyper[k] for k in
                                                       ('kernel_var', 'lengthscale', 'bias_var',

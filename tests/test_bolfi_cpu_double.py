@@ -23,6 +23,10 @@ def test_expintvar_matches_reference():
     cases.case_expintvar_matches_reference()
 
 
+def test_lcbsc_acquire_matches_reference():
+    cases.case_lcbsc_acquire_matches_reference()
+
+
 def test_incremental_factor_update():
     cases.case_incremental_factor_update()
 
