@@ -12,6 +12,9 @@
 // the TMA pipeline keeps >= ~45 KiB in flight per SM (see rowstream.cuh).
 #include "rowstream.cuh"
 
+extern "C" int elfi_b200_colmoments_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                        int64_t D, double* out, void* stream);
+
 namespace elfi {
 
 struct DistParams {
@@ -21,6 +24,8 @@ struct DistParams {
     uint32_t* mask;      // ceil(B/32) words or nullptr
     int K;
     int has_thr;
+    const double* shift_src;   // fused column moments: row 0 of S (the shift of the power sums)
+    double* mom_partial;       // (warps, 2, D) shifted power sums per warp, or nullptr
     const double* thr_dev;   // K thresholds in device memory (e.g. a quantile computed on the
                              // device), or nullptr: then thr[] below, copied from the host
     double thr[ELFI_B200_MAX_NESTED];
@@ -188,6 +193,121 @@ struct NestedConsumer {
         dist_finish<KMAX>(p, acc, p.K, row, B, lane);
     }
 };
+
+// NestedConsumer + the per-column moments of AdaptiveDistance.add_data (elfi_model.py:1104-1125)
+// from the SAME staged boxes: S is read from HBM once for the K distance columns and the
+// (count, mean, M2) update, where the reference reads it K + 1 times.  After a lane has walked its
+// row of the box, the warp sweeps the box again DOWN the rows: lane L owns the 16-byte chunk
+// c2 = L & 7 (two columns) of the eight rows 8 (L >> 3) .. + 7 -- with the 128-byte swizzle the
+// eight lanes of a quarter read one 128-byte row and the four quarters four different rows, so
+// the LDS.128 is conflict-free like the row-wise read.  Shifted power sums
+// (sum (x - c), sum (x - c)^2 with c = first row of S) go through two shuffles into per-warp
+// shared accumulators (one per column, only lanes 0..7 write, no atomics); each warp flushes them
+// once at the end and colmoments_flush_kernel adds the warps in a fixed order: deterministic.
+template <int KMAX>
+struct NestedMomentsConsumer : NestedConsumer<KMAX> {
+    typedef NestedConsumer<KMAX> Base;
+    typedef DistParams Params;
+    static constexpr bool RS_TILE_INFO = true;
+    static constexpr bool RS_FINISH = true;
+    const double* shift_s;
+    double* acc_s;          // this warp's [2][Dp]
+    int64_t row0, nrows;
+    int D;
+
+    // aux: obs [Dp] | W [K][Dp] | shift [Dp] | accumulators [RS_WARPS][2][Dp]
+    static __host__ __device__ size_t aux_bytes(int64_t Dp, int64_t K) {
+        return size_t(Dp) * 8 * (1 + K + 1 + 2 * RS_WARPS);
+    }
+    static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
+        dist_setup_shared(aux, p, D, true);
+        const int Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+        double* shift = reinterpret_cast<double*>(aux) + size_t(1 + p.K) * Dp;
+        for (int j = threadIdx.x; j < Dp; j += blockDim.x) shift[j] = j < D ? p.shift_src[j] : 0.0;
+        double* acc = shift + Dp;
+        for (int j = threadIdx.x; j < 2 * RS_WARPS * Dp; j += blockDim.x) acc[j] = 0.0;
+    }
+    __device__ NestedMomentsConsumer(const Params& p_, const uint8_t* aux, int D_, int lane)
+        : Base(p_, aux, D_, lane), row0(0), nrows(0), D(D_) {
+        shift_s = this->obs_s + size_t(1 + p_.K) * this->Dp;
+        acc_s = const_cast<double*>(shift_s) + this->Dp + size_t(threadIdx.x >> 5) * 2 * this->Dp;
+    }
+    __device__ __forceinline__ void set_tile(int64_t r0, int64_t B) { row0 = r0; nrows = B; }
+    __device__ __forceinline__ void consume(int pass, int cg, const uint8_t* box_row, int sw) {
+        Base::consume(pass, cg, box_row, sw);
+        const int lane = threadIdx.x & 31;
+        const int c2 = lane & 7, h = lane >> 3;
+        const uint8_t* box = box_row - lane * 128;
+        const double2 sh = *reinterpret_cast<const double2*>(shift_s + cg * RS_BOX_COLS + 2 * c2);
+        double s1x = 0.0, s1y = 0.0, s2x = 0.0, s2y = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = h * 8 + i;
+            const double2 v = *reinterpret_cast<const double2*>(box + r * 128 + ((c2 ^ i) << 4));
+            if (row0 + r < nrows) {
+                const double dx = v.x - sh.x, dy = v.y - sh.y;
+                s1x += dx;
+                s1y += dy;
+                s2x = fma(dx, dx, s2x);
+                s2y = fma(dy, dy, s2y);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            s1x += __shfl_xor_sync(0xffffffffu, s1x, o);
+            s1y += __shfl_xor_sync(0xffffffffu, s1y, o);
+            s2x += __shfl_xor_sync(0xffffffffu, s2x, o);
+            s2y += __shfl_xor_sync(0xffffffffu, s2y, o);
+        }
+        if (lane < 8) {
+            double2* a1 = reinterpret_cast<double2*>(acc_s + cg * RS_BOX_COLS + 2 * c2);
+            double2* a2 = reinterpret_cast<double2*>(acc_s + this->Dp + cg * RS_BOX_COLS + 2 * c2);
+            double2 t1 = *a1, t2 = *a2;
+            t1.x += s1x; t1.y += s1y; t2.x += s2x; t2.y += s2y;
+            *a1 = t1;
+            *a2 = t2;
+        }
+    }
+    __device__ __forceinline__ void finish(int64_t gw, int lane) {
+        double* out = this->p.mom_partial + gw * 2 * int64_t(D);
+        for (int j = lane; j < D; j += 32) {
+            out[j] = acc_s[j];
+            out[D + j] = acc_s[this->Dp + j];
+        }
+    }
+};
+
+// out[0*D + j] = mean_j, out[1*D + j] = M2_j from the per-warp shifted power sums
+__global__ void colmoments_flush_kernel(const double* __restrict__ S, const double* __restrict__ partial,
+                                        int64_t nwarps, int64_t B, int64_t D,
+                                        double* __restrict__ out) {
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t b = 0; b < nwarps; ++b) {
+        s1 += partial[(b * 2 + 0) * D + c];
+        s2 += partial[(b * 2 + 1) * D + c];
+    }
+    const double n = double(B);
+    out[c] = S[c] + s1 / n;
+    out[D + c] = s2 - s1 * s1 / n;
+}
+
+template <int KMAX>
+static int launch_nested_moments(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                 int64_t D, DistParams p, size_t aux, double* moments,
+                                 cudaStream_t stream) {
+    const int64_t ntiles = (B + RS_BOX_ROWS - 1) / RS_BOX_ROWS;
+    int64_t ctas = (ntiles + RS_WARPS - 1) / RS_WARPS;
+    if (ctas > ctx->sm_count) ctas = ctx->sm_count;
+    const int64_t nwarps = ctas * RS_WARPS;
+    int rc = rowstream_launch<NestedMomentsConsumer<KMAX>>(ctx, S, ldS, B, D, aux, p, stream);
+    if (rc) return rc;
+    colmoments_flush_kernel<<<unsigned((D + 127) / 128), 128, 0, stream>>>(S, p.mom_partial, nwarps,
+                                                                         B, D, moments);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
 
 // Fallback for narrow (D < 16) or TMA-incompatible matrices: one thread per row, direct
 // loads.  For D <= 8 a warp still touches a contiguous span, so sectors are fully used.
@@ -513,6 +633,64 @@ int elfi_b200_dist_euclid_thr_dev_f64(elfi_b200_ctx* ctx, const double* S, int64
     rc = launch_dist(ctx, S, ldS, B, D, obs, W, K, nullptr, d_out, mask, stream, thr_dev);
     if (rc) return rc;
     if (acc_idx != nullptr || n_acc != nullptr)
+        return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_dist_euclid_mom_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                  int64_t D, const double* obs, const double* W, int64_t K,
+                                  const double* thr_host, const double* thr_dev, double* d_out,
+                                  int32_t* acc_idx, int64_t* n_acc, double* moments,
+                                  void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr && moments != nullptr, "dist_mom: ctx or moments is NULL");
+    ELFI_REQUIRE(!(thr_host && thr_dev), "dist_mom: give thresholds on the host OR on the device");
+    const void* thr = thr_host ? static_cast<const void*>(thr_host) : thr_dev;
+    int rc = check_dist_args(S, ldS, B, D, obs, W, K, thr, acc_idx);
+    if (rc) return rc;
+    ELFI_REQUIRE(B >= 1 && d_out != nullptr, "dist_mom: needs at least one row and d_out");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const int64_t Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    const size_t aux = NestedMomentsConsumer<2>::aux_bytes(Dp, K);
+    const bool fused = W != nullptr && D >= RS_BOX_COLS && tma_compatible(S, ldS) &&
+                       rs_pick_stages(ctx->smem_optin, aux) >= 2;
+    const size_t mask_bytes = (size_t((B + 31) / 32) * 4 + 255) & ~size_t(255);
+    const size_t part_bytes = fused ? size_t(ctx->sm_count) * RS_WARPS * 2 * D * 8 : 0;
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, mask_bytes + part_bytes + 256));
+    if (!base) return ELFI_B200_ERR_NOMEM;
+    uint32_t* mask = thr ? reinterpret_cast<uint32_t*>(base) : nullptr;
+    if (!fused) {
+        // narrow / unaligned / unweighted matrices: distances, then the stand-alone moments pass
+        rc = launch_dist(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, mask, stream, thr_dev);
+        if (rc) return rc;
+        if (thr && (acc_idx != nullptr || n_acc != nullptr)) {
+            rc = launch_compact_mask(mask, B, acc_idx, n_acc, stream);
+            if (rc) return rc;
+        }
+        return elfi_b200_colmoments_f64(ctx, S, ldS, B, D, moments, stream_);
+    }
+    DistParams p;
+    memset(&p, 0, sizeof(p));
+    p.obs = obs;
+    p.W = W;
+    p.d_out = d_out;
+    p.mask = mask;
+    p.K = int(K);
+    p.has_thr = thr != nullptr;
+    p.thr_dev = thr_dev;
+    if (thr_host)
+        for (int k = 0; k < K; ++k) p.thr[k] = thr_host[k];
+    p.shift_src = S;
+    p.mom_partial = reinterpret_cast<double*>(base + mask_bytes);
+    if (K <= 2) rc = launch_nested_moments<2>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    else if (K <= 4) rc = launch_nested_moments<4>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    else if (K <= 6) rc = launch_nested_moments<6>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    else if (K <= 8) rc = launch_nested_moments<8>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    else if (K <= 16) rc = launch_nested_moments<16>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    else rc = launch_nested_moments<32>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    if (rc) return rc;
+    if (thr && (acc_idx != nullptr || n_acc != nullptr))
         return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
     return ELFI_B200_OK;
 }

@@ -28,9 +28,22 @@
 // round-robin to the global warp index.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace elfi {
+
+// Optional parts of the Consumer concept, detected at compile time:
+//   static constexpr bool RS_TILE_INFO = true;   void set_tile(int64_t row0, int64_t B);
+//       -- told the first row of every tile before its first box (e.g. to mask rows >= B when a
+//          consumer also reduces DOWN the rows of a box)
+//   static constexpr bool RS_FINISH = true;      void finish(int64_t gw, int lane);
+//       -- called once per warp after its last box (flush per-warp accumulators)
+template <class C, class = void> struct rs_has_tile_info : std::false_type {};
+template <class C> struct rs_has_tile_info<C, std::void_t<decltype(C::RS_TILE_INFO)>> : std::true_type {};
+template <class C, class = void> struct rs_has_finish : std::false_type {};
+template <class C> struct rs_has_finish<C, std::void_t<decltype(C::RS_FINISH)>> : std::true_type {};
 
 constexpr int RS_WARPS = 8;          // consumer warps per CTA
 constexpr int RS_BOX_ROWS = 32;      // rows per box (one per lane)
@@ -127,7 +140,10 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
     int64_t tile = gw;
     for (int64_t q = 0; q < nbox; ++q) {
         mbar_wait(bar0 + s * 8, parity);
-        if (cg == 0) c.begin_row();
+        if (cg == 0) {
+            c.begin_row();
+            if constexpr (rs_has_tile_info<Consumer>::value) c.set_tile(tile * RS_BOX_ROWS, B);
+        }
         c.consume(pass, col, box0_generic + size_t(s) * RS_BOX_BYTES + row_off, sw);
         __syncwarp();
         if (lane == 0 && p_q < nbox) issue();
@@ -135,6 +151,10 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
         if (++col == Gc) { col = 0; ++pass; }
         if (++cg == G) { cg = 0; pass = 0; tile += GW; }
         if (++s == ns) { s = 0; parity ^= 1; }
+    }
+    if constexpr (rs_has_finish<Consumer>::value) {
+        __syncwarp();
+        c.finish(gw, lane);
     }
 }
 

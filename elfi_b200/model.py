@@ -794,7 +794,9 @@ class AdaptiveDistance(Discrepancy):
         D = X.shape[1]
         W = np.stack([np.ones(D) if w is None else np.asarray(w, dtype=np.float64) ** 2
                       for w in ws])
-        d, idx = ops.dist_euclid(X, obs, w=W, thresholds=accept)
+        # the batch's column moments come out of the same read of X; add_data picks them up
+        d, idx, mom = ops.dist_euclid(X, obs, w=W, thresholds=accept, moments=True)
+        self._s['_batch_moments'] = (X, mom)
         return AcceptedOutput(d, idx) if accept is not None else d
 
     @property
@@ -810,13 +812,19 @@ class AdaptiveDistance(Discrepancy):
         if 'store' not in self._s:
             self.init_state()
         self._s['store'] = [0, 0, 0]
+        self._s.pop('_batch_moments', None)
 
     def add_data(self, *data):
         """Chan-merge this batch's device column moments into (n, mean, M2); algebraically the
         batch Welford update of elfi_model.py:1117-1123."""
         X = _stack_summaries(data)
         nb = X.shape[0]
-        mean_b, m2_b = ops.colmoments(X)
+        held = self._s.pop('_batch_moments', None)
+        if held is not None and held[0].data_ptr() == X.data_ptr() and \
+                held[0].shape == X.shape and held[0].stride() == X.stride():
+            mean_b, m2_b = held[1].cpu().numpy()      # fused with the distance pass
+        else:
+            mean_b, m2_b = ops.colmoments(X)
         n0, m0, s0 = self._s['store']
         n1 = n0 + nb
         delta = mean_b - m0

@@ -28,7 +28,7 @@ def _matrix(S):
     return S
 
 
-def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True, sync=True):
+def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True, sync=True, moments=False):
     """Euclidean / nested weighted distances of the rows of S to ``obs`` + acceptance.
 
     Replaces ``cdist(S, obs, 'euclidean'[, w=w])`` reached through
@@ -44,6 +44,8 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True, sync=True):
         -- accept rows with all_k(d[:, k] <= thresholds[k])
     sync : False leaves the accepted count on the device: acc_idx is then the pair
         (int32 buffer of B indices of which the first n_acc are valid, n_acc device int64[1])
+    moments : True also returns the (2, D) device array [column means; column M2] of S, computed
+        from the same read of S (AdaptiveDistance.add_data, elfi_model.py:1104-1125)
 
     Returns
     -------
@@ -87,10 +89,18 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True, sync=True):
         n_acc = dev.zeros((1,), dtype=torch.int64)
         if want_indices:
             acc_idx = dev.empty((max(B, 1),), dtype=torch.int32)
-    _lib.call('elfi_b200_dist_euclid_thr_dev_f64' if thr_on_device else
-              'elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S),
-              S.stride(0) if B > 1 else D, B, D, dev.ptr(obs_t), dev.ptr(W), K, dev.ptr(thr),
-              dev.ptr(d), dev.ptr(acc_idx), dev.ptr(n_acc), dev.stream_ptr())
+    mom = None
+    if moments:
+        mom = dev.empty((2, D))
+        _lib.call('elfi_b200_dist_euclid_mom_f64', dev.context(), dev.ptr(S),
+                  S.stride(0) if B > 1 else D, B, D, dev.ptr(obs_t), dev.ptr(W), K,
+                  None if thr_on_device else dev.ptr(thr), dev.ptr(thr) if thr_on_device else None,
+                  dev.ptr(d), dev.ptr(acc_idx), dev.ptr(n_acc), dev.ptr(mom), dev.stream_ptr())
+    else:
+        _lib.call('elfi_b200_dist_euclid_thr_dev_f64' if thr_on_device else
+                  'elfi_b200_dist_euclid_thr_f64', dev.context(), dev.ptr(S),
+                  S.stride(0) if B > 1 else D, B, D, dev.ptr(obs_t), dev.ptr(W), K, dev.ptr(thr),
+                  dev.ptr(d), dev.ptr(acc_idx), dev.ptr(n_acc), dev.stream_ptr())
     if thr is not None:
         if not sync:
             acc_idx = (acc_idx, n_acc)
@@ -99,7 +109,7 @@ def dist_euclid(S, obs, w=None, thresholds=None, want_indices=True, sync=True):
             acc_idx = acc_idx[:n] if want_indices else n
     if squeeze:
         d = d.reshape(B)
-    return d, acc_idx
+    return (d, acc_idx, mom) if moments else (d, acc_idx)
 
 
 METRIC_CODES = {'sqeuclidean': 1, 'cityblock': 2, 'chebyshev': 3, 'minkowski': 4}

@@ -85,6 +85,19 @@ int elfi_b200_dist_euclid_thr_dev_f64(elfi_b200_ctx* ctx, const double* S, int64
                                       const double* thr_dev, double* d_out, int32_t* acc_idx,
                                       int64_t* n_acc, void* stream);
 
+/* Distances + acceptance AND the per-column moments of the same batch from ONE read of S:
+ * AdaptiveDistance evaluates its K nested columns (elfi_model.py:1135-1151) and then feeds the
+ * batch to add_data (elfi_model.py:1104-1125); the reference reads S K + 1 times for that.
+ * moments (2, D) device: row 0 = column means of the batch, row 1 = M2 = sum_i (x_ij - mean_j)^2
+ * (what elfi_b200_colmoments_f64 returns; Chan-merged into (n, mean, M2) by the caller).
+ * Thresholds: thr_host or thr_dev (at most one non-NULL; both NULL = no acceptance test).
+ * W may be NULL only when the stand-alone moments pass is acceptable (the fused kernel is the
+ * weighted / nested row stream; pass a row of ones for plain Euclidean distances). */
+int elfi_b200_dist_euclid_mom_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                  int64_t D, const double* obs, const double* W, int64_t K,
+                                  const double* thr_host, const double* thr_dev, double* d_out,
+                                  int32_t* acc_idx, int64_t* n_acc, double* moments, void* stream);
+
 /* Same computation with HOST buffers (pageable or pinned): rows are streamed to the device
  * in chunks on two copy streams overlapped with the kernel; distances, accepted indices
  * and the count are copied back.  Blocks until the results are in host memory.

@@ -88,6 +88,13 @@ def dist_euclid_thr_dev_f64(ctx, S, ldS, B, D, obs, W, K, thr_dev, d_out, acc_id
     dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr_dev, d_out, acc_idx, n_acc, stream)
 
 
+def dist_euclid_mom_f64(ctx, S, ldS, B, D, obs, W, K, thr_host, thr_dev, d_out, acc_idx, n_acc, moments,
+                        stream):
+    thr = thr_host if _addr(thr_host) else thr_dev
+    dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr, d_out, acc_idx, n_acc, stream)
+    colmoments_f64(ctx, S, ldS, B, D, moments, stream)
+
+
 def accept_append_f64(ctx, acc_idx, n_acc, max_rows, n_src, src_host, ld_src_host, width_host, dst,
                       ld_dst, capacity, count, dropped, stream):
     n = int(_vec(n_acc, 1, np.int64)[0])
@@ -471,7 +478,7 @@ def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
 
 
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
-    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, accept_append_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
+    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,

@@ -143,6 +143,45 @@ def case_lcbsc_acquire_matches_reference():
     assert np.array_equal(loc, g['min_loc']) and val == float(g['min_val'])
 
 
+def case_hyper_objective_matches_sklearn():
+    """The objective of GPyRegression.optimize(): its log marginal likelihood (device Cholesky)
+    and the gradient in log-parameters that L-BFGS-B sees, against scikit-learn's
+    GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True) for the same
+    kernel sigma^2 RBF(l) + b + noise (theta = log parameters); GPy itself (SCG + paramz
+    transforms, gpy_regression.py:317-323) is not installable here."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
+    from elfi_b200.bo import JITTER, GPyRegression
+    import scipy.stats as ss
+    rs = np.random.RandomState(12)
+    n = 90
+    X = np.column_stack([rs.uniform(-2, 2, n), rs.uniform(-1, 1, n)])
+    y = np.log(0.05 + (X[:, 0] - 0.6) ** 2 + 2 * (X[:, 1] - 0.2) ** 2) + 0.2 * rs.randn(n)
+    gp = GPyRegression(['t1', 't2'], bounds={'t1': (-2, 2), 't2': (-1, 1)})
+    gp.update(X, y[:, None])
+    names = ['kernel_var', 'lengthscale', 'bias_var', 'noise_var']
+    for hyper in ([1.0, 1.0, 1.0, 0.2], [2.3, 0.6, 0.5, 0.07], [0.4, 1.7, 3.0, 0.5]):
+        h = dict(zip(names, hyper))
+        kernel = ConstantKernel(h['kernel_var']) * RBF(h['lengthscale']) + \
+            ConstantKernel(h['bias_var']) + WhiteKernel(h['noise_var'] + JITTER)
+        sk = GaussianProcessRegressor(kernel=kernel, alpha=0.0, optimizer=None).fit(X, y)
+        # sklearn orders theta as log[kernel_var, lengthscale, bias_var, noise]
+        want, want_grad = sk.log_marginal_likelihood(sk.kernel_.theta, eval_gradient=True)
+        got = gp.log_marginal_likelihood(h)
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+
+        def lml(logh):
+            return gp.log_marginal_likelihood(dict(zip(names, np.exp(logh))))
+        x0, eps = np.log(hyper), 1e-5
+        fd = np.array([(lml(x0 + eps * e) - lml(x0 - eps * e)) / (2 * eps) for e in np.eye(4)])
+        # d/dlog(noise + jitter) vs d/dlog(noise): identical up to jitter / noise ~ 1e-7
+        np.testing.assert_allclose(fd, want_grad, rtol=2e-5, atol=1e-6)
+        # the Gamma log-priors on top are the reference's (gpy_regression.py:267-280)
+        prior = sum(ss.gamma.logpdf(h[k], a=a, scale=1.0 / b) for k, (a, b) in gp._priors.items())
+        np.testing.assert_allclose(gp.log_posterior_hyper(h), got + prior, rtol=1e-12)
+    gp._fit()
+
+
 def case_expintvar_matches_reference():
     """ExpIntVar on a grid: the candidate-dependent loss equals the reference's (which factorises
     Ky per evaluation) at probe points; the acquired point is at least as good as the reference's."""

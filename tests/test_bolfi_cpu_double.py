@@ -27,6 +27,10 @@ def test_lcbsc_acquire_matches_reference():
     cases.case_lcbsc_acquire_matches_reference()
 
 
+def test_hyper_objective_matches_sklearn():
+    cases.case_hyper_objective_matches_sklearn()
+
+
 def test_incremental_factor_update():
     cases.case_incremental_factor_update()
 

@@ -68,3 +68,46 @@ def test_colmoments(B, D):
     mean, m2 = ops.colmoments(S)
     np.testing.assert_allclose(mean, S.mean(axis=0), rtol=1e-12)
     np.testing.assert_allclose(np.sqrt(m2 / B), S.std(axis=0), rtol=1e-10)
+
+
+@pytest.mark.first_device_run
+@pytest.mark.parametrize('B,D,K', [(4096, 256, 1), (100003, 33, 3), (5000, 128, 5), (31, 16, 2),
+                                   (70000, 256, 8), (1000, 2, 2), (2048, 40, 17)])
+def test_fused_distance_and_colmoments(B, D, K):
+    """elfi_b200_dist_euclid_mom_f64: nested distances + acceptance bit-identical to the plain
+    kernel, column moments of the same read equal to NumPy's (and to the stand-alone pass)."""
+    import elfi_oracle as o
+    from elfi_b200 import ops
+    rs = np.random.RandomState(B + D + K)
+    S = rs.randn(B, D) * rs.uniform(0.1, 50, D) + rs.uniform(-100, 100, D)
+    obs = rs.randn(1, D) * 20
+    W = rs.uniform(0.01, 2.0, (K, D))
+    W[0] = 1.0
+    ref = np.column_stack([o.cdist_euclid(S, obs, w=W[k]) for k in range(K)])
+    thr = np.quantile(ref, 0.6, axis=0)
+    d, idx, mom = ops.dist_euclid(S, obs, w=W, thresholds=thr, moments=True)
+    d2, idx2 = ops.dist_euclid(S, obs, w=W, thresholds=thr)
+    assert np.array_equal(d.cpu().numpy(), ref)
+    assert np.array_equal(d.cpu().numpy(), d2.cpu().numpy())
+    assert np.array_equal(idx.cpu().numpy(), idx2.cpu().numpy())
+    assert np.array_equal(idx.cpu().numpy(), np.nonzero(np.all(ref <= thr, axis=1))[0])
+    mean, m2 = mom.cpu().numpy()
+    np.testing.assert_allclose(mean, S.mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(np.sqrt(m2 / B), S.std(axis=0), rtol=1e-10)
+    mean_s, m2_s = ops.colmoments(S)
+    np.testing.assert_allclose(mean, mean_s, rtol=1e-12)
+    np.testing.assert_allclose(m2, m2_s, rtol=1e-9)
+    # a row-strided view (leading dimension > D) and device thresholds
+    from elfi_b200 import device as dev
+    big = dev.to_device(rs.randn(3000, 96))
+    view = big[:, :64]
+    obs2 = rs.randn(64)
+    Wv = rs.uniform(0.5, 1.5, (2, 64))
+    thr_dev = dev.to_device(np.array([12.0, 12.5]))
+    dv, (iv, nv), mv = ops.dist_euclid(view, obs2, w=Wv, thresholds=thr_dev, sync=False, moments=True)
+    host = view.cpu().numpy()
+    refv = np.column_stack([o.cdist_euclid(np.ascontiguousarray(host), obs2, w=Wv[k]) for k in range(2)])
+    assert np.array_equal(dv.cpu().numpy(), refv)
+    k = int(nv.item())
+    assert np.array_equal(iv[:k].cpu().numpy(), np.nonzero(np.all(refv <= [12.0, 12.5], axis=1))[0])
+    np.testing.assert_allclose(mv.cpu().numpy()[0], host.mean(axis=0), rtol=1e-11, atol=1e-13)
