@@ -192,4 +192,55 @@ struct MeanVarBoxes {
 
 using MeanVarLeaf = MeanVarBoxes<LeafSum>;
 
+// Row mean and variance from ONE sweep for rows of <= 16 * NBOX <= 64 observations (the Gaussian
+// model has 50): the row is kept in registers while the boxes go by, so the variance terms
+// (x - mean)^2 are formed from registers instead of a second sweep over the boxes.  Same
+// LeafSum order as MeanVarBoxes, hence the same bits.  G (the box index) is a compile-time
+// constant at every call site so that x[] stays in registers.
+template <int NBOX>
+struct MeanVarRegs {
+    LeafSum s;
+    double x[NBOX * LEAF_BOX];
+    int n;
+
+    ELFI_HD void begin(int n_) {
+        n = n_;
+        s.begin(n);
+    }
+    template <int G, int C>
+    ELFI_HD void keep(const double* cur) {
+        x[G * LEAF_BOX + C] = cur[C];
+        if (G * LEAF_BOX + C < n) s.template push<C % 8>(G * LEAF_BOX + C, cur[C]);
+        if constexpr (C + 1 < LEAF_BOX) keep<G, C + 1>(cur);
+    }
+    template <int G, int C>
+    ELFI_HD void keep_mid(const double* cur) {
+        x[G * LEAF_BOX + C] = cur[C];
+        s.template push_mid<C % 8>(cur[C]);
+        if constexpr (C + 1 < LEAF_BOX) keep_mid<G, C + 1>(cur);
+    }
+    template <int G>
+    ELFI_HD void box(const double* cur) {
+        if (s.all_mid(G * LEAF_BOX, G * LEAF_BOX + LEAF_BOX - 1))
+            keep_mid<G, 0>(cur);
+        else
+            keep<G, 0>(cur);
+    }
+    template <int J>
+    ELFI_HD void squares(double mean) {
+        if (J < n) {
+            const double c = leaf_sub(x[J], mean);
+            s.template push<J % 8>(J, leaf_mul(c, c));
+        }
+        if constexpr (J + 1 < NBOX * LEAF_BOX) squares<J + 1>(mean);
+    }
+    // after the last box: mean and variance of the row
+    ELFI_HD void finish(double& mean, double& var) {
+        mean = s.finish(n) / double(n);
+        s.begin(n);
+        squares<0>(mean);
+        var = s.finish(n) / double(n);
+    }
+};
+
 }  // namespace elfi

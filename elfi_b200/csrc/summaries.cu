@@ -215,6 +215,38 @@ struct MeanVarBoxConsumer {
     }
 };
 
+// Rows of <= 64 observations: one sweep, the row stays in registers (MeanVarRegs, leafsum.cuh).
+// The box index selects the register block through a switch so that every index is a constant.
+template <int NBOX>
+struct MeanVarRegsConsumer {
+    typedef SummaryParams Params;
+    static constexpr int PASSES = 1;
+    const Params& p;
+    MeanVarRegs<NBOX> st;
+
+    static __device__ void setup_shared(uint8_t*, const Params&, int) {}
+    __device__ MeanVarRegsConsumer(const Params& p_, const uint8_t*, int, int) : p(p_) {}
+    __device__ __forceinline__ void begin_row() { st.begin(p.n); }
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
+        double cur[16];
+        load_box_row(box_row, sw, cur);
+        switch (cg) {
+            case 0: st.template box<0>(cur); break;
+            case 1: if constexpr (NBOX > 1) st.template box<1>(cur); break;
+            case 2: if constexpr (NBOX > 2) st.template box<2>(cur); break;
+            default: if constexpr (NBOX > 3) st.template box<3>(cur); break;
+        }
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int) {
+        double mean, var;
+        st.finish(mean, var);
+        if (row < B) {
+            if (p.col_a >= 0) p.out[row * p.ld_out + p.col_a] = mean;
+            if (p.col_b >= 0) p.out[row * p.ld_out + p.col_b] = var;
+        }
+    }
+};
+
 typedef TreeSum<RS_PW_DEPTH> RowTreeSum;
 
 static bool summaries_termwise() {
@@ -358,6 +390,13 @@ int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
     p.col_a = col_mean;
     p.col_b = col_var;
     if (rowstream_ok(ctx, X, ldX, n)) {
+        static const bool two_sweeps = std::getenv("ELFI_B200_MEANVAR_TWO_SWEEPS") != nullptr;
+        if (!two_sweeps) {
+            if (n <= 16) return rowstream_launch<MeanVarRegsConsumer<1>>(ctx, X, ldX, B, n, 0, p, stream);
+            if (n <= 32) return rowstream_launch<MeanVarRegsConsumer<2>>(ctx, X, ldX, B, n, 0, p, stream);
+            if (n <= 48) return rowstream_launch<MeanVarRegsConsumer<3>>(ctx, X, ldX, B, n, 0, p, stream);
+            if (n <= 64) return rowstream_launch<MeanVarRegsConsumer<4>>(ctx, X, ldX, B, n, 0, p, stream);
+        }
         if (n <= LEAF_MAX_TERMS)
             return rowstream_launch<MeanVarBoxConsumer<LeafSum>>(ctx, X, ldX, B, n, 0, p, stream);
         if (summaries_termwise())

@@ -460,6 +460,11 @@ class Rejection(Sampler):
 
     def __init__(self, model, discrepancy_name=None, output_names=None, **kwargs):
         model, discrepancy_name = self._resolve_model(model, discrepancy_name)
+        # outputs the caller asked for by name travel in full in every multi-rank exchange; the
+        # summaries an adaptive distance adds for its own re-scoring stay sharded (see
+        # _gather_ranks_adaptive)
+        self._full_exchange = set(n.name if isinstance(n, em.NodeReference) else n
+                                  for n in (output_names or []))
         output_names = [discrepancy_name] + model.parameter_names + (output_names or [])
         self.adaptive = isinstance(model[discrepancy_name], em.AdaptiveDistance)
         if self.adaptive:
@@ -519,16 +524,24 @@ class Rejection(Sampler):
     def extract_result(self):
         if self.state['samples'] is None:
             raise ValueError('Nothing to extract')
-        self._gather_ranks()
-        self._update_state_meta()
-        if self.adaptive:
-            with PHASES('extract:update_distances'):
-                self._update_distances()
+        if self.adaptive and self.comm.on:
+            with PHASES('extract:gather_adaptive'):
+                self._gather_ranks_adaptive()
+            self._update_state_meta()
+        else:
+            self._gather_ranks()
+            self._update_state_meta()
+            if self.adaptive:
+                with PHASES('extract:update_distances'):
+                    self._update_distances()
         n = self.objective['n_samples']
         # the arrays stay on the device; `outputs` copies a column to the host when it is read
         twins = {k: v[:n] for k, v in self.state['samples'].items()}
         sample = Sample(outputs=DeviceOutputs(twins), **self._extract_result_kwargs())
         sample._dev = twins
+        if 'local_rows' in self.state:      # sharded summary columns of a multi-rank adaptive run
+            sample.local_rows = self.state['local_rows']
+            sample.local_summaries = self.state['local_summaries']
         return sample
 
     def _init_samples_lazy(self, batch):
@@ -683,6 +696,75 @@ class Rejection(Sampler):
         if self.adaptive:
             self._merge_adaptive_moments()
 
+    def _gather_ranks_adaptive(self):
+        """Multi-GPU exchange of an adaptive-distance population WITHOUT moving the summaries
+        (payload caveat).  The reference re-scores the kept rows centrally
+        from their D summary columns (samplers.py:279-299); here
+          1. the (n, mean, M2) column moments are Chan-merged (3 x D doubles per rank), so every
+             rank derives the same new weight vector;
+          2. each rank re-scores ITS OWN kept rows with all K + 1 nested distances;
+          3. ONE all-gather moves [old ranking key | K + 1 new distances | parameters (+ outputs
+             the caller asked for) | owner rank | local row] per kept row -- ~100 B instead of
+             8 D + ... bytes;
+          4. every rank selects the global best n by the old key and re-ranks them by the newest
+             distance: the same rows, in the same order, as the central re-scoring.
+        The summary columns of the selected rows stay on their owner ranks (`local_rows`: their
+        positions in the population, `local_summaries`: the rows) unless asked for by name."""
+        if self._gathered:
+            return
+        self._gathered = True
+        samples = self.state['samples']
+        n = self.objective['n_samples']
+        dname = self.discrepancy_name
+        node = self.model[dname]
+        self._merge_adaptive_moments()
+        node.update_distance()
+        nv = self._n_valid
+        counts = self.comm.all_gather_ints([nv, self.state['n_sim'], self.state['n_batches']])
+        cap = max(1, min(n, ((int(counts[:, 0].max()) + 31) // 32) * 32))
+        old = samples[dname]
+        old_key = (old if old.dim() == 1 else old[:, -1])[:cap].reshape(cap, 1)
+        k_new = len(node._s['w'])
+        ds = dev.zeros((cap, k_new))
+        if nv:
+            ds[:nv] = node.generate(batch_size=nv, with_values={
+                s: samples[s][:nv] for s in self.sums}).reshape(nv, k_new)
+        sharded = [s for s in self.sums if s not in self._full_exchange]
+        carried = [k for k in samples if k != dname and k not in sharded]
+        shapes = {k: tuple(samples[k].shape[1:]) for k in carried}
+        widths = [int(np.prod(shapes[k])) if shapes[k] else 1 for k in carried]
+        owner = dev.full((cap, 1), float(self.comm.rank))
+        local = dev.to_device(np.arange(cap, dtype=np.float64)).reshape(cap, 1)
+        pack = torch.cat([old_key, ds] + [samples[k][:cap].reshape(cap, w)
+                                          for k, w in zip(carried, widths)] + [owner, local], dim=1)
+        allp = self.comm.all_gather_rows(pack)
+        total = int(counts[:, 0].sum())
+        m = min(n, total)
+        top = ops.take_rows(allp, ops.argsort(allp[:, 0].contiguous())[:m])   # best n by the old key
+        new_last = top[:, k_new].contiguous()
+        order = ops.argsort(new_last)
+        ranked = ops.take_rows(top, order)
+
+        def padded(col, fill):
+            if m == n:
+                return col.contiguous()
+            return torch.cat([col, dev.full((n - m,) + tuple(col.shape[1:]), fill)])
+        # like the reference, the distance output is the UNSORTED newest column (samplers.py:294)
+        samples[dname] = padded(new_last, float('inf'))
+        off = 1 + k_new
+        for k, w in zip(carried, widths):
+            samples[k] = padded(ranked[:, off:off + w].reshape((m,) + shapes[k]), 0.0)
+            off += w
+        mine = torch.nonzero(ranked[:, off] == float(self.comm.rank)).reshape(-1)
+        rows = ops.take_rows(ranked[:, off + 1].contiguous(), mine.to(torch.int32)).to(torch.int32)
+        self.state['local_rows'] = mine
+        self.state['local_summaries'] = {s: ops.take_rows(samples[s], rows) for s in sharded}
+        for s in sharded:
+            del samples[s]
+        self._n_valid = m
+        self.state['n_sim'] = int(counts[:, 1].sum())
+        self.state['n_batches'] = int(counts[:, 2].sum())
+
     def _merge_adaptive_moments(self):
         """Chan-merge the per-rank (n, mean, M2) column moments (3 x D doubles per rank)."""
         st = self.model[self.discrepancy_name]._s
@@ -719,6 +801,9 @@ class SMC(Sampler):
         support and ``logpdf(params) -> device tensor`` (e.g. examples.ma2.DeviceProposal); the
         default draws proposals from the host RandomState exactly like the reference."""
         model, discrepancy_name = self._resolve_model(model, discrepancy_name)
+        if not hasattr(self, '_full_exchange'):
+            self._full_exchange = set(n.name if isinstance(n, em.NodeReference) else n
+                                      for n in (output_names or []))
         output_names = [discrepancy_name] + model.parameter_names + (output_names or [])
         super().__init__(model, output_names, **kwargs)
         self._prior = ModelPrior(self.model)
@@ -830,6 +915,7 @@ class SMC(Sampler):
                                     output_names=self.output_names, batch_size=self.batch_size,
                                     seed=seed, max_parallel_batches=self.max_parallel_batches,
                                     distributed=self._distributed)
+        self._rejection._full_exchange = set(getattr(self, '_full_exchange', ()))
         self._population_cache = None
 
     def _extract_population(self):
@@ -930,6 +1016,8 @@ class AdaptiveDistanceSMC(SMC):
             raise TypeError('This method requires an adaptive distance node.')
         model[discrepancy_name].init_state()
         sums = [s.name for s in model[discrepancy_name].parents]
+        self._full_exchange = set(n.name if isinstance(n, em.NodeReference) else n
+                                  for n in (output_names or []))
         if output_names is None:
             output_names = sums
         else:
@@ -948,7 +1036,8 @@ class AdaptiveDistanceSMC(SMC):
             return self._population_cache[1]
         rejection_sample = self._rejection.extract_result()
         ps = self.population_size
-        twins = {k: rejection_sample._dev[k][:ps] for k in self.output_names}
+        twins = {k: rejection_sample._dev[k][:ps] for k in self.output_names
+                 if k in rejection_sample._dev}
         meta = rejection_sample.meta
         meta['adaptive_distance_w'] = self.model[self.discrepancy_name]._s['w'][-1]
         meta['threshold'] = float(twins[self.discrepancy_name].max().item())
@@ -957,6 +1046,12 @@ class AdaptiveDistanceSMC(SMC):
                         self.parameter_names, **{k: v for k, v in meta.items()
                                                  if k not in ('method_name', 'parameter_names')})
         sample._dev = twins
+        rows = getattr(rejection_sample, 'local_rows', None)
+        if rows is not None:    # multi-rank: this rank's share of the population's summaries
+            keep = rows < ps
+            sample.local_rows = rows[keep]
+            sample.local_summaries = {s: v[keep] for s, v in
+                                      rejection_sample.local_summaries.items()}
         self._attach_weights_means_and_cov(sample)
         self._population_cache = (self._rejection, sample)
         return sample

@@ -63,9 +63,38 @@ int meanvar_rows(const double* X, int64_t ld, int64_t B, int n, double* out) {
     return 0;
 }
 
+template <int NBOX>
+void meanvar_regs_rows(const double* X, int64_t ld, int64_t B, int n, double* out) {
+    for (int64_t b = 0; b < B; ++b) {
+        elfi::MeanVarRegs<NBOX> st;
+        st.begin(n);
+        double cur[elfi::LEAF_BOX];
+        for (int g = 0; g * elfi::LEAF_BOX < n; ++g) {
+            load_box(X + b * ld, n, g * elfi::LEAF_BOX, cur);
+            switch (g) {                      // the kernel dispatches on the box index like this
+                case 0: st.template box<0>(cur); break;
+                case 1: if constexpr (NBOX > 1) st.template box<1>(cur); break;
+                case 2: if constexpr (NBOX > 2) st.template box<2>(cur); break;
+                default: if constexpr (NBOX > 3) st.template box<3>(cur); break;
+            }
+        }
+        st.finish(out[2 * b], out[2 * b + 1]);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// single-sweep mean / variance with the row held in registers (rows of <= 64 observations)
+int harness_meanvar_regs(const double* X, int64_t ld, int64_t B, int n, double* out) {
+    if (n <= 16) meanvar_regs_rows<1>(X, ld, B, n, out);
+    else if (n <= 32) meanvar_regs_rows<2>(X, ld, B, n, out);
+    else if (n <= 48) meanvar_regs_rows<3>(X, ld, B, n, out);
+    else if (n <= 64) meanvar_regs_rows<4>(X, ld, B, n, out);
+    else return -1;
+    return 0;
+}
 
 // tree = 0: single-leaf accumulator (rows of <= 128 terms); tree = 1: TreeSum (up to 8192 terms)
 int harness_autocov(const double* X, int64_t ld, int64_t B, int n, int lag_a, int lag_b,

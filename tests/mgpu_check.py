@@ -75,9 +75,24 @@ def main():
     if world == 2:
         np.testing.assert_allclose(ad.populations[0].adaptive_distance_w,
                                    ad1.populations[0].adaptive_distance_w, rtol=1e-10)
-        for k in ('t1', 't2', 'S1', 'S2'):
+        for k in ('d', 't1', 't2'):
             np.testing.assert_allclose(ad.populations[0].outputs[k], ad1.populations[0].outputs[k],
                                        rtol=1e-9)
+        # the summary columns are not exchanged: each rank keeps those of the population rows it owns
+        pop = ad.populations[0]
+        rows = pop.local_rows.cpu().numpy()
+        assert 'S1' not in pop.outputs and 0 < len(rows) < pop.n_samples
+        for k in ('S1', 'S2'):
+            np.testing.assert_allclose(pop.local_summaries[k].cpu().numpy(),
+                                       ad1.populations[0].outputs[k][rows], rtol=1e-9)
+        # ... unless they are asked for by name
+        m3 = ma2.get_model(seed_obs=4)
+        m3['d'].become(elfi.AdaptiveDistance(m3['S1'], m3['S2']))
+        named = elfi.AdaptiveDistanceSMC(m3['d'], output_names=['S1'], batch_size=100, seed=11).sample(
+            100, rounds=2, quantile=0.5, bar=False)
+        np.testing.assert_allclose(named.populations[0].outputs['S1'], ad1.populations[0].outputs['S1'],
+                                   rtol=1e-9)
+        np.testing.assert_allclose(named.weights, ad.weights, rtol=1e-9)
     assert np.all(np.isfinite(ad.weights)) and len(ad.populations) == 2
 
     # throughput mode (device priors / simulator / proposals keyed by the global batch index):

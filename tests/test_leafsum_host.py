@@ -83,6 +83,27 @@ def test_meanvar_every_length(harness):
         assert _same_bits(got[:, 1], np.var(x, axis=1)), n
 
 
+def test_meanvar_single_sweep_every_length(harness):
+    """MeanVarRegs (row kept in registers, one sweep): every row length it serves, 1..64."""
+    rs = np.random.RandomState(15)
+    for n in range(1, 65):
+        x = _rows(rs, 48, n)
+        x[3:] += 1.0
+        out = np.empty((x.shape[0], 2))
+        rc = harness.harness_meanvar_regs(_ptr(x), ctypes.c_int64(x.strides[0] // 8),
+                                          ctypes.c_int64(x.shape[0]), n, _ptr(out))
+        assert rc == 0
+        assert _same_bits(out[:, 0], np.mean(x, axis=1)), n
+        assert _same_bits(out[:, 1], np.var(x, axis=1)), n
+    from conftest import load_golden
+    g = load_golden('gauss_generate')
+    x = np.ascontiguousarray(g['gauss'])
+    out = np.empty((x.shape[0], 2))
+    harness.harness_meanvar_regs(_ptr(x), ctypes.c_int64(x.strides[0] // 8),
+                                 ctypes.c_int64(x.shape[0]), x.shape[1], _ptr(out))
+    assert _same_bits(out[:, 0], g['ss_mean']) and _same_bits(out[:, 1], g['ss_var'])
+
+
 def test_strided_rows_and_golden(harness):
     """Row stride larger than the row length, and the reference's own MA2 / Gaussian batches."""
     from conftest import load_golden
