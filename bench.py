@@ -340,14 +340,23 @@ def smc_ma2_block(dist, rank, world):
     final = {k: res.outputs[k] for k in ('d', 't1', 't2')}      # D2H of the final population
     w_final = res.weights
     barrier()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+    my_dt = time.perf_counter() - t0
+    tt = torch.tensor([my_dt], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     accepted = SMC['population'] * len(res.populations)
+
+    def per_rank(value):
+        """One value per rank (the ranks' GPUs differ under a power cap: the job takes the max)."""
+        mine = torch.tensor([float(value)], dtype=torch.float64, device='cuda')
+        if world == 1:
+            return [float(value)]
+        allv = torch.empty(world, dtype=torch.float64, device='cuda')
+        dist.all_gather_into_tensor(allv, mine)
+        return [round(v, 5) for v in allv.tolist()]
     block.update({
-        'seconds': dt, 'accepted_per_s': accepted / dt, 'simulated': int(res.n_sim),
+        'seconds': dt, 'per_rank_seconds': per_rank(my_dt), 'accepted_per_s': accepted / dt, 'simulated': int(res.n_sim),
         'simulated_per_s': res.n_sim / dt,
         'pair_terms_per_s': float(SMC['population']) ** 2 * (len(res.populations) - 1) / dt,
         'thresholds': [float(p.threshold) for p in res.populations],
@@ -355,6 +364,7 @@ def smc_ma2_block(dist, rank, world):
         'all_gather_calls': samplers.COMM_STATS['all_gather_calls'],
         'all_gather_bytes_received_per_rank': samplers.COMM_STATS['all_gather_bytes'],
         'd2h_bytes_result': int(sum(v.nbytes for v in final.values()) + w_final.nbytes)})
+    gen = max(1, len(res.populations) - 1)
     # a second run with synchronising phase timers (not the timed one) for the breakdown
     samplers.PHASES.on = True
     samplers.PHASES.tot.clear()
@@ -364,7 +374,11 @@ def smc_ma2_block(dist, rank, world):
     samplers.PHASES.on = False
     phases = samplers.PHASES.report()
     block['phases_s'] = phases
-    gen = max(1, len(res.populations) - 1)
+    block['per_rank_mixture_density_s'] = per_rank(phases.get('weights:gm_logpdf', 0.0))
+    block['per_rank_simulate_distance_merge_s'] = per_rank(
+        phases.get('run_batch', 0.0) + phases.get('prepare_new_batch', 0.0) +
+        phases.get('update', 0.0) - (phases.get('weights_means_cov', 0.0) if gen > 1 else 0.0) *
+        (gen - 1) / gen)
     block['per_generation_ms'] = {
         'mixture_density_kernel': 1e3 * phases.get('weights:gm_logpdf', 0.0) / gen,
         'all_gather_population': 1e3 * phases.get('gather:all_gather', 0.0) / len(res.populations),
