@@ -7,10 +7,11 @@
 //
 // The mixture density is the only O(N_new * N_prev) object on the path (1e12 pair terms per
 // generation at 1e6 particles): it is bound by the FP64 pipe, not by HBM.  Per pair and
-// parameter dimension p: p DSUB + p DFMA for the squared whitened distance, then
-// exp(-maha/2) by range reduction (round via the 2^52 trick, no 64-bit conversions, which run
-// at quarter rate) and a degree-7 polynomial: relative error < 1e-8 per term, far inside the
-// 1e-5 relative tolerance on the weights.  Accumulation is fp64.
+// parameter dimension p: p DFMA + 1 DADD for the (expanded, centred) squared whitened distance
+// with the log-weight folded in, then 2^(-nt) by range reduction (round via the 2^52 trick, no
+// 64-bit conversions, which run at quarter rate) and a degree-6 minimax polynomial: relative
+// error < 2e-9 per term, far inside the 1e-5 relative tolerance on the weights.  Accumulation
+// is fp64.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -129,47 +130,61 @@ __global__ void wstats_final_kernel(const double* __restrict__ partial, int nblo
 
 // ---------------------------------------------------------------------------------------------
 // K9: Gaussian mixture density.
-// The whitened coordinates are pre-scaled by sqrt(log2(e)/2), so that for a pair
-//   exp(-maha/2) = 2^(-nt),  nt = |y_i - m_j|^2 >= 0.
+// Coordinates are centred at the first component (any point of the cloud: the proposal covariance
+// is twice the population's own variance, so after centring |y| is a few units), whitened with
+// Linv and pre-scaled by sqrt(log2(e)/2), so that for a pair
+//   w_j exp(-maha/2) = 2^(-nt),  nt = |y_i|^2 + (|m_j|^2 - log2 w_j) - 2 y_i . m_j.
+// The squared distance is expanded: per component the kernel reads (-2 m_j, c_j = |m_j|^2 -
+// log2 w_j), per point it keeps (y_i, |y_i|^2), and a pair costs P DFMA + 1 DADD instead of P DSUB
+// + P DFMA + the weight multiply.  The cancellation error is |y|^2 * 2^-52 ~ 1e-14 ABSOLUTE in nt,
+// i.e. 1e-14 relative in the term (what matters for a density), thanks to the centring.
 // 2^(-nt): k = rint(-nt) through the 2^52 trick (no 64-bit conversions, which run on the slow
-// XU pipe), f = -nt - k in [-.5, .5], 2^f by a degree-7 polynomial (coefficients ln2^i / i!,
-// relative error < 6e-9), scaled by 2^k through the exponent field; nt > 1020 flushes to 0.
-// fp64-pipe instructions per pair: 2P (distance) + 3 (range reduction) + 7 (polynomial)
-// + 1 (compare) + 1 (accumulate) = 2P + 12.
+// XU pipe), f = -nt - k in [-.5, .5], 2^f by the degree-6 minimax polynomial (relative error
+// < 1.9e-9, Remez on [-.5, .5]), scaled by 2^k through the exponent field; nt > 1020 flushes to 0
+// (and so does a zero weight, whose c_j is +inf).
+// fp64-pipe instructions per pair: P + 1 (distance) + 3 (range reduction) + 6 (polynomial)
+// + 1 (compare) + 1 (accumulate) = P + 12  (round 1: 2P + 12).
 __device__ __forceinline__ double exp2_neg(double nt) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
     const double tm = magic - nt;
     const double kd = tm - magic;             // rint(-nt)
     const double f = -nt - kd;
-    double pz = 1.5252733804059841e-05;       // ln2^7 / 7!
-    pz = fma(pz, f, 1.5403530393381609e-04);  // ln2^6 / 6!
-    pz = fma(pz, f, 1.3333558146428443e-03);  // ln2^5 / 5!
-    pz = fma(pz, f, 9.6181291076284772e-03);  // ln2^4 / 4!
-    pz = fma(pz, f, 5.5504108664821580e-02);  // ln2^3 / 3!
-    pz = fma(pz, f, 2.4022650695910071e-01);  // ln2^2 / 2!
-    pz = fma(pz, f, 6.9314718055994531e-01);  // ln2
-    pz = fma(pz, f, 1.0);
+    double pz = 1.5345812158740182e-04;
+    pz = fma(pz, f, 1.3399931209474140e-03);
+    pz = fma(pz, f, 9.6184889565227916e-03);
+    pz = fma(pz, f, 5.5503287769976638e-02);
+    pz = fma(pz, f, 2.4022646890639572e-01);
+    pz = fma(pz, f, 6.9314720573725268e-01);
+    pz = fma(pz, f, 1.0000000005541663e+00);
     const int k = __double2loint(tm);         // low word of (magic - nt) holds rint(-nt)
     const int hi = __double2hiint(pz) + (k << 20);
     const double r = __hiloint2double(hi, __double2loint(pz));
     return (nt <= 1020.0) ? r : 0.0;
 }
 
-// whitened coordinates: y = Linv * x (Linv lower triangular, row-major p x p); for the
-// components also the normalised weight in column p.
+// Whitened, centred, scaled coordinates y = s Linv (x - centre) with s = sqrt(log2(e)/2).
+//   points     (mode 0): out[i] = (y_0 .. y_{p-1}, |y|^2)
+//   components (mode 1): out[j] = (-2 y_0 .. -2 y_{p-1}, |y|^2 - log2(w_j / sum w))
 __global__ void gm_whiten_kernel(const double* __restrict__ x, int64_t ld, int64_t n, int p,
-                                 const double* __restrict__ Linv, const double* __restrict__ w,
-                                 const double* __restrict__ wsum, double* __restrict__ out,
-                                 int out_ld) {
+                                 const double* __restrict__ Linv, const double* __restrict__ centre,
+                                 int mode, const double* __restrict__ w,
+                                 const double* __restrict__ wsum, double* __restrict__ out) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double scale = 0.8493218002880191;   // sqrt(log2(e) / 2)
+    double yy = 0.0;
     for (int a = 0; a < p; ++a) {
         double s = 0.0;
-        for (int b = 0; b <= a; ++b) s = fma(Linv[a * p + b], x[i * ld + b], s);
-        out[i * out_ld + a] = s * scale;
+        for (int b = 0; b <= a; ++b) s = fma(Linv[a * p + b], x[i * ld + b] - centre[b], s);
+        s *= scale;
+        yy = fma(s, s, yy);
+        out[i * (p + 1) + a] = mode ? -2.0 * s : s;
     }
-    if (out_ld > p) out[i * out_ld + p] = w ? w[i] / wsum[0] : 1.0 / double(n);
+    if (mode) {
+        const double wn = w ? w[i] / wsum[0] : 1.0 / double(n);
+        yy -= log2(wn);                        // w = 0: +inf, the component never contributes
+    }
+    out[i * (p + 1) + p] = yy;
 }
 
 // grid = (point blocks, component chunks).  Each CTA accumulates its chunk of the mixture for
@@ -182,14 +197,14 @@ gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict
               int64_t chunk_len, double* __restrict__ partial) {
     constexpr int TILE = 512;
     __shared__ double sm[TILE * (P + 1)];
-    double x[R][P];
+    double x[R][P + 1];
     double acc[R];
     const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         acc[r] = 0.0;
 #pragma unroll
-        for (int a = 0; a < P; ++a) x[r][a] = (i0 + r < N) ? xw[(i0 + r) * P + a] : 0.0;
+        for (int a = 0; a <= P; ++a) x[r][a] = (i0 + r < N) ? xw[(i0 + r) * (P + 1) + a] : 0.0;
     }
     const int64_t jbeg = int64_t(blockIdx.y) * chunk_len;
     const int64_t jend = (jbeg + chunk_len < M) ? jbeg + chunk_len : M;
@@ -204,16 +219,13 @@ gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict
             double m[P];
 #pragma unroll
             for (int a = 0; a < P; ++a) m[a] = sm[j * (P + 1) + a];
-            const double wj = sm[j * (P + 1) + P];
+            const double cj = sm[j * (P + 1) + P];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                double nt = 0.0;
+                double g = cj;
 #pragma unroll
-                for (int a = 0; a < P; ++a) {
-                    const double d = x[r][a] - m[a];
-                    nt = fma(d, d, nt);
-                }
-                acc[r] = fma(wj, exp2_neg(nt), acc[r]);
+                for (int a = 0; a < P; ++a) g = fma(x[r][a], m[a], g);
+                acc[r] += exp2_neg(g + x[r][P]);
             }
         }
     }
@@ -237,16 +249,13 @@ gm_pdf_generic_kernel(const double* __restrict__ xw, int64_t N, const double* __
                       int64_t M, int p, double lognorm, double* __restrict__ logq) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    double x[WS_MAXP];
-    for (int a = 0; a < p; ++a) x[a] = xw[i * p + a];
+    double x[WS_MAXP + 1];
+    for (int a = 0; a <= p; ++a) x[a] = xw[i * (p + 1) + a];
     double acc = 0.0;
     for (int64_t j = 0; j < M; ++j) {
-        double nt = 0.0;
-        for (int a = 0; a < p; ++a) {
-            const double d = x[a] - __ldg(mw + j * (p + 1) + a);
-            nt = fma(d, d, nt);
-        }
-        acc = fma(__ldg(mw + j * (p + 1) + p), exp2_neg(nt), acc);
+        double g = __ldg(mw + j * (p + 1) + p);
+        for (int a = 0; a < p; ++a) g = fma(x[a], __ldg(mw + j * (p + 1) + a), g);
+        acc += exp2_neg(g + x[p]);
     }
     logq[i] = log(acc) + lognorm;
 }
@@ -348,7 +357,7 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
         ELFI_REQUIRE(chunks <= 65535, "gm_logpdf: too many component chunks (%lld)", (long long)chunks);
     }
     const size_t off_xw = align(size_t(p) * p * 8);
-    const size_t off_mw = off_xw + align(size_t(N) * p * 8);
+    const size_t off_mw = off_xw + align(size_t(N) * (p + 1) * 8);
     const size_t off_ws = off_mw + align(size_t(M) * (p + 1) * 8);
     const size_t off_part = off_ws + 256;
     uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, off_part + size_t(chunks) * N * 8 + 256));
@@ -360,10 +369,10 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     double* partial = reinterpret_cast<double*>(base + off_part);
     ELFI_CUDA_OK(cudaMemcpyAsync(Linv, Linv_host, size_t(p) * p * 8, cudaMemcpyHostToDevice, stream));
     if (w) sum_kernel<<<1, 1024, 0, stream>>>(w, M, wsum);
-    gm_whiten_kernel<<<unsigned((N + 255) / 256), 256, 0, stream>>>(x, ldx, N, int(p), Linv, nullptr,
-                                                                   nullptr, xw, int(p));
-    gm_whiten_kernel<<<unsigned((M + 255) / 256), 256, 0, stream>>>(means, ldm, M, int(p), Linv, w,
-                                                                   wsum, mw, int(p + 1));
+    gm_whiten_kernel<<<unsigned((N + 255) / 256), 256, 0, stream>>>(x, ldx, N, int(p), Linv, means, 0,
+                                                                   nullptr, nullptr, xw);
+    gm_whiten_kernel<<<unsigned((M + 255) / 256), 256, 0, stream>>>(means, ldm, M, int(p), Linv, means,
+                                                                   1, w, wsum, mw);
     const double lognorm = -0.5 * (double(p) * 1.8378770664093453 + logdet);  // log(2 pi)
     if (p <= 4) {
         dim3 grid(static_cast<unsigned>(xblocks), static_cast<unsigned>(chunks));
