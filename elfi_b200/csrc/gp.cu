@@ -214,16 +214,44 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k, int* __restric
     }
 }
 
-// Panel below the diagonal block: X L_kk^T = A_panel, one thread per row.
+// Diagonal block + panel below it in ONE launch: every CTA factors the 64x64 diagonal block
+// itself in shared memory (redundantly -- the same ~64 dependent steps would otherwise run in a
+// separate single-CTA kernel before the panel could start), then solves X L_kk^T = A_panel for its
+// 128 rows, one thread per row.  CTA 0 writes the factored diagonal block back.
 __global__ void __launch_bounds__(128)
-potrf_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n) {
+potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
+                        int* __restrict__ info) {
     __shared__ double l[GP_NB][GP_NB + 1];
-    for (int idx = threadIdx.x; idx < GP_NB * GP_NB; idx += 128) {
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
         const int r = idx / GP_NB, c = idx % GP_NB;
         l[r][c] = A[(k + r) * lda + k + c];
     }
     __syncthreads();
-    const int64_t row = k + GP_NB + int64_t(blockIdx.x) * 128 + threadIdx.x;
+    {
+        const int r = tid >> 1, q = tid & 1;      // two threads per row of the trailing update
+        for (int j = 0; j < GP_NB; ++j) {
+            if (tid == 0) {
+                const double d = l[j][j];
+                if (!(d > 0.0) && blockIdx.x == 0) atomicExch(info, int(k + j + 1));
+                l[j][j] = sqrt(d);
+            }
+            __syncthreads();
+            if (tid > j && tid < GP_NB) l[tid][j] /= l[j][j];
+            __syncthreads();
+            if (r > j) {
+                const double lrj = l[r][j];
+                for (int c = j + 1 + q; c <= r; c += 2) l[r][c] = fma(-lrj, l[c][j], l[r][c]);
+            }
+            __syncthreads();
+        }
+    }
+    if (blockIdx.x == 0)
+        for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
+            const int rr = idx / GP_NB, c = idx % GP_NB;
+            A[(k + rr) * lda + k + c] = (c <= rr) ? l[rr][c] : 0.0;
+        }
+    const int64_t row = k + GP_NB + int64_t(blockIdx.x) * 128 + tid;
     if (row >= n) return;
     double x[GP_NB];
     double* a = A + row * lda + k;
@@ -505,10 +533,11 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
     }
     // blocked Cholesky, lower, in place
     for (int64_t k = 0; k < n_pad; k += GP_NB) {
-        potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
         const int64_t below = n_pad - (k + GP_NB);
+        if (below <= 0) potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
         if (below > 0) {
-            potrf_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(L, n_pad, k, n_pad);
+            potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(L, n_pad, k,
+                                                                                   n_pad, info);
             GemmArgs g;
             memset(&g, 0, sizeof(g));
             g.A = L + (k + GP_NB) * n_pad + k; g.lda = n_pad;
@@ -528,29 +557,38 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
     double* T = static_cast<double*>(ctx_scratch(ctx, size_t(n_pad) * n_pad * 8 + 256));
     if (!T) return ELFI_B200_ERR_NOMEM;
     for (int64_t s = GP_NB; s < n_pad; s *= 2) {
-        // pairs (top block [o, o+s), bottom block [o+s, min(o+2s, n_pad)))
+        // pairs (top block [o, o+s), bottom block [o+s, min(o+2s, n_pad))), o = pi * 2s: all full
+        // pairs of a level go out as ONE batched launch per product (grid.z = pair, the operands
+        // of consecutive pairs are 2s rows AND columns apart: stride 2s (n_pad + 1)); a trailing
+        // partial pair (s2 < s) is launched on its own.  ~2 log2(n_pad / 64) launches instead of
+        // 2 (n_pad / 64 - 1).
         const int64_t npairs = (n_pad + 2 * s - 1) / (2 * s);
-        for (int64_t pi = 0; pi < npairs; ++pi) {
-            const int64_t o = pi * 2 * s;
-            const int64_t s2 = (o + 2 * s <= n_pad) ? s : (n_pad - o - s);
+        const int64_t nfull = n_pad / (2 * s);
+        for (int pass = 0; pass < 2; ++pass) {
+            const int64_t first = pass == 0 ? 0 : nfull;
+            const int64_t count = pass == 0 ? nfull : npairs - nfull;
+            if (count <= 0) continue;
+            const int64_t o = first * 2 * s;
+            const int64_t s2 = pass == 0 ? s : (n_pad - o - s);
             if (s2 <= 0) continue;
+            const int64_t diag_stride = 2 * s * (n_pad + 1), row_stride = 2 * s * n_pad;
             // Tt (s x s2) = U11 (s x s) * L21^T          [Tt[c, r] = sum_k U11[c, k] L21[r, k]]
             GemmArgs g;
             memset(&g, 0, sizeof(g));
-            g.A = U + o * n_pad + o; g.lda = n_pad;
-            g.B = L + (o + s) * n_pad + o; g.ldb = n_pad;
-            g.C = T; g.ldc = n_pad;
+            g.A = U + o * n_pad + o; g.lda = n_pad; g.strideA = diag_stride;
+            g.B = L + (o + s) * n_pad + o; g.ldb = n_pad; g.strideB = diag_stride;
+            g.C = T + o * n_pad; g.ldc = n_pad; g.strideC = row_stride;
             g.M = s; g.N = s2; g.K = s; g.alpha = 1.0; g.beta = 0.0; g.mode = 0;
-            int rc = launch_gemm(g, 1, stream);
+            int rc = launch_gemm(g, count, stream);
             if (rc) return rc;
             // W21 (s2 x s) = -W22 (s2 x s2) * Tt^T        [W21[r, c] = -sum_k W22[r, k] Tt[c, k]]
             memset(&g, 0, sizeof(g));
-            g.A = W + (o + s) * n_pad + (o + s); g.lda = n_pad;
-            g.B = T; g.ldb = n_pad;
-            g.C = W + (o + s) * n_pad + o; g.ldc = n_pad;
-            g.Ct = U + o * n_pad + (o + s); g.ldct = n_pad;
+            g.A = W + (o + s) * n_pad + (o + s); g.lda = n_pad; g.strideA = diag_stride;
+            g.B = T + o * n_pad; g.ldb = n_pad; g.strideB = row_stride;
+            g.C = W + (o + s) * n_pad + o; g.ldc = n_pad; g.strideC = diag_stride;
+            g.Ct = U + o * n_pad + (o + s); g.ldct = n_pad; g.strideCt = diag_stride;
             g.M = s2; g.N = s; g.K = s2; g.alpha = -1.0; g.beta = 0.0; g.mode = 0;
-            rc = launch_gemm(g, 1, stream);
+            rc = launch_gemm(g, count, stream);
             if (rc) return rc;
         }
     }
