@@ -63,18 +63,29 @@ def main():
         return smc.sample(n, quantiles=[args.quantile] * pops, bar=False)
 
     for _ in range(args.warm):
-        run(min(args.n, 20000), min(args.batch, 20000), 2)      # warm-up: contexts, scratch, NCCL
+        # warm-up at FULL size with two populations (one weights step): contexts, scratch arenas,
+        # the caching allocator and the NCCL buffers reach their final sizes before the timed run
+        run(args.n, args.batch, 2)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    from elfi_b200.samplers import PHASES
+    from elfi_b200.samplers import COMM_STATS, PHASES
     PHASES.tot.clear()
+    COMM_STATS.update(all_gather_calls=0, all_gather_bytes=0)
     t0 = time.perf_counter()
     res = run(args.n, args.batch, args.pops)
+    final = {k: res.outputs[k] for k in [res.discrepancy_name] + list(res.parameter_names)}
+    w_final = res.weights
     torch.cuda.synchronize()
+    my_dt = time.perf_counter() - t0
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
+    per_rank = [my_dt]
+    if world > 1:
+        allv = torch.empty(world, dtype=torch.float64, device='cuda')
+        dist.all_gather_into_tensor(allv, torch.tensor([my_dt], dtype=torch.float64, device='cuda'))
+        per_rank = [round(v, 4) for v in allv.tolist()]
     if int(os.environ.get('RANK', '0')) == 0:
         accepted = args.n * len(res.populations)
         out = {'bench': 'smc_abc_{}_throughput_mode'.format(args.model), 'n_gpus': world, 'population': args.n,
@@ -84,7 +95,16 @@ def main():
                'pair_terms': float(args.n) ** 2 * (len(res.populations) - 1),
                'pair_terms_per_s': float(args.n) ** 2 * (len(res.populations) - 1) / dt,
                'posterior_means': [float(v) for v in res.sample_means_array],
-               'thresholds': [float(p.threshold) for p in res.populations]}
+               'thresholds': [float(p.threshold) for p in res.populations],
+               'per_rank_seconds': per_rank,
+               'all_gather_calls': COMM_STATS['all_gather_calls'],
+               'all_gather_bytes_received_per_rank': COMM_STATS['all_gather_bytes'],
+               'exchange_MB_per_generation': COMM_STATS['all_gather_bytes'] / 1e6 /
+               max(1, len(res.populations)),
+               'n_sim_per_population': [int(p.n_sim) for p in res.populations]}
+        if hasattr(res.populations[-1], 'adaptive_distance_w'):
+            w_ad = res.populations[-1].adaptive_distance_w
+            out['adaptive_distance_w_range'] = [float(min(w_ad)), float(max(w_ad))]
         from elfi_b200.samplers import PHASES
         if PHASES.on:
             out['phases_s'] = PHASES.report()
