@@ -392,6 +392,92 @@ def smc_ma2_block(dist, rank, world):
     return block
 
 
+def bolfi_config4_block():
+    """BASELINE config #4: 2000 evidence points, RBF + bias GP in fp64, LCBSC on a
+    1e5-point grid.  Device: fit (Gram + Cholesky + inverse + alpha), the rank-b update that
+    replaces refits in the BO loop, the grid prediction + LCBSC on the DMMA path; beside them the
+    same steps on the host cores with SciPy (the oracle's restatement of the reference's own
+    NumPy formulas, gpy_regression.py:127-160 -- GPy itself is not installable)."""
+    import ctypes
+    import torch
+    from elfi_b200 import _lib
+    from elfi_b200 import device as dev
+    from elfi_b200.bo import LCBSC, GPyRegression
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import elfi_oracle as o
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    n, m = 2000, 100_000
+    rs = np.random.RandomState(0)
+    X = rs.uniform([-2, -1], [2, 1], (n, 2))
+    y = np.log(0.05 + (X[:, 0] - 0.6) ** 2 + 2 * (X[:, 1] - 0.2) ** 2) + 0.1 * rs.randn(n)
+    gp = GPyRegression(['t1', 't2'], bounds={'t1': (-2, 2), 't2': (-1, 1)}, incremental=False)
+    gp.update(X, y[:, None])
+    gp._hyper = dict(gp._hyper_anchor)          # the _default_kernel heuristics, fixed (SURVEY 8d)
+    h = gp._hyper
+    fit_ms = timed(lambda: gp._fit())
+    g1, g2 = np.meshgrid(np.linspace(-2, 2, 400), np.linspace(-1, 1, 250))
+    grid_host = np.column_stack([g1.ravel(), g2.ravel()])
+    grid = dev.to_device(grid_host)
+    acq = LCBSC(gp, seed=0)
+    beta = float(acq._beta(10))
+    grid_ms = timed(lambda: gp.predict_device(grid, noiseless=True, beta=beta), reps=3, warm=1)
+    flops = (m * n * n / 2 + m * n) * 2.0
+    peaks = (ctypes.c_double * 2)()
+    _lib.call('elfi_b200_probe_fp64_f64', dev.context(), peaks)
+    # rank-b update (b = 5 new evidence points, the BOLFI batch of the reference's test)
+    inc = GPyRegression(['t1', 't2'], bounds={'t1': (-2, 2), 't2': (-1, 1)}, incremental=True)
+    inc.update(X[:n - 40], y[:n - 40, None])
+    inc._hyper = dict(h)
+    inc._fit()
+    k = [0]
+
+    def append5():
+        lo = n - 40 + 5 * (k[0] % 8)
+        k[0] += 1
+        if k[0] % 8 == 1 and k[0] > 1:        # rewind: keep n inside the same padded size
+            inc._X, inc._Y = inc._X[:n - 40], inc._Y[:n - 40]
+            inc._fit()
+        inc.update(X[lo:lo + 5], y[lo:lo + 5, None])
+    upd_ms = timed(append5, reps=5, warm=1)
+    # parity of what was timed + the host baseline
+    mean, var, a_dev = gp.predict_device(grid[:2000], noiseless=True, beta=beta)
+    t0 = time.perf_counter()
+    L, alpha = o.gp_fit(X, y, h['kernel_var'], h['lengthscale'], h['bias_var'], h['noise_var'])
+    cpu_fit = time.perf_counter() - t0
+    rows = 20_000                                                  # bounded sample of the grid
+    t0 = time.perf_counter()
+    mu_h, var_h = o.gp_predict(grid_host[:rows], X, L, alpha, h['kernel_var'], h['lengthscale'],
+                               h['bias_var'])
+    cpu_grid = (time.perf_counter() - t0) * (m / rows)
+    err_mu = float(np.max(np.abs(mean.cpu().numpy() - mu_h[:2000, 0]) / (np.abs(mu_h[:2000, 0]) + 1e-12)))
+    err_var = float(np.max(np.abs(var.cpu().numpy() - var_h[:2000, 0]) / np.abs(var_h[:2000, 0])))
+    return {'what': 'GP fit n=2000 + LCBSC on a 400 x 250 grid, fp64 (config #4)',
+            'fit_ms': fit_ms, 'rank5_update_ms': upd_ms, 'grid_predict_lcbsc_ms': grid_ms,
+            'grid_tflops': flops / (grid_ms * 1e-3) / 1e12,
+            'fp64_peak_tflops_probe': {'dfma': peaks[0], 'dmma': peaks[1]},
+            'grid_frac_of_dmma_peak': flops / (grid_ms * 1e-3) / 1e12 / peaks[1],
+            'max_rel_err_mean_vs_scipy': err_mu, 'max_rel_err_var_vs_scipy': err_var,
+            'cpu_scipy': {'cores': os.cpu_count(), 'fit_ms': cpu_fit * 1e3,
+                          'grid_ms_extrapolated_from_rows': cpu_grid * 1e3, 'rows_timed': rows,
+                          'what': 'oracle restatement of gpy_regression.py:127-160 (SciPy cholesky / '
+                                  'solve_triangular, multi-threaded BLAS)'},
+            'speedup_fit': cpu_fit * 1e3 / fit_ms, 'speedup_grid': cpu_grid * 1e3 / grid_ms}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -564,6 +650,12 @@ def run_ours(args):
     del S, d, idx, cand
     torch.cuda.empty_cache()
     smc = smc_ma2_block(dist, rank, world)
+    bolfi = None
+    if world == 1:
+        try:
+            bolfi = bolfi_config4_block()
+        except Exception as exc:      # report, never hide
+            bolfi = {'error': repr(exc)}
 
     if rank == 0:
         peak, how = peaks()
@@ -602,6 +694,8 @@ def run_ours(args):
             'api_throughput_mode': api,
             'smc_ma2': smc,
         }
+        if bolfi is not None:
+            line['bolfi_config4'] = bolfi
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line), flush=True)

@@ -143,3 +143,37 @@ def test_bolfi_ma2_smoke():
     assert abs(res.x_min['t1'][0] - 0.6) < 0.6 and abs(res.x_min['t2'][0] - 0.2) < 0.6
     lp = post.logpdf(np.array([[0.6, 0.2], [-1.5, 0.9]]))
     assert lp[0] > lp[1]
+
+
+@pytest.mark.first_device_run
+def test_bolfi_ma2_reference_bounds():
+    """The reference's own BOLFI test (tests/functional/test_inference.py:136-190) at its own
+    size and error bound: 300 evidence points, |x_min - true| < 0.2 for both parameters,
+    continuation keeps the acquired points, the maximum-likelihood point of the extracted
+    posterior and the NUTS sample mean are within 0.2 as well."""
+    import elfi_b200 as elfi
+    from elfi_b200.bo import minimize
+    from elfi_b200.examples import ma2
+    m = ma2.get_model(n_obs=100, true_params=[.6, .2], seed_obs=4)
+    log_d = elfi.Operation(np.log, m['d'], name='log_d')
+    bolfi = elfi.BOLFI(log_d, initial_evidence=20, update_interval=10, batch_size=5,
+                       bounds={'t1': (-2, 2), 't2': (-1, 1)}, acq_noise_var=.1, seed=1)
+    n = 300
+    res = bolfi.infer(n, bar=False)
+    assert bolfi.target_model.n_evidence == n
+    acq_x = bolfi.target_model.X.copy()
+    assert abs(res.x_min['t1'][0] - 0.6) < 0.2 and abs(res.x_min['t2'][0] - 0.2) < 0.2, res.x_min
+    res = bolfi.infer(n + 10, bar=False)
+    assert bolfi.target_model.n_evidence == n + 10
+    assert np.array_equal(bolfi.target_model.X[:n, :], acq_x)
+    post = bolfi.extract_posterior()
+    post_ml = minimize(lambda x: -post._unnormalized_loglikelihood(x), post.model.bounds,
+                       grad=lambda x: -post._gradient_unnormalized_loglikelihood(x),
+                       prior=post.prior, n_start_points=post.n_inits, maxiter=post.max_opt_iters,
+                       random_state=np.random.RandomState(0))[0]
+    assert abs(post_ml[0] - 0.6) < 0.2 and abs(post_ml[1] - 0.2) < 0.2, post_ml
+    n_samples, n_chains = 400, 4
+    sample = bolfi.sample(n_samples, n_chains=n_chains)
+    assert len(sample.samples['t1']) == n_samples // 2 * n_chains
+    assert abs(np.mean(sample.samples['t1']) - 0.6) < 0.2
+    assert abs(np.mean(sample.samples['t2']) - 0.2) < 0.2
