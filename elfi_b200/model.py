@@ -720,7 +720,7 @@ def device_metric_discrepancy(metric, *summaries, observed, p=2.0, accept=None):
     obs = _stack_observed(observed)
     if obs.shape[0] != 1:
         raise ValueError('observed summaries must form a single row')
-    thr = None if accept is None else np.atleast_1d(accept)
+    thr = None if accept is None else np.atleast_1d(dev.to_host(accept))
     d, idx = ops.dist_metric(X, obs, metric, p=p, threshold=thr)
     return AcceptedOutput(d, idx) if accept is not None else d
 

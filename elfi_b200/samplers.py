@@ -500,11 +500,14 @@ class Rejection(Sampler):
         thr = self.objective.get('threshold')
         if thr is None:
             # quantile / n_sim mode: once the best-n buffer is full only rows at or below its
-            # current n-th distance can enter it (single-column distances only)
-            cur = self.state.get('threshold')
-            if self.state.get('samples') is not None and np.ndim(cur) == 0 and np.isfinite(cur) \
-                    and not self.adaptive:
-                return {self.discrepancy_name: float(cur)}
+            # current n-th distance can enter it.  The threshold is handed over as a DEVICE scalar
+            # (a view of the buffer's n-th entry): no host round trip between the merge of one
+            # batch and the distance kernel of the next (single-column distances only).
+            n = self.objective['n_samples']
+            if self.state.get('samples') is not None and self._n_valid >= n and not self.adaptive:
+                d = self.state['samples'][self.discrepancy_name]
+                if d.dim() == 1:
+                    return {self.discrepancy_name: d[n - 1:n]}
             return None
         return {self.discrepancy_name: np.atleast_1d(np.asarray(thr, dtype=np.float64))}
 
@@ -517,9 +520,7 @@ class Rejection(Sampler):
             self._init_samples_lazy(batch)
         self._merge_batch(batch)
         if self.state['n_batches'] % self._group == 0:
-            if self.objective.get('threshold') is None:
-                self._update_state_meta()     # quantile mode: the running n-th distance prunes
-            self._update_objective_n_batches()
+            self._update_objective_n_batches()     # threshold mode only; state meta: at extraction
 
     def extract_result(self):
         if self.state['samples'] is None:

@@ -46,12 +46,17 @@ def test_gp_predict_matches_oracle(n, p):
 
 
 def test_default_hyperparameters_follow_reference_heuristics():
+    """gpy_regression.py:242-284: the kernel starts from GPy's unit values; the heuristics from the
+    bounds and the first data parameterise the Gamma priors (Gamma.from_EV(v, v): shape v, rate 1)
+    and the noise variance."""
     gp, X, y = _model(50)
     h = gp.hyperparameters
-    assert h['lengthscale'] == pytest.approx((2.0 - (-2.0)) / 3.)      # (max - min bounds) / 3
-    assert h['kernel_var'] == pytest.approx((np.max(y) / 3.) ** 2)
-    assert h['bias_var'] == pytest.approx(h['kernel_var'] / 4.)
+    assert h['kernel_var'] == 1.0 and h['lengthscale'] == 1.0 and h['bias_var'] == 1.0
     assert h['noise_var'] == pytest.approx(np.max(y) ** 2 / 100.)
+    kernel_var = (np.max(y) / 3.) ** 2
+    assert gp._priors['lengthscale'] == (pytest.approx((2.0 - (-2.0)) / 3.), 1.0)
+    assert gp._priors['kernel_var'] == (pytest.approx(kernel_var), 1.0)
+    assert gp._priors['bias_var'] == (pytest.approx(kernel_var / 4.), 1.0)
 
 
 def test_gp_gradients_match_oracle():
