@@ -25,7 +25,8 @@ constexpr int GP_NB = 64;          // Cholesky panel width / base block of the i
 constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16;
 constexpr int GM_LDS = 20;         // padded row stride (doubles) of the smem tiles
 constexpr int GM_THREADS = 256;
-constexpr size_t GM_SMEM = size_t(2) * 2 * GM_BM * GM_LDS * sizeof(double);
+constexpr int GM_STAGES = 3;       // cp.async ring: two slabs in flight while one is consumed
+constexpr size_t GM_SMEM = size_t(GM_STAGES) * 2 * GM_BM * GM_LDS * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
     const uint32_t d = smem_u32(smem_dst);
@@ -53,12 +54,16 @@ struct GemmArgs {
 };
 
 // C = alpha * A * B^T + beta * C on the fp64 tensor path.  CTA tile 128x128x16, 8 warps as
-// 2 (M) x 4 (N), warp tile 64x32 = 8x4 DMMA tiles; cp.async double buffering; batch = grid.z.
+// 2 (M) x 4 (N), warp tile 64x32 = 8x4 DMMA tiles; 3-stage cp.async ring with ONE block barrier
+// per 16-wide slab (round 1: double buffering with two barriers, during which the tensor pipe
+// idled: ncu showed `wait` / `math_pipe_throttle` stalls at 58 % of the DMMA peak); batch = grid.z.
+// (mma.m16n8k16.f64 is no alternative: ptxas lowers it to eight DMMA.8 on sm_100a,
+// profiles/r2_dmma_m16n8k16_sass.md.)
 __global__ void __launch_bounds__(GM_THREADS)
 gemm_nt_dmma_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem_d[];
-    double* As = smem_d;                                  // [2][BM][LDS]
-    double* Bs = smem_d + size_t(2) * GM_BM * GM_LDS;     // [2][BN][LDS]
+    double* As = smem_d;                                          // [STAGES][BM][LDS]
+    double* Bs = smem_d + size_t(GM_STAGES) * GM_BM * GM_LDS;     // [STAGES][BN][LDS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int grp = lane >> 2, tig = lane & 3;
@@ -95,16 +100,18 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     };
 
     const int64_t nk = (Kend + GM_BK - 1) / GM_BK;
-    if (nk > 0) load_stage(0, 0);
+    for (int st = 0; st < GM_STAGES - 1; ++st)
+        if (st < nk) load_stage(st, int64_t(st) * GM_BK);
+    int cur = 0;
     for (int64_t kt = 0; kt < nk; ++kt) {
-        const int cur = int(kt & 1);
-        if (kt + 1 < nk) {
-            load_stage(cur ^ 1, (kt + 1) * GM_BK);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        // slab kt has landed when at most one younger group is still pending
+        if (kt + 1 < nk) cp_async_wait<GM_STAGES - 2>(); else cp_async_wait<0>();
+        __syncthreads();   // slab kt visible to all; everyone is done with slab kt - 1
+        if (kt + GM_STAGES - 1 < nk) {
+            int nxt = cur + GM_STAGES - 1;
+            if (nxt >= GM_STAGES) nxt -= GM_STAGES;
+            load_stage(nxt, (kt + GM_STAGES - 1) * GM_BK);   // reuses the buffer of slab kt - 1
         }
-        __syncthreads();
         const double* as = As + size_t(cur) * GM_BM * GM_LDS + size_t(wm * 64) * GM_LDS;
         const double* bs = Bs + size_t(cur) * GM_BN * GM_LDS + size_t(wn * 32) * GM_LDS;
 #pragma unroll
@@ -119,7 +126,7 @@ gemm_nt_dmma_kernel(GemmArgs g) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        __syncthreads();
+        if (++cur == GM_STAGES) cur = 0;
     }
     double* Ct = g.Ct ? g.Ct + bz * g.strideCt : nullptr;
 #pragma unroll
