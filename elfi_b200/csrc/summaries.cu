@@ -165,8 +165,9 @@ struct MeanVarConsumer {
 //   Sum = LeafSum   every reduced run has <= 128 terms, so NumPy's tree is one leaf and the state
 //                   is 8 accumulators per sum: same results as the consumers above at a fraction
 //                   of the integer bookkeeping (profiles/r1_summ_instruction_mix.md).  Default.
-//   Sum = TreeSum   longer rows, same front end (opt-in with ELFI_B200_SUMM_TERMWISE=1 until it
-//                   has been timed on the device; the TermGrouper consumers stay the default).
+//   Sum = TreeSum   longer rows, same front end; default for rows of more than 128 terms since its
+//                   device timing (ELFI_B200_SUMM_TERMWISE=0 falls back to the TermGrouper
+//                   consumers).
 template <class Sum, int LAG_A, int LAG_B>
 struct AutocovBoxConsumer {
     typedef SummaryParams Params;
@@ -249,10 +250,14 @@ struct MeanVarRegsConsumer {
 
 typedef TreeSum<RS_PW_DEPTH> RowTreeSum;
 
+// Rows of 129..7688 terms: the term-wise TreeSum front end is the default since it was timed on
+// the device (autocov(1,2) 4e5 x 256: 0.152 ms = 0.83 of the HBM peak against 0.225 ms = 0.56 for
+// the TermGrouper consumers; mean/var 0.183 against 0.350 ms; profiles/r2_kernels.md).
+// ELFI_B200_SUMM_TERMWISE=0 selects the round-1 consumers.
 static bool summaries_termwise() {
     static const bool on = [] {
         const char* v = std::getenv("ELFI_B200_SUMM_TERMWISE");
-        return v != nullptr && v[0] == '1';
+        return !(v != nullptr && v[0] == '0');
     }();
     return on;
 }
