@@ -506,17 +506,39 @@ def run_ours(args):
     n_acc = torch.zeros(1, dtype=torch.int64, device='cuda')
     cand = ops.CandidateBuffer(B, [1, 1, 1])
     ctx = dev.context()
-    stream = torch.cuda.current_stream()
 
-    def step():
+    def step_eager():
         _lib.call('elfi_b200_dist_euclid_thr_f64', ctx, dev.ptr(S), D, B, D, dev.ptr(obs), None, 1,
-                  dev.ptr(thr_arr), dev.ptr(d), dev.ptr(idx), dev.ptr(n_acc),
-                  ctypes.c_void_p(stream.cuda_stream))
+                  dev.ptr(thr_arr), dev.ptr(d), dev.ptr(idx), dev.ptr(n_acc), dev.stream_ptr())
         cand.append([d, t1, t2], idx, n_acc, B)
 
     def kernel_only():
         _lib.call('elfi_b200_dist_euclid_thr_f64', ctx, dev.ptr(S), D, B, D, dev.ptr(obs), None, 1,
-                  dev.ptr(thr_arr), dev.ptr(d), None, None, ctypes.c_void_p(stream.cuda_stream))
+                  dev.ptr(thr_arr), dev.ptr(d), None, None, dev.stream_ptr())
+
+    # The step is 4 short launches behind a 0.16 ms kernel: on a busy host the Python launch loop,
+    # not the GPU, would set the pace.  Capture ONE step in a CUDA graph and replay it per step
+    # (the library launches on the stream it is given, so it captures like any other stream work);
+    # fall back to eager launches if the capture is refused.
+    for _ in range(3):
+        step_eager()
+    torch.cuda.synchronize()
+    launch_mode = 'cuda_graph (one replay per step)'
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_eager()
+        torch.cuda.synchronize()
+        step = graph.replay
+        step()
+        torch.cuda.synchronize()
+    except Exception as exc:
+        launch_mode = 'eager ({})'.format(type(exc).__name__)
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        step = step_eager
 
     def barrier():
         if world > 1:
@@ -534,9 +556,11 @@ def run_ours(args):
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
+    host_ms_per_step = (time.perf_counter() - t_host) * 1e3 / args.steps    # launch cost only
     best, count, dropped = cand.best(N_SAMPLES)     # sort + gather of the K steps' accepted rows
     e1.record()
     barrier()
@@ -672,6 +696,7 @@ def run_ours(args):
             'parity_check': check,
             # distance, mask compaction, append, count update per step + the final sort/gather
             'gpu_launches': 4 * args.steps + 26,
+            'launch_mode': launch_mode, 'host_launch_ms_per_step': host_ms_per_step,
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'accepted particles/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

@@ -332,14 +332,19 @@ class GPyRegression:
         self._fit()
 
     def log_posterior_hyper(self, hyper=None):
-        """log marginal likelihood + Gamma log-priors (the quantity `optimize` maximises)."""
+        """The quantity `optimize` maximises: log marginal likelihood + Gamma log-priors + the log
+        Jacobian of GPy's positivity transform for the priored parameters.  GPy optimises its
+        positive parameters through Logexp (x = log(1 + e^u)) and, for a parameter that carries a
+        prior, adds log|dx/du| = log(1 - e^-x) to the log-prior (paramz Priorizable.log_prior);
+        without that term the reference's Gamma priors with shape < 1 (heuristic variance < 1) are
+        unbounded at zero and a full optimisation walks the kernel variance to nothing."""
         h = hyper or self._hyper
         try:
             val = self.log_marginal_likelihood(dict(h))
         except (np.linalg.LinAlgError, _lib.ElfiB200Error):
             return -1e25
         for k, (a, b) in self._priors.items():
-            val += ss.gamma.logpdf(h[k], a=a, scale=1.0 / b)
+            val += ss.gamma.logpdf(h[k], a=a, scale=1.0 / b) + np.log(-np.expm1(-h[k]))
         return val if np.isfinite(val) else -1e25
 
     def copy(self):

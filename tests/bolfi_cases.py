@@ -176,8 +176,10 @@ def case_hyper_objective_matches_sklearn():
         fd = np.array([(lml(x0 + eps * e) - lml(x0 - eps * e)) / (2 * eps) for e in np.eye(4)])
         # d/dlog(noise + jitter) vs d/dlog(noise): identical up to jitter / noise ~ 1e-7
         np.testing.assert_allclose(fd, want_grad, rtol=2e-5, atol=1e-6)
-        # the Gamma log-priors on top are the reference's (gpy_regression.py:267-280)
-        prior = sum(ss.gamma.logpdf(h[k], a=a, scale=1.0 / b) for k, (a, b) in gp._priors.items())
+        # on top: the reference's Gamma log-priors (gpy_regression.py:267-280) and, as in GPy, the
+        # log Jacobian log(1 - e^-x) of the Logexp transform of every priored parameter
+        prior = sum(ss.gamma.logpdf(h[k], a=a, scale=1.0 / b) + np.log(-np.expm1(-h[k]))
+                    for k, (a, b) in gp._priors.items())
         np.testing.assert_allclose(gp.log_posterior_hyper(h), got + prior, rtol=1e-12)
     gp._fit()
 
