@@ -322,7 +322,11 @@ class _PointCache:
         return None
 
     def store(self, x, logpdf, grad):
-        self.entries.append((np.asarray(x).tobytes(), logpdf, grad))
+        key = np.asarray(x).tobytes()
+        # a point first seen in a density-only round is stored without a gradient: replace that
+        # entry, or the later gradient request keeps missing and the point is re-evaluated
+        self.entries = [e for e in self.entries if e[0] != key]
+        self.entries.append((key, logpdf, grad))
         if len(self.entries) > self.size:
             del self.entries[0]
 

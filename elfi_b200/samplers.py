@@ -298,6 +298,11 @@ class ParameterInference:
         self._compiled = em.compile_net(self.model.source_net, self.output_names)
         self._distributed = distributed
         self.comm = Comm(distributed)
+        if self.comm.on and pool is not None and type(pool).__name__ == 'ArrayPool':
+            # an appendable .npy store is written in batch-index order by ONE writer; rank r's
+            # first batch index is r and all ranks would share the same files
+            raise ValueError('ArrayPool cannot be shared by the ranks of a distributed run; use an '
+                             'OutputPool (device-resident, per rank) or distributed=False')
         self.max_parallel_batches = max_parallel_batches or self.comm.size
         if self.max_parallel_batches <= 0:
             raise ValueError('Value for max_parallel_batches ({}) must be at least one.'.format(
