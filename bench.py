@@ -507,38 +507,14 @@ def run_ours(args):
     cand = ops.CandidateBuffer(B, [1, 1, 1])
     ctx = dev.context()
 
-    def step_eager():
-        _lib.call('elfi_b200_dist_euclid_thr_f64', ctx, dev.ptr(S), D, B, D, dev.ptr(obs), None, 1,
-                  dev.ptr(thr_arr), dev.ptr(d), dev.ptr(idx), dev.ptr(n_acc), dev.stream_ptr())
-        cand.append([d, t1, t2], idx, n_acc, B)
+    # one library call per step (distance + compaction + append; arguments marshalled once): the
+    # host side of a step costs ~10 us, so a busy shared host cannot starve the 0.17 ms kernel
+    # (two Python-level calls per step measured 0.32-1.0 ms per step on loaded hosts)
+    step = cand.bind_batch(S, obs, thr_arr, d, idx, n_acc, [t1, t2])
 
     def kernel_only():
         _lib.call('elfi_b200_dist_euclid_thr_f64', ctx, dev.ptr(S), D, B, D, dev.ptr(obs), None, 1,
                   dev.ptr(thr_arr), dev.ptr(d), None, None, dev.stream_ptr())
-
-    # The step is 4 short launches behind a 0.16 ms kernel: on a busy host the Python launch loop,
-    # not the GPU, would set the pace.  Capture ONE step in a CUDA graph and replay it per step
-    # (the library launches on the stream it is given, so it captures like any other stream work);
-    # fall back to eager launches if the capture is refused.
-    for _ in range(3):
-        step_eager()
-    torch.cuda.synchronize()
-    launch_mode = 'cuda_graph (one replay per step)'
-    try:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_eager()
-        torch.cuda.synchronize()
-        step = graph.replay
-        step()
-        torch.cuda.synchronize()
-    except Exception as exc:
-        launch_mode = 'eager ({})'.format(type(exc).__name__)
-        try:
-            torch.cuda.synchronize()
-        except Exception:
-            pass
-        step = step_eager
 
     def barrier():
         if world > 1:
@@ -696,7 +672,7 @@ def run_ours(args):
             'parity_check': check,
             # distance, mask compaction, append, count update per step + the final sort/gather
             'gpu_launches': 4 * args.steps + 26,
-            'launch_mode': launch_mode, 'host_launch_ms_per_step': host_ms_per_step,
+            'host_launch_ms_per_step': host_ms_per_step,
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'accepted particles/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

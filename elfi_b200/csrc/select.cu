@@ -694,6 +694,48 @@ int elfi_b200_accept_append_f64(elfi_b200_ctx* ctx, const int32_t* acc_idx, cons
     return ELFI_B200_OK;
 }
 
+// One batch of a threshold-mode rejection round in ONE call: distances + acceptance + compaction
+// (elfi_b200_dist_euclid_thr[_dev]_f64) and the append of the accepted rows [d | extra sources]
+// to the candidate buffer (elfi_b200_accept_append_f64); four launches, no synchronisation.
+extern "C" int elfi_b200_dist_euclid_thr_f64(elfi_b200_ctx*, const double*, int64_t, int64_t, int64_t,
+                                             const double*, const double*, int64_t, const double*,
+                                             double*, int32_t*, int64_t*, void*);
+extern "C" int elfi_b200_dist_euclid_thr_dev_f64(elfi_b200_ctx*, const double*, int64_t, int64_t,
+                                                 int64_t, const double*, const double*, int64_t,
+                                                 const double*, double*, int32_t*, int64_t*, void*);
+
+int elfi_b200_rejection_batch_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                  int64_t D, const double* obs, const double* W, int64_t K,
+                                  const double* thr_host, const double* thr_dev, double* d_out,
+                                  int32_t* acc_idx, int64_t* n_acc, int64_t n_extra,
+                                  const double* const* extra_host, const int64_t* ld_extra_host,
+                                  const int64_t* width_extra_host, double* dst, int64_t ld_dst,
+                                  int64_t capacity, int64_t* count, int64_t* dropped,
+                                  void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx && acc_idx && n_acc && d_out, "rejection_batch: NULL argument");
+    ELFI_REQUIRE((thr_host != nullptr) != (thr_dev != nullptr),
+                 "rejection_batch: thresholds on the host OR on the device");
+    ELFI_REQUIRE(n_extra >= 0 && n_extra < APPEND_MAX_SRC, "rejection_batch: 0..%d extra sources",
+                 APPEND_MAX_SRC - 1);
+    int rc = thr_host
+        ? elfi_b200_dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, acc_idx, n_acc,
+                                        stream_)
+        : elfi_b200_dist_euclid_thr_dev_f64(ctx, S, ldS, B, D, obs, W, K, thr_dev, d_out, acc_idx,
+                                            n_acc, stream_);
+    if (rc) return rc;
+    const double* src[APPEND_MAX_SRC];
+    int64_t ld[APPEND_MAX_SRC], width[APPEND_MAX_SRC];
+    src[0] = d_out; ld[0] = K; width[0] = K;
+    for (int64_t k = 0; k < n_extra; ++k) {
+        src[k + 1] = extra_host[k];
+        ld[k + 1] = ld_extra_host[k];
+        width[k + 1] = width_extra_host[k];
+    }
+    return elfi_b200_accept_append_f64(ctx, acc_idx, n_acc, B, n_extra + 1, src, ld, width, dst,
+                                       ld_dst, capacity, count, dropped, stream_);
+}
+
 int elfi_b200_wquantile_f64(elfi_b200_ctx* ctx, const double* x, const double* w, int64_t n,
                             double alpha, double* out, void* stream_) {
     using namespace elfi;

@@ -320,6 +320,38 @@ class CandidateBuffer:
                   int(max_rows), n, pp, pl, pw, prow, self.width, self.capacity, pcount, pdrop,
                   dev.stream_ptr())
 
+    def bind_batch(self, S, obs, thresholds, d_out, acc_idx, n_acc, extras, w=None):
+        """A zero-argument callable running ONE threshold-mode batch -- distances of S + acceptance
+        + append of the accepted rows [d | extras] to this buffer -- as a single library call
+        (elfi_b200_rejection_batch_f64) with every argument marshalled once: ~10 us of host time
+        per batch, so that a busy host cannot starve a 0.17 ms kernel.  All tensors are device
+        tensors the caller keeps alive; `thresholds` is a host sequence or a device tensor."""
+        S = _matrix(S)
+        B, D = S.shape
+        W = None if w is None else dev.to_device(w).reshape(-1, D)
+        K = 1 if W is None else W.shape[0]
+        extras = [_as_2d(t) for t in extras]
+        if [K] + [t.shape[1] for t in extras] != self.widths:
+            raise ValueError('d / extra widths do not match the buffer layout')
+        thr_dev = thresholds if dev.is_device_array(thresholds) else None
+        thr_host = None if thr_dev is not None else np.ascontiguousarray(
+            np.atleast_1d(thresholds), dtype=np.float64)
+        n = len(extras)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in extras])
+        lds = (ctypes.c_int64 * max(n, 1))(*[_ld(t) for t in extras])
+        wid = (ctypes.c_int64 * max(n, 1))(*[t.shape[1] for t in extras])
+        keep = (S, obs, W, thr_dev, thr_host, d_out, acc_idx, n_acc, extras, ptrs, lds, wid)
+        args = (dev.context(), dev.ptr(S), S.stride(0) if B > 1 else D, B, D, dev.ptr(obs),
+                dev.ptr(W), K, dev.ptr(thr_host), dev.ptr(thr_dev), dev.ptr(d_out),
+                dev.ptr(acc_idx), dev.ptr(n_acc), n, ctypes.cast(ptrs, ctypes.c_void_p),
+                ctypes.cast(lds, ctypes.c_void_p), ctypes.cast(wid, ctypes.c_void_p),
+                dev.ptr(self.rows), self.width, self.capacity, dev.ptr(self.count),
+                dev.ptr(self.dropped))
+
+        def run(_keep=keep):
+            _lib.call('elfi_b200_rejection_batch_f64', *args, dev.stream_ptr())
+        return run
+
     def best(self, n, key_col=0):
         """(rows sorted by column key_col, first n; count, dropped) -- one D2H of the counters."""
         count, dropped = int(self.count.item()), int(self.dropped.item())

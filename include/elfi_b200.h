@@ -180,6 +180,17 @@ int elfi_b200_accept_append_f64(elfi_b200_ctx* ctx, const int32_t* acc_idx, cons
                                 const int64_t* ld_src_host, const int64_t* width_host, double* dst,
                                 int64_t ld_dst, int64_t capacity, int64_t* count, int64_t* dropped,
                                 void* stream);
+/* One batch of a threshold-mode rejection round in one call (Rejection.update ->
+ * _merge_batch, samplers.py:140-230): elfi_b200_dist_euclid_thr[_dev]_f64 followed by
+ * elfi_b200_accept_append_f64 of the rows [d (K columns) | extra sources] -- four launches, no
+ * synchronisation, one host -> library transition.  Exactly one of thr_host / thr_dev is given. */
+int elfi_b200_rejection_batch_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                  int64_t D, const double* obs, const double* W, int64_t K,
+                                  const double* thr_host, const double* thr_dev, double* d_out,
+                                  int32_t* acc_idx, int64_t* n_acc, int64_t n_extra,
+                                  const double* const* extra_host, const int64_t* ld_extra_host,
+                                  const int64_t* width_extra_host, double* dst, int64_t ld_dst,
+                                  int64_t capacity, int64_t* count, int64_t* dropped, void* stream);
 int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA, int64_t nA,
                                const double* B, int64_t ldB, const int32_t* mapB,
                                const int32_t* perm, int64_t n, int64_t width, double* dst,

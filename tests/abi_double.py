@@ -117,6 +117,20 @@ def accept_append_f64(ctx, acc_idx, n_acc, max_rows, n_src, src_host, ld_src_hos
     cnt[0] += rows
 
 
+def rejection_batch_f64(ctx, S, ldS, B, D, obs, W, K, thr_host, thr_dev, d_out, acc_idx, n_acc, n_extra,
+                        extra_host, ld_extra_host, width_extra_host, dst, ld_dst, capacity, count,
+                        dropped, stream):
+    thr = thr_host if _addr(thr_host) else thr_dev
+    dist_euclid_thr_f64(ctx, S, ldS, B, D, obs, W, K, thr, d_out, acc_idx, n_acc, stream)
+    ptrs = np.concatenate([[_addr(d_out)], _vec(extra_host, max(n_extra, 1), np.uint64)[:n_extra]]
+                          ).astype(np.uint64)
+    lds = np.concatenate([[K], _vec(ld_extra_host, max(n_extra, 1), np.int64)[:n_extra]]).astype(np.int64)
+    wid = np.concatenate([[K], _vec(width_extra_host, max(n_extra, 1), np.int64)[:n_extra]]).astype(np.int64)
+    accept_append_f64(ctx, acc_idx, n_acc, B, n_extra + 1, ctypes.c_void_p(ptrs.ctypes.data),
+                      ctypes.c_void_p(lds.ctypes.data), ctypes.c_void_p(wid.ctypes.data), dst, ld_dst,
+                      capacity, count, dropped, stream)
+
+
 def dist_euclid_thr_f64_host(ctx, S, ldS, B, D, obs, W, K, thr_host, d_out, acc_idx, n_acc):
     Sm = _mat(S, B, D, ldS)
     d = _distances(Sm, _vec(obs, D), _mat(W, K, D), K) if B else np.empty((0, K))
@@ -478,7 +492,7 @@ def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
 
 
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
-    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
+    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, rejection_batch_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,

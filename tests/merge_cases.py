@@ -30,7 +30,7 @@ def case_device_thresholds_and_append():
     rs = np.random.RandomState(3)
     B, D, n = 5000, 24, 300
     obs = rs.randn(1, D)
-    batches_host, buf = [], ops.CandidateBuffer(n + 2 * B, [1, 1, 1])
+    batches_host, batches_S, buf = [], [], ops.CandidateBuffer(n + 2 * B, [1, 1, 1])
     thr = None
     for step in range(4):
         S = rs.randn(B, D)
@@ -45,6 +45,7 @@ def case_device_thresholds_and_append():
         assert np.array_equal(idx[:k].cpu().numpy(), o.accept_indices(ref_d, thr))
         buf.append([d, dev.to_device(t1), dev.to_device(t2)], idx, n_acc, B)
         batches_host.append({'d': ref_d, 't1': t1, 't2': t2})
+        batches_S.append(S)
     top, count, dropped = buf.best(n)
     want = reference_merge(batches_host, thr, n)
     total = sum(int((b['d'] <= thr).sum()) for b in batches_host)
@@ -54,6 +55,23 @@ def case_device_thresholds_and_append():
     assert np.array_equal(top[:, 0], want['d'][:m])
     assert np.array_equal(top[:, 1], want['t1'][:m])
     assert np.array_equal(top[:, 2], want['t2'][:m])
+    # the same batches through the one-call form (elfi_b200_rejection_batch_f64, arguments bound
+    # once): identical candidate buffer
+    import torch
+    bound = ops.CandidateBuffer(n + 2 * B, [1, 1, 1])
+    Sd = dev.to_device(batches_S[0])
+    d_out, idx_out = dev.empty((B,)), dev.empty((B,), dtype=torch.int32)
+    n_out = dev.zeros((1,), dtype=torch.int64)
+    t1d, t2d = dev.to_device(batches_host[0]['t1']), dev.to_device(batches_host[0]['t2'])
+    run = bound.bind_batch(Sd, dev.to_device(obs.ravel()), [thr], d_out, idx_out, n_out, [t1d, t2d])
+    for S_h, b in zip(batches_S, batches_host):
+        Sd.copy_(dev.to_device(S_h))
+        t1d.copy_(dev.to_device(b['t1']))
+        t2d.copy_(dev.to_device(b['t2']))
+        run()
+    top2, count2, dropped2 = bound.best(n)
+    assert count2 == count and dropped2 == 0
+    assert np.array_equal(top2.cpu().numpy(), top)
     # a full buffer drops the overflow and says so
     small = ops.CandidateBuffer(10, [1])
     dd, (idx, n_acc) = ops.dist_euclid(S, obs, thresholds=dev.to_device(np.array([np.inf])),
