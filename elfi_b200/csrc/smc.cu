@@ -162,6 +162,27 @@ __device__ __forceinline__ double exp2_neg(double nt) {
     return (nt <= 1020.0) ? r : 0.0;
 }
 
+// Mixed-precision variant of exp2_neg (opt-in, ELFI_B200_GM_MODE=mixed): the range reduction
+// stays in fp64 (the integer / fraction split of nt needs it), but 2^f for f in [-.5, .5] comes
+// from the special-function unit in fp32 (ex2.approx: 2 ulp, ~1.7e-7 relative) and is widened
+// back to fp64 with integer operations while the exponent k is added -- no polynomial: the
+// fp64 pipe issues 8 instructions per pair at P = 2 instead of 14, the rest runs on the
+// XU (F2F + MUFU) and integer pipes concurrently.  Accuracy ~2e-7 per term against the 1e-5
+// relative tolerance on the weights; the fp64 path (1.9e-9) stays the default.
+__device__ __forceinline__ double exp2_neg_mixed(double nt) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double tm = magic - nt;
+    const double kd = tm - magic;             // rint(-nt)
+    const float f = __double2float_rn(-nt - kd);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f));     // in [0.707, 1.415]
+    const unsigned eb = __float_as_uint(e);
+    const int k = __double2loint(tm);
+    const int hi = int(((eb >> 23) + unsigned(1023 - 127 + k)) << 20) | int((eb >> 3) & 0xFFFFFu);
+    const double r = __hiloint2double(hi, int(eb << 29));
+    return (nt <= 1020.0) ? r : 0.0;
+}
+
 // Whitened, centred, scaled coordinates y = s Linv (x - centre) with s = sqrt(log2(e)/2).
 //   points     (mode 0): out[i] = (y_0 .. y_{p-1}, |y|^2)
 //   components (mode 1): out[j] = (-2 y_0 .. -2 y_{p-1}, |y|^2 - log2(w_j / sum w))
@@ -191,7 +212,7 @@ __global__ void gm_whiten_kernel(const double* __restrict__ x, int64_t ld, int64
 // 128 * R points and writes one partial sum per point; gm_finish_kernel adds the chunks in a
 // fixed order (deterministic) and takes the log.  The 2-D grid keeps >= 8 CTAs per SM even when a
 // rank owns only ~1e5 points, which the dependent polynomial chains need to fill the fp64 pipe.
-template <int P, int R>
+template <int P, int R, bool MIXED = false>
 __global__ void __launch_bounds__(128)
 gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict__ mw, int64_t M,
               int64_t chunk_len, double* __restrict__ partial) {
@@ -225,7 +246,7 @@ gm_pdf_kernel(const double* __restrict__ xw, int64_t N, const double* __restrict
                 double g = cj;
 #pragma unroll
                 for (int a = 0; a < P; ++a) g = fma(x[r][a], m[a], g);
-                acc[r] += exp2_neg(g + x[r][P]);
+                acc[r] += MIXED ? exp2_neg_mixed(g + x[r][P]) : exp2_neg(g + x[r][P]);
             }
         }
     }
@@ -376,11 +397,24 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     const double lognorm = -0.5 * (double(p) * 1.8378770664093453 + logdet);  // log(2 pi)
     if (p <= 4) {
         dim3 grid(static_cast<unsigned>(xblocks), static_cast<unsigned>(chunks));
-        switch (p) {
-            case 1: gm_pdf_kernel<1, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
-            case 2: gm_pdf_kernel<2, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
-            case 3: gm_pdf_kernel<3, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
-            default: gm_pdf_kernel<4, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+        static const bool mixed = [] {
+            const char* v = getenv("ELFI_B200_GM_MODE");
+            return v != nullptr && v[0] == 'm';
+        }();
+        if (mixed) {
+            switch (p) {
+                case 1: gm_pdf_kernel<1, R, true><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+                case 2: gm_pdf_kernel<2, R, true><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+                case 3: gm_pdf_kernel<3, R, true><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+                default: gm_pdf_kernel<4, R, true><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+            }
+        } else {
+            switch (p) {
+                case 1: gm_pdf_kernel<1, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+                case 2: gm_pdf_kernel<2, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+                case 3: gm_pdf_kernel<3, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+                default: gm_pdf_kernel<4, R><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
+            }
         }
         gm_finish_kernel<<<unsigned((N + 255) / 256), 256, 0, stream>>>(partial, N, int(chunks), lognorm, logq);
     } else {

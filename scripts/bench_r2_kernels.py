@@ -112,6 +112,9 @@ for N in (125_000, 1_000_000):
              tflops_equiv=N * M * 16 / (ms * 1e-3) / 1e12)
     out.append(e)
     print(json.dumps(e), flush=True)
+    if N == 125_000:      # kept for an accuracy comparison between ELFI_B200_GM_MODE variants
+        np.save(os.path.join(ROOT, 'gpurun_out', 'gm_logq_{}.npy'.format(TAG)),
+                ops.gm_logpdf(xs, means, cov, w, validate=False).cpu().numpy())
 
 with open(os.path.join(ROOT, 'gpurun_out', 'r2_kernels_{}.json'.format(TAG)), 'w') as f:
     json.dump(out, f, indent=1)
