@@ -347,9 +347,10 @@ int elfi_b200_weighted_stats_f64(elfi_b200_ctx* ctx, const double* x, int64_t ld
     return ELFI_B200_OK;
 }
 
-int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t N,
-                            const double* means, int64_t ldm, const double* w, int64_t M, int64_t p,
-                            const double* Linv_host, double logdet, double* logq, void* stream_) {
+static int gm_logpdf_impl(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t N,
+                          const double* means, int64_t ldm, const double* w, int64_t M, int64_t p,
+                          const double* Linv_host, double logdet, double* logq, void* stream_,
+                          bool mixed_entry) {
     using namespace elfi;
     ELFI_REQUIRE(ctx && x && means && Linv_host && logq, "gm_logpdf: NULL argument");
     ELFI_REQUIRE(N >= 0 && M >= 1 && p >= 1 && p <= WS_MAXP && ldx >= p && ldm >= p,
@@ -397,10 +398,12 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     const double lognorm = -0.5 * (double(p) * 1.8378770664093453 + logdet);  // log(2 pi)
     if (p <= 4) {
         dim3 grid(static_cast<unsigned>(xblocks), static_cast<unsigned>(chunks));
-        static const bool mixed = [] {
+        // ELFI_B200_GM_MODE = fp64 | mixed overrides the choice of the entry point (measurements)
+        static const int forced = [] {
             const char* v = getenv("ELFI_B200_GM_MODE");
-            return v != nullptr && v[0] == 'm';
+            return v == nullptr ? 0 : (v[0] == 'm' ? 2 : (v[0] == 'f' ? 1 : 0));
         }();
+        const bool mixed = forced == 2 || (forced == 0 && mixed_entry);
         if (mixed) {
             switch (p) {
                 case 1: gm_pdf_kernel<1, R, true><<<grid, 128, 0, stream>>>(xw, N, mw, M, chunk_len, partial); break;
@@ -423,6 +426,19 @@ int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, in
     }
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
+}
+
+int elfi_b200_gm_logpdf_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t N,
+                            const double* means, int64_t ldm, const double* w, int64_t M, int64_t p,
+                            const double* Linv_host, double logdet, double* logq, void* stream_) {
+    return gm_logpdf_impl(ctx, x, ldx, N, means, ldm, w, M, p, Linv_host, logdet, logq, stream_, false);
+}
+
+int elfi_b200_gm_logpdf_mixed_f64(elfi_b200_ctx* ctx, const double* x, int64_t ldx, int64_t N,
+                                  const double* means, int64_t ldm, const double* w, int64_t M,
+                                  int64_t p, const double* Linv_host, double logdet, double* logq,
+                                  void* stream_) {
+    return gm_logpdf_impl(ctx, x, ldx, N, means, ldm, w, M, p, Linv_host, logdet, logq, stream_, true);
 }
 
 int elfi_b200_smc_weights_f64(elfi_b200_ctx* ctx, const double* logprior, const double* logq,

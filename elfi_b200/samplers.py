@@ -960,14 +960,16 @@ class SMC(Sampler):
                 with PHASES('weights:gm_logpdf'):
                     if hi > lo:
                         q_part[:hi - lo] = ops.gm_logpdf(params_dev[lo:hi], prev._means_dev,
-                                                         prev.cov, w_prev, validate=False)
+                                                         prev.cov, w_prev, validate=False,
+                                                         mixed=self._device_proposal is not None)
                 with PHASES('weights:all_gather'):
                     q_logpdf = self.comm.all_gather_rows(q_part)
                 q_logpdf = q_logpdf[:N]   # equal-capacity shards: only the tail is padding
             else:
                 with PHASES('weights:gm_logpdf'):
                     q_logpdf = ops.gm_logpdf(params_dev, prev._means_dev, prev.cov, w_prev,
-                                             validate=False)
+                                             validate=False,
+                                             mixed=self._device_proposal is not None)
             with PHASES('weights:prior_logpdf'):
                 if self._device_proposal is not None:
                     p_logpdf = self._device_proposal.logpdf(params_dev)

@@ -256,6 +256,10 @@ def gm_logpdf_f64(ctx, x, ldx, N, means, ldm, w, M, p, Linv_host, logdet, logq, 
     _vec(logq, N)[:] = o.gm_logpdf(x, means, L @ L.T, weights)
 
 
+def gm_logpdf_mixed_f64(*args):
+    gm_logpdf_f64(*args)
+
+
 def smc_weights_f64(ctx, logprior, logq, n, w, stream):
     with np.errstate(all='ignore'):
         _vec(w, n)[:] = np.exp(_vec(logprior, n) - _vec(logq, n))
@@ -494,7 +498,7 @@ def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
     dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, rejection_batch_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
-    weighted_stats_f64, gm_logpdf_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
+    weighted_stats_f64, gm_logpdf_f64, gm_logpdf_mixed_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,
     gm_rvs_f64, gm_cdf_f64, gm_rvs_cdf_f64, prior_gauss_f64, logprior_gauss_f64, sim_gauss_f64, sim_gnk_f64, logprior_box_f64)}
 

@@ -46,6 +46,31 @@ def test_gm_logpdf_vs_oracle(p):
     np.testing.assert_allclose(got[finite], ref[finite], rtol=0, atol=1e-7)
 
 
+@pytest.mark.first_device_run
+@pytest.mark.parametrize('p', [1, 2, 3, 4])
+def test_gm_logpdf_mixed_vs_oracle(p):
+    """elfi_b200_gm_logpdf_mixed_f64 (2^f from the fp32 special-function unit; throughput mode):
+    densities within 1e-6 of the oracle -- 10x inside the 1e-5 tolerance on SMC weights -- and the
+    same underflow pattern as the fp64 path."""
+    from elfi_b200 import ops
+    rs = np.random.RandomState(10 + p)
+    M, N = 3000, 1777
+    means = rs.randn(M, p)
+    w = rs.rand(M)
+    w[::11] = 0.0
+    A = rs.randn(p, p)
+    cov = A @ A.T / p + np.eye(p) * 0.1
+    x = rs.randn(N, p) * 1.5
+    x[:5] += 40.0
+    ref = o.gm_logpdf(x, means, cov, w)
+    got = ops.gm_logpdf(x, means, cov, w, mixed=True).cpu().numpy()
+    exact = ops.gm_logpdf(x, means, cov, w).cpu().numpy()
+    finite = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), finite)
+    np.testing.assert_allclose(np.exp(got[finite] - ref[finite]), 1.0, rtol=1e-6)
+    np.testing.assert_allclose(np.exp(exact[finite] - ref[finite]), 1.0, rtol=1e-7)
+
+
 def test_fast_exp_accuracy_through_weights():
     """w = exp(logprior - logq) within 1e-5 relative of the oracle (north_star tolerance)."""
     from elfi_b200 import ops
