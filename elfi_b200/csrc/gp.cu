@@ -17,6 +17,8 @@
 // Variance uses the explicit inverse factor W = L^-1 instead of a triangular solve per query
 // chunk:  v_i = k** - || W k_i ||^2.  The product is a GEMM with a triangular K-range (row a
 // of W is zero beyond column a), i.e. n^2 m / 2 FMAs = 0.4 TFLOP at n = 2000, m = 1e5.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace elfi {
@@ -557,24 +559,59 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
         gp_cov_kernel<<<grid, 256, 0, stream>>>(X, ldX, n, X, ldX, n, int(p), kernel_var, f, bias_var,
                                                 noise_var, 1, L, n_pad, n_pad, n_pad);
     }
-    // blocked Cholesky, lower, in place
+    // Blocked Cholesky, lower, in place, with a one-panel look-ahead on a second stream.  Panel p
+    // (diagonal block + rows below) is factored on the caller's stream; its trailing update is
+    // split: the NEXT block column (the only one the following panel needs) is updated on the
+    // caller's stream right away, the rest of the trailing matrix on the context's side stream,
+    // where it overlaps with the next panel's latency-bound factorisation.  Ordering: the side
+    // stream waits for the panel (ev_panel); the caller's stream waits for rest(p - 1) before it
+    // touches block column p + 1 again (ev_rest).  ELFI_B200_GP_LOOKAHEAD=0: one stream.
+    static const bool lookahead = [] {
+        const char* v = getenv("ELFI_B200_GP_LOOKAHEAD");
+        return !(v != nullptr && v[0] == '0');
+    }();
+    cudaStream_t side = ctx->copy_stream[0];
+    cudaEvent_t ev_panel = ctx->copy_event[0], ev_rest = ctx->copy_event[1];
+    bool rest_pending = false;
+    auto syrk = [&](int64_t k, int64_t c0, int64_t rows, int64_t cols, int mode, cudaStream_t st) {
+        // C[c0.., c0..(c0 + cols)) -= P P^T with P = L[.., k .. k + 64): rows x cols block at (c0, c0)
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.A = L + c0 * n_pad + k; g.lda = n_pad;
+        g.B = g.A; g.ldb = n_pad;
+        g.C = L + c0 * n_pad + c0; g.ldc = n_pad;
+        g.M = rows; g.N = cols; g.K = GP_NB;
+        g.alpha = -1.0; g.beta = 1.0; g.mode = mode;
+        return launch_gemm(g, 1, st);
+    };
     for (int64_t k = 0; k < n_pad; k += GP_NB) {
         const int64_t below = n_pad - (k + GP_NB);
-        if (below <= 0) potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
-        if (below > 0) {
-            potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(L, n_pad, k,
-                                                                                   n_pad, info);
-            GemmArgs g;
-            memset(&g, 0, sizeof(g));
-            g.A = L + (k + GP_NB) * n_pad + k; g.lda = n_pad;
-            g.B = g.A; g.ldb = n_pad;
-            g.C = L + (k + GP_NB) * n_pad + (k + GP_NB); g.ldc = n_pad;
-            g.M = below; g.N = below; g.K = GP_NB;
-            g.alpha = -1.0; g.beta = 1.0; g.mode = 1;
-            int rc = launch_gemm(g, 1, stream);
+        if (below <= 0) {
+            if (rest_pending) { ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0)); rest_pending = false; }
+            potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
+            continue;
+        }
+        potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(L, n_pad, k, n_pad,
+                                                                                info);
+        if (!lookahead) {
+            int rc = syrk(k, k + GP_NB, below, below, 1, stream);
             if (rc) return rc;
+            continue;
+        }
+        ELFI_CUDA_OK(cudaEventRecord(ev_panel, stream));
+        if (rest_pending) { ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0)); rest_pending = false; }
+        int rc = syrk(k, k + GP_NB, below, GP_NB, 0, stream);          // next block column
+        if (rc) return rc;
+        const int64_t below2 = below - GP_NB;
+        if (below2 > 0) {
+            ELFI_CUDA_OK(cudaStreamWaitEvent(side, ev_panel, 0));
+            rc = syrk(k, k + 2 * GP_NB, below2, below2, 1, side);     // rest of the trailing matrix
+            if (rc) return rc;
+            ELFI_CUDA_OK(cudaEventRecord(ev_rest, side));
+            rest_pending = true;
         }
     }
+    if (rest_pending) ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0));
     // W = L^-1 (and U = W^T) by recursive doubling over diagonal blocks:
     //   [[L11, 0], [L21, L22]]^-1 = [[W11, 0], [-W22 L21 W11, W22]]
     ELFI_CUDA_OK(cudaMemsetAsync(W, 0, size_t(n_pad) * n_pad * 8, stream));
