@@ -523,6 +523,12 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    # untimed rehearsal of the whole timed region (K steps + the final selection over K steps'
+    # worth of accepted rows): the caching allocator and the sort scratch reach their final sizes
+    # here -- a first-time cudaMalloc inside the timed region cost ~3 ms on the slowest of 8 ranks
+    cand.reset()
+    for _ in range(args.steps):
+        step()
     cand.best(N_SAMPLES)
     barrier()
     cand.reset()

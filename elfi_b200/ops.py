@@ -286,12 +286,12 @@ class CandidateBuffer:
         self.width = sum(self.widths)
         self.capacity = int(capacity)
         self.rows = dev.empty((self.capacity, self.width))
-        self.count = dev.zeros((1,), dtype=torch.int64)
-        self.dropped = dev.zeros((1,), dtype=torch.int64)
+        self._counters = dev.zeros((2,), dtype=torch.int64)      # [count, dropped]: one D2H reads both
+        self.count = self._counters[0:1]
+        self.dropped = self._counters[1:2]
 
     def reset(self):
-        self.count.zero_()
-        self.dropped.zero_()
+        self._counters.zero_()
 
     def _descriptors(self, sources):
         """ctypes descriptor arrays of a source list, cached while the same buffers come back
@@ -354,7 +354,7 @@ class CandidateBuffer:
 
     def best(self, n, key_col=0):
         """(rows sorted by column key_col, first n; count, dropped) -- one D2H of the counters."""
-        count, dropped = int(self.count.item()), int(self.dropped.item())
+        count, dropped = (int(v) for v in self._counters.cpu().tolist())
         keys = self.rows[:count, key_col].contiguous()
         perm = argsort(keys)
         return take_rows(self.rows, perm[:min(n, count)]), count, dropped
