@@ -226,10 +226,12 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k, int* __restric
 // Diagonal block + panel below it in ONE launch: every CTA factors the 64x64 diagonal block
 // itself in shared memory (redundantly -- the same ~64 dependent steps would otherwise run in a
 // separate single-CTA kernel before the panel could start), then solves X L_kk^T = A_panel for its
-// 128 rows, one thread per row.  CTA 0 writes the factored diagonal block back.
+// 128 rows, one thread per row.  CTA 0 stores the factored diagonal block in `Dout` (64 x 64, a
+// side buffer: the other CTAs of the launch may still be reading the unfactored block from A);
+// diag_copy_kernel puts all blocks into place after the last panel.
 __global__ void __launch_bounds__(128)
 potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
-                        int* __restrict__ info) {
+                        int* __restrict__ info, double* __restrict__ Dout) {
     __shared__ double l[GP_NB][GP_NB + 1];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
@@ -279,21 +281,33 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
         for (int cc = 0; cc < GP_NB / 2; ++cc) l[r][2 * cc + q] = (2 * cc + q <= r) ? a[cc] : 0.0;
         __syncthreads();
     }
+    if (blockIdx.x == 0)
+        for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) Dout[idx] = l[idx / GP_NB][idx % GP_NB];
     const int64_t row = k + GP_NB + int64_t(blockIdx.x) * 128 + tid;
     if (row >= n) return;
     double x[GP_NB];
     double* a = A + row * lda + k;
 #pragma unroll
     for (int c = 0; c < GP_NB; ++c) x[c] = a[c];
+    // X L^T = A row by row, right-looking: once x_c is final it is eliminated from all later
+    // columns -- 63 - c INDEPENDENT FMAs per step instead of one dependent chain of c FMAs
 #pragma unroll
     for (int c = 0; c < GP_NB; ++c) {
-        double v = x[c];
+        x[c] = x[c] / l[c][c];
 #pragma unroll
-        for (int j = 0; j < c; ++j) v = fma(-x[j], l[c][j], v);
-        x[c] = v / l[c][c];
+        for (int c2 = c + 1; c2 < GP_NB; ++c2) x[c2] = fma(-x[c], l[c2][c], x[c2]);
     }
 #pragma unroll
     for (int c = 0; c < GP_NB; ++c) a[c] = x[c];
+}
+
+// A[k + r][k + c] = D[block][r][c] for the first `nblocks` diagonal blocks
+__global__ void __launch_bounds__(256)
+diag_copy_kernel(const double* __restrict__ D, double* __restrict__ A, int64_t lda) {
+    const int64_t k = int64_t(blockIdx.x) * GP_NB;
+    const double* d = D + int64_t(blockIdx.x) * GP_NB * GP_NB;
+    for (int idx = threadIdx.x; idx < GP_NB * GP_NB; idx += 256)
+        A[(k + idx / GP_NB) * lda + k + idx % GP_NB] = d[idx];
 }
 
 // Inverse of every 64x64 diagonal block of L: W_bb = L_bb^-1 (lower), also U_bb = W_bb^T.
@@ -566,6 +580,9 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
     // where it overlaps with the next panel's latency-bound factorisation.  Ordering: the side
     // stream waits for the panel (ev_panel); the caller's stream waits for rest(p - 1) before it
     // touches block column p + 1 again (ev_rest).  ELFI_B200_GP_LOOKAHEAD=0: one stream.
+    double* T = static_cast<double*>(ctx_scratch(ctx, size_t(n_pad) * n_pad * 8 + 256));
+    if (!T) return ELFI_B200_ERR_NOMEM;
+    double* Dblocks = T;     // (n_pad / 64) factored diagonal blocks, copied into L after the loop
     static const bool lookahead = [] {
         const char* v = getenv("ELFI_B200_GP_LOOKAHEAD");
         return !(v != nullptr && v[0] == '0');
@@ -591,8 +608,8 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
             potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
             continue;
         }
-        potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(L, n_pad, k, n_pad,
-                                                                                info);
+        potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(
+            L, n_pad, k, n_pad, info, Dblocks + (k / GP_NB) * GP_NB * GP_NB);
         if (!lookahead) {
             int rc = syrk(k, k + GP_NB, below, below, 1, stream);
             if (rc) return rc;
@@ -612,13 +629,13 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
         }
     }
     if (rest_pending) ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0));
+    if (n_pad > GP_NB)
+        diag_copy_kernel<<<unsigned(n_pad / GP_NB - 1), 256, 0, stream>>>(Dblocks, L, n_pad);
     // W = L^-1 (and U = W^T) by recursive doubling over diagonal blocks:
     //   [[L11, 0], [L21, L22]]^-1 = [[W11, 0], [-W22 L21 W11, W22]]
     ELFI_CUDA_OK(cudaMemsetAsync(W, 0, size_t(n_pad) * n_pad * 8, stream));
     ELFI_CUDA_OK(cudaMemsetAsync(U, 0, size_t(n_pad) * n_pad * 8, stream));
     trtri_diag_kernel<<<unsigned(n_pad / GP_NB), 64, 0, stream>>>(L, W, U, n_pad);
-    double* T = static_cast<double*>(ctx_scratch(ctx, size_t(n_pad) * n_pad * 8 + 256));
-    if (!T) return ELFI_B200_ERR_NOMEM;
     for (int64_t s = GP_NB; s < n_pad; s *= 2) {
         // pairs (top block [o, o+s), bottom block [o+s, min(o+2s, n_pad))), o = pi * 2s: all full
         // pairs of a level go out as ONE batched launch per product (grid.z = pair, the operands

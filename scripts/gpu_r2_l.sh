@@ -1,7 +1,8 @@
 #!/bin/bash
 # round 2, call L (1 GPU): GP fit after the register factorisation + look-ahead: parity, timing, launch list
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gp_gpu.py tests/test_bolfi_gpu.py -m gpu -q 2>&1 | tail -4
+timeout 60 python scripts/debug_gp_fit.py 2>&1 | grep "max err"
+timeout 600 python -m pytest tests/test_gp_gpu.py tests/test_bolfi_gpu.py -m gpu -q 2>&1 | tail -6
 timeout 300 python scripts/bench_kernels.py > gpurun_out/r2l_bench_kernels.log 2>&1; grep -E "K10|K12|rank-1" gpurun_out/r2l_bench_kernels.log | cut -c1-200
 ELFI_B200_GP_LOOKAHEAD=0 timeout 300 python scripts/bench_kernels.py > gpurun_out/r2l_bench_kernels_nolook.log 2>&1; grep -E "K10" gpurun_out/r2l_bench_kernels_nolook.log | cut -c1-200
 timeout 120 python scripts/bench_sort_inputs.py 2>&1 | tail -6
