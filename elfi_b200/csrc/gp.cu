@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(128)
 potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
                         int* __restrict__ info, double* __restrict__ Dout) {
     __shared__ double l[GP_NB][GP_NB + 1];
+    __shared__ double dinv[GP_NB];          // 1 / l_jj
     const int tid = threadIdx.x;
     for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
         const int r = idx / GP_NB, c = idx % GP_NB;
@@ -248,22 +249,27 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
         // barrier + shared-memory latency; this one ~10 us).  j is a compile-time constant in
         // the unrolled loop, so every register index is static.
         __shared__ double colj[GP_NB];
-        __shared__ double piv_s;
+        __shared__ double piv_inv;
         const int r = tid >> 1, q = tid & 1;
         double a[GP_NB / 2];
 #pragma unroll
         for (int cc = 0; cc < GP_NB / 2; ++cc) a[cc] = l[r][2 * cc + q];
 #pragma unroll
         for (int j = 0; j < GP_NB; ++j) {
+            // one reciprocal square root per column (by the pivot owner); every other thread
+            // multiplies -- fp64 sqrt and division are ~50-instruction sequences and used to sit
+            // on the critical path of all 64 steps (and of the 64 steps of the panel solve below)
             if (r == j && q == (j & 1)) {
                 const double d = a[j >> 1];
                 if (!(d > 0.0) && blockIdx.x == 0) atomicExch(info, int(k + j + 1));
-                a[j >> 1] = sqrt(d);
-                piv_s = a[j >> 1];
+                const double inv = rsqrt(d);
+                a[j >> 1] = d * inv;
+                piv_inv = inv;
+                dinv[j] = inv;
             }
             __syncthreads();
             if (q == (j & 1) && r > j) {
-                a[j >> 1] = a[j >> 1] / piv_s;
+                a[j >> 1] = a[j >> 1] * piv_inv;
                 colj[r] = a[j >> 1];
             }
             __syncthreads();
@@ -293,7 +299,7 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
     // columns -- 63 - c INDEPENDENT FMAs per step instead of one dependent chain of c FMAs
 #pragma unroll
     for (int c = 0; c < GP_NB; ++c) {
-        x[c] = x[c] / l[c][c];
+        x[c] = x[c] * dinv[c];
 #pragma unroll
         for (int c2 = c + 1; c2 < GP_NB; ++c2) x[c2] = fma(-x[c], l[c2][c], x[c2]);
     }
