@@ -52,6 +52,21 @@ def test_reference_rejection_with_device_operators():
     assert np.array_equal(res.discrepancies, g['out_d'])
     assert np.array_equal(res.samples['t1'], g['out_t1'])
     assert np.array_equal(res.samples['t2'], g['out_t2'])
+    # the reference's own SMC (proposals, importance weights, weighted quantile: all reference
+    # host code) on the same device-operator model: every population equals the golden of the
+    # all-host reference run bit for bit
+    gs = load_golden('ma2_smc_thresholds')
+    try:
+        elfi.set_client(bc.Client(devices=[0]))
+        smc = elfi.SMC(m['d'], batch_size=1000, seed=20).sample(150, thresholds=[.6, .3, .15],
+                                                                bar=False)
+    finally:
+        elfi.set_client(old)
+    assert len(smc.populations) == int(gs['n_pops']) and smc.n_sim == int(gs['n_sim'])
+    for i, pop in enumerate(smc.populations):
+        assert np.array_equal(pop.discrepancies, gs['pop{}_out_d'.format(i)])
+        assert np.array_equal(pop.samples['t1'], gs['pop{}_out_t1'.format(i)])
+        assert np.array_equal(pop.weights, gs['pop{}_weights'.format(i)])
     # the stubs alone against SciPy / NumPy
     from scipy.spatial.distance import cdist
     rs = np.random.RandomState(5)
