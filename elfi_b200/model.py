@@ -62,6 +62,10 @@ def observed_name(name):
     return "_{}_observed".format(name)
 
 
+def is_observed_name(name):
+    return isinstance(name, str) and name.startswith('_') and name.endswith('_observed')
+
+
 def is_array(output):
     return hasattr(output, 'shape') and output.ndim > 0
 
@@ -425,6 +429,12 @@ def execute_batch(model, outputs, context, batch_index, with_values=None, accept
     for node, attr in net.nodes(data=True):
         if 'output' in attr and node not in values:
             values[node] = attr['output']
+    # observed twins are deterministic functions of the observed data (checked at compile time):
+    # computed in the first batch of an inference, reused by the following ones (the reference
+    # recomputes them per batch; here that would be kernel launches and a D2H per batch)
+    obs_cache = context.caches.setdefault('observed', {}).setdefault(id(net), {})
+    for node, out in obs_cache.items():
+        values.setdefault(node, out)
 
     # ---- which nodes must run: ancestors of the outputs not cut off by a known value
     needed = [o for o in outputs if o not in values]
@@ -448,6 +458,8 @@ def execute_batch(model, outputs, context, batch_index, with_values=None, accept
             extras[('accepted', node)] = out.accepted
             out = out.value
         values[node] = out
+        if is_observed_name(node) and compiled is not None:
+            obs_cache[node] = out
     result = {k: values[k] for k in outputs}
     result.update(extras)
     return result
@@ -696,9 +708,19 @@ def _stack_summaries(summaries):
     return torch.cat(cols, dim=1)
 
 
+_OBSERVED_ROWS = {}     # id(observed tuple) -> (the tuple, stacked host row): one D2H per inference
+
+
 def _stack_observed(observed):
+    hit = _OBSERVED_ROWS.get(id(observed))
+    if hit is not None and hit[0] is observed:
+        return hit[1]
     obs = [np.atleast_2d(dev.to_host(o)) for o in observed]
-    return np.concatenate(obs, axis=1).astype(np.float64)
+    row = np.concatenate(obs, axis=1).astype(np.float64)
+    if len(_OBSERVED_ROWS) > 64:
+        _OBSERVED_ROWS.clear()
+    _OBSERVED_ROWS[id(observed)] = (observed, row)
+    return row
 
 
 def device_euclidean_discrepancy(*summaries, observed, w=None, accept=None):
