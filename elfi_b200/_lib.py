@@ -23,6 +23,7 @@ SIGNATURES = {
     'elfi_b200_ctx_create': [c_int, ctypes.POINTER(c_ptr)],
     'elfi_b200_ctx_destroy': [c_ptr],
     'elfi_b200_ctx_sm_count': [c_ptr],
+    'elfi_b200_allgather_particles': [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr],
     'elfi_b200_dist_euclid_thr_f64': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,
                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'elfi_b200_dist_euclid_thr_dev_f64': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64,

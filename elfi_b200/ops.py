@@ -360,6 +360,32 @@ class CandidateBuffer:
         return take_rows(self.rows, perm[:min(n, count)]), count, dropped
 
 
+def allgather_particles(blocks):
+    """Single-process multi-GPU all-gather (elfi_b200_allgather_particles): `blocks` = one
+    (rows, width) fp64 CUDA tensor per GPU (equal shapes, each on its own device); returns one
+    (len(blocks) * rows, width) tensor per GPU holding the blocks in list order.  The copies are
+    enqueued on each device's current stream."""
+    n = len(blocks)
+    blocks = [b.contiguous() for b in blocks]
+    rows = blocks[0].shape[0]
+    width = int(np.prod(blocks[0].shape[1:])) if blocks[0].dim() > 1 else 1
+    if any(tuple(b.shape) != tuple(blocks[0].shape) or b.dtype != torch.float64 for b in blocks):
+        raise ValueError('blocks must be fp64 tensors of equal shape')
+    outs, streams, ctxs = [], [], []
+    for b in blocks:
+        with torch.cuda.device(b.device):
+            outs.append(torch.empty((n * rows,) + tuple(b.shape[1:]), dtype=torch.float64,
+                                    device=b.device))
+            streams.append(torch.cuda.current_stream(b.device).cuda_stream)
+            ctxs.append(dev.context(b.device).value)
+    arr = ctypes.c_void_p * n
+    _lib.call('elfi_b200_allgather_particles', ctypes.cast(arr(*ctxs), ctypes.c_void_p), n,
+              ctypes.cast(arr(*[b.data_ptr() for b in blocks]), ctypes.c_void_p), rows, width,
+              ctypes.cast(arr(*[o.data_ptr() for o in outs]), ctypes.c_void_p),
+              ctypes.cast(arr(*streams), ctypes.c_void_p))
+    return outs
+
+
 def weighted_sample_quantile(x, alpha, weights=None):
     """elfi/methods/utils.py:379-411 on the device; returns a Python float."""
     x = dev.to_device(x).reshape(-1)

@@ -50,6 +50,20 @@ int elfi_b200_ctx_destroy(elfi_b200_ctx* ctx);
 /* Number of SMs of the context's device (grid sizing is a multiple of this). */
 int elfi_b200_ctx_sm_count(const elfi_b200_ctx* ctx);
 
+/* ---- single-process multi-GPU exchange ----------------------------------------------------
+ * The per-generation all-gather of accepted particles / weights (the
+ * reference merges the batches of its workers in the master, samplers.py:140-237) for a process
+ * that drives several GPUs itself (one context per GPU, e.g. the thread-per-GPU client): GPU g
+ * contributes send[g] (rows x width doubles in ITS memory) and receives the context-ordered
+ * concatenation (n_ctx * rows x width) in recv[g].  ctxs / send / recv / streams are HOST arrays
+ * of n_ctx entries; streams[g] is the stream of GPU g on which send[g] was produced and on which
+ * recv[g] is consumed afterwards (the call only enqueues copies and event waits).  Copies are
+ * peer-to-peer (NVLink when peer access can be enabled, otherwise staged by the driver).
+ * One-process-per-GPU runs use torch.distributed / NCCL instead. */
+int elfi_b200_allgather_particles(elfi_b200_ctx* const* ctxs, int64_t n_ctx,
+                                  const double* const* send, int64_t rows, int64_t width,
+                                  double* const* recv, void* const* streams);
+
 /* ---- distance + acceptance ------------------------------------------------------------
  * Replaces, for the Euclidean family, the body of
  *   elfi/model/utils.py:37-52        distance_as_discrepancy  (column_stack + dist + flatten)
