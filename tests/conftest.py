@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 # GPU run order: kernel-level parity first (a failure there explains every failure above it),
 # then operators inside the model graph, samplers, throughput mode, pools, BOLFI, multi-GPU.
-_GPU_ORDER = ['test_distance_gpu', 'test_summaries_gpu', 'test_select_gpu', 'test_smc_gpu',
+_GPU_ORDER = ['test_distance_gpu', 'test_summaries_gpu', 'test_select_gpu', 'test_merge_gpu', 'test_smc_gpu',
               'test_kliep_gpu', 'test_gp_gpu', 'test_model_gpu', 'test_samplers_gpu',
               'test_throughput_gpu', 'test_store_gpu', 'test_bolfi_gpu', 'test_multigpu_gpu']
 

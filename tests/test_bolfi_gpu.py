@@ -5,7 +5,7 @@ import pytest
 
 import bolfi_cases as cases
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_device_run]
+pytestmark = pytest.mark.gpu
 
 
 def test_posterior_matches_reference():

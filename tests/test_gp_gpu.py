@@ -150,7 +150,6 @@ def test_bolfi_ma2_smoke():
     assert lp[0] > lp[1]
 
 
-@pytest.mark.first_device_run
 def test_bolfi_ma2_reference_bounds():
     """The reference's own BOLFI test (tests/functional/test_inference.py:136-190) at its own
     size and error bound: 300 evidence points, |x_min - true| < 0.2 for both parameters,

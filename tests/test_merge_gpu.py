@@ -4,7 +4,7 @@ import pytest
 
 import merge_cases as cases
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_device_run]
+pytestmark = pytest.mark.gpu
 
 
 def test_device_thresholds_and_append():

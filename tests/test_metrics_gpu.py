@@ -4,7 +4,7 @@ import pytest
 
 import metric_cases as cases
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_device_run]
+pytestmark = pytest.mark.gpu
 
 
 def test_operator_matches_scipy():

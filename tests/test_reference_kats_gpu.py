@@ -4,7 +4,7 @@ import pytest
 
 import test_reference_kats_cpu_double as _kats
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_device_run]
+pytestmark = pytest.mark.gpu
 
 test_weighted_sample_quantile = _kats.test_weighted_sample_quantile
 test_weighted_var = _kats.test_weighted_var

@@ -46,7 +46,6 @@ def test_gm_logpdf_vs_oracle(p):
     np.testing.assert_allclose(got[finite], ref[finite], rtol=0, atol=1e-7)
 
 
-@pytest.mark.first_device_run
 @pytest.mark.parametrize('p', [1, 2, 3, 4])
 def test_gm_logpdf_mixed_vs_oracle(p):
     """elfi_b200_gm_logpdf_mixed_f64 (2^f from the fp32 special-function unit; throughput mode):
@@ -95,7 +94,6 @@ def test_colmoments(B, D):
     np.testing.assert_allclose(np.sqrt(m2 / B), S.std(axis=0), rtol=1e-10)
 
 
-@pytest.mark.first_device_run
 @pytest.mark.parametrize('B,D,K', [(4096, 256, 1), (100003, 33, 3), (5000, 128, 5), (31, 16, 2),
                                    (70000, 256, 8), (1000, 2, 2), (2048, 40, 17)])
 def test_fused_distance_and_colmoments(B, D, K):

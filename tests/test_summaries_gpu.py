@@ -81,7 +81,6 @@ def test_full_size_ma2_native():
     assert np.array_equal(S[rows, 1].cpu().numpy(), o.autocov(xs, 2))
 
 
-@pytest.mark.first_device_run
 def test_signed_zero_rows_match_numpy_bits():
     """All-zero / negative-zero rows: the sign of the result follows NumPy's r[k] = a[k] start."""
     from elfi_b200 import ops
@@ -99,7 +98,6 @@ def test_signed_zero_rows_match_numpy_bits():
     assert np.array_equal(mv.view(np.int64), refmv.view(np.int64))
 
 
-@pytest.mark.first_device_run
 @pytest.mark.parametrize('B,n', [(40, 7688), (24, 7696), (16, 8192)])
 def test_long_rows_around_the_stack_bound(B, n):
     """7688 terms is the longest run the 6-level pairwise stack of the row-stream kernels holds;

@@ -171,7 +171,6 @@ def _gnk_q(prm, z, c=0.8):
     return A + B * (1 + c * ((1 - np.exp(-g * z)) / (1 + np.exp(-g * z)))) * (1 + z**2)**k * z
 
 
-@pytest.mark.first_device_run
 def test_gnk_simulator_distribution_and_streams():
     """sim_gnk draws follow the g-and-k quantile function (gnk.py:60-66): the fraction of draws
     below Q(Phi^-1(p)) is p; rows are a pure function of (seed, offset + row, column)."""
@@ -203,7 +202,6 @@ def test_gnk_simulator_distribution_and_streams():
     assert np.array_equal(Y5[1::2], Y[1::2])
 
 
-@pytest.mark.first_device_run
 def test_logprior_box_matches_scipy():
     from elfi_b200 import ops
     rs = np.random.RandomState(4)
@@ -224,7 +222,6 @@ def test_logprior_box_matches_scipy():
     np.testing.assert_allclose(got2[np.isfinite(ref2)], ref2[np.isfinite(ref2)], rtol=1e-14)
 
 
-@pytest.mark.first_device_run
 def test_gnk_adaptive_distance_smc_throughput_mode_statistics():
     """config #5's model with priors, simulator and proposals on the device vs the host-RNG path
     (statistical parity: the two use different random streams)."""
