@@ -69,7 +69,13 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     const int grp = lane >> 2, tig = lane & 3;
-    const int64_t row0 = int64_t(blockIdx.y) * GM_BM, col0 = int64_t(blockIdx.x) * GM_BN;
+    // mode 2 (triangular K-range): a tile's work grows with its column, and CTAs are dispatched
+    // in blockIdx order -- hand out the long-K tiles first so that the last wave is the short ones
+    // (column tile = slow index, longest first; all row tiles of one column tile back to back)
+    const int64_t lin = int64_t(blockIdx.y) * gridDim.x + blockIdx.x;
+    const int64_t bx = g.mode == 2 ? int64_t(gridDim.x) - 1 - lin / gridDim.y : int64_t(blockIdx.x);
+    const int64_t by = g.mode == 2 ? lin % gridDim.y : int64_t(blockIdx.y);
+    const int64_t row0 = by * GM_BM, col0 = bx * GM_BN;
     if (g.mode == 1 && col0 > row0 + GM_BM - 1) return;
     const int64_t bz = blockIdx.z;
     const double* A = g.A + bz * g.strideA;
