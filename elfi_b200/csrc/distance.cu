@@ -476,6 +476,7 @@ int launch_dist(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int
 // one column (K = 1).  Zero padding (TMA fill, obs pad) adds |0|, 0^2, 0^p or max(acc, 0): no-ops.
 struct MetricParams : DistParams {
     double pexp;       // Minkowski exponent
+    const double* V;   // (D) component variances of 'seuclidean', else nullptr
 };
 
 template <int METRIC>
@@ -583,6 +584,134 @@ static int launch_metric(elfi_b200_ctx* ctx, int metric, double pexp, const doub
         default:
             return launch_metric_t<ELFI_B200_METRIC_MINKOWSKI>(ctx, S, ldS, B, D, p, stream);
     }
+}
+
+// 'seuclidean' (cdist(..., 'seuclidean', V=V)): SciPy 1.18's compiled loop keeps TWO running sums,
+// terms (d*d)/V_j with even j in one and odd j in the other over the first D - D%2 columns, adds
+// the two, then adds the last term when D is odd, then takes the root (probed against the
+// installed SciPy for D = 1..69, 127..129, 255, 1000: bit-identical; tests/test_oracle.py pins
+// it).  The division is IEEE (__ddiv_rn), so a weight row 1/V through WeightedConsumer differs in
+// the last bits.  Padding: TMA zero-fills columns >= D, obs pads with 0 and V with 1, so a padded
+// term is (0*0)/1 = +0, a no-op on the non-negative sums.
+struct SeuclidTerm {
+    double even, odd, last;
+    int j_last;   // D - 1 when D is odd (that term is added after the two sums meet), else -1
+    __device__ __forceinline__ void begin(int D) {
+        even = 0.0;
+        odd = 0.0;
+        last = 0.0;
+        j_last = (D & 1) ? D - 1 : -1;
+    }
+    // j0 is even; (t0, t1) are the terms of columns j0 and j0 + 1
+    __device__ __forceinline__ void pair(int j0, double t0, double t1) {
+        if (j0 == j_last) {
+            last = t0;
+        } else {
+            even = __dadd_rn(even, t0);
+            odd = __dadd_rn(odd, t1);
+        }
+    }
+    __device__ __forceinline__ double value() const {
+        const double s = __dadd_rn(even, odd);
+        return sqrt(j_last >= 0 ? __dadd_rn(s, last) : s);
+    }
+};
+
+__device__ __forceinline__ double seuclid_term(double x, double o, double v) {
+    const double d = __dsub_rn(x, o);
+    return __ddiv_rn(__dmul_rn(d, d), v);
+}
+
+__device__ __forceinline__ void seuclid_finish(const MetricParams& p, double dist, int64_t row,
+                                               int64_t B, int lane, bool whole_warp) {
+    bool ok = row < B;
+    if (ok) {
+        p.d_out[row] = dist;
+        if (p.has_thr) ok = dist <= p.threshold(0);
+    }
+    if (p.mask != nullptr) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok && p.has_thr);
+        if (lane == 0 && (whole_warp || (row - lane) < B)) p.mask[row >> 5] = bits;
+    }
+}
+
+struct SeuclidConsumer {
+    typedef MetricParams Params;
+    static constexpr int PASSES = 1;
+    const Params& p;
+    const double* obs_s;
+    const double* v_s;
+    int D;
+    SeuclidTerm acc;
+
+    static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
+        const int Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+        double* obs_s = reinterpret_cast<double*>(aux);
+        for (int j = threadIdx.x; j < Dp; j += blockDim.x) {
+            obs_s[j] = j < D ? p.obs[j] : 0.0;
+            obs_s[Dp + j] = j < D ? p.V[j] : 1.0;
+        }
+    }
+    __device__ SeuclidConsumer(const Params& p_, const uint8_t* aux, int D_, int)
+        : p(p_), obs_s(reinterpret_cast<const double*>(aux)), D(D_) {
+        v_s = obs_s + ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+        acc.begin(D);
+    }
+    __device__ __forceinline__ void begin_row() { acc.begin(D); }
+    __device__ __forceinline__ void consume(int, int cg, const uint8_t* box_row, int sw) {
+        const double2* o = reinterpret_cast<const double2*>(obs_s + cg * RS_BOX_COLS);
+        const double2* vv = reinterpret_cast<const double2*>(v_s + cg * RS_BOX_COLS);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double2 x = *reinterpret_cast<const double2*>(box_row + ((c ^ sw) << 4));
+            const double2 ob = o[c];
+            const double2 v = vv[c];
+            acc.pair(cg * RS_BOX_COLS + 2 * c, seuclid_term(x.x, ob.x, v.x),
+                     seuclid_term(x.y, ob.y, v.y));
+        }
+    }
+    __device__ __forceinline__ void end_row(int64_t row, int64_t B, int lane) {
+        seuclid_finish(p, acc.value(), row, B, lane, true);
+    }
+};
+
+__global__ void __launch_bounds__(256)
+seuclid_direct_kernel(const double* __restrict__ S, int64_t ld, int64_t B, int D, MetricParams p) {
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    SeuclidTerm acc;
+    acc.begin(D);
+    if (row < B) {
+        const double* r = S + row * ld;
+        for (int j = 0; j < D; j += 2) {
+            const double t0 = seuclid_term(__ldg(r + j), __ldg(p.obs + j), __ldg(p.V + j));
+            const double t1 = j + 1 < D
+                ? seuclid_term(__ldg(r + j + 1), __ldg(p.obs + j + 1), __ldg(p.V + j + 1)) : 0.0;
+            acc.pair(j, t0, t1);
+        }
+    }
+    seuclid_finish(p, acc.value(), row, B, threadIdx.x & 31, false);
+}
+
+static int launch_seuclid(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B, int64_t D,
+                          const double* obs, const double* V, const double* thr_host,
+                          double* d_out, uint32_t* mask, cudaStream_t stream) {
+    MetricParams p;
+    memset(&p, 0, sizeof(p));
+    p.obs = obs;
+    p.V = V;
+    p.d_out = d_out;
+    p.mask = mask;
+    p.K = 1;
+    p.has_thr = thr_host != nullptr;
+    if (thr_host) p.thr[0] = thr_host[0];
+    if (B == 0) return ELFI_B200_OK;
+    const int64_t Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    const size_t aux = size_t(Dp) * 8 * 2;
+    if (D >= RS_BOX_COLS && tma_compatible(S, ldS) && rs_pick_stages(ctx->smem_optin, aux) >= 2)
+        return rowstream_launch<SeuclidConsumer>(ctx, S, ldS, B, D, aux, p, stream);
+    seuclid_direct_kernel<<<unsigned((B + 255) / 256), 256, 0, stream>>>(S, ldS, B, int(D), p);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
 }
 
 static int check_dist_args(const void* S, int64_t ldS, int64_t B, int64_t D, const void* obs,
@@ -818,6 +947,30 @@ int elfi_b200_dist_metric_thr_f64(elfi_b200_ctx* ctx, int32_t metric, double pex
         if (!mask) return ELFI_B200_ERR_NOMEM;
     }
     rc = launch_metric(ctx, int(metric), pexp, S, ldS, B, D, obs, thr_host, d_out, mask, stream);
+    if (rc) return rc;
+    if (thr_host != nullptr && (acc_idx != nullptr || n_acc != nullptr))
+        return launch_compact_mask(mask, B, acc_idx, n_acc, stream);
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_dist_seuclidean_thr_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                      int64_t D, const double* obs, const double* V,
+                                      const double* thr_host, double* d_out, int32_t* acc_idx,
+                                      int64_t* n_acc, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "dist_seuclidean: ctx is NULL");
+    ELFI_REQUIRE(V != nullptr, "dist_seuclidean: V is NULL");
+    int rc = check_dist_args(S, ldS, B, D, obs, nullptr, 1, thr_host, acc_idx);
+    if (rc) return rc;
+    ELFI_REQUIRE(B == 0 || d_out != nullptr, "dist_seuclidean: d_out is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    uint32_t* mask = nullptr;
+    if (thr_host != nullptr) {
+        mask = static_cast<uint32_t*>(ctx_scratch(ctx, size_t((B + 31) / 32) * 4 + 256));
+        if (!mask) return ELFI_B200_ERR_NOMEM;
+    }
+    rc = launch_seuclid(ctx, S, ldS, B, D, obs, V, thr_host, d_out, mask, stream);
     if (rc) return rc;
     if (thr_host != nullptr && (acc_idx != nullptr || n_acc != nullptr))
         return launch_compact_mask(mask, B, acc_idx, n_acc, stream);

@@ -747,11 +747,23 @@ def device_metric_discrepancy(metric, *summaries, observed, p=2.0, accept=None):
     return AcceptedOutput(d, idx) if accept is not None else d
 
 
+def device_seuclidean_discrepancy(*summaries, observed, V, accept=None):
+    """distance_as_discrepancy for cdist's 'seuclidean' (V = component variances)."""
+    X = _stack_summaries(summaries)
+    obs = _stack_observed(observed)
+    if obs.shape[0] != 1:
+        raise ValueError('observed summaries must form a single row')
+    thr = None if accept is None else np.atleast_1d(dev.to_host(accept))
+    d, idx = ops.dist_seuclidean(X, obs, V, threshold=thr)
+    return AcceptedOutput(d, idx) if accept is not None else d
+
+
 def host_distance_as_discrepancy(dist, *summaries, observed):
     """Generic path for metrics without a CUDA kernel: explicit error, never a silent fallback."""
     raise NotImplementedError(
         "elfi_b200.Distance implements the Euclidean family on the device "
-        "('euclidean', 'seuclidean' via w=1/V, weighted Euclidean via w=). Metric {!r} has no "
+        "('euclidean' with or without w=, 'seuclidean' with V=) and 'sqeuclidean', 'cityblock', "
+        "'chebyshev', 'minkowski' (p=) unweighted. Metric {!r} with these keywords has no "
         "CUDA kernel; use elfi_b200.Discrepancy with your own callable.".format(dist))
 
 
@@ -774,8 +786,8 @@ class Distance(Discrepancy):
                 op = partial(device_euclidean_discrepancy, w=cd.get('w'))
                 state['_uses_accept'] = True
             elif distance == 'seuclidean' and set(cd) == {'V'}:
-                op = partial(device_euclidean_discrepancy,
-                             w=1.0 / np.asarray(cd['V'], dtype=np.float64))
+                op = partial(device_seuclidean_discrepancy,
+                             V=np.asarray(cd['V'], dtype=np.float64))
                 state['_uses_accept'] = True
             elif distance in DEVICE_METRICS and not (set(cd) - {'p'}) and \
                     (distance == 'minkowski' or not cd):

@@ -157,6 +157,41 @@ def dist_metric(S, obs, metric, p=2.0, threshold=None, want_indices=True):
     return d, acc_idx
 
 
+def dist_seuclidean(S, obs, V, threshold=None, want_indices=True):
+    """cdist(S, obs, 'seuclidean', V=V) + acceptance on the device, bit-identical to SciPy (two
+    running sums and an IEEE division per term; elfi/model/elfi_model.py:1016-1037 forwards the
+    metric string and V to cdist).  Returns (d (B,), acc_idx or None)."""
+    S = _matrix(S)
+    B, D = S.shape
+    obs_t = dev.to_device(obs).reshape(-1)
+    if obs_t.numel() != D:
+        raise ValueError('XA and XB must have the same number of columns '
+                         '(i.e. feature dimension.)')
+    V = np.ascontiguousarray(np.asarray(V, dtype=np.float64).reshape(-1))
+    if V.shape[0] != D:
+        raise ValueError('Variance vector V must be of the same dimension as the vectors on '
+                         'which the distances are computed.')
+    V_t = dev.to_device(V)
+    thr = None
+    if threshold is not None:
+        thr = np.ascontiguousarray(np.atleast_1d(threshold), dtype=np.float64)
+        if thr.shape[0] != 1:
+            raise ValueError('need one threshold per distance column ({} != 1)'.format(thr.shape[0]))
+    d = dev.empty((B,))
+    acc_idx = n_acc = None
+    if thr is not None:
+        n_acc = dev.zeros((1,), dtype=torch.int64)
+        if want_indices:
+            acc_idx = dev.empty((max(B, 1),), dtype=torch.int32)
+    _lib.call('elfi_b200_dist_seuclidean_thr_f64', dev.context(), dev.ptr(S),
+              S.stride(0) if B > 1 else D, B, D, dev.ptr(obs_t), dev.ptr(V_t), dev.ptr(thr),
+              dev.ptr(d), dev.ptr(acc_idx), dev.ptr(n_acc), dev.stream_ptr())
+    if thr is not None:
+        n = int(n_acc.item())
+        acc_idx = acc_idx[:n] if want_indices else n
+    return d, acc_idx
+
+
 def dist_euclid_host(S, obs, w=None, thresholds=None, return_distances=True):
     """Host-buffer variant (elfi_b200_dist_euclid_thr_f64_host): numpy in, numpy out."""
     S = np.asarray(S, dtype=np.float64)

@@ -137,6 +137,17 @@ int elfi_b200_dist_metric_thr_f64(elfi_b200_ctx* ctx, int32_t metric, double pex
                                   const double* thr_host, double* d_out, int32_t* acc_idx,
                                   int64_t* n_acc, void* stream);
 
+/* cdist(S, obs, 'seuclidean', V=V) (elfi/model/elfi_model.py:1016-1037 with the V keyword of the
+ * Distance docstring, elfi_model.py:996-1003): d_i = sqrt(sum_j (S_ij - obs_j)^2 / V_j) in the
+ * summation order of SciPy's compiled loop -- two running sums over the even and the odd columns of
+ * the first D - D%2 columns, their sum, then the last term when D is odd -- with an IEEE division
+ * per term, so the result is bit-identical to cdist.  V (D) device, strictly positive.  Other
+ * arguments and the acceptance outputs as for elfi_b200_dist_metric_thr_f64. */
+int elfi_b200_dist_seuclidean_thr_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
+                                      int64_t D, const double* obs, const double* V,
+                                      const double* thr_host, double* d_out, int32_t* acc_idx,
+                                      int64_t* n_acc, void* stream);
+
 /* ---- summary statistics ----------------------------------------------------------------
  * Row-wise summaries with NumPy's pairwise summation order (bit-identical results).
  *

@@ -108,6 +108,31 @@ void oracle_cdist_metric(const double *S, int64_t ld, int64_t B, int64_t D, cons
     }
 }
 
+/* cdist(S, obs, 'seuclidean', V=V) as SciPy 1.18's compiled loop evaluates it: terms (d*d)/V_j,
+ * even columns in one running sum and odd columns in another over the first D - D%2 columns,
+ * the two added, then the last term when D is odd (pinned bit for bit against the installed SciPy
+ * by tests/test_oracle.py; a single left-to-right sum differs in the last bits). */
+void oracle_cdist_seuclidean(const double *S, int64_t ld, int64_t B, int64_t D, const double *obs,
+                             const double *V, double *out)
+{
+    const int64_t D2 = D - D % 2;
+    for (int64_t i = 0; i < B; ++i) {
+        const double *x = S + i * ld;
+        double even = 0.0, odd = 0.0;
+        for (int64_t j = 0; j < D2; j += 2) {
+            double d0 = x[j] - obs[j], d1 = x[j + 1] - obs[j + 1];
+            even += (d0 * d0) / V[j];
+            odd += (d1 * d1) / V[j + 1];
+        }
+        double s = even + odd;
+        if (D2 < D) {
+            double d = x[D2] - obs[D2];
+            s += (d * d) / V[D2];
+        }
+        out[i] = sqrt(s);
+    }
+}
+
 /* --------------------------------------------------------------------------
  * NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
  * DOUBLE_pairwise_sum), used by every np.sum/np.mean/np.var along a contiguous

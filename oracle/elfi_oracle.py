@@ -103,6 +103,22 @@ def cdist_metric(S, obs, metric, p=2.0):
     return out
 
 
+def cdist_seuclidean(S, obs, V):
+    """scipy.spatial.distance.cdist(S, obs(1,D), 'seuclidean', V=V) flattened to (B,): the
+    Distance('seuclidean', ..., V=) node of elfi/model/elfi_model.py:1016-1037, in the two-sum
+    order of SciPy's compiled loop (oracle/c/elfi_oracle.c)."""
+    S = _c64(S)
+    if S.ndim == 1:
+        S = S[:, None]
+    obs = _c64(obs).reshape(-1)
+    V = _c64(V).reshape(-1)
+    assert obs.shape[0] == S.shape[1] == V.shape[0]
+    out = np.empty(len(S), dtype=np.float64)
+    _lib().oracle_cdist_seuclidean(_p(S), ctypes.c_int64(S.shape[1]), ctypes.c_int64(len(S)),
+                                   ctypes.c_int64(S.shape[1]), _p(obs), _p(V), _p(out))
+    return out
+
+
 def nested_distance(S, obs, weights, threads=1):
     """AdaptiveDistance.nested_distance (elfi/model/elfi_model.py:1135-1151).
 

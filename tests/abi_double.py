@@ -161,6 +161,21 @@ def dist_metric_thr_f64(ctx, metric, pexp, S, ldS, B, D, obs, thr_host, d_out, a
             _vec(n_acc, 1, np.int64)[0] = len(idx)
 
 
+def dist_seuclidean_thr_f64(ctx, S, ldS, B, D, obs, V, thr_host, d_out, acc_idx, n_acc, stream):
+    _require(_addr(V), 'dist_seuclidean: V is NULL')
+    d = o.cdist_seuclidean(np.ascontiguousarray(_mat(S, B, D, ldS)), _vec(obs, D), _vec(V, D)) \
+        if B else np.empty(0)
+    if B:
+        _vec(d_out, B)[:] = d
+    thr = _vec(thr_host, 1)
+    if thr is not None:
+        idx = o.accept_indices(d, thr) if B else np.empty(0, dtype=np.int32)
+        if _addr(acc_idx):
+            _vec(acc_idx, max(B, 1), np.int32)[:len(idx)] = idx
+        if _addr(n_acc):
+            _vec(n_acc, 1, np.int64)[0] = len(idx)
+
+
 def summary_autocov_f64(ctx, X, ldX, B, n, lags_host, nlags, out, ld_out, stream):
     X = _mat(X, B, n, ldX)
     lags = _vec(lags_host, nlags, np.int32)
@@ -496,7 +511,7 @@ def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
 
 
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
-    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, rejection_batch_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, summary_autocov_f64, summary_meanvar_f64,
+    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, rejection_batch_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, dist_seuclidean_thr_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, gm_logpdf_mixed_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,

@@ -12,3 +12,11 @@ def test_operator_matches_scipy():
 
 def test_distance_nodes_in_a_model():
     cases.case_distance_nodes_in_a_model()
+
+
+def test_seuclidean_matches_scipy():
+    cases.case_seuclidean_matches_scipy(exact=True)
+
+
+def test_seuclidean_node_in_a_model():
+    cases.case_seuclidean_node_in_a_model()

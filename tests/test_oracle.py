@@ -185,3 +185,28 @@ def test_other_cdist_metrics_are_sequential(metric, kw):
             np.testing.assert_allclose(got, ref, rtol=2e-16 * 8)
         else:
             assert np.array_equal(got, ref), (metric, B, D)
+
+
+def test_seuclidean_two_sum_order():
+    """SciPy's 'seuclidean' loop is NOT one left-to-right sum: even and odd columns accumulate
+    separately, meet, then the odd-D tail is added.  The C restatement (and the device kernel of
+    elfi_b200_dist_seuclidean_thr_f64 that follows it) is bit-identical to the installed SciPy;
+    a sequential sum and the w = 1/V route are not."""
+    from scipy.spatial.distance import cdist
+    rs = np.random.RandomState(5)
+    sequential_differs = False
+    for D in list(range(1, 41)) + [63, 64, 65, 127, 128, 129, 255, 1000]:
+        B = 200
+        S = rs.randn(B, D) * rs.uniform(0.1, 100)
+        obs = rs.randn(1, D)
+        V = rs.uniform(0.01, 50, D)
+        ref = cdist(S, obs, 'seuclidean', V=V).ravel()
+        assert np.array_equal(o.cdist_seuclidean(S, obs, V), ref), D
+        if D >= 16 and not np.array_equal(o.cdist_euclid(S, obs, w=1.0 / V), ref):
+            sequential_differs = True
+    assert sequential_differs
+    # several observed rows use the same loop per pair
+    S, O, V = rs.randn(50, 9), rs.randn(3, 9), rs.uniform(0.1, 3, 9)
+    ref = cdist(S, O, 'seuclidean', V=V)
+    for k in range(3):
+        assert np.array_equal(o.cdist_seuclidean(S, O[k:k + 1], V), ref[:, k])
