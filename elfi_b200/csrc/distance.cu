@@ -10,6 +10,8 @@
 // Roofline: HBM.  The fp64 pipe does 3 (unweighted) or 4 (weighted) issue slots per element,
 // ~20 % of the memory time at D=128 on B200, so the kernel is bandwidth bound as long as
 // the TMA pipeline keeps >= ~45 KiB in flight per SM (see rowstream.cuh).
+#include <cstdlib>
+
 #include "rowstream.cuh"
 
 extern "C" int elfi_b200_colmoments_f64(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
@@ -215,9 +217,9 @@ struct NestedMomentsConsumer : NestedConsumer<KMAX> {
     int64_t row0, nrows;
     int D;
 
-    // aux: obs [Dp] | W [K][Dp] | shift [Dp] | accumulators [RS_WARPS][2][Dp]
-    static __host__ __device__ size_t aux_bytes(int64_t Dp, int64_t K) {
-        return size_t(Dp) * 8 * (1 + K + 1 + 2 * RS_WARPS);
+    // aux: obs [Dp] | W [K][Dp] | shift [Dp] | accumulators [warps][2][Dp]
+    static __host__ __device__ size_t aux_bytes(int64_t Dp, int64_t K, int warps = RS_WARPS) {
+        return size_t(Dp) * 8 * (1 + K + 1 + 2 * warps);
     }
     static __device__ void setup_shared(uint8_t* aux, const Params& p, int D) {
         dist_setup_shared(aux, p, D, true);
@@ -225,7 +227,8 @@ struct NestedMomentsConsumer : NestedConsumer<KMAX> {
         double* shift = reinterpret_cast<double*>(aux) + size_t(1 + p.K) * Dp;
         for (int j = threadIdx.x; j < Dp; j += blockDim.x) shift[j] = j < D ? p.shift_src[j] : 0.0;
         double* acc = shift + Dp;
-        for (int j = threadIdx.x; j < 2 * RS_WARPS * Dp; j += blockDim.x) acc[j] = 0.0;
+        const int warps = blockDim.x >> 5;
+        for (int j = threadIdx.x; j < 2 * warps * Dp; j += blockDim.x) acc[j] = 0.0;
     }
     __device__ NestedMomentsConsumer(const Params& p_, const uint8_t* aux, int D_, int lane)
         : Base(p_, aux, D_, lane), row0(0), nrows(0), D(D_) {
@@ -304,15 +307,39 @@ colmoments_flush_kernel(const double* __restrict__ S, const double* __restrict__
     }
 }
 
+// Warps per CTA of the fused kernel: 12 when the ring still gets >= 3 slots next to the per-warp
+// accumulators (two warps per scheduler leave the fp64 pipe half idle: long dependent chains of
+// K + 2 accumulators per lane), else 8.  Measured at 5e5 x 256: K = 2 0.232 -> 0.214 ms, K = 6
+// 0.297 -> 0.279 ms; 16 warps (128 registers, 2-slot ring) gives the 8-warp time back, and the
+// plain nested kernels do not gain from either.  ELFI_B200_FUSED_WARPS=8 restores 8 (KMAX <= 8).
+template <int KMAX>
+static int fused_moments_warps(elfi_b200_ctx* ctx, int64_t Dp, int64_t K) {
+    int warps = 12;
+    if (const char* e = getenv("ELFI_B200_FUSED_WARPS")) warps = atoi(e);
+    if (KMAX > 8 || warps != 12) return RS_WARPS;
+    const size_t aux = NestedMomentsConsumer<KMAX>::aux_bytes(Dp, K, warps);
+    return rs_pick_stages(ctx->smem_optin, aux, warps) >= 3 ? warps : RS_WARPS;
+}
+
 template <int KMAX>
 static int launch_nested_moments(elfi_b200_ctx* ctx, const double* S, int64_t ldS, int64_t B,
-                                 int64_t D, DistParams p, size_t aux, double* moments,
-                                 cudaStream_t stream) {
+                                 int64_t D, DistParams p, double* moments, cudaStream_t stream) {
+    const int64_t Dp = ((D + RS_BOX_COLS - 1) / RS_BOX_COLS) * RS_BOX_COLS;
+    const int warps = fused_moments_warps<KMAX>(ctx, Dp, p.K);
+    const size_t aux = NestedMomentsConsumer<KMAX>::aux_bytes(Dp, p.K, warps);
     const int64_t ntiles = (B + RS_BOX_ROWS - 1) / RS_BOX_ROWS;
-    int64_t ctas = (ntiles + RS_WARPS - 1) / RS_WARPS;
+    int64_t ctas = (ntiles + warps - 1) / warps;
     if (ctas > ctx->sm_count) ctas = ctx->sm_count;
-    const int64_t nwarps = ctas * RS_WARPS;
-    int rc = rowstream_launch<NestedMomentsConsumer<KMAX>>(ctx, S, ldS, B, D, aux, p, stream);
+    const int64_t nwarps = ctas * warps;
+    int rc;
+    if constexpr (KMAX <= 8) {
+        if (warps == 12)
+            rc = rowstream_launch<NestedMomentsConsumer<KMAX>, 12>(ctx, S, ldS, B, D, aux, p, stream);
+        else
+            rc = rowstream_launch<NestedMomentsConsumer<KMAX>>(ctx, S, ldS, B, D, aux, p, stream);
+    } else {
+        rc = rowstream_launch<NestedMomentsConsumer<KMAX>>(ctx, S, ldS, B, D, aux, p, stream);
+    }
     if (rc) return rc;
     colmoments_flush_kernel<<<unsigned((D + 31) / 32), dim3(32, 32), 0, stream>>>(
         S, p.mom_partial, nwarps, B, D, moments);
@@ -796,7 +823,7 @@ int elfi_b200_dist_euclid_mom_f64(elfi_b200_ctx* ctx, const double* S, int64_t l
     const bool fused = W != nullptr && D >= RS_BOX_COLS && tma_compatible(S, ldS) &&
                        rs_pick_stages(ctx->smem_optin, aux) >= 2;
     const size_t mask_bytes = (size_t((B + 31) / 32) * 4 + 255) & ~size_t(255);
-    const size_t part_bytes = fused ? size_t(ctx->sm_count) * RS_WARPS * 2 * D * 8 : 0;
+    const size_t part_bytes = fused ? size_t(ctx->sm_count) * 16 * 2 * D * 8 : 0;   // <= 16 warps
     uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, mask_bytes + part_bytes + 256));
     if (!base) return ELFI_B200_ERR_NOMEM;
     uint32_t* mask = thr ? reinterpret_cast<uint32_t*>(base) : nullptr;
@@ -823,12 +850,12 @@ int elfi_b200_dist_euclid_mom_f64(elfi_b200_ctx* ctx, const double* S, int64_t l
         for (int k = 0; k < K; ++k) p.thr[k] = thr_host[k];
     p.shift_src = S;
     p.mom_partial = reinterpret_cast<double*>(base + mask_bytes);
-    if (K <= 2) rc = launch_nested_moments<2>(ctx, S, ldS, B, D, p, aux, moments, stream);
-    else if (K <= 4) rc = launch_nested_moments<4>(ctx, S, ldS, B, D, p, aux, moments, stream);
-    else if (K <= 6) rc = launch_nested_moments<6>(ctx, S, ldS, B, D, p, aux, moments, stream);
-    else if (K <= 8) rc = launch_nested_moments<8>(ctx, S, ldS, B, D, p, aux, moments, stream);
-    else if (K <= 16) rc = launch_nested_moments<16>(ctx, S, ldS, B, D, p, aux, moments, stream);
-    else rc = launch_nested_moments<32>(ctx, S, ldS, B, D, p, aux, moments, stream);
+    if (K <= 2) rc = launch_nested_moments<2>(ctx, S, ldS, B, D, p, moments, stream);
+    else if (K <= 4) rc = launch_nested_moments<4>(ctx, S, ldS, B, D, p, moments, stream);
+    else if (K <= 6) rc = launch_nested_moments<6>(ctx, S, ldS, B, D, p, moments, stream);
+    else if (K <= 8) rc = launch_nested_moments<8>(ctx, S, ldS, B, D, p, moments, stream);
+    else if (K <= 16) rc = launch_nested_moments<16>(ctx, S, ldS, B, D, p, moments, stream);
+    else rc = launch_nested_moments<32>(ctx, S, ldS, B, D, p, moments, stream);
     if (rc) return rc;
     if (thr && (acc_idx != nullptr || n_acc != nullptr))
         return launch_compact_mask(mask, B, acc_idx, n_acc, stream);

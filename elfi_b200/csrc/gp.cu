@@ -197,49 +197,53 @@ gp_cov_kernel(const double* __restrict__ Aq, int64_t lda, int64_t na, const doub
 }
 
 // ---- K11: blocked Cholesky (right-looking, panel width 64) ------------------------------------
-// Factor the diagonal block A[k:k+64, k:k+64] in place (lower); info != 0 on a bad pivot.
-__global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k, int* __restrict__ info) {
-    __shared__ double s[GP_NB][GP_NB + 1];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < GP_NB * GP_NB; idx += 256) {
-        const int r = idx / GP_NB, c = idx % GP_NB;
-        s[r][c] = A[(k + r) * lda + k + c];
-    }
-    __syncthreads();
-    const int r = tid >> 2, q = tid & 3;
-    for (int j = 0; j < GP_NB; ++j) {
-        if (tid == 0) {
-            const double d = s[j][j];
-            if (!(d > 0.0)) atomicExch(info, int(k + j + 1));
-            s[j][j] = sqrt(d);
+// Code size matters here: the first register-resident version unrolled all 64 column steps (static
+// register indices) into ~10 000 instructions of straight-line code that every warp executes
+// exactly once -- 160 KB of instruction fetch per CTA, ~65 us per launch with the arithmetic itself
+// worth ~15 us.  The loops below are real loops; register indices stay static because
+//   * the factorisation scans its 32 registers per thread with the column test on the VALUE of
+//     the column index (entered through a jump table at the first live register), and
+//   * the substitution ROTATES its right-hand side: the live entry is always v[0], and the FMA of
+//     step c writes v[i-1] from v[i].
+
+// Forward substitution L x = v for one right-hand side in registers (equivalently one row of
+// X L^T = V).  l: the 64 x 64 lower factor in shared memory, dinv[j] = 1 / l_jj.  emit(c, x_c) is
+// called for c = 0 .. 63 in order.
+template <class Emit>
+__device__ __forceinline__ void forward_solve_rotating(double (&v)[GP_NB],
+                                                       const double (*l)[GP_NB + 1],
+                                                       const double* dinv, Emit emit) {
+#pragma unroll 1
+    for (int c = 0; c < GP_NB; ++c) {
+        const double xc = v[0] * dinv[c];
+        emit(c, xc);
+        const int live = GP_NB - c;   // rows c + i < 64 still carry x_c
+#pragma unroll
+        for (int i = 1; i < GP_NB; ++i) {
+            const double lic = i < live ? l[c + i][c] : 0.0;
+            v[i - 1] = fma(-xc, lic, v[i]);
         }
-        __syncthreads();
-        if (tid > j && tid < GP_NB) s[tid][j] /= s[j][j];
-        __syncthreads();
-        if (r > j) {
-            const double lrj = s[r][j];
-            for (int c = j + 1 + q; c <= r; c += 4) s[r][c] = fma(-lrj, s[c][j], s[r][c]);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < GP_NB * GP_NB; idx += 256) {
-        const int rr = idx / GP_NB, c = idx % GP_NB;
-        A[(k + rr) * lda + k + c] = (c <= rr) ? s[rr][c] : 0.0;
     }
 }
 
 // Diagonal block + panel below it in ONE launch: every CTA factors the 64x64 diagonal block
-// itself in shared memory (redundantly -- the same ~64 dependent steps would otherwise run in a
-// separate single-CTA kernel before the panel could start), then solves X L_kk^T = A_panel for its
-// 128 rows, one thread per row.  CTA 0 stores the factored diagonal block in `Dout` (64 x 64, a
-// side buffer: the other CTAs of the launch may still be reading the unfactored block from A);
-// diag_copy_kernel puts all blocks into place after the last panel.
+// itself (redundantly -- the same 64 dependent steps would otherwise run in a separate single-CTA
+// kernel before the panel could start), then solves X L_kk^T = A_panel for its 128 rows, one
+// thread per row.  CTA 0 stores the factored diagonal block in `Dout` (64 x 64, a side buffer: the
+// other CTAs of the launch may still be reading the unfactored block from A); diag_copy_kernel
+// puts all blocks into place after the last panel.
+//
+// Factorisation: thread (r, q) holds the columns c = 2 cc + q of row r in registers.  Step j
+// reads the raw (updated, unscaled) column j that step j - 1 published, every thread takes the
+// reciprocal square root of the pivot itself (no broadcast round trip), applies the rank-1 update
+// to its registers and publishes its element of column j + 1 into the other half of a double
+// buffer: ONE block barrier per column.
 __global__ void __launch_bounds__(128)
 potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
                         int* __restrict__ info, double* __restrict__ Dout) {
     __shared__ double l[GP_NB][GP_NB + 1];
     __shared__ double dinv[GP_NB];          // 1 / l_jj
+    __shared__ double raw[2][GP_NB];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
         const int r = idx / GP_NB, c = idx % GP_NB;
@@ -247,48 +251,47 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
     }
     __syncthreads();
     {
-        // Right-looking factorisation with the matrix in REGISTERS: thread (r, q) holds the
-        // columns c = 2 cc + q of row r.  Per column j: the pivot owner publishes sqrt(a_jj), the
-        // owners of column j scale it and publish it, everyone applies the rank-1 update from
-        // the published column -- two block barriers per column and only the column itself goes
-        // through shared memory (the all-in-shared-memory version spent ~40 us per block in
-        // barrier + shared-memory latency; this one ~10 us).  j is a compile-time constant in
-        // the unrolled loop, so every register index is static.
-        __shared__ double colj[GP_NB];
-        __shared__ double piv_inv;
         const int r = tid >> 1, q = tid & 1;
         double a[GP_NB / 2];
 #pragma unroll
         for (int cc = 0; cc < GP_NB / 2; ++cc) a[cc] = l[r][2 * cc + q];
-#pragma unroll
+        if (q == 0) raw[0][r] = a[0];
+        __syncthreads();
+#pragma unroll 1
         for (int j = 0; j < GP_NB; ++j) {
-            // one reciprocal square root per column (by the pivot owner); every other thread
-            // multiplies -- fp64 sqrt and division are ~50-instruction sequences and used to sit
-            // on the critical path of all 64 steps (and of the 64 steps of the panel solve below)
-            if (r == j && q == (j & 1)) {
-                const double d = a[j >> 1];
+            const double* col = raw[j & 1];
+            double* nxt = raw[(j + 1) & 1];
+            const double d = col[j];
+            const double inv = rsqrt(d);
+            if (tid == 0) {
                 if (!(d > 0.0) && blockIdx.x == 0) atomicExch(info, int(k + j + 1));
-                const double inv = rsqrt(d);
-                a[j >> 1] = d * inv;
-                piv_inv = inv;
                 dinv[j] = inv;
             }
-            __syncthreads();
-            if (q == (j & 1) && r > j) {
-                a[j >> 1] = a[j >> 1] * piv_inv;
-                colj[r] = a[j >> 1];
+            const double lrj = col[r] * inv;   // l_rj for r > j; sqrt(d) for r == j
+            // registers below cc = j / 2 hold finished columns: enter the scan at the first live one
+#define ELFI_POTRF_STEP(CC)                                                          \
+            case CC: {                                                               \
+                const int c = 2 * CC + q;                                            \
+                if (c == j) {                                                        \
+                    a[CC] = lrj;                                                     \
+                } else if (c > j && c <= r) {                                        \
+                    a[CC] = fma(-lrj, col[c] * inv, a[CC]);                          \
+                    if (c == j + 1) nxt[r] = a[CC];                                  \
+                }                                                                    \
             }
-            __syncthreads();
-            if (r > j) {
-                const double lrj = colj[r];
-#pragma unroll
-                for (int cc = j >> 1; cc < GP_NB / 2; ++cc) {
-                    const int c = 2 * cc + q;
-                    if (c > j && c <= r) a[cc] = fma(-lrj, colj[c], a[cc]);
-                }
+            switch (j >> 1) {
+                ELFI_POTRF_STEP(0) ELFI_POTRF_STEP(1) ELFI_POTRF_STEP(2) ELFI_POTRF_STEP(3)
+                ELFI_POTRF_STEP(4) ELFI_POTRF_STEP(5) ELFI_POTRF_STEP(6) ELFI_POTRF_STEP(7)
+                ELFI_POTRF_STEP(8) ELFI_POTRF_STEP(9) ELFI_POTRF_STEP(10) ELFI_POTRF_STEP(11)
+                ELFI_POTRF_STEP(12) ELFI_POTRF_STEP(13) ELFI_POTRF_STEP(14) ELFI_POTRF_STEP(15)
+                ELFI_POTRF_STEP(16) ELFI_POTRF_STEP(17) ELFI_POTRF_STEP(18) ELFI_POTRF_STEP(19)
+                ELFI_POTRF_STEP(20) ELFI_POTRF_STEP(21) ELFI_POTRF_STEP(22) ELFI_POTRF_STEP(23)
+                ELFI_POTRF_STEP(24) ELFI_POTRF_STEP(25) ELFI_POTRF_STEP(26) ELFI_POTRF_STEP(27)
+                ELFI_POTRF_STEP(28) ELFI_POTRF_STEP(29) ELFI_POTRF_STEP(30) ELFI_POTRF_STEP(31)
             }
+#undef ELFI_POTRF_STEP
+            __syncthreads();
         }
-        __syncthreads();
 #pragma unroll
         for (int cc = 0; cc < GP_NB / 2; ++cc) l[r][2 * cc + q] = (2 * cc + q <= r) ? a[cc] : 0.0;
         __syncthreads();
@@ -302,15 +305,8 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
 #pragma unroll
     for (int c = 0; c < GP_NB; ++c) x[c] = a[c];
     // X L^T = A row by row, right-looking: once x_c is final it is eliminated from all later
-    // columns -- 63 - c INDEPENDENT FMAs per step instead of one dependent chain of c FMAs
-#pragma unroll
-    for (int c = 0; c < GP_NB; ++c) {
-        x[c] = x[c] * dinv[c];
-#pragma unroll
-        for (int c2 = c + 1; c2 < GP_NB; ++c2) x[c2] = fma(-x[c], l[c2][c], x[c2]);
-    }
-#pragma unroll
-    for (int c = 0; c < GP_NB; ++c) a[c] = x[c];
+    // columns -- independent FMAs per step instead of one dependent chain
+    forward_solve_rotating(x, l, dinv, [&](int c, double xc) { a[c] = xc; });
 }
 
 // A[k + r][k + c] = D[block][r][c] for the first `nblocks` diagonal blocks
@@ -327,27 +323,24 @@ __global__ void __launch_bounds__(64)
 trtri_diag_kernel(const double* __restrict__ L, double* __restrict__ W, double* __restrict__ U,
                   int64_t ld) {
     __shared__ double l[GP_NB][GP_NB + 1];
+    __shared__ double dinv[GP_NB];
     const int64_t k = int64_t(blockIdx.x) * GP_NB;
     for (int idx = threadIdx.x; idx < GP_NB * GP_NB; idx += 64) {
         const int r = idx / GP_NB, c = idx % GP_NB;
         l[r][c] = L[(k + r) * ld + k + c];
     }
     __syncthreads();
+    dinv[threadIdx.x] = 1.0 / l[threadIdx.x][threadIdx.x];
+    __syncthreads();
     // thread c solves L x = e_c  (column c of the inverse)
     const int c = threadIdx.x;
-    double x[GP_NB];
+    double v[GP_NB];
 #pragma unroll
-    for (int r = 0; r < GP_NB; ++r) {
-        double v = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int j = 0; j < r; ++j) v = fma(-l[r][j], x[j], v);
-        x[r] = (r >= c) ? v / l[r][r] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < GP_NB; ++r) {
-        W[(k + r) * ld + k + c] = x[r];
-        U[(k + c) * ld + k + r] = x[r];
-    }
+    for (int r = 0; r < GP_NB; ++r) v[r] = (r == c) ? 1.0 : 0.0;
+    forward_solve_rotating(v, l, dinv, [&](int r, double xr) {
+        W[(k + r) * ld + k + c] = xr;
+        U[(k + c) * ld + k + r] = xr;
+    });
 }
 
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
@@ -616,8 +609,10 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
     for (int64_t k = 0; k < n_pad; k += GP_NB) {
         const int64_t below = n_pad - (k + GP_NB);
         if (below <= 0) {
+            // last block: the same kernel, one CTA, no rows below
             if (rest_pending) { ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0)); rest_pending = false; }
-            potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
+            potrf_diag_panel_kernel<<<1, 128, 0, stream>>>(
+                L, n_pad, k, n_pad, info, Dblocks + (k / GP_NB) * GP_NB * GP_NB);
             continue;
         }
         potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(
@@ -641,8 +636,7 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
         }
     }
     if (rest_pending) ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0));
-    if (n_pad > GP_NB)
-        diag_copy_kernel<<<unsigned(n_pad / GP_NB - 1), 256, 0, stream>>>(Dblocks, L, n_pad);
+    diag_copy_kernel<<<unsigned(n_pad / GP_NB), 256, 0, stream>>>(Dblocks, L, n_pad);
     // W = L^-1 (and U = W^T) by recursive doubling over diagonal blocks:
     //   [[L11, 0], [L21, L22]]^-1 = [[W11, 0], [-W22 L21 W11, W22]]
     ELFI_CUDA_OK(cudaMemsetAsync(W, 0, size_t(n_pad) * n_pad * 8, stream));

@@ -45,7 +45,7 @@ template <class C> struct rs_has_tile_info<C, std::void_t<decltype(C::RS_TILE_IN
 template <class C, class = void> struct rs_has_finish : std::false_type {};
 template <class C> struct rs_has_finish<C, std::void_t<decltype(C::RS_FINISH)>> : std::true_type {};
 
-constexpr int RS_WARPS = 8;          // consumer warps per CTA
+constexpr int RS_WARPS = 8;          // consumer warps per CTA (default; see WARPS below)
 constexpr int RS_BOX_ROWS = 32;      // rows per box (one per lane)
 constexpr int RS_BOX_COLS = 16;      // fp64 columns per box (128 bytes)
 constexpr int RS_BOX_BYTES = RS_BOX_ROWS * RS_BOX_COLS * 8;
@@ -55,16 +55,20 @@ constexpr int RS_MAX_STAGES = 6;
 //   [RS_WARPS][ns][4096]  boxes
 //   [RS_WARPS][ns] u64    mbarriers
 //   consumer area         (obs / weights ...), 16-byte aligned
-__host__ __device__ inline size_t rs_box_bytes(int ns) { return size_t(RS_WARPS) * ns * RS_BOX_BYTES; }
-__host__ __device__ inline size_t rs_bar_bytes(int ns) { return size_t(RS_WARPS) * ns * 8; }
-__host__ __device__ inline size_t rs_aux_offset(int ns) {
-    return (rs_box_bytes(ns) + rs_bar_bytes(ns) + 15) & ~size_t(15);
+__host__ __device__ inline size_t rs_box_bytes(int ns, int warps = RS_WARPS) {
+    return size_t(warps) * ns * RS_BOX_BYTES;
+}
+__host__ __device__ inline size_t rs_bar_bytes(int ns, int warps = RS_WARPS) {
+    return size_t(warps) * ns * 8;
+}
+__host__ __device__ inline size_t rs_aux_offset(int ns, int warps = RS_WARPS) {
+    return (rs_box_bytes(ns, warps) + rs_bar_bytes(ns, warps) + 15) & ~size_t(15);
 }
 
 // Picks the deepest pipeline that fits next to `aux_bytes` of consumer shared memory.
-inline int rs_pick_stages(size_t smem_optin, size_t aux_bytes) {
+inline int rs_pick_stages(size_t smem_optin, size_t aux_bytes, int warps = RS_WARPS) {
     for (int ns = RS_MAX_STAGES; ns >= 2; --ns)
-        if (rs_aux_offset(ns) + aux_bytes + 1024 <= smem_optin) return ns;
+        if (rs_aux_offset(ns, warps) + aux_bytes + 1024 <= smem_optin) return ns;
     return 0;
 }
 
@@ -78,19 +82,24 @@ inline int rs_pick_stages(size_t smem_optin, size_t aux_bytes) {
 //   void end_row(int64_t row, int64_t B, int lane);   // row may be >= B (zero-filled tile)
 // With PASSES > 1 a tile's column groups are requested again right after the first sweep
 // (second sweep hits L2: a tile is at most a few tens of KiB), e.g. mean then variance.
-template <class Consumer>
-__global__ void __launch_bounds__(RS_WARPS * 32, 1)
+//
+// WARPS: consumers whose per-element arithmetic is a long dependent fp64 chain (nested distances,
+// fused column moments) cannot hide its latency with two warps per scheduler; they may run with
+// 12 warps and a shallower ring (the bytes in flight, WARPS * (ns-1) * 4 KiB, stay above the
+// Little's-law requirement).  A consumer sees the count as blockDim.x >> 5.
+template <class Consumer, int WARPS = RS_WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int ns,
                  typename Consumer::Params params) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    uint8_t* aux = smem + rs_aux_offset(ns);
+    uint8_t* aux = smem + rs_aux_offset(ns, WARPS);
 
     Consumer::setup_shared(aux, params, D);
 
     const uint32_t box0 = smem_u32(smem) + uint32_t(warp) * ns * RS_BOX_BYTES;
-    const uint32_t bar0 = smem_u32(smem + rs_box_bytes(ns)) + uint32_t(warp) * ns * 8;
+    const uint32_t bar0 = smem_u32(smem + rs_box_bytes(ns, WARPS)) + uint32_t(warp) * ns * 8;
     const uint8_t* box0_generic = smem + size_t(warp) * ns * RS_BOX_BYTES;
 
     if (lane == 0) {
@@ -103,8 +112,8 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
     const int Gc = (D + RS_BOX_COLS - 1) / RS_BOX_COLS;   // column groups per sweep
     const int G = Gc * Consumer::PASSES;                  // boxes per tile
     const int64_t ntiles = (B + RS_BOX_ROWS - 1) / RS_BOX_ROWS;
-    const int64_t gw = int64_t(blockIdx.x) * RS_WARPS + warp;
-    const int64_t GW = int64_t(gridDim.x) * RS_WARPS;
+    const int64_t gw = int64_t(blockIdx.x) * WARPS + warp;
+    const int64_t GW = int64_t(gridDim.x) * WARPS;
     const int64_t my_tiles = gw < ntiles ? (ntiles - gw + GW - 1) / GW : 0;
     const int64_t nbox = my_tiles * G;
 
@@ -159,7 +168,7 @@ rowstream_kernel(const __grid_constant__ CUtensorMap map, int64_t B, int D, int 
 }
 
 // Host-side launcher: encodes the tensor map, sizes the pipeline and the persistent grid.
-template <class Consumer>
+template <class Consumer, int WARPS = RS_WARPS>
 int rowstream_launch(elfi_b200_ctx* ctx, const double* M, int64_t ld, int64_t B, int64_t D,
                      size_t aux_bytes, const typename Consumer::Params& params,
                      cudaStream_t stream) {
@@ -167,20 +176,19 @@ int rowstream_launch(elfi_b200_ctx* ctx, const double* M, int64_t ld, int64_t B,
                  "matrix too large for int32 TMA coordinates (B=%lld, D=%lld)", (long long)B,
                  (long long)D);
     if (B == 0) return ELFI_B200_OK;
-    const int ns = rs_pick_stages(ctx->smem_optin, aux_bytes);
+    const int ns = rs_pick_stages(ctx->smem_optin, aux_bytes, WARPS);
     ELFI_REQUIRE(ns >= 2, "row too wide for the shared-memory pipeline (D=%lld)", (long long)D);
     CUtensorMap map;
     int rc = make_rowmajor_f64_map(ctx, M, B, D, ld, RS_BOX_ROWS, &map);
     if (rc) return rc;
-    const size_t smem_bytes = rs_aux_offset(ns) + aux_bytes;
-    auto kern = rowstream_kernel<Consumer>;
+    const size_t smem_bytes = rs_aux_offset(ns, WARPS) + aux_bytes;
+    auto kern = rowstream_kernel<Consumer, WARPS>;
     ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem_bytes)));
     const int64_t ntiles = (B + RS_BOX_ROWS - 1) / RS_BOX_ROWS;
-    int64_t ctas = (ntiles + RS_WARPS - 1) / RS_WARPS;
+    int64_t ctas = (ntiles + WARPS - 1) / WARPS;
     if (ctas > ctx->sm_count) ctas = ctx->sm_count;
-    kern<<<dim3(unsigned(ctas)), dim3(RS_WARPS * 32), smem_bytes, stream>>>(map, B, int(D), ns,
-                                                                            params);
+    kern<<<dim3(unsigned(ctas)), dim3(WARPS * 32), smem_bytes, stream>>>(map, B, int(D), ns, params);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

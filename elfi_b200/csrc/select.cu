@@ -10,6 +10,8 @@
 // (<= 2e6 pairs = 24 MB) are L2 resident, so the sort is latency/issue bound, not HBM bound;
 // passes whose digit is constant over all keys (typical for the high exponent bits of
 // distances) degenerate to a copy.
+#include <cstdlib>
+
 #include "eqweight.h"
 #include "pairwise.cuh"
 
@@ -491,6 +493,117 @@ rowsort_kernel(const double* __restrict__ X, int64_t ldX, int64_t B, int n, int 
     }
 }
 
+// Rows of up to 512 keys: the same network with the keys in REGISTERS.  Lane L holds the KPL
+// consecutive elements L*KPL .. L*KPL + KPL-1, so compare-exchange distances j < KPL stay inside
+// a thread and j >= KPL are one shuffle per key with lane L ^ (j / KPL): no shared memory, no
+// bank conflicts, no __syncwarp between stages (the shared-memory network above spends its time
+// there: 6.9 ms for 1e6 x 256).  A lane's elements are contiguous in memory: 16-byte loads and
+// stores when the row is aligned and entirely inside [0, n).
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+    asm volatile("shfl.sync.bfly.b32 %0, %0, %2, 0x1f, 0xffffffff;\n\t"
+                 "shfl.sync.bfly.b32 %1, %1, %2, 0x1f, 0xffffffff;"
+                 : "+r"(lo), "+r"(hi) : "r"(m));
+    return (uint64_t(hi) << 32) | lo;
+}
+
+template <int KPL>
+__device__ __forceinline__ void bitonic_in_registers(uint64_t (&key)[KPL], int lane) {
+    constexpr int N = KPL * 32;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+        // sort direction of the k-block the element sits in: bit k of i = L*KPL + r
+        const bool lane_up = (k >= N) ? true : ((lane & (k >= KPL ? k / KPL : 1)) == 0);
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= KPL) {
+                const int m = j / KPL;
+                const bool keep_min = ((lane & m) == 0) == lane_up;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    const uint64_t o = shfl_xor_u64(key[r], m);
+                    key[r] = ((o < key[r]) == keep_min) ? o : key[r];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    if ((r & j) == 0) {
+                        const bool up = (k < KPL) ? ((r & k) == 0) : lane_up;
+                        const uint64_t a = key[r], b = key[r | j];
+                        const bool sw = (a > b) == up;
+                        key[r] = sw ? b : a;
+                        key[r | j] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(256)
+rowsort_regs_kernel(const double* __restrict__ X, int64_t ldX, int64_t B, int n_,
+                    double* __restrict__ out, int64_t ld_out, int vec_in, int vec_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = int64_t(gridDim.x) * 8;
+    const int first = lane * KPL;
+    // block-uniform loop bounds: the shuffles below sit in provably convergent code (a per-warp
+    // row loop makes ptxas bracket every shuffle with WARPSYNC.COLLECTIVE / ENDCOLLECTIVE)
+    for (int64_t base = int64_t(blockIdx.x) * 8; base < B; base += nwarps) {
+        const int64_t row = base + (threadIdx.x >> 5);
+        const bool live = row < B;
+        const int n = live ? n_ : 0;
+        const bool whole = first + KPL <= n;
+        uint64_t key[KPL];
+        const double* x = X + row * ldX + first;
+        bool loaded = false;
+        if constexpr (KPL >= 2) {
+            if (vec_in && whole) {
+#pragma unroll
+                for (int r = 0; r < KPL; r += 2) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(x + r));
+                    key[r] = key_to_u64(v.x);
+                    key[r + 1] = key_to_u64(v.y);
+                }
+                loaded = true;
+            }
+        }
+        if (!loaded) {
+#pragma unroll
+            for (int r = 0; r < KPL; ++r)
+                key[r] = first + r < n ? key_to_u64(__ldg(x + r)) : ~uint64_t(0);
+        }
+        bitonic_in_registers<KPL>(key, lane);
+        double* y = out + row * ld_out + first;
+        bool stored = false;
+        if constexpr (KPL >= 2) {
+            if (vec_out && whole) {
+#pragma unroll
+                for (int r = 0; r < KPL; r += 2)
+                    *reinterpret_cast<double2*>(y + r) =
+                        make_double2(u64_to_key(key[r]), u64_to_key(key[r + 1]));
+                stored = true;
+            }
+        }
+        if (!stored) {
+#pragma unroll
+            for (int r = 0; r < KPL; ++r)
+                if (first + r < n) y[r] = u64_to_key(key[r]);
+        }
+    }
+}
+
+template <int KPL>
+static void launch_rowsort_regs(const double* X, int64_t ldX, int64_t B, int n, double* out,
+                                int64_t ld_out, int sm_count, cudaStream_t stream) {
+    int64_t blocks = (B + 7) / 8;
+    if (blocks > int64_t(sm_count) * 8) blocks = int64_t(sm_count) * 8;
+    const int vec_in = (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (ldX % 2 == 0);
+    const int vec_out = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (ld_out % 2 == 0);
+    rowsort_regs_kernel<KPL><<<unsigned(blocks), 256, 0, stream>>>(X, ldX, B, n, out, ld_out,
+                                                                   vec_in, vec_out);
+}
+
 // ---- fast path of the weighted quantile -----------------------------------------------------------
 // A blocked parallel scan gives cumulative weights c~_k whose distance to the reference's
 // sequential np.cumsum values is bounded by eps = 4 n 2^-53 (both are within ~n u of the exact
@@ -799,6 +912,18 @@ int elfi_b200_rowsort_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, int6
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     int npow2 = 2;
     while (npow2 < n) npow2 <<= 1;
+    if (npow2 <= 512 && getenv("ELFI_B200_ROWSORT_SMEM") == nullptr) {
+        const int kpl = npow2 <= 32 ? 1 : npow2 / 32;
+        switch (kpl) {
+            case 1: launch_rowsort_regs<1>(X, ldX, B, int(n), out, ld_out, ctx->sm_count, stream); break;
+            case 2: launch_rowsort_regs<2>(X, ldX, B, int(n), out, ld_out, ctx->sm_count, stream); break;
+            case 4: launch_rowsort_regs<4>(X, ldX, B, int(n), out, ld_out, ctx->sm_count, stream); break;
+            case 8: launch_rowsort_regs<8>(X, ldX, B, int(n), out, ld_out, ctx->sm_count, stream); break;
+            default: launch_rowsort_regs<16>(X, ldX, B, int(n), out, ld_out, ctx->sm_count, stream); break;
+        }
+        ELFI_CUDA_OK(cudaGetLastError());
+        return ELFI_B200_OK;
+    }
     const size_t smem = size_t(8) * npow2 * 8;
     ELFI_CUDA_OK(cudaFuncSetAttribute(rowsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));

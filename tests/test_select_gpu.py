@@ -91,7 +91,8 @@ def test_weighted_quantile_vs_oracle(n):
 
 
 @pytest.mark.parametrize('B,n', [(1000, 256), (37, 1), (500, 2), (333, 50), (100, 257), (64, 1000),
-                                 (9, 2048)])
+                                 (9, 2048), (77, 31), (77, 32), (77, 33), (300, 64), (41, 100),
+                                 (129, 127), (50, 511), (50, 512), (50, 513), (3001, 255)])
 def test_rowsort_matches_numpy(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B + n)
@@ -103,6 +104,10 @@ def test_rowsort_matches_numpy(B, n):
         x[::3, 2] = x[::3, 4]                 # ties
     got = ops.rowsort(x).cpu().numpy()
     assert np.array_equal(got, np.sort(x, axis=1), equal_nan=True)
+    if n >= 4:                                # strided rows, odd offset: the unaligned load path
+        from elfi_b200 import device as dev
+        got = ops.rowsort(dev.to_device(x)[:, 1:n - 1]).cpu().numpy()
+        assert np.array_equal(got, np.sort(x[:, 1:n - 1], axis=1), equal_nan=True)
 
 
 def test_rowsort_rejects_too_wide_rows_without_poisoning_the_context():
