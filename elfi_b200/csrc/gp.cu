@@ -26,9 +26,7 @@ namespace elfi {
 constexpr int GP_NB = 64;          // Cholesky panel width / base block of the inverse
 constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16;
 constexpr int GM_LDS = 20;         // padded row stride (doubles) of the smem tiles
-constexpr int GM_THREADS = 256;
 constexpr int GM_STAGES = 3;       // cp.async ring: two slabs in flight while one is consumed
-constexpr size_t GM_SMEM = size_t(GM_STAGES) * 2 * GM_BM * GM_LDS * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
     const uint32_t d = smem_u32(smem_dst);
@@ -55,19 +53,36 @@ struct GemmArgs {
     int mode;   // 0 full; 1 lower tiles only (SYRK-style); 2 K limited to col0 + BN (B lower-tri)
 };
 
-// C = alpha * A * B^T + beta * C on the fp64 tensor path.  CTA tile 128x128x16, 8 warps as
-// 2 (M) x 4 (N), warp tile 64x32 = 8x4 DMMA tiles; 3-stage cp.async ring with ONE block barrier
-// per 16-wide slab (round 1: double buffering with two barriers, during which the tensor pipe
-// idled: ncu showed `wait` / `math_pipe_throttle` stalls at 58 % of the DMMA peak); batch = grid.z.
+// C = alpha * A * B^T + beta * C on the fp64 tensor path.  CTA tile BM x BN x 16, WARPS_M x WARPS_N
+// warps, each a (BM / WARPS_M) x (BN / WARPS_N) tile of 8x8 DMMA tiles; 3-stage cp.async ring with
+// ONE block barrier per 16-wide slab (round 1: double buffering with two barriers, during which
+// the tensor pipe idled: ncu showed `wait` / `math_pipe_throttle` stalls at 58 % of the DMMA
+// peak); batch = grid.z.  Two instances:
+//   128 x 128, 2 x 4 warps  -- the n^2 m / 2 prediction product and the large trailing updates;
+//    64 x  64, 2 x 2 warps  -- products with fewer than ~100 large tiles (the next-block-column
+//                              update of every Cholesky panel: 128 x 64 x 64 useful per CTA in a
+//                              128 x 128 tile; the levels of the recursive inverse: at most 64
+//                              large tiles on 148 SMs): four times the CTAs, three CTAs per SM.
 // (mma.m16n8k16.f64 is no alternative: ptxas lowers it to eight DMMA.8 on sm_100a,
 // profiles/r2_dmma_m16n8k16_sass.md.)
-__global__ void __launch_bounds__(GM_THREADS)
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+struct GemmCfg {
+    static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
+    static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
+    static constexpr int TM = WTM / 8, TN = WTN / 8;
+    static constexpr size_t SMEM = size_t(GM_STAGES) * (BM + BN) * GM_LDS * sizeof(double);
+};
+
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
 gemm_nt_dmma_kernel(GemmArgs g) {
+    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N>;
+    constexpr int TM = Cfg::TM, TN = Cfg::TN;
     extern __shared__ __align__(16) double smem_d[];
-    double* As = smem_d;                                          // [STAGES][BM][LDS]
-    double* Bs = smem_d + size_t(GM_STAGES) * GM_BM * GM_LDS;     // [STAGES][BN][LDS]
+    double* As = smem_d;                                       // [STAGES][BM][LDS]
+    double* Bs = smem_d + size_t(GM_STAGES) * BM * GM_LDS;     // [STAGES][BN][LDS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int grp = lane >> 2, tig = lane & 3;
     // mode 2 (triangular K-range): a tile's work grows with its column, and CTAs are dispatched
     // in blockIdx order -- hand out the long-K tiles first so that the last wave is the short ones
@@ -75,33 +90,39 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     const int64_t lin = int64_t(blockIdx.y) * gridDim.x + blockIdx.x;
     const int64_t bx = g.mode == 2 ? int64_t(gridDim.x) - 1 - lin / gridDim.y : int64_t(blockIdx.x);
     const int64_t by = g.mode == 2 ? lin % gridDim.y : int64_t(blockIdx.y);
-    const int64_t row0 = by * GM_BM, col0 = bx * GM_BN;
-    if (g.mode == 1 && col0 > row0 + GM_BM - 1) return;
+    const int64_t row0 = by * BM, col0 = bx * BN;
+    if (g.mode == 1 && col0 > row0 + BM - 1) return;
     const int64_t bz = blockIdx.z;
     const double* A = g.A + bz * g.strideA;
     const double* B = g.B + bz * g.strideB;
     double* C = g.C + bz * g.strideC;
     int64_t Kend = g.K;
-    if (g.mode == 2 && col0 + GM_BN < Kend) Kend = col0 + GM_BN;
+    if (g.mode == 2 && col0 + BN < Kend) Kend = col0 + BN;
 
-    double acc[8][4][2];
+    double acc[TM][TN][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto load_stage = [&](int stage, int64_t k0) {
-        // 128 rows x 8 chunks of 16 bytes per matrix; 4 chunks per thread per matrix
+        // BM (BN) rows x 8 chunks of 16 bytes per matrix
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int idx = tid + it * GM_THREADS;       // 0..1023
+        for (int it = 0; it < BM * 8 / Cfg::THREADS; ++it) {
+            const int idx = tid + it * Cfg::THREADS;
             const int r = idx >> 3, ch = idx & 7;
             const int64_t k = k0 + ch * 2;
             const bool pa = (row0 + r < g.M) && (k < Kend);
-            const bool pb = (col0 + r < g.N) && (k < Kend);
-            cp_async16(As + (size_t(stage) * GM_BM + r) * GM_LDS + ch * 2,
+            cp_async16(As + (size_t(stage) * BM + r) * GM_LDS + ch * 2,
                        pa ? A + (row0 + r) * g.lda + k : A, pa);
-            cp_async16(Bs + (size_t(stage) * GM_BN + r) * GM_LDS + ch * 2,
+        }
+#pragma unroll
+        for (int it = 0; it < BN * 8 / Cfg::THREADS; ++it) {
+            const int idx = tid + it * Cfg::THREADS;
+            const int r = idx >> 3, ch = idx & 7;
+            const int64_t k = k0 + ch * 2;
+            const bool pb = (col0 + r < g.N) && (k < Kend);
+            cp_async16(Bs + (size_t(stage) * BN + r) * GM_LDS + ch * 2,
                        pb ? B + (col0 + r) * g.ldb + k : B, pb);
         }
         cp_async_commit();
@@ -120,32 +141,32 @@ gemm_nt_dmma_kernel(GemmArgs g) {
             if (nxt >= GM_STAGES) nxt -= GM_STAGES;
             load_stage(nxt, (kt + GM_STAGES - 1) * GM_BK);   // reuses the buffer of slab kt - 1
         }
-        const double* as = As + size_t(cur) * GM_BM * GM_LDS + size_t(wm * 64) * GM_LDS;
-        const double* bs = Bs + size_t(cur) * GM_BN * GM_LDS + size_t(wn * 32) * GM_LDS;
+        const double* as = As + size_t(cur) * BM * GM_LDS + size_t(wm * Cfg::WTM) * GM_LDS;
+        const double* bs = Bs + size_t(cur) * BN * GM_LDS + size_t(wn * Cfg::WTN) * GM_LDS;
 #pragma unroll
         for (int kk = 0; kk < GM_BK; kk += 4) {
-            double af[8], bf[4];
+            double af[TM], bf[TN];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = as[(i * 8 + grp) * GM_LDS + kk + tig];
+            for (int i = 0; i < TM; ++i) af[i] = as[(i * 8 + grp) * GM_LDS + kk + tig];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = bs[(j * 8 + grp) * GM_LDS + kk + tig];
+            for (int j = 0; j < TN; ++j) bf[j] = bs[(j * 8 + grp) * GM_LDS + kk + tig];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < TN; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         if (++cur == GM_STAGES) cur = 0;
     }
     double* Ct = g.Ct ? g.Ct + bz * g.strideCt : nullptr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t r = row0 + wm * 64 + i * 8 + grp;
+    for (int i = 0; i < TM; ++i) {
+        const int64_t r = row0 + wm * Cfg::WTM + i * 8 + grp;
         if (r >= g.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TN; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int64_t c = col0 + wn * 32 + j * 8 + tig * 2 + e;
+                const int64_t c = col0 + wn * Cfg::WTN + j * 8 + tig * 2 + e;
                 if (c >= g.N) continue;
                 double v = g.alpha * acc[i][j][e];
                 if (g.beta != 0.0) v += g.beta * C[r * g.ldc + c];
@@ -156,18 +177,32 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     }
 }
 
-static int launch_gemm(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
-    if (g.M <= 0 || g.N <= 0 || batch <= 0) return ELFI_B200_OK;
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+static int launch_gemm_cfg(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
+    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N>;
+    auto kern = gemm_nt_dmma_kernel<BM, BN, WARPS_M, WARPS_N>;
     static bool attr_set = false;
     if (!attr_set) {
-        ELFI_CUDA_OK(cudaFuncSetAttribute(gemm_nt_dmma_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(GM_SMEM)));
+        ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(Cfg::SMEM)));
         attr_set = true;
     }
-    dim3 grid(unsigned((g.N + GM_BN - 1) / GM_BN), unsigned((g.M + GM_BM - 1) / GM_BM), unsigned(batch));
-    gemm_nt_dmma_kernel<<<grid, GM_THREADS, GM_SMEM, stream>>>(g);
+    dim3 grid(unsigned((g.N + BN - 1) / BN), unsigned((g.M + BM - 1) / BM), unsigned(batch));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(g);
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
+}
+
+static int launch_gemm(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return ELFI_B200_OK;
+    static const int small_below = [] {
+        const char* v = getenv("ELFI_B200_GEMM_SMALL_BELOW");   // 0 = always the large tile
+        return v ? atoi(v) : 100;
+    }();
+    int64_t tiles = ((g.M + GM_BM - 1) / GM_BM) * ((g.N + GM_BN - 1) / GM_BN) * batch;
+    if (g.mode == 1) tiles = tiles / 2 + 1;
+    if (g.mode != 2 && tiles < small_below) return launch_gemm_cfg<64, 64, 2, 2>(g, batch, stream);
+    return launch_gemm_cfg<GM_BM, GM_BN, 2, 4>(g, batch, stream);
 }
 
 // ---- K10: Gram / cross-covariance ----------------------------------------------------------
@@ -197,53 +232,49 @@ gp_cov_kernel(const double* __restrict__ Aq, int64_t lda, int64_t na, const doub
 }
 
 // ---- K11: blocked Cholesky (right-looking, panel width 64) ------------------------------------
-// Code size matters here: the first register-resident version unrolled all 64 column steps (static
-// register indices) into ~10 000 instructions of straight-line code that every warp executes
-// exactly once -- 160 KB of instruction fetch per CTA, ~65 us per launch with the arithmetic itself
-// worth ~15 us.  The loops below are real loops; register indices stay static because
-//   * the factorisation scans its 32 registers per thread with the column test on the VALUE of
-//     the column index (entered through a jump table at the first live register), and
-//   * the substitution ROTATES its right-hand side: the live entry is always v[0], and the FMA of
-//     step c writes v[i-1] from v[i].
-
-// Forward substitution L x = v for one right-hand side in registers (equivalently one row of
-// X L^T = V).  l: the 64 x 64 lower factor in shared memory, dinv[j] = 1 / l_jj.  emit(c, x_c) is
-// called for c = 0 .. 63 in order.
-template <class Emit>
-__device__ __forceinline__ void forward_solve_rotating(double (&v)[GP_NB],
-                                                       const double (*l)[GP_NB + 1],
-                                                       const double* dinv, Emit emit) {
-#pragma unroll 1
-    for (int c = 0; c < GP_NB; ++c) {
-        const double xc = v[0] * dinv[c];
-        emit(c, xc);
-        const int live = GP_NB - c;   // rows c + i < 64 still carry x_c
-#pragma unroll
-        for (int i = 1; i < GP_NB; ++i) {
-            const double lic = i < live ? l[c + i][c] : 0.0;
-            v[i - 1] = fma(-xc, lic, v[i]);
+// Factor the diagonal block A[k:k+64, k:k+64] in place (lower); info != 0 on a bad pivot.
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k, int* __restrict__ info) {
+    __shared__ double s[GP_NB][GP_NB + 1];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < GP_NB * GP_NB; idx += 256) {
+        const int r = idx / GP_NB, c = idx % GP_NB;
+        s[r][c] = A[(k + r) * lda + k + c];
+    }
+    __syncthreads();
+    const int r = tid >> 2, q = tid & 3;
+    for (int j = 0; j < GP_NB; ++j) {
+        if (tid == 0) {
+            const double d = s[j][j];
+            if (!(d > 0.0)) atomicExch(info, int(k + j + 1));
+            s[j][j] = sqrt(d);
         }
+        __syncthreads();
+        if (tid > j && tid < GP_NB) s[tid][j] /= s[j][j];
+        __syncthreads();
+        if (r > j) {
+            const double lrj = s[r][j];
+            for (int c = j + 1 + q; c <= r; c += 4) s[r][c] = fma(-lrj, s[c][j], s[r][c]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < GP_NB * GP_NB; idx += 256) {
+        const int rr = idx / GP_NB, c = idx % GP_NB;
+        A[(k + rr) * lda + k + c] = (c <= rr) ? s[rr][c] : 0.0;
     }
 }
 
 // Diagonal block + panel below it in ONE launch: every CTA factors the 64x64 diagonal block
-// itself (redundantly -- the same 64 dependent steps would otherwise run in a separate single-CTA
-// kernel before the panel could start), then solves X L_kk^T = A_panel for its 128 rows, one
-// thread per row.  CTA 0 stores the factored diagonal block in `Dout` (64 x 64, a side buffer: the
-// other CTAs of the launch may still be reading the unfactored block from A); diag_copy_kernel
-// puts all blocks into place after the last panel.
-//
-// Factorisation: thread (r, q) holds the columns c = 2 cc + q of row r in registers.  Step j
-// reads the raw (updated, unscaled) column j that step j - 1 published, every thread takes the
-// reciprocal square root of the pivot itself (no broadcast round trip), applies the rank-1 update
-// to its registers and publishes its element of column j + 1 into the other half of a double
-// buffer: ONE block barrier per column.
+// itself in shared memory (redundantly -- the same ~64 dependent steps would otherwise run in a
+// separate single-CTA kernel before the panel could start), then solves X L_kk^T = A_panel for its
+// 128 rows, one thread per row.  CTA 0 stores the factored diagonal block in `Dout` (64 x 64, a
+// side buffer: the other CTAs of the launch may still be reading the unfactored block from A);
+// diag_copy_kernel puts all blocks into place after the last panel.
 __global__ void __launch_bounds__(128)
 potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t n,
                         int* __restrict__ info, double* __restrict__ Dout) {
     __shared__ double l[GP_NB][GP_NB + 1];
     __shared__ double dinv[GP_NB];          // 1 / l_jj
-    __shared__ double raw[2][GP_NB];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < GP_NB * GP_NB; idx += 128) {
         const int r = idx / GP_NB, c = idx % GP_NB;
@@ -251,47 +282,48 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
     }
     __syncthreads();
     {
+        // Right-looking factorisation with the matrix in REGISTERS: thread (r, q) holds the
+        // columns c = 2 cc + q of row r.  Per column j: the pivot owner publishes sqrt(a_jj), the
+        // owners of column j scale it and publish it, everyone applies the rank-1 update from
+        // the published column -- two block barriers per column and only the column itself goes
+        // through shared memory (the all-in-shared-memory version spent ~40 us per block in
+        // barrier + shared-memory latency; this one ~10 us).  j is a compile-time constant in
+        // the unrolled loop, so every register index is static.
+        __shared__ double colj[GP_NB];
+        __shared__ double piv_inv;
         const int r = tid >> 1, q = tid & 1;
         double a[GP_NB / 2];
 #pragma unroll
         for (int cc = 0; cc < GP_NB / 2; ++cc) a[cc] = l[r][2 * cc + q];
-        if (q == 0) raw[0][r] = a[0];
-        __syncthreads();
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < GP_NB; ++j) {
-            const double* col = raw[j & 1];
-            double* nxt = raw[(j + 1) & 1];
-            const double d = col[j];
-            const double inv = rsqrt(d);
-            if (tid == 0) {
+            // one reciprocal square root per column (by the pivot owner); every other thread
+            // multiplies -- fp64 sqrt and division are ~50-instruction sequences and used to sit
+            // on the critical path of all 64 steps (and of the 64 steps of the panel solve below)
+            if (r == j && q == (j & 1)) {
+                const double d = a[j >> 1];
                 if (!(d > 0.0) && blockIdx.x == 0) atomicExch(info, int(k + j + 1));
+                const double inv = rsqrt(d);
+                a[j >> 1] = d * inv;
+                piv_inv = inv;
                 dinv[j] = inv;
             }
-            const double lrj = col[r] * inv;   // l_rj for r > j; sqrt(d) for r == j
-            // registers below cc = j / 2 hold finished columns: enter the scan at the first live one
-#define ELFI_POTRF_STEP(CC)                                                          \
-            case CC: {                                                               \
-                const int c = 2 * CC + q;                                            \
-                if (c == j) {                                                        \
-                    a[CC] = lrj;                                                     \
-                } else if (c > j && c <= r) {                                        \
-                    a[CC] = fma(-lrj, col[c] * inv, a[CC]);                          \
-                    if (c == j + 1) nxt[r] = a[CC];                                  \
-                }                                                                    \
-            }
-            switch (j >> 1) {
-                ELFI_POTRF_STEP(0) ELFI_POTRF_STEP(1) ELFI_POTRF_STEP(2) ELFI_POTRF_STEP(3)
-                ELFI_POTRF_STEP(4) ELFI_POTRF_STEP(5) ELFI_POTRF_STEP(6) ELFI_POTRF_STEP(7)
-                ELFI_POTRF_STEP(8) ELFI_POTRF_STEP(9) ELFI_POTRF_STEP(10) ELFI_POTRF_STEP(11)
-                ELFI_POTRF_STEP(12) ELFI_POTRF_STEP(13) ELFI_POTRF_STEP(14) ELFI_POTRF_STEP(15)
-                ELFI_POTRF_STEP(16) ELFI_POTRF_STEP(17) ELFI_POTRF_STEP(18) ELFI_POTRF_STEP(19)
-                ELFI_POTRF_STEP(20) ELFI_POTRF_STEP(21) ELFI_POTRF_STEP(22) ELFI_POTRF_STEP(23)
-                ELFI_POTRF_STEP(24) ELFI_POTRF_STEP(25) ELFI_POTRF_STEP(26) ELFI_POTRF_STEP(27)
-                ELFI_POTRF_STEP(28) ELFI_POTRF_STEP(29) ELFI_POTRF_STEP(30) ELFI_POTRF_STEP(31)
-            }
-#undef ELFI_POTRF_STEP
             __syncthreads();
+            if (q == (j & 1) && r > j) {
+                a[j >> 1] = a[j >> 1] * piv_inv;
+                colj[r] = a[j >> 1];
+            }
+            __syncthreads();
+            if (r > j) {
+                const double lrj = colj[r];
+#pragma unroll
+                for (int cc = j >> 1; cc < GP_NB / 2; ++cc) {
+                    const int c = 2 * cc + q;
+                    if (c > j && c <= r) a[cc] = fma(-lrj, colj[c], a[cc]);
+                }
+            }
         }
+        __syncthreads();
 #pragma unroll
         for (int cc = 0; cc < GP_NB / 2; ++cc) l[r][2 * cc + q] = (2 * cc + q <= r) ? a[cc] : 0.0;
         __syncthreads();
@@ -305,8 +337,15 @@ potrf_diag_panel_kernel(double* __restrict__ A, int64_t lda, int64_t k, int64_t 
 #pragma unroll
     for (int c = 0; c < GP_NB; ++c) x[c] = a[c];
     // X L^T = A row by row, right-looking: once x_c is final it is eliminated from all later
-    // columns -- independent FMAs per step instead of one dependent chain
-    forward_solve_rotating(x, l, dinv, [&](int c, double xc) { a[c] = xc; });
+    // columns -- 63 - c INDEPENDENT FMAs per step instead of one dependent chain of c FMAs
+#pragma unroll
+    for (int c = 0; c < GP_NB; ++c) {
+        x[c] = x[c] * dinv[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < GP_NB; ++c2) x[c2] = fma(-x[c], l[c2][c], x[c2]);
+    }
+#pragma unroll
+    for (int c = 0; c < GP_NB; ++c) a[c] = x[c];
 }
 
 // A[k + r][k + c] = D[block][r][c] for the first `nblocks` diagonal blocks
@@ -323,24 +362,27 @@ __global__ void __launch_bounds__(64)
 trtri_diag_kernel(const double* __restrict__ L, double* __restrict__ W, double* __restrict__ U,
                   int64_t ld) {
     __shared__ double l[GP_NB][GP_NB + 1];
-    __shared__ double dinv[GP_NB];
     const int64_t k = int64_t(blockIdx.x) * GP_NB;
     for (int idx = threadIdx.x; idx < GP_NB * GP_NB; idx += 64) {
         const int r = idx / GP_NB, c = idx % GP_NB;
         l[r][c] = L[(k + r) * ld + k + c];
     }
     __syncthreads();
-    dinv[threadIdx.x] = 1.0 / l[threadIdx.x][threadIdx.x];
-    __syncthreads();
     // thread c solves L x = e_c  (column c of the inverse)
     const int c = threadIdx.x;
-    double v[GP_NB];
+    double x[GP_NB];
 #pragma unroll
-    for (int r = 0; r < GP_NB; ++r) v[r] = (r == c) ? 1.0 : 0.0;
-    forward_solve_rotating(v, l, dinv, [&](int r, double xr) {
-        W[(k + r) * ld + k + c] = xr;
-        U[(k + c) * ld + k + r] = xr;
-    });
+    for (int r = 0; r < GP_NB; ++r) {
+        double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < r; ++j) v = fma(-l[r][j], x[j], v);
+        x[r] = (r >= c) ? v / l[r][r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < GP_NB; ++r) {
+        W[(k + r) * ld + k + c] = x[r];
+        U[(k + c) * ld + k + r] = x[r];
+    }
 }
 
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
@@ -609,10 +651,8 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
     for (int64_t k = 0; k < n_pad; k += GP_NB) {
         const int64_t below = n_pad - (k + GP_NB);
         if (below <= 0) {
-            // last block: the same kernel, one CTA, no rows below
             if (rest_pending) { ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0)); rest_pending = false; }
-            potrf_diag_panel_kernel<<<1, 128, 0, stream>>>(
-                L, n_pad, k, n_pad, info, Dblocks + (k / GP_NB) * GP_NB * GP_NB);
+            potrf_diag_kernel<<<1, 256, 0, stream>>>(L, n_pad, k, info);
             continue;
         }
         potrf_diag_panel_kernel<<<unsigned((below + 127) / 128), 128, 0, stream>>>(
@@ -636,7 +676,8 @@ int elfi_b200_gp_fit_f64(elfi_b200_ctx* ctx, const double* X, int64_t ldX, const
         }
     }
     if (rest_pending) ELFI_CUDA_OK(cudaStreamWaitEvent(stream, ev_rest, 0));
-    diag_copy_kernel<<<unsigned(n_pad / GP_NB), 256, 0, stream>>>(Dblocks, L, n_pad);
+    if (n_pad > GP_NB)
+        diag_copy_kernel<<<unsigned(n_pad / GP_NB - 1), 256, 0, stream>>>(Dblocks, L, n_pad);
     // W = L^-1 (and U = W^T) by recursive doubling over diagonal blocks:
     //   [[L11, 0], [L21, L22]]^-1 = [[W11, 0], [-W22 L21 W11, W22]]
     ELFI_CUDA_OK(cudaMemsetAsync(W, 0, size_t(n_pad) * n_pad * 8, stream));
