@@ -433,46 +433,106 @@ predict_rows_kernel(const double* __restrict__ Ks, const double* __restrict__ V,
     }
 }
 
-// ---- K13: gradients for a few query points (one CTA per point) ----------------------------------
-// kx_j = s2 exp(f r2_j); t = W (kx + b); u = W^T t = Ky^-1 (kx + b);
-// mean = (kx + b) . alpha ; var = s2 + b - |t|^2 ; grad_mu_d = sum_j dk_jd alpha_j ;
-// grad_var_d = -2 sum_j dk_jd u_j with dk_jd = 2 f (x_d - X_jd) kx_j      (gpy_regression.py:211-218)
+// ---- K13: gradients / whitening for a few query points -----------------------------------------
+// Acquisition optimisers, NUTS chains and rank-b factor updates ask for t = W k_q, u = W^T t at a
+// handful of points per call.  Round 1 gave every point its own CTA, which walks the whole 16 MB
+// triangle of W with 8 warps: ~0.5 ms per triangular product however few points there are --
+// 1.0 ms per lock-step round of a 10-start LCBSC minimisation, the inner loop of BOLFI.fit.  The
+// products are matrix-vector shaped: spread the ROWS of W over the grid instead (8 rows per CTA,
+// one per warp), keep the <= 16 right-hand sides of a chunk in shared memory, and W is read once
+// per chunk at L2 speed (m = 10, n = 2000: 1.01 -> 0.078 ms; W stays L2 resident between calls).
+//   kx_j = s2 exp(f r2_j); t = W (kx + b); u = W^T t = Ky^-1 (kx + b);
+//   mean = (kx + b) . alpha ; var = s2 + b - |t|^2 ; grad_mu_d = sum_j dk_jd alpha_j ;
+//   grad_var_d = -2 sum_j dk_jd u_j with dk_jd = 2 f (x_d - X_jd) kx_j     (gpy_regression.py:211-218)
+//
+// out[q][r] = sum_{c in range(r)} M[r][c] V[q][c],  range(r) = [0, r] (lower) or [r, n) (upper)
+template <int MQ>
 __global__ void __launch_bounds__(256)
-predict_grad_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __restrict__ X,
-                    int64_t ldx, int64_t n, int p, const double* __restrict__ W,
-                    const double* __restrict__ U, int64_t ldw, const double* __restrict__ alpha,
-                    double s2, double f, double bias, double* __restrict__ mean,
-                    double* __restrict__ var, double* __restrict__ gmean, double* __restrict__ gvar) {
-    extern __shared__ double sh[];
-    double* kx = sh;            // n
-    double* t = sh + n;         // n
-    double* u = sh + 2 * n;     // n
+gp_trimv_kernel(const double* __restrict__ M, int64_t ldm, int64_t n, const double* __restrict__ V,
+                int64_t ldv, int mq, int lower, double* __restrict__ out, int64_t ldo) {
+    __shared__ double vs[MQ][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = int64_t(blockIdx.x) * 8, r = r0 + warp;
+    const int64_t r_last = (r0 + 7 < n - 1) ? r0 + 7 : n - 1;
+    const int64_t c_lo = lower ? 0 : (r0 / 256) * 256;
+    const int64_t c_hi = lower ? r_last + 1 : n;
+    double acc[MQ];
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) acc[q] = 0.0;
+    for (int64_t c0 = c_lo; c0 < c_hi; c0 += 256) {
+        __syncthreads();
+        for (int idx = tid; idx < MQ * 256; idx += 256) {
+            const int q = idx >> 8, cc = idx & 255;
+            vs[q][cc] = (q < mq && c0 + cc < n) ? V[q * ldv + c0 + cc] : 0.0;
+        }
+        __syncthreads();
+        if (r < n) {
+            double w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t c = c0 + k * 32 + lane;
+                const bool in = lower ? (c <= r) : (c >= r && c < n);
+                w[k] = in ? M[r * ldm + c] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int q = 0; q < MQ; ++q) acc[q] = fma(w[k], vs[q][k * 32 + lane], acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < MQ; ++q)
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0 && r < n)
+#pragma unroll
+        for (int q = 0; q < MQ; ++q)
+            if (q < mq) out[q * ldo + r] = acc[q];
+}
+
+static int launch_trimv(const double* M, int64_t ldm, int64_t n, const double* V, int64_t ldv,
+                        int64_t mq, int lower, double* out, int64_t ldo, cudaStream_t stream) {
+    const unsigned grid = unsigned((n + 7) / 8);
+    if (mq <= 4)
+        gp_trimv_kernel<4><<<grid, 256, 0, stream>>>(M, ldm, n, V, ldv, int(mq), lower, out, ldo);
+    else if (mq <= 8)
+        gp_trimv_kernel<8><<<grid, 256, 0, stream>>>(M, ldm, n, V, ldv, int(mq), lower, out, ldo);
+    else
+        gp_trimv_kernel<16><<<grid, 256, 0, stream>>>(M, ldm, n, V, ldv, int(mq), lower, out, ldo);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+constexpr int64_t GP_FEW_CHUNK = 16;   // right-hand sides per launch
+
+// kq[q][j] = s2 exp(f |x_q - X_j|^2) + bias
+__global__ void __launch_bounds__(256)
+gp_kvec_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __restrict__ X,
+               int64_t ldx, int64_t n, int p, double s2, double f, double bias,
+               double* __restrict__ kq, int64_t ldk) {
+    const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t q = blockIdx.y;
+    if (j >= n) return;
+    double r2 = 0.0;
+    for (int a = 0; a < p; ++a) {
+        const double d = Xq[q * ldq + a] - X[j * ldx + a];
+        r2 = fma(d, d, r2);
+    }
+    kq[q * ldk + j] = s2 * exp(r2 * f) + bias;
+}
+
+// Mean, variance and their gradients from precomputed kq = kx + b, t = W kq, u = W^T t.
+__global__ void __launch_bounds__(256)
+gp_grad_finish_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __restrict__ X,
+                      int64_t ldx, int64_t n, int p, const double* __restrict__ kq,
+                      const double* __restrict__ t, const double* __restrict__ u, int64_t ld,
+                      const double* __restrict__ alpha, double s2, double f, double bias,
+                      double* __restrict__ mean, double* __restrict__ var,
+                      double* __restrict__ gmean, double* __restrict__ gvar) {
     __shared__ double red[32];
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t j = tid; j < n; j += 256) {
-        double r2 = 0.0;
-        for (int a = 0; a < p; ++a) {
-            const double d = Xq[q * ldq + a] - X[j * ldx + a];
-            r2 = fma(d, d, r2);
-        }
-        kx[j] = s2 * exp(r2 * f);
-    }
-    __syncthreads();
-    for (int64_t r = warp; r < n; r += 8) {
-        double acc = 0.0;
-        for (int64_t c = lane; c <= r; c += 32) acc = fma(W[r * ldw + c], kx[c] + bias, acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) t[r] = acc;
-    }
-    __syncthreads();
-    for (int64_t r = warp; r < n; r += 8) {
-        double acc = 0.0;
-        for (int64_t c = r + lane; c < n; c += 32) acc = fma(U[r * ldw + c], t[c], acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) u[r] = acc;
-    }
-    __syncthreads();
+    const double* kqq = kq + q * ld;
+    const double* tq = t + q * ld;
+    const double* uq = u + q * ld;
     auto block_sum = [&](double v) -> double {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         __syncthreads();
@@ -484,8 +544,8 @@ predict_grad_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __
     };
     double pm = 0.0, pq = 0.0;
     for (int64_t j = tid; j < n; j += 256) {
-        pm = fma(kx[j] + bias, alpha[j], pm);
-        pq = fma(t[j], t[j], pq);
+        pm = fma(kqq[j], alpha[j], pm);
+        pq = fma(tq[j], tq[j], pq);
     }
     const double mu = block_sum(pm);
     const double qq = block_sum(pq);
@@ -493,13 +553,14 @@ predict_grad_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __
         if (mean) mean[q] = mu;
         if (var) var[q] = s2 + bias - qq;
     }
+    if (gmean == nullptr && gvar == nullptr) return;
     for (int d = 0; d < p; ++d) {
         double gm = 0.0, gv = 0.0;
         const double xd = Xq[q * ldq + d];
         for (int64_t j = tid; j < n; j += 256) {
-            const double dk = 2.0 * f * (xd - X[j * ldx + d]) * kx[j];
+            const double dk = 2.0 * f * (xd - X[j * ldx + d]) * (kqq[j] - bias);
             gm = fma(dk, alpha[j], gm);
-            gv = fma(dk, u[j], gv);
+            gv = fma(dk, uq[j], gv);
         }
         gm = block_sum(gm);
         gv = block_sum(gv);
@@ -513,50 +574,8 @@ predict_grad_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __
 // ---- posterior cross-covariance pieces (ExpIntVar, acquisition.py:776-821) ----------------------
 // The reference evaluates cov(x_a, x_b | evidence) = k(x_a, x_b) - k_a^T Ky^-1 k_b with a fresh
 // cho_factor of Ky per call (acquisition.py:807).  With W = L^-1 from the fit, Ky^-1 = W^T W, so
-// the covariance is k(x_a, x_b) - (W k_a) . (W k_b): whiten each point once (one CTA per point, the
-// first two phases of predict_grad_kernel), then every covariance is a dot product of length n.
-__global__ void __launch_bounds__(256)
-gp_whiten_kernel(const double* __restrict__ Xq, int64_t ldq, const double* __restrict__ X,
-                 int64_t ldx, int64_t n, int p, const double* __restrict__ W, int64_t ldw,
-                 double s2, double f, double bias, double* __restrict__ T, int64_t ldT) {
-    extern __shared__ double kq[];   // n: k(x_q, X_j) of the RBF + bias kernel
-    const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t j = tid; j < n; j += 256) {
-        double r2 = 0.0;
-        for (int a = 0; a < p; ++a) {
-            const double d = Xq[q * ldq + a] - X[j * ldx + a];
-            r2 = fma(d, d, r2);
-        }
-        kq[j] = s2 * exp(r2 * f) + bias;
-    }
-    __syncthreads();
-    for (int64_t r = warp; r < n; r += 8) {
-        double acc = 0.0;
-        for (int64_t c = lane; c <= r; c += 32) acc = fma(W[r * ldw + c], kq[c], acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) T[q * ldT + r] = acc;
-    }
-}
-
-// out[q, r] = sum_{c >= r} U[r, c] T[q, c]  (= W^T t_q; U = W^T is upper triangular): the third
-// phase of predict_grad_kernel for a batch of whitened vectors.  Used by the rank-b factor update.
-__global__ void __launch_bounds__(256)
-gp_apply_wt_kernel(const double* __restrict__ T, int64_t ldT, const double* __restrict__ U,
-                   int64_t ldw, int64_t n, double* __restrict__ out, int64_t ldo) {
-    extern __shared__ double tq[];   // n
-    const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t j = tid; j < n; j += 256) tq[j] = T[q * ldT + j];
-    __syncthreads();
-    for (int64_t r = warp; r < n; r += 8) {
-        double acc = 0.0;
-        for (int64_t c = r + lane; c < n; c += 32) acc = fma(U[r * ldw + c], tq[c], acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) out[q * ldo + r] = acc;
-    }
-}
-
+// the covariance is k(x_a, x_b) - (W k_a) . (W k_b): whiten each point once (gp_kvec_kernel +
+// gp_trimv_kernel above), then every covariance is a dot product of length n.
 // cov[b * ma + a] = k(x_a, x_b) - T_a . T_b, one warp per pair (a, b)
 __global__ void __launch_bounds__(256)
 gp_cross_cov_kernel(const double* __restrict__ Xa, int64_t lda, int64_t ma,
@@ -780,17 +799,29 @@ int elfi_b200_gp_predict_grad_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t 
     using namespace elfi;
     ELFI_REQUIRE(ctx && Xq && X && W && U && alpha, "gp_predict_grad: NULL argument");
     ELFI_REQUIRE(m >= 0 && n >= 1 && p >= 1 && ldq >= p && ldX >= p, "gp_predict_grad: bad shape");
-    ELFI_REQUIRE(size_t(3) * n * 8 <= 200 * 1024, "gp_predict_grad: n=%lld too large (<= 8533)",
-                 (long long)n);
     if (m == 0) return ELFI_B200_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
-    const size_t smem = size_t(3) * n * 8;
-    ELFI_CUDA_OK(cudaFuncSetAttribute(predict_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(smem)));
-    predict_grad_kernel<<<unsigned(m), 256, smem, stream>>>(
-        Xq, ldq, X, ldX, n, int(p), W, U, n_pad, alpha, kernel_var,
-        -0.5 / (lengthscale * lengthscale), bias_var, mean, var, grad_mean, grad_var);
+    const double f = -0.5 / (lengthscale * lengthscale);
+    double* kq = static_cast<double*>(ctx_scratch(ctx, size_t(3) * GP_FEW_CHUNK * n_pad * 8 + 256));
+    if (!kq) return ELFI_B200_ERR_NOMEM;
+    double* t = kq + GP_FEW_CHUNK * n_pad;
+    double* u = t + GP_FEW_CHUNK * n_pad;
+    for (int64_t q0 = 0; q0 < m; q0 += GP_FEW_CHUNK) {
+        const int64_t mq = (m - q0) < GP_FEW_CHUNK ? (m - q0) : GP_FEW_CHUNK;
+        gp_kvec_kernel<<<dim3(unsigned((n + 255) / 256), unsigned(mq)), 256, 0, stream>>>(
+            Xq + q0 * ldq, ldq, X, ldX, n, int(p), kernel_var, f, bias_var, kq, n_pad);
+        int rc = launch_trimv(W, n_pad, n, kq, n_pad, mq, 1, t, n_pad, stream);
+        if (rc) return rc;
+        if (grad_mean != nullptr || grad_var != nullptr) {
+            rc = launch_trimv(U, n_pad, n, t, n_pad, mq, 0, u, n_pad, stream);
+            if (rc) return rc;
+        }
+        gp_grad_finish_kernel<<<unsigned(mq), 256, 0, stream>>>(
+            Xq + q0 * ldq, ldq, X, ldX, n, int(p), kq, t, u, n_pad, alpha, kernel_var, f,
+            bias_var, mean ? mean + q0 : nullptr, var ? var + q0 : nullptr,
+            grad_mean ? grad_mean + q0 * p : nullptr, grad_var ? grad_var + q0 * p : nullptr);
+    }
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }
@@ -819,16 +850,19 @@ int elfi_b200_gp_whiten_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, i
     ELFI_REQUIRE(m >= 0 && n >= 1 && p >= 1 && ldq >= p && ldX >= p && ldT >= n,
                  "gp_whiten: bad shape");
     ELFI_REQUIRE(n_pad == elfi_b200_gp_padded_size(n), "gp_whiten: bad n_pad");
-    ELFI_REQUIRE(size_t(n) * 8 <= 200 * 1024, "gp_whiten: n=%lld too large (<= 25600)", (long long)n);
     if (m == 0) return ELFI_B200_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
-    const size_t smem = size_t(n) * 8;
-    ELFI_CUDA_OK(cudaFuncSetAttribute(gp_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(smem)));
-    gp_whiten_kernel<<<unsigned(m), 256, smem, stream>>>(Xq, ldq, X, ldX, n, int(p), W, n_pad, kernel_var,
-                                                         -0.5 / (lengthscale * lengthscale), bias_var,
-                                                         T, ldT);
+    const double f = -0.5 / (lengthscale * lengthscale);
+    double* kq = static_cast<double*>(ctx_scratch(ctx, size_t(GP_FEW_CHUNK) * n_pad * 8 + 256));
+    if (!kq) return ELFI_B200_ERR_NOMEM;
+    for (int64_t q0 = 0; q0 < m; q0 += GP_FEW_CHUNK) {
+        const int64_t mq = (m - q0) < GP_FEW_CHUNK ? (m - q0) : GP_FEW_CHUNK;
+        gp_kvec_kernel<<<dim3(unsigned((n + 255) / 256), unsigned(mq)), 256, 0, stream>>>(
+            Xq + q0 * ldq, ldq, X, ldX, n, int(p), kernel_var, f, bias_var, kq, n_pad);
+        int rc = launch_trimv(W, n_pad, n, kq, n_pad, mq, 1, T + q0 * ldT, ldT, stream);
+        if (rc) return rc;
+    }
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }
@@ -839,15 +873,14 @@ int elfi_b200_gp_apply_wt_f64(elfi_b200_ctx* ctx, const double* T, int64_t ldT, 
     using namespace elfi;
     ELFI_REQUIRE(ctx && U && (m == 0 || (T && out)), "gp_apply_wt: NULL argument");
     ELFI_REQUIRE(m >= 0 && n >= 1 && ldT >= n && ldo >= n && n_pad >= n, "gp_apply_wt: bad shape");
-    ELFI_REQUIRE(size_t(n) * 8 <= 200 * 1024, "gp_apply_wt: n=%lld too large (<= 25600)", (long long)n);
     if (m == 0) return ELFI_B200_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
-    const size_t smem = size_t(n) * 8;
-    ELFI_CUDA_OK(cudaFuncSetAttribute(gp_apply_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(smem)));
-    gp_apply_wt_kernel<<<unsigned(m), 256, smem, stream>>>(T, ldT, U, n_pad, n, out, ldo);
-    ELFI_CUDA_OK(cudaGetLastError());
+    for (int64_t q0 = 0; q0 < m; q0 += GP_FEW_CHUNK) {
+        const int64_t mq = (m - q0) < GP_FEW_CHUNK ? (m - q0) : GP_FEW_CHUNK;
+        int rc = launch_trimv(U, n_pad, n, T + q0 * ldT, ldT, mq, 0, out + q0 * ldo, ldo, stream);
+        if (rc) return rc;
+    }
     return ELFI_B200_OK;
 }
 

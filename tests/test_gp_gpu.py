@@ -73,6 +73,29 @@ def test_gp_gradients_match_oracle():
     np.testing.assert_allclose(gv, gv_o, rtol=RTOL, atol=1e-9)
 
 
+def test_chunked_triangular_products_are_consistent():
+    """gp_trimv_kernel handles the query points in chunks of up to 16 right-hand sides (templates
+    for 4, 8, 16): one call with 80 points, calls of 20 and calls of 16 agree, and the whitened
+    vectors reproduce the predictive variance of the GEMM path."""
+    from elfi_b200 import device as dev
+    for n in (77, 400, 1300):
+        gp, X, y = _model(n, 2, seed=n)
+        xq = np.random.RandomState(4).uniform(-1, 1, (80, 2))
+        gm_a, gv_a = gp.predictive_gradients(xq)
+        parts = [gp.predictive_gradients(xq[i:i + 20]) for i in range(0, 80, 20)]
+        gm_b = np.vstack([q[0] for q in parts])
+        gv_b = np.vstack([q[1] for q in parts])
+        np.testing.assert_allclose(gm_b, gm_a, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(gv_b, gv_a, rtol=1e-10, atol=1e-12)
+        _, T_a = gp.whiten(xq)
+        T_b = np.vstack([dev.to_host(gp.whiten(xq[i:i + 16])[1]) for i in range(0, 80, 16)])
+        np.testing.assert_allclose(T_b, dev.to_host(T_a), rtol=1e-10, atol=1e-13)
+        mu, var = gp.predict(xq[:5], noiseless=True)
+        h = gp.hyperparameters
+        np.testing.assert_allclose(var.ravel(), h['kernel_var'] + h['bias_var'] -
+                                   np.sum(T_b[:5] ** 2, axis=1), rtol=1e-9, atol=1e-12)
+
+
 def test_lcbsc_value_and_gradient():
     from elfi_b200.bo import LCBSC, JITTER
     gp, X, y = _model(256, 2, seed=8)
