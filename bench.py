@@ -453,6 +453,10 @@ def bolfi_config4_block():
             inc._fit()
         inc.update(X[lo:lo + 5], y[lo:lo + 5, None])
     upd_ms = timed(append5, reps=5, warm=1)
+    # one lock-step round of the multi-start acquisition optimiser: LCBSC value + gradient at 10
+    # points through the public acquisition class, host arrays in and out
+    starts = grid_host[::10_000][:10].copy()
+    acq_round_ms = timed(lambda: acq.evaluate_with_gradient(starts, 10), reps=10, warm=3)
     # parity of what was timed + the host baseline
     mean, var, a_dev = gp.predict_device(grid[:2000], noiseless=True, beta=beta)
     t0 = time.perf_counter()
@@ -467,6 +471,7 @@ def bolfi_config4_block():
     err_var = float(np.max(np.abs(var.cpu().numpy() - var_h[:2000, 0]) / np.abs(var_h[:2000, 0])))
     return {'what': 'GP fit n=2000 + LCBSC on a 400 x 250 grid, fp64 (config #4)',
             'fit_ms': fit_ms, 'rank5_update_ms': upd_ms, 'grid_predict_lcbsc_ms': grid_ms,
+            'lcbsc_value_gradient_10_points_ms': acq_round_ms,
             'grid_tflops': flops / (grid_ms * 1e-3) / 1e12,
             'fp64_peak_tflops_probe': {'dfma': peaks[0], 'dmma': peaks[1]},
             'grid_frac_of_dmma_peak': flops / (grid_ms * 1e-3) / 1e12 / peaks[1],

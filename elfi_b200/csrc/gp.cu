@@ -502,6 +502,7 @@ static int launch_trimv(const double* M, int64_t ldm, int64_t n, const double* V
     return ELFI_B200_OK;
 }
 constexpr int64_t GP_FEW_CHUNK = 16;   // right-hand sides per launch
+constexpr int64_t GP_PREDICT_FEW = 160;// elfi_b200_gp_predict_f64: up to this many points go this way
 
 // kq[q][j] = s2 exp(f |x_q - X_j|^2) + bias
 __global__ void __launch_bounds__(256)
@@ -525,7 +526,8 @@ gp_grad_finish_kernel(const double* __restrict__ Xq, int64_t ldq, const double* 
                       int64_t ldx, int64_t n, int p, const double* __restrict__ kq,
                       const double* __restrict__ t, const double* __restrict__ u, int64_t ld,
                       const double* __restrict__ alpha, double s2, double f, double bias,
-                      double* __restrict__ mean, double* __restrict__ var,
+                      double noise_add, double beta, double* __restrict__ mean,
+                      double* __restrict__ var, double* __restrict__ acq,
                       double* __restrict__ gmean, double* __restrict__ gvar) {
     __shared__ double red[32];
     const int64_t q = blockIdx.x;
@@ -550,8 +552,10 @@ gp_grad_finish_kernel(const double* __restrict__ Xq, int64_t ldq, const double* 
     const double mu = block_sum(pm);
     const double qq = block_sum(pq);
     if (tid == 0) {
+        const double vr = s2 + bias - qq;
         if (mean) mean[q] = mu;
-        if (var) var[q] = s2 + bias - qq;
+        if (var) var[q] = vr + noise_add;
+        if (acq) acq[q] = mu - sqrt(beta * vr);      // LCBSC uses the noiseless variance
     }
     if (gmean == nullptr && gvar == nullptr) return;
     for (int d = 0; d < p; ++d) {
@@ -762,6 +766,26 @@ int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     const double f = -0.5 / (lengthscale * lengthscale);
+    if (m <= GP_PREDICT_FEW) {
+        // a handful of points (posterior evaluations of the MCMC chains, acquisition values): the
+        // row-parallel matrix-vector path of the gradients instead of a 128-row GEMM chunk
+        double* kq = static_cast<double*>(ctx_scratch(ctx, size_t(2) * GP_FEW_CHUNK * n_pad * 8 + 256));
+        if (!kq) return ELFI_B200_ERR_NOMEM;
+        double* t = kq + GP_FEW_CHUNK * n_pad;
+        for (int64_t q0 = 0; q0 < m; q0 += GP_FEW_CHUNK) {
+            const int64_t mq = (m - q0) < GP_FEW_CHUNK ? (m - q0) : GP_FEW_CHUNK;
+            gp_kvec_kernel<<<dim3(unsigned((n + 255) / 256), unsigned(mq)), 256, 0, stream>>>(
+                Xq + q0 * ldq, ldq, X, ldX, n, int(p), kernel_var, f, bias_var, kq, n_pad);
+            int rc = launch_trimv(W, n_pad, n, kq, n_pad, mq, 1, t, n_pad, stream);
+            if (rc) return rc;
+            gp_grad_finish_kernel<<<unsigned(mq), 256, 0, stream>>>(
+                Xq + q0 * ldq, ldq, X, ldX, n, int(p), kq, t, t, n_pad, alpha, kernel_var, f,
+                bias_var, noise_add, beta, mean ? mean + q0 : nullptr, var ? var + q0 : nullptr,
+                acq ? acq + q0 : nullptr, nullptr, nullptr);
+        }
+        ELFI_CUDA_OK(cudaGetLastError());
+        return ELFI_B200_OK;
+    }
     // query chunks: Ks (mc x n_pad) and V (mc x n_pad) live in scratch
     int64_t mc = 8192;
     if (mc > m) mc = ((m + 127) / 128) * 128;
@@ -819,7 +843,7 @@ int elfi_b200_gp_predict_grad_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t 
         }
         gp_grad_finish_kernel<<<unsigned(mq), 256, 0, stream>>>(
             Xq + q0 * ldq, ldq, X, ldX, n, int(p), kq, t, u, n_pad, alpha, kernel_var, f,
-            bias_var, mean ? mean + q0 : nullptr, var ? var + q0 : nullptr,
+            bias_var, 0.0, 0.0, mean ? mean + q0 : nullptr, var ? var + q0 : nullptr, nullptr,
             grad_mean ? grad_mean + q0 * p : nullptr, grad_var ? grad_var + q0 * p : nullptr);
     }
     ELFI_CUDA_OK(cudaGetLastError());

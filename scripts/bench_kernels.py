@@ -131,6 +131,11 @@ def main():
     rec('K12 GP predict + LCBSC m=1e5 n=2000', ms, best, flops=(m * n * n / 2 + m * n) * 2.0,
         frac_dmma_peak=(m * n * n / 2 + m * n) * 2.0 / (ms * 1e-3) / 1e12 / dmma)
     xq = grid[:10].contiguous()
+    ms, best = timeit(lambda: gp.predict_device(xq, noiseless=True, beta=20.0), reps=5, warm=2, per_batch=3)
+    rec('GP predict + LCBSC m=10 n=2000 (row-parallel path)', ms, best)
+    xq128 = grid[:128].contiguous()
+    ms, best = timeit(lambda: gp.predict_device(xq128, noiseless=True, beta=20.0), reps=5, warm=2, per_batch=3)
+    rec('GP predict + LCBSC m=128 n=2000 (GEMM path)', ms, best)
     ms, best = timeit(lambda: gp._predict_grad_device(xq), reps=5, warm=2, per_batch=3)
     rec('K13 GP predictive gradients m=10 n=2000', ms, best)
     try:
