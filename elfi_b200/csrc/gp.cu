@@ -24,8 +24,9 @@
 namespace elfi {
 
 constexpr int GP_NB = 64;          // Cholesky panel width / base block of the inverse
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16;
-constexpr int GM_LDS = 20;         // padded row stride (doubles) of the smem tiles
+constexpr int GM_BM = 128, GM_BN = 128;
+// k-slab width BK (16 or 32); smem rows are padded to BK + 4 doubles: the 16 lanes of a half warp
+// (grp 0..3 x tig 0..3) then read 16 distinct 8-byte banks
 constexpr int GM_STAGES = 3;       // cp.async ring: two slabs in flight while one is consumed
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
@@ -51,6 +52,10 @@ struct GemmArgs {
     int64_t M, N, K;
     double alpha, beta;
     int mode;   // 0 full; 1 lower tiles only (SYRK-style); 2 K limited to col0 + BN (B lower-tri)
+    // When set, C is not stored: the CTA of column tile bx writes, for each of its rows r,
+    // rowsq[bx * ld_rowsq + r] = sum over the tile's columns of (A B^T)[r][c]^2 (alpha must be 1,
+    // beta 0) -- the predictive variance needs |W k_i|^2, not W k_i.
+    double* rowsq; int64_t ld_rowsq;
 };
 
 // C = alpha * A * B^T + beta * C on the fp64 tensor path.  CTA tile BM x BN x 16, WARPS_M x WARPS_N
@@ -65,19 +70,21 @@ struct GemmArgs {
 //                              large tiles on 148 SMs): four times the CTAs, three CTAs per SM.
 // (mma.m16n8k16.f64 is no alternative: ptxas lowers it to eight DMMA.8 on sm_100a,
 // profiles/r2_dmma_m16n8k16_sass.md.)
-template <int BM, int BN, int WARPS_M, int WARPS_N>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int BK>
 struct GemmCfg {
     static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
     static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
     static constexpr int TM = WTM / 8, TN = WTN / 8;
-    static constexpr size_t SMEM = size_t(GM_STAGES) * (BM + BN) * GM_LDS * sizeof(double);
+    static constexpr int LDS = BK + 4;
+    static constexpr size_t SMEM = size_t(GM_STAGES) * (BM + BN) * LDS * sizeof(double);
 };
 
-template <int BM, int BN, int WARPS_M, int WARPS_N>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int BK>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
 gemm_nt_dmma_kernel(GemmArgs g) {
-    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N>;
+    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, BK>;
     constexpr int TM = Cfg::TM, TN = Cfg::TN;
+    constexpr int GM_BK = BK, GM_LDS = Cfg::LDS, CHUNKS = BK / 2;   // 16-byte chunks per row
     extern __shared__ __align__(16) double smem_d[];
     double* As = smem_d;                                       // [STAGES][BM][LDS]
     double* Bs = smem_d + size_t(GM_STAGES) * BM * GM_LDS;     // [STAGES][BN][LDS]
@@ -106,20 +113,20 @@ gemm_nt_dmma_kernel(GemmArgs g) {
         for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto load_stage = [&](int stage, int64_t k0) {
-        // BM (BN) rows x 8 chunks of 16 bytes per matrix
+        // BM (BN) rows x CHUNKS chunks of 16 bytes per matrix
 #pragma unroll
-        for (int it = 0; it < BM * 8 / Cfg::THREADS; ++it) {
+        for (int it = 0; it < BM * CHUNKS / Cfg::THREADS; ++it) {
             const int idx = tid + it * Cfg::THREADS;
-            const int r = idx >> 3, ch = idx & 7;
+            const int r = idx / CHUNKS, ch = idx % CHUNKS;
             const int64_t k = k0 + ch * 2;
             const bool pa = (row0 + r < g.M) && (k < Kend);
             cp_async16(As + (size_t(stage) * BM + r) * GM_LDS + ch * 2,
                        pa ? A + (row0 + r) * g.lda + k : A, pa);
         }
 #pragma unroll
-        for (int it = 0; it < BN * 8 / Cfg::THREADS; ++it) {
+        for (int it = 0; it < BN * CHUNKS / Cfg::THREADS; ++it) {
             const int idx = tid + it * Cfg::THREADS;
-            const int r = idx >> 3, ch = idx & 7;
+            const int r = idx / CHUNKS, ch = idx % CHUNKS;
             const int64_t k = k0 + ch * 2;
             const bool pb = (col0 + r < g.N) && (k < Kend);
             cp_async16(Bs + (size_t(stage) * BN + r) * GM_LDS + ch * 2,
@@ -157,6 +164,30 @@ gemm_nt_dmma_kernel(GemmArgs g) {
         }
         if (++cur == GM_STAGES) cur = 0;
     }
+    if (g.rowsq != nullptr) {
+        __syncthreads();                       // every warp is done with the last slab
+        double* red = smem_d;                  // [WARPS_N][BM]
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            double sq = 0.0;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                sq = fma(acc[i][j][0], acc[i][j][0], sq);
+                sq = fma(acc[i][j][1], acc[i][j][1], sq);
+            }
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            if (tig == 0) red[wn * BM + wm * Cfg::WTM + i * 8 + grp] = sq;
+        }
+        __syncthreads();
+        for (int r = tid; r < BM; r += Cfg::THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < WARPS_N; ++w) t += red[w * BM + r];
+            if (row0 + r < g.M) g.rowsq[bx * g.ld_rowsq + row0 + r] = t;
+        }
+        return;
+    }
     double* Ct = g.Ct ? g.Ct + bz * g.strideCt : nullptr;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -177,10 +208,10 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int BK>
 static int launch_gemm_cfg(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
-    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N>;
-    auto kern = gemm_nt_dmma_kernel<BM, BN, WARPS_M, WARPS_N>;
+    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, BK>;
+    auto kern = gemm_nt_dmma_kernel<BM, BN, WARPS_M, WARPS_N, BK>;
     static bool attr_set = false;
     if (!attr_set) {
         ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -201,8 +232,15 @@ static int launch_gemm(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
     }();
     int64_t tiles = ((g.M + GM_BM - 1) / GM_BM) * ((g.N + GM_BN - 1) / GM_BN) * batch;
     if (g.mode == 1) tiles = tiles / 2 + 1;
-    if (g.mode != 2 && tiles < small_below) return launch_gemm_cfg<64, 64, 2, 2>(g, batch, stream);
-    return launch_gemm_cfg<GM_BM, GM_BN, 2, 4>(g, batch, stream);
+    if (g.mode != 2 && tiles < small_below) return launch_gemm_cfg<64, 64, 2, 2, 16>(g, batch, stream);
+    // 32-wide slabs halve the block barriers of the large tile (221 KB of shared memory, 230
+    // registers): the 1e5 x 2000 grid prediction 16.40 -> 15.96 ms.  ELFI_B200_GEMM_BK32=0: 16.
+    static const bool wide_slab = [] {
+        const char* v = getenv("ELFI_B200_GEMM_BK32");
+        return !(v != nullptr && v[0] == '0');
+    }();
+    if (wide_slab) return launch_gemm_cfg<GM_BM, GM_BN, 2, 4, 32>(g, batch, stream);
+    return launch_gemm_cfg<GM_BM, GM_BN, 2, 4, 16>(g, batch, stream);
 }
 
 // ---- K10: Gram / cross-covariance ----------------------------------------------------------
@@ -405,22 +443,23 @@ rowdot_kernel(const double* __restrict__ M, int64_t ld, int64_t nrows, int64_t n
     if (lane == 0) out[r] = acc;
 }
 
-// ---- K12: prediction epilogues -----------------------------------------------------------------
-// mean_i = sum_j Ks[i, j] alpha_j ; var_i = kss - sum_a V[i, a]^2 (+ noise) ; LCBSC optional
+// ---- K12: prediction epilogue -------------------------------------------------------------------
+// mean_i = sum_j Ks[i, j] alpha_j ; var_i = kss - |W k_i|^2 (+ noise) ; LCBSC optional.  The
+// variance product leaves per-column-tile sums of squares instead of V = K* W^T:
+// var_i = kss - sum_t rowsq[t][i]  (V is then never written or read: 2 x 134 MB less HBM traffic
+// per 8192-query chunk).
 __global__ void __launch_bounds__(256)
-predict_rows_kernel(const double* __restrict__ Ks, const double* __restrict__ V, int64_t ld,
-                    int64_t mrows, int64_t n, const double* __restrict__ alpha, double kss,
-                    double noise_add, double beta, double* __restrict__ mean,
-                    double* __restrict__ var, double* __restrict__ acq) {
+predict_rows_sq_kernel(const double* __restrict__ Ks, int64_t ld, int64_t mrows, int64_t n,
+                       const double* __restrict__ alpha, const double* __restrict__ rowsq,
+                       int64_t ld_rowsq, int ntiles, double kss, double noise_add, double beta,
+                       double* __restrict__ mean, double* __restrict__ var,
+                       double* __restrict__ acq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = int64_t(blockIdx.x) * 8 + warp;
     if (i >= mrows) return;
     double mu = 0.0, q = 0.0;
-    for (int64_t j = lane; j < n; j += 32) {
-        mu = fma(Ks[i * ld + j], alpha[j], mu);
-        const double v = V[i * ld + j];
-        q = fma(v, v, q);
-    }
+    for (int64_t j = lane; j < n; j += 32) mu = fma(Ks[i * ld + j], alpha[j], mu);
+    for (int t = lane; t < ntiles; t += 32) q += rowsq[t * ld_rowsq + i];
     for (int o = 16; o > 0; o >>= 1) {
         mu += __shfl_xor_sync(0xffffffffu, mu, o);
         q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -789,10 +828,12 @@ int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, 
     // query chunks: Ks (mc x n_pad) and V (mc x n_pad) live in scratch
     int64_t mc = 8192;
     if (mc > m) mc = ((m + 127) / 128) * 128;
-    const size_t bytes = size_t(2) * mc * n_pad * 8 + 256;
+    // scratch: Ks (mc x n_pad), then the per-column-tile sums of squares (ntiles x mc)
+    const int ntiles = int(n_pad / GM_BN);
+    const size_t bytes = (size_t(mc) * n_pad + size_t(ntiles) * mc) * 8 + 256;
     double* Ks = static_cast<double*>(ctx_scratch(ctx, bytes));
     if (!Ks) return ELFI_B200_ERR_NOMEM;
-    double* V = Ks + size_t(mc) * n_pad;
+    double* rowsq = Ks + size_t(mc) * n_pad;
     for (int64_t q0 = 0; q0 < m; q0 += mc) {
         const int64_t rows = (m - q0) < mc ? (m - q0) : mc;
         dim3 grid(unsigned((n_pad + 255) / 256), unsigned(rows));
@@ -802,12 +843,13 @@ int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, 
         memset(&g, 0, sizeof(g));
         g.A = Ks; g.lda = n_pad;
         g.B = W; g.ldb = n_pad;
-        g.C = V; g.ldc = n_pad;
+        g.C = nullptr; g.ldc = n_pad;          // V = K* W^T is consumed in the epilogue
+        g.rowsq = rowsq; g.ld_rowsq = mc;
         g.M = rows; g.N = n_pad; g.K = n_pad; g.alpha = 1.0; g.beta = 0.0; g.mode = 2;
         int rc = launch_gemm(g, 1, stream);
         if (rc) return rc;
-        predict_rows_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
-            Ks, V, n_pad, rows, n, alpha, kernel_var + bias_var, noise_add, beta,
+        predict_rows_sq_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
+            Ks, n_pad, rows, n, alpha, rowsq, mc, ntiles, kernel_var + bias_var, noise_add, beta,
             mean ? mean + q0 : nullptr, var ? var + q0 : nullptr, acq ? acq + q0 : nullptr);
     }
     ELFI_CUDA_OK(cudaGetLastError());
