@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(KL_MAXB)
 kliep_update_kernel(const double* __restrict__ partial, int nblocks, int nb, const double* __restrict__ b,
                     double eps, double* __restrict__ alpha) {
     __shared__ double red[KL_MAXB];
-    __shared__ double s_bb, s_ba;
     const int j = threadIdx.x;
     double g = 0.0;
     if (j < nb)
@@ -153,7 +152,6 @@ kliep_update_kernel(const double* __restrict__ partial, int nblocks, int nb, con
     a = fmax(0.0, a + (1.0 - ba) * (bj / bb));
     const double ba2 = dot(bj * a);
     if (j < nb) alpha[j] = a / ba2;
-    (void)s_bb; (void)s_ba;
 }
 
 __global__ void kliep_reduce2_kernel(const double* __restrict__ partial, int nblocks,
