@@ -298,6 +298,23 @@ gather2_rows_kernel(const double* __restrict__ A, int64_t ldA, int64_t nA,
     }
 }
 
+// keys of the virtual concatenation [A (nA rows); B[mapB] (nB rows)] of a top-n merge; a key is
+// the last of kw columns (the reference ranks by the last distance column, samplers.py:232)
+__global__ void __launch_bounds__(256)
+merge_keys_kernel(const double* __restrict__ keysA, int64_t ldA, int64_t nA,
+                  const double* __restrict__ keysB, int64_t ldB, const int32_t* __restrict__ mapB,
+                  int64_t nB, double* __restrict__ out) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nA + nB; i += stride) {
+        if (i < nA) {
+            out[i] = keysA[i * ldA];
+        } else {
+            const int64_t rb = mapB ? int64_t(mapB[i - nA]) : (i - nA);
+            out[i] = keysB[rb * ldB];
+        }
+    }
+}
+
 // ---- weighted quantile ---------------------------------------------------------------------
 // The reference normalises with np.sum (pairwise order) and accumulates with np.cumsum
 // (strictly sequential); with equal weights and round alphas (e.g. SMC round 0, alpha = 0.5)
@@ -766,6 +783,52 @@ int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA,
     if (blocks > int64_t(ctx->sm_count) * 16) blocks = int64_t(ctx->sm_count) * 16;
     gather2_rows_kernel<<<unsigned(blocks), 256, 0, stream>>>(A, ldA, nA, Bm, ldB, mapB, perm, n,
                                                              width, dst, ld_dst);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
+int elfi_b200_topn_merge_f64(elfi_b200_ctx* ctx, const double* keysA, int64_t ld_keysA, int64_t nA,
+                             const double* keysB, int64_t ld_keysB, const int32_t* mapB, int64_t nB,
+                             int64_t n_keep, int64_t n_out, const double* const* A_host,
+                             const int64_t* ldA_host, const double* const* B_host,
+                             const int64_t* ldB_host, const int64_t* width_host,
+                             double* const* dst_host, const int64_t* ld_dst_host, void* stream_) {
+    using namespace elfi;
+    ELFI_REQUIRE(ctx != nullptr, "topn_merge: ctx is NULL");
+    ELFI_REQUIRE(nA >= 0 && nB >= 0 && n_keep >= 0 && n_keep <= nA + nB && n_out >= 0,
+                 "topn_merge: bad sizes (nA=%lld nB=%lld n_keep=%lld)", (long long)nA, (long long)nB,
+                 (long long)n_keep);
+    const int64_t n = nA + nB;
+    ELFI_REQUIRE(n < (int64_t(1) << 31), "topn_merge: too many rows");
+    if (n == 0 || n_keep == 0) return ELFI_B200_OK;
+    ELFI_REQUIRE((nA == 0 || keysA) && (nB == 0 || keysB), "topn_merge: keys are NULL");
+    ELFI_REQUIRE(n_out == 0 || (A_host && ldA_host && B_host && ldB_host && width_host && dst_host &&
+                                ld_dst_host), "topn_merge: output descriptors are NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ELFI_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t sort_bytes = sort_scratch_bytes(n);
+    uint8_t* base = static_cast<uint8_t*>(ctx_scratch(ctx, sort_bytes + align256(size_t(n) * 8) + 256));
+    if (!base) return ELFI_B200_ERR_NOMEM;
+    SortScratch s = carve_sort(base, n);
+    double* keys = reinterpret_cast<double*>(base + sort_bytes);
+    int blocks = int((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    merge_keys_kernel<<<blocks, 256, 0, stream>>>(keysA, ld_keysA, nA, keysB, ld_keysB, mapB, nB, keys);
+    int rc = sort_pairs_device(keys, n, s, ctx->sm_count, stream);
+    if (rc) return rc;
+    const int32_t* perm = s.v[0];
+    for (int64_t k = 0; k < n_out; ++k) {
+        const int64_t width = width_host[k];
+        ELFI_REQUIRE(width >= 1 && dst_host[k] && ld_dst_host[k] >= width &&
+                     (nA == 0 || (A_host[k] && ldA_host[k] >= width)) &&
+                     (nB == 0 || (B_host[k] && ldB_host[k] >= width)),
+                     "topn_merge: bad descriptor of output %lld", (long long)k);
+        int64_t gb = (n_keep * width + 255) / 256;
+        if (gb > int64_t(ctx->sm_count) * 16) gb = int64_t(ctx->sm_count) * 16;
+        gather2_rows_kernel<<<unsigned(gb), 256, 0, stream>>>(A_host[k], ldA_host[k], nA, B_host[k],
+                                                              ldB_host[k], mapB, perm, n_keep, width,
+                                                              dst_host[k], ld_dst_host[k]);
+    }
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

@@ -312,6 +312,38 @@ def take_rows2(a, b, perm, n_out, map_b=None):
     return dst.reshape((n_out,) + tuple(shape[1:]))
 
 
+def merge_topn(state, batch, key_state, key_batch, map_b, n_keep):
+    """Rejection._merge_batch (samplers.py:226-237) as one library call: the virtual concatenation
+    [state[k]; batch[k][map_b]] is ranked by [key_state; key_batch[map_b]] (1-d views, possibly a
+    strided column of a (rows, K) distance matrix) and the n_keep smallest rows of every output k
+    come back as new device arrays.  map_b None: every batch row is a candidate."""
+    if map_b is not None and map_b.dtype != torch.int32:
+        raise TypeError('map_b must be an int32 device array of batch row indices')
+    n_a = int(key_state.shape[0])
+    n_b = int(map_b.numel()) if map_b is not None else int(key_batch.shape[0])
+    a2 = [_as_2d(t) for t in state]
+    b2 = [_as_2d(dev.to_device(t)) for t in batch]
+    widths = [t.shape[1] for t in b2]
+    outs = [dev.empty((n_keep, w)) for w in widths]
+    n = len(outs)
+    if n_keep and n:
+        arr_p, arr_i = ctypes.c_void_p * n, ctypes.c_int64 * n
+        pa = arr_p(*[t.data_ptr() if n_a else 0 for t in a2])
+        la = arr_i(*[_ld(t) if n_a else w for t, w in zip(a2, widths)])
+        pb = arr_p(*[t.data_ptr() for t in b2])
+        lb = arr_i(*[_ld(t) for t in b2])
+        wd = arr_i(*widths)
+        pd = arr_p(*[t.data_ptr() for t in outs])
+        ld = arr_i(*widths)
+        cast = lambda a: ctypes.cast(a, ctypes.c_void_p)   # noqa: E731
+        _lib.call('elfi_b200_topn_merge_f64', dev.context(), dev.ptr(key_state) if n_a else None,
+                  key_state.stride(0) if n_a > 1 else 1, n_a, dev.ptr(key_batch),
+                  key_batch.stride(0) if key_batch.shape[0] > 1 else 1, dev.ptr(map_b), n_b,
+                  n_keep, n, cast(pa), cast(la), cast(pb), cast(lb), cast(wd), cast(pd), cast(ld),
+                  dev.stream_ptr())
+    return [o.reshape((n_keep,) + tuple(t.shape[1:])) for o, t in zip(outs, batch)]
+
+
 class CandidateBuffer:
     """Packed (capacity, width) device buffer of accepted rows + device-side row count: the tail
     of the reference's sample buffers (samplers.py:196-230) filled without host round trips."""

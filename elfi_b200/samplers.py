@@ -604,10 +604,10 @@ class Rejection(Sampler):
         n_out = min(n, nv + n_cand)
         key_state = samples[dname] if samples[dname].dim() == 1 else samples[dname][:, -1]
         key_batch = d_batch if d_batch.dim() == 1 else d_batch[:, -1]
-        cand_keys = key_batch if map_b is None else ops.take_rows(key_batch, map_b)
-        perm = ops.argsort(torch.cat([key_state[:nv], cand_keys]))
-        for node in samples:
-            top = ops.take_rows2(samples[node][:nv], _to_dev_f64(batch[node]), perm, n_out, map_b)
+        nodes = list(samples)
+        tops = ops.merge_topn([samples[k][:nv] for k in nodes], [_to_dev_f64(batch[k]) for k in nodes],
+                              key_state[:nv], key_batch, map_b, n_out)
+        for node, top in zip(nodes, tops):
             if n_out == n:
                 samples[node] = top
             else:

@@ -221,6 +221,23 @@ int elfi_b200_gather2_rows_f64(elfi_b200_ctx* ctx, const double* A, int64_t ldA,
                                const int32_t* perm, int64_t n, int64_t width, double* dst,
                                int64_t ld_dst, void* stream);
 
+/* elfi_b200_topn_merge_f64: Rejection._merge_batch (samplers.py:226-237) in one call.  The
+ * reference appends the accepted rows of a batch behind its best-n buffers, argsorts the distance
+ * column over n + batch rows and permutes every output; here the virtual concatenation
+ *     [A (nA rows of the current best-n) ; B[mapB] (nB accepted rows of the batch, mapB NULL = 0..nB-1)]
+ * is ranked by its keys (keysA / keysB: the LAST distance column, addressed with a leading
+ * dimension so that a column of a (rows, K) matrix can be passed in place; stable, NaN last) and
+ * the n_keep smallest rows of each of the n_out outputs are gathered from their two sources:
+ *     dst_host[k] (n_keep, width_host[k]) <- rows of A_host[k] (nA, width) / B_host[k] (batch, width).
+ * The seven descriptor arrays are HOST arrays of length n_out; destinations must not alias sources.
+ * merge_keys + 8-bit radix passes + one gather per output on `stream`, no synchronisation. */
+int elfi_b200_topn_merge_f64(elfi_b200_ctx* ctx, const double* keysA, int64_t ld_keysA, int64_t nA,
+                             const double* keysB, int64_t ld_keysB, const int32_t* mapB, int64_t nB,
+                             int64_t n_keep, int64_t n_out, const double* const* A_host,
+                             const int64_t* ldA_host, const double* const* B_host,
+                             const int64_t* ldB_host, const int64_t* width_host,
+                             double* const* dst_host, const int64_t* ld_dst_host, void* stream);
+
 /* elfi_b200_wquantile_f64: weighted_sample_quantile (elfi/methods/utils.py:379-411).
  *   x (n), w (n) or NULL (equal weights), 0 <= alpha <= 1.
  *   out[0] = alpha-quantile (an element of x), out[1] = its rank in sorted order (as double).

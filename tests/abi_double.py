@@ -233,6 +233,29 @@ def gather2_rows_f64(ctx, A, ldA, nA, B, ldB, mapB, perm, n, width, dst, ld_dst,
         out[from_b] = _mat(B, int(rows_b.max()) + 1, width, ldB)[rows_b]
 
 
+def topn_merge_f64(ctx, keysA, ld_keysA, nA, keysB, ld_keysB, mapB, nB, n_keep, n_out, A_host, ldA_host,
+                   B_host, ldB_host, width_host, dst_host, ld_dst_host, stream):
+    _require(0 <= n_keep <= nA + nB, 'topn_merge: bad sizes')
+    if not (nA + nB and n_keep):
+        return
+    mb = _vec(mapB, nB, np.int32).astype(np.int64) if _addr(mapB) and nB else np.arange(nB)
+    ka = _mat(keysA, nA, 1, ld_keysA)[:, 0] if nA else np.empty(0)
+    kb = _mat(keysB, int(mb.max()) + 1, 1, ld_keysB)[mb, 0] if nB else np.empty(0)
+    order = np.argsort(np.concatenate([ka, kb]), kind='stable')[:n_keep]
+    pa, la = _vec(A_host, max(n_out, 1), np.uint64), _vec(ldA_host, max(n_out, 1), np.int64)
+    pb, lb = _vec(B_host, max(n_out, 1), np.uint64), _vec(ldB_host, max(n_out, 1), np.int64)
+    wd = _vec(width_host, max(n_out, 1), np.int64)
+    pd, ld = _vec(dst_host, max(n_out, 1), np.uint64), _vec(ld_dst_host, max(n_out, 1), np.int64)
+    for k in range(n_out):
+        w = int(wd[k])
+        rows = []
+        if nA:
+            rows.append(_mat(int(pa[k]), nA, w, int(la[k])))
+        if nB:
+            rows.append(_mat(int(pb[k]), int(mb.max()) + 1, w, int(lb[k]))[mb])
+        _mat(int(pd[k]), n_keep, w, int(ld[k]))[:] = np.concatenate(rows)[order]
+
+
 def wquantile_f64(ctx, x, w, n, alpha, out, stream):
     _require(n >= 1 and 0.0 <= alpha <= 1.0, 'wquantile: bad arguments')
     x = _vec(x, n).copy()
@@ -511,7 +534,7 @@ def logprior_box_f64(ctx, x, ldx, B, p, box_host, out, stream):
 
 
 _TABLE = {'elfi_b200_' + f.__name__: f for f in (
-    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, rejection_batch_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, dist_seuclidean_thr_f64, summary_autocov_f64, summary_meanvar_f64,
+    dist_euclid_thr_f64, dist_euclid_thr_dev_f64, dist_euclid_mom_f64, accept_append_f64, rejection_batch_f64, dist_euclid_thr_f64_host, dist_metric_thr_f64, dist_seuclidean_thr_f64, topn_merge_f64, summary_autocov_f64, summary_meanvar_f64,
     sort_pairs_f64, gather_rows_f64, gather2_rows_f64, wquantile_f64, colmoments_f64,
     weighted_stats_f64, gm_logpdf_f64, gm_logpdf_mixed_f64, smc_weights_f64, rowsort_f64, kliep_fit_f64, gp_fit_f64,
     gp_predict_f64, gp_predict_grad_f64, gp_whiten_f64, gp_apply_wt_f64, gp_cross_cov_f64, lcbsc_f64, prior_ma2_f64, logprior_ma2_f64, sim_ma2_f64,

@@ -89,3 +89,47 @@ def case_device_thresholds_and_append():
     assert int(wide.count.item()) == 40
     got = wide.rows[:40].cpu().numpy()
     assert np.array_equal(got[:, :2], a.cpu().numpy()) and np.array_equal(got[:, 2], bcol.cpu().numpy())
+
+
+def case_topn_merge_matches_reference_merge():
+    """elfi_b200_topn_merge_f64 (ops.merge_topn) against the reference's append + argsort +
+    permute (samplers.py:226-237): several batches, a (rows, K) distance matrix whose LAST column
+    is the key, a 1-d and a 2-d payload, ties and a NaN key, the buffer filling up from empty."""
+    import torch
+    from elfi_b200 import device as dev
+    from elfi_b200 import ops
+    rs = np.random.RandomState(11)
+    n, B, K = 300, 1000, 3
+    state = {'d': dev.empty((n, K)), 'p': dev.empty((n,)), 'S': dev.empty((n, 5))}
+    host = {'d': np.zeros((0, K)), 'p': np.zeros(0), 'S': np.zeros((0, 5))}
+    nv = 0
+    for it in range(5):
+        d = np.abs(rs.randn(B, K))
+        d[::7, -1] = d[3, -1]                      # ties: stable order decides
+        if it == 2:
+            d[5, -1] = np.nan                       # ranks last
+        batch = {'d': d, 'p': rs.randn(B), 'S': rs.randn(B, 5)}
+        if it % 2:
+            acc = np.nonzero(d[:, -1] <= 0.5)[0].astype(np.int32)
+            map_b = dev.to_device(acc, dtype=torch.int32)
+        else:
+            acc, map_b = np.arange(B), None
+        n_out = min(n, nv + len(acc))
+        names = list(state)
+        bdev = {k: dev.to_device(batch[k]) for k in names}
+        tops = ops.merge_topn([state[k][:nv] for k in names], [bdev[k] for k in names],
+                              state['d'][:nv, -1], bdev['d'][:, -1], map_b, n_out)
+        cat = {k: np.concatenate([host[k], batch[k][acc]]) for k in names}
+        order = np.argsort(cat['d'][:, -1], kind='stable')[:n_out]
+        for k, top in zip(names, tops):
+            want = cat[k][order]
+            got = top.cpu().numpy()
+            assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True), (it, k)
+            host[k] = want
+            state[k][:n_out] = top
+        nv = n_out
+    assert nv == n
+    # nothing to keep / nothing to merge
+    empty = ops.merge_topn([state['p'][:0]], [dev.to_device(np.zeros(4))], state['d'][:0, -1],
+                           dev.to_device(np.ones(4)), None, 0)
+    assert empty[0].shape == (0,)

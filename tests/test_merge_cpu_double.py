@@ -9,3 +9,7 @@ pytestmark = pytest.mark.usefixtures('cpu_double')
 
 def test_device_thresholds_and_append():
     cases.case_device_thresholds_and_append()
+
+
+def test_topn_merge_matches_reference_merge():
+    cases.case_topn_merge_matches_reference_merge()

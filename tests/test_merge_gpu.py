@@ -11,6 +11,10 @@ def test_device_thresholds_and_append():
     cases.case_device_thresholds_and_append()
 
 
+def test_topn_merge_matches_reference_merge():
+    cases.case_topn_merge_matches_reference_merge()
+
+
 def test_allgather_particles_single_process():
     """elfi_b200_allgather_particles: every GPU receives the context-ordered concatenation of all
     blocks (two GPUs when the box has them; two blocks of one GPU otherwise -- same code path with
