@@ -12,7 +12,10 @@
 //                                 rejection of draws outside the prior support)
 // The random numbers are a pure function of (seed, stream, row, index): the simulator can be
 // replayed (e.g. to materialise X for a test) and any sharding of rows gives the same particles.
+#include <cstdlib>
+
 #include "gnkmath.cuh"
+#include "leafsum.cuh"
 #include "pairwise.cuh"
 
 namespace elfi {
@@ -90,9 +93,33 @@ __global__ void logprior_ma2_kernel(const double* __restrict__ x, int64_t ld, in
     out[i] = lp;
 }
 
+// Elements k0 + E .. k0 + 7 of a group of eight: their lag-1 / lag-2 products into the leaf sums
+// (E is a template parameter because the slot of a product, index % 8, must be static).
+template <int E>
+__device__ __forceinline__ void ma2_leaf_products(LeafSum& l1, LeafSum& l2, const double (&x)[8],
+                                                  double xm1, double xm2, bool mid, int k0,
+                                                  int cnt) {
+    const double prev1 = (E == 0) ? xm1 : x[E >= 1 ? E - 1 : 0];
+    const double prev2 = (E == 0) ? xm2 : (E == 1 ? xm1 : x[E >= 2 ? E - 2 : 0]);
+    if (mid) {
+        l1.push_mid<(E + 7) & 7>(__dmul_rn(x[E], prev1));
+        l2.push_mid<(E + 6) & 7>(__dmul_rn(x[E], prev2));
+    } else if (E < cnt) {
+        const int k = k0 + E;
+        if (k >= 1) l1.push<(E + 7) & 7>(k - 1, __dmul_rn(x[E], prev1));
+        if (k >= 2) l2.push<(E + 6) & 7>(k - 2, __dmul_rn(x[E], prev2));
+    }
+    if constexpr (E + 1 < 8) ma2_leaf_products<E + 1>(l1, l2, x, xm1, xm2, mid, k0, cnt);
+}
+
 // ---- MA2 simulator (+ fused autocovariance) ---------------------------------------------------
 // One thread per row; normals are generated eight at a time (4 Philox blocks).
-template <bool WRITE_X, bool SUMMARIES>
+// LEAF: both product rows fit one leaf of NumPy's pairwise sum (n_obs - 1 <= 128, e.g. the 99 / 98
+// products of the benchmark model): eight running sums per lag (leafsum.cuh) instead of the general
+// PairwiseStream tree with its per-level stack -- the kernel drops from 255 registers to well under
+// half, i.e. more than two resident blocks per SM for a kernel whose Box-Muller chains need the
+// latency hiding (0.79 ms for 1e6 x 100 at 8 warps per SM against ~0.3 ms of fp64-pipe time).
+template <bool WRITE_X, bool SUMMARIES, bool LEAF>
 __global__ void __launch_bounds__(128)
 sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int64_t B, int n_obs,
                uint64_t seed, uint64_t offset, double* __restrict__ X, int64_t ldX,
@@ -104,9 +131,15 @@ sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int
     const uint32_t r0 = uint32_t(row), r1 = uint32_t(row >> 32);
     const double a1 = t1[i], a2 = t2[i];
     PairwiseStream<6> p1, p2;      // lag-1 and lag-2 product sums (rows up to 7688 terms)
+    LeafSum l1, l2;                // the same sums when a row is a single leaf
     if (SUMMARIES) {
-        p1.begin(n_obs - 1);
-        p2.begin(n_obs - 2);
+        if constexpr (LEAF) {
+            l1.begin(n_obs - 1);
+            l2.begin(n_obs - 2);
+        } else {
+            p1.begin(n_obs - 1);
+            p2.begin(n_obs - 2);
+        }
     }
     // w has n_obs + 2 entries; x_k = w_{k+2} + a1 w_{k+1} + a2 w_k
     double wm2, wm1;   // w_{k}, w_{k+1} before the current group
@@ -139,7 +172,13 @@ sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int
             for (int e = 0; e < 8; ++e)
                 if (e < cnt) X[i * ldX + k0 + e] = x[e];
         }
-        if (SUMMARIES) {
+        if constexpr (SUMMARIES && LEAF) {
+            // product index k - 1 (lag 1) / k - 2 (lag 2) of element k = k0 + e goes straight into
+            // its running sum; slot = index % 8 is static because k0 is a multiple of 8
+            const bool mid = cnt == 8 && l1.all_mid(k0 - 1, k0 + 6) && l2.all_mid(k0 - 2, k0 + 5);
+            ma2_leaf_products<0>(l1, l2, x, xm1, xm2, mid, k0, cnt);
+        }
+        if constexpr (SUMMARIES && !LEAF) {
             // lag-1 products p[j] = x[j+1] x[j], j = k - 1 for element k; lag-2: j = k - 2.
             // Feed aligned groups of 8 products: group g of lag 1 needs x[8g .. 8g+8].
             // b1[] holds products with indices 8(g) .. 8g+7 once x[8g+8] is known, so products are
@@ -165,7 +204,11 @@ sim_ma2_kernel(const double* __restrict__ t1, const double* __restrict__ t2, int
         xm2 = x[6];
         xm1 = x[7];
     }
-    if (SUMMARIES) {
+    if constexpr (SUMMARIES && LEAF) {
+        S[i * ldS + 0] = l1.finish(n_obs - 1) / double(n_obs - 1);
+        S[i * ldS + 1] = l2.finish(n_obs - 2) / double(n_obs - 2);
+    }
+    if constexpr (SUMMARIES && !LEAF) {
         const int m1 = n_obs - 1, m2 = n_obs - 2;
         if (m1 % 8) p1.feed8(m1 - m1 % 8, b1, m1 % 8);
         if (m2 % 8) p2.feed8(m2 - m2 % 8, b2, m2 % 8);
@@ -422,9 +465,13 @@ int elfi_b200_sim_ma2_f64(elfi_b200_ctx* ctx, const double* t1, const double* t2
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     const unsigned blocks = unsigned((B + 127) / 128);
-    if (X && S) sim_ma2_kernel<true, true><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS);
-    else if (X) sim_ma2_kernel<true, false><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS);
-    else sim_ma2_kernel<false, true><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS);
+    const bool leaf = n_obs - 1 <= LEAF_MAX_TERMS && getenv("ELFI_B200_SIM_MA2_TREE") == nullptr;
+#define ELFI_SIM_MA2(WX, SM, LF) \
+    sim_ma2_kernel<WX, SM, LF><<<blocks, 128, 0, stream>>>(t1, t2, B, int(n_obs), seed, offset, X, ldX, S, ldS)
+    if (X && S) { if (leaf) ELFI_SIM_MA2(true, true, true); else ELFI_SIM_MA2(true, true, false); }
+    else if (X) ELFI_SIM_MA2(true, false, false);
+    else { if (leaf) ELFI_SIM_MA2(false, true, true); else ELFI_SIM_MA2(false, true, false); }
+#undef ELFI_SIM_MA2
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }

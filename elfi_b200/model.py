@@ -708,10 +708,11 @@ def _stack_summaries(summaries):
     return torch.cat(cols, dim=1)
 
 
-_OBSERVED_ROWS = {}     # id(observed tuple) -> (the tuple, stacked host row): one D2H per inference
+_OBSERVED_ROWS = {}     # id(observed tuple) -> [the tuple, stacked host row, its device twin]
 
 
 def _stack_observed(observed):
+    """The observed summaries as one (1, D) host row; one D2H per inference, not per batch."""
     hit = _OBSERVED_ROWS.get(id(observed))
     if hit is not None and hit[0] is observed:
         return hit[1]
@@ -719,17 +720,45 @@ def _stack_observed(observed):
     row = np.concatenate(obs, axis=1).astype(np.float64)
     if len(_OBSERVED_ROWS) > 64:
         _OBSERVED_ROWS.clear()
-    _OBSERVED_ROWS[id(observed)] = (observed, row)
+    _OBSERVED_ROWS[id(observed)] = [observed, row, None]
     return row
+
+
+def _observed_on_device(observed):
+    """Device twin of :func:`_stack_observed` (a pageable H2D copy synchronises the stream: made
+    once per inference, the distance kernels of all batches read the same D doubles)."""
+    row = _stack_observed(observed)
+    hit = _OBSERVED_ROWS[id(observed)]
+    if hit[2] is None:
+        hit[2] = dev.to_device(row.ravel())
+    return hit[2]
+
+
+_DEVICE_CONSTANTS = {}  # id(host array) -> (the array, device twin): operator constants (w, V)
+
+
+def _device_constant(arr):
+    """Device twin of a host array that an operator was constructed with (cdist's w / V): copied
+    once, not with every batch (each pageable H2D copy synchronises the stream)."""
+    if arr is None or dev.is_device_array(arr):
+        return arr
+    hit = _DEVICE_CONSTANTS.get(id(arr))
+    if hit is not None and hit[0] is arr:
+        return hit[1]
+    if len(_DEVICE_CONSTANTS) > 64:
+        _DEVICE_CONSTANTS.clear()
+    twin = dev.to_device(np.asarray(arr, dtype=np.float64))
+    _DEVICE_CONSTANTS[id(arr)] = (arr, twin)
+    return twin
 
 
 def device_euclidean_discrepancy(*summaries, observed, w=None, accept=None):
     """distance_as_discrepancy (elfi/model/utils.py:37-52) for the Euclidean family, on device."""
     X = _stack_summaries(summaries)
-    obs = _stack_observed(observed)
-    if obs.shape[0] != 1:
+    if _stack_observed(observed).shape[0] != 1:
         raise ValueError('observed summaries must form a single row')
-    d, idx = ops.dist_euclid(X, obs, w=w, thresholds=accept)
+    d, idx = ops.dist_euclid(X, _observed_on_device(observed), w=_device_constant(w),
+                             thresholds=accept)
     return AcceptedOutput(d, idx) if accept is not None else d
 
 
@@ -739,22 +768,21 @@ DEVICE_METRICS = ('sqeuclidean', 'cityblock', 'chebyshev', 'minkowski')
 def device_metric_discrepancy(metric, *summaries, observed, p=2.0, accept=None):
     """distance_as_discrepancy for the other unweighted cdist metrics that have a kernel."""
     X = _stack_summaries(summaries)
-    obs = _stack_observed(observed)
-    if obs.shape[0] != 1:
+    if _stack_observed(observed).shape[0] != 1:
         raise ValueError('observed summaries must form a single row')
     thr = None if accept is None else np.atleast_1d(dev.to_host(accept))
-    d, idx = ops.dist_metric(X, obs, metric, p=p, threshold=thr)
+    d, idx = ops.dist_metric(X, _observed_on_device(observed), metric, p=p, threshold=thr)
     return AcceptedOutput(d, idx) if accept is not None else d
 
 
 def device_seuclidean_discrepancy(*summaries, observed, V, accept=None):
     """distance_as_discrepancy for cdist's 'seuclidean' (V = component variances)."""
     X = _stack_summaries(summaries)
-    obs = _stack_observed(observed)
-    if obs.shape[0] != 1:
+    if _stack_observed(observed).shape[0] != 1:
         raise ValueError('observed summaries must form a single row')
     thr = None if accept is None else np.atleast_1d(dev.to_host(accept))
-    d, idx = ops.dist_seuclidean(X, obs, V, threshold=thr)
+    d, idx = ops.dist_seuclidean(X, _observed_on_device(observed), _device_constant(V),
+                                 threshold=thr)
     return AcceptedOutput(d, idx) if accept is not None else d
 
 
@@ -823,13 +851,17 @@ class AdaptiveDistance(Discrepancy):
     # the operation is a bound method of a reference; look the state up at call time
     def _nested_discrepancy(self, *summaries, observed, accept=None):
         X = _stack_summaries(summaries)
-        obs = _stack_observed(observed)
         ws = self.state['attr_dict']['w']
         D = X.shape[1]
-        W = np.stack([np.ones(D) if w is None else np.asarray(w, dtype=np.float64) ** 2
-                      for w in ws])
+        key = tuple(id(w) for w in ws)       # (K, D) squared weights: rebuilt when a round is added
+        held = self._s.get('_W_dev')
+        if held is None or held[0] != key or held[1].shape[1] != D:
+            W = np.stack([np.ones(D) if w is None else np.asarray(w, dtype=np.float64) ** 2
+                          for w in ws])
+            held = self._s['_W_dev'] = (key, dev.to_device(W))
         # the batch's column moments come out of the same read of X; add_data picks them up
-        d, idx, mom = ops.dist_euclid(X, obs, w=W, thresholds=accept, moments=True)
+        d, idx, mom = ops.dist_euclid(X, _observed_on_device(observed), w=held[1],
+                                      thresholds=accept, moments=True)
         self._s['_batch_moments'] = (X, mom)
         return AcceptedOutput(d, idx) if accept is not None else d
 

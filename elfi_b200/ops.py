@@ -167,11 +167,10 @@ def dist_seuclidean(S, obs, V, threshold=None, want_indices=True):
     if obs_t.numel() != D:
         raise ValueError('XA and XB must have the same number of columns '
                          '(i.e. feature dimension.)')
-    V = np.ascontiguousarray(np.asarray(V, dtype=np.float64).reshape(-1))
-    if V.shape[0] != D:
+    V_t = dev.to_device(V)
+    if V_t.dim() != 1 or V_t.shape[0] != D:
         raise ValueError('Variance vector V must be of the same dimension as the vectors on '
                          'which the distances are computed.')
-    V_t = dev.to_device(V)
     thr = None
     if threshold is not None:
         thr = np.ascontiguousarray(np.atleast_1d(threshold), dtype=np.float64)
