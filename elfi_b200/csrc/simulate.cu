@@ -291,7 +291,20 @@ __global__ void logprior_gauss_kernel(const double* __restrict__ x, int64_t ld, 
 // y_ij = mu_i + sigma_i z_ij (gauss.py:11-35) with np.mean / np.var summaries (gauss.py:142-173,
 // NumPy pairwise order).  The variance needs the mean first: the counter-based normals are simply
 // generated a second time instead of being stored.
-template <bool WRITE_Y>
+// Terms k0 + E .. k0 + 7 of a group of eight into a single-leaf sum (static slots).
+template <int E>
+__device__ __forceinline__ void leaf_feed8(LeafSum& s, int k0, const double (&t)[8], int cnt,
+                                           bool mid) {
+    if (mid) s.push_mid<E>(t[E]);
+    else if (E < cnt) s.push<E>(k0 + E, t[E]);
+    if constexpr (E + 1 < 8) leaf_feed8<E + 1>(s, k0, t, cnt, mid);
+}
+
+// LEAF: n_obs <= 128, the row sums are single leaves of NumPy's pairwise sum (fewer registers, more
+// resident blocks; keeping the draws in registers to generate them only once was tried and is
+// slower -- 180 registers, two blocks per SM: the Box-Muller chains need the occupancy more than
+// they need the halved work: 0.715 against 0.562 ms for 1e6 x 50).
+template <bool WRITE_Y, bool LEAF>
 __global__ void __launch_bounds__(128)
 sim_gauss_kernel(const double* __restrict__ mu, const double* __restrict__ sigma, int64_t B, int n_obs,
                  uint64_t seed, uint64_t offset, double* __restrict__ Y, int64_t ldY,
@@ -303,9 +316,12 @@ sim_gauss_kernel(const double* __restrict__ mu, const double* __restrict__ sigma
     const uint32_t r0 = uint32_t(row), r1 = uint32_t(row >> 32);
     const double m = mu[i], sg = sigma[i];
     PairwiseStream<6> pw;
+    LeafSum lf;
     double mean = 0.0;
     for (int pass = 0; pass < (S ? 2 : 1); ++pass) {
-        if (S) pw.begin(n_obs);
+        if (S) {
+            if constexpr (LEAF) lf.begin(n_obs); else pw.begin(n_obs);
+        }
         double t[8];
         for (int k0 = 0; k0 < n_obs; k0 += 8) {
             double y[8];
@@ -332,11 +348,14 @@ sim_gauss_kernel(const double* __restrict__ mu, const double* __restrict__ sigma
                         t[e] = __dmul_rn(c, c);
                     }
                 }
-                pw.feed8(k0, t, cnt);
+                if constexpr (LEAF)
+                    leaf_feed8<0>(lf, k0, t, cnt, cnt == 8 && lf.all_mid(k0, k0 + 7));
+                else
+                    pw.feed8(k0, t, cnt);
             }
         }
         if (S) {
-            const double v = pw.finish() / double(n_obs);
+            const double v = (LEAF ? lf.finish(n_obs) : pw.finish()) / double(n_obs);
             if (pass == 0) { mean = v; S[i * ldS] = v; } else { S[i * ldS + 1] = v; }
         }
     }
@@ -578,8 +597,12 @@ int elfi_b200_sim_gauss_f64(elfi_b200_ctx* ctx, const double* mu, const double* 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ELFI_CUDA_OK(cudaSetDevice(ctx->device));
     const unsigned blocks = unsigned((B + 127) / 128);
-    if (Y) sim_gauss_kernel<true><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS);
-    else sim_gauss_kernel<false><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS);
+    const bool leaf = n_obs <= LEAF_MAX_TERMS && getenv("ELFI_B200_SIM_GAUSS_TREE") == nullptr;
+#define ELFI_SIM_GAUSS(WY, LF) \
+    sim_gauss_kernel<WY, LF><<<blocks, 128, 0, stream>>>(mu, sigma, B, int(n_obs), seed, offset, Y, ldY, S, ldS)
+    if (Y) { if (leaf) ELFI_SIM_GAUSS(true, true); else ELFI_SIM_GAUSS(true, false); }
+    else { if (leaf) ELFI_SIM_GAUSS(false, true); else ELFI_SIM_GAUSS(false, false); }
+#undef ELFI_SIM_GAUSS
     ELFI_CUDA_OK(cudaGetLastError());
     return ELFI_B200_OK;
 }
