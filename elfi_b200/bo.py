@@ -51,32 +51,12 @@ class GPyRegression:
         update (O(b n^2), 3 small launches) instead of a refit whenever the hyper-parameters and
         the padded size are unchanged; equal to a refit to ~1e-7 (the reference rebuilds the GP on
         every update, gpy_regression.py:286-315).  `incremental=False` refits every time."""
-        if parameter_names is None:
-            input_dim = 1
-        elif isinstance(parameter_names, (list, tuple)):
-            input_dim = len(parameter_names)
-        else:
-            raise ValueError("Keyword `parameter_names` must be a list of strings")
-        if bounds is None:
-            logger.warning('Parameter bounds not specified. Using [0,1] for each parameter.')
-            bounds = [(0, 1)] * input_dim
-        elif len(bounds) != input_dim:
-            raise ValueError('Length of `bounds` ({}) does not match the length of '
-                             '`parameter_names` ({}).'.format(len(bounds), input_dim))
-        elif isinstance(bounds, dict):
-            if len(bounds) == 1:
-                bounds = [bounds[n] for n in bounds.keys()]
-            else:
-                bounds = [bounds[n] for n in parameter_names]
-        else:
-            raise ValueError("Keyword `bounds` must be a dictionary "
-                             "`{'parameter_name': (lower, upper), ... }`")
+        if not (parameter_names is None or isinstance(parameter_names, (list, tuple))):
+            raise ValueError('`parameter_names` must be a list of strings')
         self.parameter_names = parameter_names
-        self.input_dim = input_dim
-        self.bounds = bounds
-        self.gp_params = gp_params
-        self.optimizer = optimizer
-        self.max_opt_iters = max_opt_iters
+        self.input_dim = 1 if parameter_names is None else len(parameter_names)
+        self.bounds = self._bounds_in_parameter_order(bounds)
+        self.gp_params, self.optimizer, self.max_opt_iters = gp_params, optimizer, max_opt_iters
         self.incremental = bool(incremental)
         self._X = None          # host (n, p)
         self._Y = None          # host (n, 1)
@@ -84,6 +64,21 @@ class GPyRegression:
         self._priors = None     # Gamma prior (a, b) per hyper-parameter
         self._factor = None     # device tensors of the current fit
         self.is_sampling = False   # duck-type attribute (gpy_regression.py:64); no cached path here
+
+    def _bounds_in_parameter_order(self, bounds):
+        """{name: (lower, upper)} -> [(lower, upper)] in the order of the parameter names; the
+        unit box (with a warning) when no bounds are given."""
+        if bounds is None:
+            logger.warning('No parameter bounds given: using [0, 1] for every parameter.')
+            return [(0, 1)] * self.input_dim
+        if len(bounds) != self.input_dim:
+            raise ValueError('{} bounds were given for {} parameters'.format(len(bounds),
+                                                                             self.input_dim))
+        if not isinstance(bounds, dict):
+            raise ValueError('`bounds` must be a dictionary {parameter name: (lower, upper)}')
+        if self.input_dim == 1:
+            return list(bounds.values())
+        return [bounds[name] for name in self.parameter_names]
 
     # ---- data / state ---------------------------------------------------------------------
     @property
@@ -357,33 +352,35 @@ class GPyRegression:
 
 
 # ------------------------------------------------------------------------------ acquisition
+def _multistart_points(bounds, n, prior, random_state):
+    """(n, dim) start points inside the box `bounds`: draws from `prior` clipped to the box, or,
+    without a prior, uniform draws taken one coordinate after the other (which is how the
+    reference consumes the RandomState, elfi/methods/bo/utils.py:77-88; goldens depend on it)."""
+    if prior is None:
+        rs = random_state or np.random
+        return np.column_stack([rs.uniform(lo, hi, n) for lo, hi in bounds])
+    lows, highs = np.asarray(bounds, dtype=float).T
+    draws = np.asarray(prior.rvs(n, random_state=random_state)).reshape(n, -1)
+    return np.clip(draws, lows, highs)
+
+
+def _best_of(runs, bounds):
+    """The local optimum with the smallest value (first one on ties), clipped to the box."""
+    values = np.array([np.ravel(run.fun)[0] for run in runs], dtype=float)
+    k = int(np.argmin(values))
+    lows, highs = np.asarray(bounds, dtype=float).T
+    return np.clip(runs[k].x, lows, highs), values[k]
+
+
 def minimize(fun, bounds, method='L-BFGS-B', constraints=None, grad=None, prior=None,
              n_start_points=10, maxiter=1000, random_state=None):
-    """Multi-start local minimisation (elfi/methods/bo/utils.py:40-111)."""
-    ndim = len(bounds)
-    start_points = np.empty((n_start_points, ndim))
-    if prior is None:
-        random_state = random_state or np.random
-        for i in range(ndim):
-            start_points[:, i] = random_state.uniform(*bounds[i], n_start_points)
-    else:
-        start_points = prior.rvs(n_start_points, random_state=random_state)
-        if len(start_points.shape) == 1:
-            start_points = start_points[:, None]
-        for i in range(ndim):
-            start_points[:, i] = np.clip(start_points[:, i], *bounds[i])
-    locs, vals = [], np.empty(n_start_points)
-    for i in range(n_start_points):
-        result = scipy.optimize.minimize(fun, start_points[i, :], method=method, jac=grad,
-                                         bounds=bounds, constraints=constraints,
-                                         options={'maxiter': maxiter})
-        locs.append(result['x'])
-        vals[i] = result['fun']
-    ind_min = np.argmin(vals)
-    locs_out = locs[ind_min]
-    for i in range(ndim):
-        locs_out[i] = np.clip(locs_out[i], *bounds[i])
-    return locs[ind_min], vals[ind_min]
+    """Multi-start local minimisation with the interface of elfi/methods/bo/utils.py:40-111:
+    one SciPy local search per start point, the best end point wins."""
+    starts = _multistart_points(bounds, n_start_points, prior, random_state)
+    runs = [scipy.optimize.minimize(fun, x0, method=method, jac=grad, bounds=bounds,
+                                    constraints=constraints, options=dict(maxiter=maxiter))
+            for x0 in starts]
+    return _best_of(runs, bounds)
 
 
 class _Rendezvous:
@@ -447,19 +444,7 @@ def minimize_lockstep(batch_fun, bounds, method='L-BFGS-B', constraints=None, pr
     per start and point.  Start points, local optimiser and selection are
     those of `minimize`, so with the same function values the result is the same.  With
     with_grad=False the optimiser differentiates numerically (batch_fun returns (values, None))."""
-    ndim = len(bounds)
-    start_points = np.empty((n_start_points, ndim))
-    if prior is None:
-        random_state = random_state or np.random
-        for i in range(ndim):
-            start_points[:, i] = random_state.uniform(*bounds[i], n_start_points)
-    else:
-        start_points = prior.rvs(n_start_points, random_state=random_state)
-        if len(start_points.shape) == 1:
-            start_points = start_points[:, None]
-        for i in range(ndim):
-            start_points[:, i] = np.clip(start_points[:, i], *bounds[i])
-
+    start_points = _multistart_points(bounds, n_start_points, prior, random_state)
     meet = _Rendezvous(n_start_points)
     results = [None] * n_start_points
 
@@ -489,12 +474,7 @@ def minimize_lockstep(batch_fun, bounds, method='L-BFGS-B', constraints=None, pr
     for res in results:
         if isinstance(res, BaseException):
             raise res
-    vals = np.array([res['fun'] for res in results], dtype=float).ravel()
-    best = int(np.argmin(vals))
-    loc = results[best]['x']
-    for i in range(ndim):
-        loc[i] = np.clip(loc[i], *bounds[i])
-    return loc, vals[best]
+    return _best_of(results, bounds)
 
 
 class AcquisitionBase:
@@ -502,35 +482,35 @@ class AcquisitionBase:
 
     def __init__(self, model, prior=None, n_inits=10, max_opt_iters=1000, noise_var=None,
                  exploration_rate=10, seed=None, constraints=None):
-        self.model = model
-        self.prior = prior
-        self.n_inits = int(n_inits)
-        self.max_opt_iters = int(max_opt_iters)
-        self.constraints = constraints
-        if noise_var is not None:
-            self._check_noise_var(noise_var)
-            if isinstance(noise_var, dict):
-                noise_var = list(map(noise_var.get, self.model.parameter_names))
-        self.noise_var = noise_var
+        self.model, self.prior, self.constraints = model, prior, constraints
+        self.n_inits, self.max_opt_iters = int(n_inits), int(max_opt_iters)
+        self.noise_var = self._per_parameter_noise(noise_var)
         self.exploration_rate = exploration_rate
-        self.random_state = np.random if seed is None else np.random.RandomState(seed)
-        self.seed = 0 if seed is None else seed
+        self.seed = seed or 0
+        self.random_state = np.random.RandomState(seed) if seed is not None else np.random
 
-    def _check_noise_var(self, noise_var):
+    def _per_parameter_noise(self, noise_var):
+        """Acquisition noise variance: None, one non-negative number for all parameters, or
+        {parameter name: non-negative number} naming exactly the GP's parameters (returned as a
+        list in parameter order).  Anything else is a ValueError."""
+        if noise_var is None:
+            return None
+        names = self.model.parameter_names
         if isinstance(noise_var, dict):
-            if not set(noise_var) == set(self.model.parameter_names):
-                raise ValueError("Acquisition noise dictionary should contain all parameters.")
-            if not all(isinstance(x, (int, float)) for x in noise_var.values()):
-                raise ValueError("Acquisition noise dictionary values should all be int or float.")
-            if any([x < 0 for x in noise_var.values()]):
-                raise ValueError("Acquisition noises values should all be "
-                                 "non-negative int or float.")
+            if set(noise_var) != set(names):
+                raise ValueError('The acquisition noise dictionary must name every parameter '
+                                 '(and nothing else): {}'.format(names))
+            variances = [noise_var[n] for n in names]
         elif isinstance(noise_var, (int, float)):
-            if noise_var < 0:
-                raise ValueError("Acquisition noise should be non-negative int or float.")
+            variances = [noise_var]
         else:
-            raise ValueError("Either acquisition noise is a float or it is a dictionary of "
-                             "floats defining variance for each parameter dimension.")
+            raise ValueError('Acquisition noise is a number or a dictionary {parameter name: '
+                             'number} of variances')
+        for v in variances:
+            if not isinstance(v, (int, float)) or v < 0:
+                raise ValueError('Acquisition noise variances must be non-negative numbers, '
+                                 'got {!r}'.format(v))
+        return variances if isinstance(noise_var, dict) else noise_var
 
     def evaluate(self, x, t=None):
         raise NotImplementedError
@@ -563,19 +543,17 @@ class AcquisitionBase:
         return self._add_noise(x)
 
     def _add_noise(self, x):
-        if self.noise_var is not None:
-            noise_var = np.asanyarray(self.noise_var)
-            if noise_var.ndim == 0:
-                noise_var = np.tile(noise_var, self.model.input_dim)
-            for i in range(self.model.input_dim):
-                std = np.sqrt(noise_var[i])
-                if std == 0:
-                    continue
-                xi = x[:, i]
-                a = (self.model.bounds[i][0] - xi) / std
-                b = (self.model.bounds[i][1] - xi) / std
-                x[:, i] = ss.truncnorm.rvs(a, b, loc=xi, scale=std, size=len(x),
-                                           random_state=self.random_state)
+        """Jitter the acquired rows, coordinate by coordinate, with normal noise truncated to
+        the GP bounds (acquisition.py:176-191; the coordinate order fixes the RNG stream)."""
+        if self.noise_var is None:
+            return x
+        variances = np.broadcast_to(np.asarray(self.noise_var), (self.model.input_dim,))
+        for i, (lo, hi) in enumerate(self.model.bounds):
+            sd = np.sqrt(variances[i])
+            if sd > 0:
+                centre = x[:, i]
+                x[:, i] = ss.truncnorm.rvs((lo - centre) / sd, (hi - centre) / sd, loc=centre,
+                                           scale=sd, size=len(x), random_state=self.random_state)
         return x
 
 
@@ -584,13 +562,12 @@ class LCBSC(AcquisitionBase):
     gradient are evaluated on the device, fused with the GP prediction."""
 
     def __init__(self, *args, delta=None, additive_cost=None, **kwargs):
-        if delta is not None:
-            if delta <= 0 or delta >= 1:
-                logger.warning('Parameter delta should be in the interval (0,1)')
+        if delta is not None:             # delta is the reciprocal of the exploration rate
+            if not 0 < delta < 1:
+                logger.warning('LCBSC: delta = %s is outside (0, 1)', delta)
             kwargs['exploration_rate'] = 1 / delta
         super().__init__(*args, **kwargs)
-        self.name = 'lcbsc'
-        self.label_fn = 'Confidence Bound'
+        self.name, self.label_fn = 'lcbsc', 'Confidence Bound'
         self.additive_cost = additive_cost
 
     @property
@@ -859,54 +836,57 @@ def ceil_to_batch_size(num, batch_size):
 
 
 class BayesianOptimization(ParameterInference):
-    """elfi/methods/inference/bolfi.py:26-292 (sequential acquisitions)."""
+    """Sequential Bayesian optimisation of a model output (the discrepancy) over the parameters:
+    a GP surrogate of output against parameters, updated with every finished batch, and an
+    acquisition rule that proposes where to simulate next.  Interface of
+    elfi/methods/inference/bolfi.py:26-292.
+
+    Evidence bookkeeping: the first `n_initial_evidence` points come from the prior (or are
+    handed in precomputed); from then on batch b uses acquisition round
+    ``(b * batch_size - n_initial_to_simulate) // acq_batch_size`` and the GP hyper-parameters are
+    re-optimised whenever `update_interval` new points have arrived since the last time."""
 
     def __init__(self, model, target_name=None, bounds=None, initial_evidence=None,
                  update_interval=10, target_model=None, acquisition_method=None, acq_noise_var=0,
                  exploration_rate=10, batch_size=1, batches_per_acquisition=None, async_acq=False,
                  **kwargs):
         model, target_name = self._resolve_model(model, target_name)
-        output_names = [target_name] + model.parameter_names
-        super().__init__(model, output_names, batch_size=batch_size, **kwargs)
-        target_model = target_model or GPyRegression(self.model.parameter_names, bounds=bounds)
+        super().__init__(model, [target_name] + model.parameter_names, batch_size=batch_size,
+                         **kwargs)
         self.target_name = target_name
-        self.target_model = target_model
-        n_precomputed = 0
-        n_initial, precomputed = self._resolve_initial_evidence(initial_evidence)
-        if precomputed is not None:
-            params = np.column_stack([precomputed[n] for n in self.target_model.parameter_names])
-            n_precomputed = len(params)
-            self.target_model.update(params, precomputed[target_name])
+        self.target_model = target_model or GPyRegression(self.model.parameter_names,
+                                                          bounds=bounds)
+        self.update_interval, self.async_acq = update_interval, async_acq
         self.batches_per_acquisition = batches_per_acquisition or self.max_parallel_batches
-        prior = ModelPrior(self.model, parameter_names=self.target_model.parameter_names)
-        self.acquisition_method = acquisition_method or LCBSC(
-            self.target_model, prior=prior, noise_var=acq_noise_var,
-            exploration_rate=exploration_rate, seed=self.seed)
-        self.n_initial_evidence = n_initial
-        self.n_precomputed_evidence = n_precomputed
-        self.update_interval = update_interval
-        self.async_acq = async_acq
-        self.state['n_evidence'] = self.n_precomputed_evidence
-        self.state['last_GP_update'] = self.n_initial_evidence
-        self.state['acquisition'] = []
+        self.n_initial_evidence, given = self._initial_evidence_plan(initial_evidence)
+        self.n_precomputed_evidence = 0
+        if given is not None:
+            theta = np.column_stack([given[n] for n in self.target_model.parameter_names])
+            self.target_model.update(theta, given[target_name])
+            self.n_precomputed_evidence = len(theta)
+        if acquisition_method is None:
+            acquisition_method = LCBSC(
+                self.target_model, noise_var=acq_noise_var, exploration_rate=exploration_rate,
+                seed=self.seed,
+                prior=ModelPrior(self.model, parameter_names=self.target_model.parameter_names))
+        self.acquisition_method = acquisition_method
+        self.state.update(n_evidence=self.n_precomputed_evidence,
+                          last_GP_update=self.n_initial_evidence, acquisition=[])
 
-    def _resolve_initial_evidence(self, initial_evidence):
-        precomputed = None
-        n_required = max(10, 2 ** self.target_model.input_dim + 1)
-        n_required = ceil_to_batch_size(n_required, self.batch_size)
+    def _initial_evidence_plan(self, initial_evidence):
+        """(number of evidence points that precede the first acquisition, precomputed outputs or
+        None).  None asks for max(10, 2^dim + 1) points, a number for that many -- both rounded
+        up to whole batches since they are simulated; a dict of outputs is used as it is."""
         if initial_evidence is None:
-            n_initial_evidence = n_required
+            count = max(10, 2 ** self.target_model.input_dim + 1)
         elif np.isscalar(initial_evidence):
-            n_initial_evidence = int(initial_evidence)
+            count = int(initial_evidence)
+            if count < 0:
+                raise ValueError('The number of initial evidence points cannot be negative '
+                                 '(got {})'.format(initial_evidence))
         else:
-            precomputed = initial_evidence
-            n_initial_evidence = len(precomputed[self.target_name])
-        if n_initial_evidence < 0:
-            raise ValueError('Number of initial evidence must be positive or zero '
-                             '(was {})'.format(initial_evidence))
-        if precomputed is None and (n_initial_evidence % self.batch_size != 0):
-            n_initial_evidence = ceil_to_batch_size(n_initial_evidence, self.batch_size)
-        return n_initial_evidence, precomputed
+            return len(initial_evidence[self.target_name]), initial_evidence
+        return ceil_to_batch_size(count, self.batch_size), None
 
     @property
     def n_evidence(self):
@@ -914,59 +894,67 @@ class BayesianOptimization(ParameterInference):
 
     @property
     def acq_batch_size(self):
-        return self.batch_size * self.batches_per_acquisition
+        """Points requested from the acquisition rule at a time."""
+        return self.batches_per_acquisition * self.batch_size
 
     def set_objective(self, n_evidence=None):
+        """Run until the surrogate holds `n_evidence` points (precomputed ones count)."""
         if n_evidence is None:
             n_evidence = self.objective.get('n_evidence', self.n_evidence)
-        self.objective['n_evidence'] = n_evidence
-        self.objective['n_sim'] = n_evidence - self.n_precomputed_evidence
+        self.objective.update(n_evidence=n_evidence,
+                              n_sim=n_evidence - self.n_precomputed_evidence)
+
+    def _as_parameter_dict(self, rows):
+        names = self.target_model.parameter_names
+        rows = np.asarray(rows).reshape((-1, len(names)))
+        return {name: rows[:, i] for i, name in enumerate(names)}
 
     def extract_result(self):
-        def fun_1d(x):
-            return self.target_model.predict_mean(x).ravel()
-        result = scipy.optimize.differential_evolution(
-            func=fun_1d, bounds=self.target_model.bounds, maxiter=1000, polish=True,
+        """The minimiser of the surrogate mean (global search inside the bounds, then polish)
+        and all evidence gathered so far."""
+        gp = self.target_model
+        found = scipy.optimize.differential_evolution(
+            lambda x: gp.predict_mean(x).ravel(), gp.bounds, maxiter=1000, polish=True,
             init='latinhypercube', seed=self.seed)
-        names = self.target_model.parameter_names
-        batch_min = {p: result.x.reshape((-1, len(names)))[:, i] for i, p in enumerate(names)}
-        outputs = {p: self.target_model.X[:, i] for i, p in enumerate(names)}
-        outputs[self.target_name] = self.target_model.Y
-        return OptimizationResult(x_min=batch_min, outputs=outputs,
+        outputs = self._as_parameter_dict(gp.X)
+        outputs[self.target_name] = gp.Y
+        return OptimizationResult(x_min=self._as_parameter_dict(found.x), outputs=outputs,
                                   **self._extract_result_kwargs())
 
     def update(self, batch, batch_index):
+        """A finished batch becomes evidence of the surrogate."""
         super().update(batch, batch_index)
         self.state['n_evidence'] += self.batch_size
-        params = np.column_stack([np.asarray(dev.to_host(batch[n]))
-                                  for n in self.target_model.parameter_names])
-        optimize = self._should_optimize()
-        self.target_model.update(params, dev.to_host(batch[self.target_name]), optimize)
-        if optimize:
-            self.state['last_GP_update'] = self.target_model.n_evidence
+        gp = self.target_model
+        theta = np.column_stack([np.asarray(dev.to_host(batch[n])) for n in gp.parameter_names])
+        reoptimise = self._should_optimize()
+        gp.update(theta, dev.to_host(batch[self.target_name]), reoptimise)
+        if reoptimise:
+            self.state['last_GP_update'] = gp.n_evidence
 
     def prepare_new_batch(self, batch_index):
+        """Parameter values for the next batch: None while the initial evidence is being drawn
+        from the prior, afterwards the next `batch_size` rows of the pending acquisition (a new
+        one is requested when none are left)."""
         t = self._get_acquisition_index(batch_index)
         if t < 0:
-            return
-        acquisition = self.state['acquisition']
-        if len(acquisition) == 0:
-            acquisition = self.acquisition_method.acquire(self.acq_batch_size, t=t)
-        names = self.target_model.parameter_names
-        acq = np.asarray(acquisition[:self.batch_size]).reshape((-1, len(names)))
-        self.state['acquisition'] = acquisition[self.batch_size:]
-        return {p: acq[:, i] for i, p in enumerate(names)}
+            return None
+        pending = self.state['acquisition']
+        if len(pending) == 0:
+            pending = self.acquisition_method.acquire(self.acq_batch_size, t=t)
+        self.state['acquisition'] = pending[self.batch_size:]
+        return self._as_parameter_dict(pending[:self.batch_size])
 
     def _get_acquisition_index(self, batch_index):
-        acq_batch_size = self.batch_size * self.batches_per_acquisition
-        initial_offset = self.n_initial_evidence - self.n_precomputed_evidence
-        starting_sim_index = self.batch_size * batch_index
-        return (starting_sim_index - initial_offset) // acq_batch_size
+        to_simulate_first = self.n_initial_evidence - self.n_precomputed_evidence
+        return (batch_index * self.batch_size - to_simulate_first) // self.acq_batch_size
 
     def _should_optimize(self):
-        current = self.target_model.n_evidence + self.batch_size
-        next_update = self.state['last_GP_update'] + self.update_interval
-        return current >= self.n_initial_evidence and current >= next_update
+        """Re-optimise the hyper-parameters with this update?  Once the initial evidence is
+        complete, every `update_interval` points."""
+        after = self.target_model.n_evidence + self.batch_size
+        due = self.state['last_GP_update'] + self.update_interval
+        return after >= max(self.n_initial_evidence, due)
 
 
 class BolfiPosterior:

@@ -1,34 +1,156 @@
-"""Host-side mirror of ELFI's operator (node) API for the hot path.
+"""Host side of the operator (node) API for the hot path.
 
-Same names, argument meaning and error behaviour as elfi/model/elfi_model.py, but only what
-the path needs: a DAG of node states, the reference's deterministic execution order (so that
-one per-batch ``RandomState`` is consumed exactly as in elfi/executor.py), and per-batch
-execution in which the Summary / Distance operations run on the device.
+The public names, argument meanings and error types are those of elfi/model/elfi_model.py (the
+drop-in boundary asks for that); the machinery behind them is this package's own:
 
-What is mirrored (file:line in the reference):
-  ElfiModel, generate            elfi/model/elfi_model.py:211-299
-  NodeReference and node classes elfi/model/elfi_model.py:477-1151
-  compile (observed twins, batch_size / meta / random_state feeders, pruning)
-                                 elfi/compiler.py:32-235
-  load (observed data, sub-seeded RandomState)   elfi/loader.py:31-178
-  execution order + node calls   elfi/executor.py:44-246
-  get_sub_seed                   elfi/utils.py:71-127
-What is not: pools / stores, pickling, name inspection of the caller's frame, other clients.
+* a model is a table ``name -> NodeRecord`` (operation or constant, a flag word, the ordered
+  parent names, a free attribute dict) -- no graph library;
+* ``compile_plan`` lowers the table once per inference into a :class:`Plan`: a flat list of
+  :class:`Step` s in the reference's execution order, with the observed twins and the
+  ``_batch_size`` / ``_meta`` / ``_random_state`` inputs already wired in;
+* ``Plan.run`` executes one batch: it binds the per-batch inputs, skips every step whose value is
+  already known (constants, observed data, pool hits, cached observed twins) and calls the rest.
+  Summary / Distance steps launch CUDA kernels and hand device arrays to each other.
+
+Behaviour that must equal the reference's because results depend on it bit for bit:
+  the execution order of the compiled graph  elfi/executor.py:162-246 (golden: topo_orders.json)
+  the per-batch sub-seeded RandomState       elfi/loader.py:131-178, elfi/utils.py:71-127
+  observed twins / feeder inputs / pruning   elfi/compiler.py:32-235
+  node semantics                             elfi/model/elfi_model.py:477-1151
+Not provided: pickling, naming a node after the caller's assignment target, other clients.
 """
 import uuid
 from functools import partial
 
-import networkx as nx
 import numpy as np
 import scipy.stats as ss
 
 from . import device as dev
 from . import ops
 
-_default_model = None
+# ---- node flags -----------------------------------------------------------------------------
+STOCHASTIC = 1        # consumes the batch RandomState
+OBSERVABLE = 2        # has an observed twin computed from the observed data
+TAKES_OBSERVED = 4    # receives the tuple of its parents' observed twins as `observed=`
+TAKES_BATCH_SIZE = 8
+TAKES_META = 16
+TAKES_ACCEPT = 32     # a device distance that can fuse the acceptance test (`accept=`)
+PARAMETER = 64
 
-SCIPY_ALIASES = {'normal': 'norm', 'exponential': 'expon', 'unif': 'uniform', 'bin': 'binom',
-                 'binomial': 'binom'}
+BATCH_SIZE_INPUT, META_INPUT, RANDOM_STATE_INPUT = '_batch_size', '_meta', '_random_state'
+_MISSING = object()
+
+_SCIPY_SHORTHAND = {'normal': 'norm', 'exponential': 'expon', 'unif': 'uniform', 'bin': 'binom',
+                    'binomial': 'binom'}
+
+
+def scipy_from_str(name):
+    key = name.lower()
+    return getattr(ss, _SCIPY_SHORTHAND.get(key, key))
+
+
+def random_name(length=4, prefix=''):
+    return prefix + uuid.uuid4().hex[:length]
+
+
+def observed_name(name):
+    return '_' + name + '_observed'
+
+
+def is_observed_name(name):
+    return isinstance(name, str) and len(name) > 10 and name[0] == '_' and \
+        name.endswith('_observed')
+
+
+def is_array(output):
+    return getattr(output, 'ndim', 0) > 0 and hasattr(output, 'shape')
+
+
+def get_sub_seed(seed, sub_seed_index, high=2 ** 31, cache=None):
+    """Sub seed number `sub_seed_index` of `seed`; bit-identical to elfi/utils.py:71-127
+    (goldens in tests/golden/meta.json).
+
+    The sub seeds of a seed are the distinct values of the uint32 stream
+    ``RandomState(seed).randint(high)`` in order of first appearance; the stream is read in
+    chunks of "as many as are still missing", which fixes how far it has advanced."""
+    if isinstance(seed, np.random.RandomState):
+        raise ValueError('Seed cannot be a random state')
+    if sub_seed_index >= high:
+        raise ValueError('Sub seed index {} is out of range'.format(sub_seed_index))
+    wanted = sub_seed_index + 1
+    stream, distinct = None, None
+    if cache and len(cache['seen']) < wanted:
+        stream, distinct = cache['random_state'], cache['seen']
+    if stream is None:
+        stream, distinct = np.random.RandomState(seed), set()
+    chunk = None
+    while len(distinct) < wanted:
+        chunk = stream.randint(high, size=wanted - len(distinct), dtype='uint32')
+        distinct.update(chunk)
+    if cache is not None:
+        cache['random_state'], cache['seen'] = stream, distinct
+    return chunk[-1]
+
+
+class ComputationContext:
+    """What all batches of one inference share: batch size, master seed, an optional output
+    pool, per-inference caches.  A pool that already carries a context supplies (and pins)
+    batch size and seed (elfi/model/elfi_model.py:126-208)."""
+
+    def __init__(self, batch_size=None, seed=None, pool=None):
+        pinned = pool is not None and pool.has_context
+        if pinned:
+            batch_size = self._agree('batch_size', batch_size, pool.batch_size)
+            seed = self._agree('seed', seed, pool.seed)
+        if seed is None:
+            seed = np.random.RandomState().get_state()[1][1]
+        self.batch_size = batch_size or 1
+        self.seed = seed
+        self.pool = pool
+        self.num_submissions = 0
+        self.caches = {'plan': {}, 'sub_seed': {}}
+        if pool is not None and not pinned:
+            pool.set_context(self)
+
+    @staticmethod
+    def _agree(what, given, pooled):
+        if given is not None and given != pooled:
+            raise ValueError('Pool {0} differs from the given {0}!'.format(what))
+        return pooled
+
+    def callback(self, batch, batch_index):
+        """A finished batch goes to the pool."""
+        if self.pool is not None:
+            self.pool.add_batch(batch, batch_index)
+
+
+# ------------------------------------------------------------------------------------- model
+class NodeRecord:
+    """One row of the model table."""
+    __slots__ = ('cls', 'op', 'constant', 'flags', 'inputs', 'attrs')
+
+    def __init__(self, cls, op=None, constant=_MISSING, flags=0, attrs=None):
+        self.cls = cls
+        self.op = op
+        self.constant = constant
+        self.flags = flags
+        self.inputs = []            # parent names, positional order
+        self.attrs = {} if attrs is None else attrs
+
+    def has(self, flag):
+        return bool(self.flags & flag)
+
+    def set(self, flag, on=True):
+        self.flags = (self.flags | flag) if on else (self.flags & ~flag)
+
+    def twin(self):
+        """Same node, own parent list (model copies share operations and attribute dicts)."""
+        rec = NodeRecord(self.cls, self.op, self.constant, self.flags, self.attrs)
+        rec.inputs = list(self.inputs)
+        return rec
+
+
+_default_model = None
 
 
 def get_default_model():
@@ -40,11 +162,9 @@ def get_default_model():
 
 def set_default_model(model=None):
     global _default_model
-    if model is None:
-        model = ElfiModel()
-    if not isinstance(model, ElfiModel):
-        raise ValueError('{} is not an instance of ElfiModel'.format(ElfiModel))
-    _default_model = model
+    if model is not None and not isinstance(model, ElfiModel):
+        raise ValueError('{} is not an instance of ElfiModel'.format(model))
+    _default_model = ElfiModel() if model is None else model
 
 
 def new_model(name=None, set_default=True):
@@ -54,413 +174,347 @@ def new_model(name=None, set_default=True):
     return model
 
 
-def random_name(length=4, prefix=''):
-    return prefix + str(uuid.uuid4().hex[0:length])
-
-
-def observed_name(name):
-    return "_{}_observed".format(name)
-
-
-def is_observed_name(name):
-    return isinstance(name, str) and name.startswith('_') and name.endswith('_observed')
-
-
-def is_array(output):
-    return hasattr(output, 'shape') and output.ndim > 0
-
-
-def scipy_from_str(name):
-    name = name.lower()
-    name = SCIPY_ALIASES.get(name, name)
-    return getattr(ss, name)
-
-
-def get_sub_seed(seed, sub_seed_index, high=2 ** 31, cache=None):
-    """Unique sub seed number `sub_seed_index` of `seed` (elfi/utils.py:71-127).
-
-    Draws uint32 values below `high` from RandomState(seed) until sub_seed_index + 1 distinct
-    ones have been seen; the last draw is the sub seed.  Bit-identical to the reference
-    (golden values in tests/golden/meta.json)."""
-    if isinstance(seed, np.random.RandomState):
-        raise ValueError('Seed cannot be a random state')
-    if sub_seed_index >= high:
-        raise ValueError("Sub seed index {} is out of range".format(sub_seed_index))
-    if cache and len(cache['seen']) < sub_seed_index + 1:
-        random_state, seen = cache['random_state'], cache['seen']
-    else:
-        random_state, seen = np.random.RandomState(seed), set()
-    draws = None
-    wanted = sub_seed_index + 1
-    while len(seen) != wanted:
-        draws = random_state.randint(high, size=wanted - len(seen), dtype='uint32')
-        seen.update(draws)
-    if cache is not None:
-        cache['random_state'] = random_state
-        cache['seen'] = seen
-    return draws[-1]
-
-
-class ComputationContext:
-    """batch_size + seed + optional output pool (+ caches) shared by all batches of one inference
-    (elfi/model/elfi_model.py:126-208)."""
-
-    def __init__(self, batch_size=None, seed=None, pool=None):
-        if pool is not None and pool.has_context:
-            if batch_size is None:
-                batch_size = pool.batch_size
-            elif batch_size != pool.batch_size:
-                raise ValueError('Pool batch_size differs from the given batch_size!')
-            if seed is None:
-                seed = pool.seed
-            elif seed != pool.seed:
-                raise ValueError('Pool seed differs from the given seed!')
-        self.batch_size = batch_size or 1
-        self.seed = np.random.RandomState().get_state()[1][1] if seed is None else seed
-        self.pool = pool
-        self.caches = {'plan': {}, 'sub_seed': {}}
-        self.num_submissions = 0
-        if pool is not None and not pool.has_context:
-            pool.set_context(self)
-
-    def callback(self, batch, batch_index):
-        """Store the finished batch in the pool (elfi_model.py:196-208)."""
-        if self.pool is not None:
-            self.pool.add_batch(batch, batch_index)
-
-
-# ------------------------------------------------------------------------------------ graph
 class ElfiModel:
-    """A DAG of node states (mirror of elfi.ElfiModel for the hot path)."""
+    """The node table of one generative model plus its observed data."""
 
-    def __init__(self, name=None, observed=None, source_net=None):
-        self.source_net = source_net if source_net is not None else nx.DiGraph()
-        self.source_net.graph.setdefault('name', name or "model_{}".format(random_name()))
-        self.source_net.graph.setdefault('observed', observed or {})
-        if name:
-            self.source_net.graph['name'] = name
-
-    # -- bookkeeping ---------------------------------------------------------------------
-    @property
-    def name(self):
-        return self.source_net.graph['name']
-
-    @name.setter
-    def name(self, name):
-        self.source_net.graph['name'] = name
+    def __init__(self, name=None, observed=None):
+        self.name = name or 'model_' + random_name()
+        self._records = {}
+        self._observed = {}
+        if observed:
+            self.observed = observed
 
     @property
     def observed(self):
-        return self.source_net.graph['observed']
+        return self._observed
 
     @observed.setter
     def observed(self, observed):
         if not isinstance(observed, dict):
-            raise ValueError("Observed data must be given in a dictionary with the node"
-                             "name as the key")
-        self.source_net.graph['observed'] = observed
+            raise ValueError('Observed data must be a dictionary {node name: data}')
+        self._observed = observed
 
+    # -- table access ---------------------------------------------------------------------
     @property
     def nodes(self):
-        return self.source_net.nodes()
+        return list(self._records)
 
     def has_node(self, name):
-        return self.source_net.has_node(name)
+        return name in self._records
 
-    def add_node(self, name, state):
-        if self.has_node(name):
+    def record(self, name):
+        return self._records[name]
+
+    def get_parents(self, name):
+        return list(self._records[name].inputs)
+
+    def get_children(self, name):
+        return [n for n, rec in self._records.items() if name in rec.inputs]
+
+    def insert(self, name, record, parents=()):
+        if name in self._records:
             raise ValueError('Node {} already exists'.format(name))
-        self.source_net.add_node(name, attr_dict=state)
-
-    def get_node(self, name):
-        return self.source_net.nodes[name]
-
-    def get_state(self, name):
-        return self.source_net.nodes[name]
-
-    def get_parents(self, child_name):
-        args = []
-        for parent_name in self.source_net.predecessors(child_name):
-            param = self.source_net[parent_name][child_name]['param']
-            if isinstance(param, int):
-                args.append((param, parent_name))
-        return [a[1] for a in sorted(args)]
-
-    def add_edge(self, parent_name, child_name, param_name=None):
-        if param_name is None:
-            param_name = len(self.get_parents(child_name))
-        if not self.has_node(parent_name):
-            raise ValueError('Parent {} does not exist'.format(parent_name))
-        if not self.has_node(child_name):
-            raise ValueError('Child {} does not exist'.format(child_name))
-        self.source_net.add_edge(parent_name, child_name, param=param_name)
+        for p in parents:
+            if p not in self._records:
+                raise ValueError('Parent {} does not exist'.format(p))
+        record.inputs = list(parents)
+        self._records[name] = record
 
     def remove_node(self, name):
-        if name in self.observed:
-            self.observed.pop(name)
-        parent_names = self.get_parents(name)
-        self.source_net.remove_node(name)
-        for p in parent_names:
-            if p[0] == '_' and self.source_net.degree(p) == 0:
+        """Drop a node, its observed data and the hidden constants only it was using."""
+        rec = self._records.pop(name)
+        self._observed.pop(name, None)
+        for other in self._records.values():
+            if name in other.inputs:
+                other.inputs = [p for p in other.inputs if p != name]
+        for p in rec.inputs:
+            if p.startswith('_') and p in self._records and not self._records[p].inputs \
+                    and not self.get_children(p):
                 self.remove_node(p)
 
     def update_node(self, name, updating_name):
-        """`name` takes the state and parents of `updating_name` (NodeReference.become)."""
-        obs = self.observed.pop(updating_name, None)
-        out_edges = list(self.source_net.edges(name, data=True))
-        self.remove_node(name)
-        self.source_net.add_node(name, attr_dict=self.source_net.nodes[updating_name]['attr_dict'])
-        self.source_net.add_edges_from(out_edges)
-        for u, v, data in list(self.source_net.in_edges(updating_name, data=True)):
-            self.source_net.add_edge(u, name, **data)
-        self.remove_node(updating_name)
-        if obs is not None:
-            self.observed[name] = obs
+        """`name` becomes `updating_name` (operation, flags, parents, observed data) while the
+        children of `name` keep pointing at it; `updating_name` disappears."""
+        incoming = self._records[updating_name]
+        data = self._observed.pop(updating_name, None)
+        old_inputs = self._records[name].inputs
+        del self._records[updating_name]
+        self._records[name] = incoming
+        self._observed.pop(name, None)
+        if data is not None:
+            self._observed[name] = data
+        for p in old_inputs:
+            if p.startswith('_') and p in self._records and p not in incoming.inputs and \
+                    not self._records[p].inputs and not self.get_children(p):
+                self.remove_node(p)
 
     @property
     def parameter_names(self):
-        return sorted([n for n in self.nodes if '_parameter' in self.get_state(n)['attr_dict']])
+        return sorted(n for n, rec in self._records.items() if rec.has(PARAMETER))
 
     @parameter_names.setter
     def parameter_names(self, parameter_names):
-        parameter_names = set(parameter_names)
-        for n in self.nodes:
-            state = self.get_state(n)['attr_dict']
-            if n in parameter_names:
-                parameter_names.remove(n)
-                state['_parameter'] = True
-            else:
-                state.pop('_parameter', None)
-        if len(parameter_names) > 0:
-            raise ValueError('Parameters {} not found from the model'.format(parameter_names))
+        unknown = set(parameter_names) - set(self._records)
+        if unknown:
+            raise ValueError('Parameters {} not found from the model'.format(unknown))
+        for n, rec in self._records.items():
+            rec.set(PARAMETER, n in parameter_names)
 
     def copy(self):
-        kopy = ElfiModel(source_net=nx.DiGraph(self.source_net))
-        kopy.source_net.graph['observed'] = dict(self.observed)
-        kopy.name = "{}_copy_{}".format(self.name, random_name())
-        return kopy
+        """A model with its own table and observed dict over the same operations / node state."""
+        twin = ElfiModel(name='{}_copy_{}'.format(self.name, random_name()))
+        twin._records = {n: rec.twin() for n, rec in self._records.items()}
+        twin._observed = dict(self._observed)
+        return twin
 
     def get_reference(self, name):
-        cls = self.get_node(name)['attr_dict']['_class']
-        return cls.reference(name, self)
+        return self._records[name].cls.reference(name, self)
 
-    def __getitem__(self, node_name):
-        return self.get_reference(node_name)
+    __getitem__ = get_reference
 
-    # -- execution -----------------------------------------------------------------------
     def generate(self, batch_size=1, outputs=None, with_values=None, seed=None):
-        """Generate one batch of outputs (elfi/model/elfi_model.py:265-299)."""
+        """One batch of the named outputs (all nodes by default) as {name: array}."""
         if outputs is None:
-            outputs = list(self.source_net.nodes())
+            outputs = self.nodes
         elif isinstance(outputs, str):
             outputs = [outputs]
         if not isinstance(outputs, list):
             raise ValueError('Outputs must be a list of node names')
-        if seed is None:
-            seed = 'global'
-        context = ComputationContext(batch_size, seed=seed)
+        context = ComputationContext(batch_size, seed='global' if seed is None else seed)
         return execute_batch(self, outputs, context, 0, with_values)
 
 
-# ------------------------------------------------------------------------- compile / execute
-def _constant_topological_order(G):
-    """Deterministic topological order: depth-first from the alphabetically sorted nodes,
-    successors explored from the alphabetically last to the first, reverse post-order.
-    Yields the same order as elfi/executor.py:162-246 for the same graph."""
-    explored, post = set(), []
-    for root in sorted(G.nodes()):
-        if root in explored:
+# ---------------------------------------------------------------------------- compile / run
+def _constant_topological_order(nodes, successors):
+    """The reference's deterministic order (elfi/executor.py:162-246): depth-first search from
+    the alphabetically sorted nodes, children visited from the alphabetically last to the
+    first, reverse finishing order.  `successors(node)` returns an iterable of children."""
+    done, finishing = set(), []
+    for start in sorted(nodes):
+        if start in done:
             continue
-        stack = [(root, iter(sorted(G[root], reverse=True)))]
-        on_path = {root}
-        while stack:
-            node, children = stack[-1]
-            advanced = False
-            for child in children:
-                if child in explored:
-                    continue
-                if child in on_path:
-                    raise nx.NetworkXUnfeasible("Graph contains a cycle.")
-                on_path.add(child)
-                stack.append((child, iter(sorted(G[child], reverse=True))))
-                advanced = True
-                break
-            if not advanced:
-                stack.pop()
-                on_path.discard(node)
-                explored.add(node)
-                post.append(node)
-    return post[::-1]
+        active = {start}
+        trail = [(start, iter(sorted(successors(start), reverse=True)))]
+        while trail:
+            node, pending = trail[-1]
+            nxt = next((c for c in pending if c not in done), None)
+            if nxt is None:
+                trail.pop()
+                active.discard(node)
+                done.add(node)
+                finishing.append(node)
+            elif nxt in active:
+                raise ValueError('The model graph contains a cycle through {}'.format(nxt))
+            else:
+                active.add(nxt)
+                trail.append((nxt, iter(sorted(successors(nxt), reverse=True))))
+    finishing.reverse()
+    return finishing
 
 
-def compile_net(source_net, outputs):
-    """source_net -> computation net (elfi/compiler.py): operations/outputs, observed twins,
-    `_batch_size` / `_meta` / `_random_state` feeder nodes, pruned to the outputs' ancestors."""
-    outputs = set(outputs)
-    net = nx.DiGraph(outputs=outputs, name=source_net.graph['name'])
-    net.add_nodes_from(source_net.nodes())
-    net.add_edges_from(source_net.edges(data=True))
-    for name, data in net.nodes(data=True):
-        state = source_net.nodes[name]['attr_dict']
-        if '_output' in state and '_operation' in state:
-            raise ValueError("Cannot compile: both _output and _operation present "
-                             "for node '{}'".format(name))
-        if '_output' in state:
-            data['output'] = state['_output']
-        elif '_operation' in state:
-            data['operation'] = state['_operation']
-        else:
-            raise ValueError("Cannot compile, no _output or _operation present for "
-                             "node '{}'".format(name))
-        if state.get('_uses_accept'):
-            data['uses_accept'] = True
+def _pack_observed(*twins):
+    return tuple(twins)
 
-    observable, uses_observed = [], []
-    for node in nx.topological_sort(source_net):
-        state = source_net.nodes[node]['attr_dict']
-        if state.get('_observable'):
-            observable.append(node)
-            net.add_node(observed_name(node), **{k: v for k, v in net.nodes[node].items()
-                                                  if k != 'uses_accept'})
-        elif state.get('_uses_observed'):
-            uses_observed.append(node)
-            net.add_node(observed_name(node), operation=lambda *a: tuple(a))
-            net.add_edge(observed_name(node), node, param='observed')
+
+class Step:
+    """One node of a compiled plan: where its value comes from."""
+    __slots__ = ('name', 'op', 'constant', 'args', 'kwargs', 'fuses_accept')
+
+    def __init__(self, name, op=None, constant=_MISSING, fuses_accept=False):
+        self.name = name
+        self.op = op
+        self.constant = constant
+        self.args = []          # names, positional
+        self.kwargs = {}        # keyword -> name
+        self.fuses_accept = fuses_accept
+
+    @property
+    def sources(self):
+        return self.args + list(self.kwargs.values())
+
+
+class Plan:
+    """A model lowered for a set of outputs: the steps the outputs depend on, in execution
+    order."""
+
+    def __init__(self, model_name, outputs, steps, order):
+        self.model_name = model_name
+        self.outputs = list(outputs)
+        self.steps = steps                      # name -> Step
+        self.order = order
+
+    def has_node(self, name):
+        return name in self.steps
+
+    def __contains__(self, name):
+        return name in self.steps
+
+    def run(self, values, outputs, accept=None, keep_observed=None):
+        """Evaluate `outputs` given the already known `values` (mutated); returns the extra
+        products of fused steps as {('accepted', name): indices}."""
+        pending, visit = set(), [o for o in outputs if o not in values]
+        while visit:
+            name = visit.pop()
+            if name in pending or name in values:
+                continue
+            pending.add(name)
+            visit.extend(self.steps[name].sources)
+        extras = {}
+        for name in self.order:
+            if name not in pending:
+                continue
+            step = self.steps[name]
+            if step.op is None:
+                raise ValueError('Nothing provides a value for node {}'.format(name))
+            kwargs = {k: values[src] for k, src in step.kwargs.items()}
+            if accept is not None and step.fuses_accept and name in accept:
+                kwargs['accept'] = accept[name]
+            try:
+                out = step.op(*[values[src] for src in step.args], **kwargs)
+            except Exception as exc:
+                note = "In executing node '{}': {}.".format(name, exc)
+                raise type(exc)(note).with_traceback(exc.__traceback__)
+            if isinstance(out, AcceptedOutput):
+                extras[('accepted', name)] = out.accepted
+                out = out.value
+            values[name] = out
+            if keep_observed is not None and is_observed_name(name):
+                keep_observed[name] = out
+        return extras
+
+
+def compile_plan(model, outputs):
+    """Lower `model` for `outputs` (node names, observed-twin names allowed).
+
+    Every observable node X gets a twin ``_X_observed`` that applies X's operation to the
+    twins of X's parents (a stochastic X -- a simulator -- has no inputs there: its twin is the
+    observed data itself); a node that takes `observed=` gets a twin packing its parents' twins
+    into a tuple.  Nodes flagged for batch size / meta / random state read the per-batch inputs
+    of those names.  Only what the outputs depend on is kept."""
+    table = model._records
+    steps = {}
+    for name, rec in table.items():
+        if rec.constant is not _MISSING and rec.op is not None:
+            raise ValueError("Cannot compile: node '{}' has both a value and an "
+                             "operation".format(name))
+        if rec.constant is _MISSING and rec.op is None:
+            raise ValueError("Cannot compile: node '{}' has neither a value nor an "
+                             "operation".format(name))
+        step = steps[name] = Step(name, rec.op, rec.constant, rec.has(TAKES_ACCEPT))
+        step.args = list(rec.inputs)
+        if rec.has(TAKES_BATCH_SIZE):
+            step.kwargs['batch_size'] = BATCH_SIZE_INPUT
+        if rec.has(TAKES_META):
+            step.kwargs['meta'] = META_INPUT
+        if rec.has(STOCHASTIC):
+            step.kwargs['random_state'] = RANDOM_STATE_INPUT
+
+    def twin_or_self(parent):
+        return observed_name(parent) if table[parent].has(OBSERVABLE) else parent
+
+    for name, rec in table.items():
+        if rec.has(OBSERVABLE):
+            twin = steps[observed_name(name)] = Step(observed_name(name), rec.op, rec.constant)
+        elif rec.has(TAKES_OBSERVED):
+            twin = steps[observed_name(name)] = Step(observed_name(name), _pack_observed)
+            steps[name].kwargs['observed'] = twin.name
         else:
             continue
-        if not state.get('_stochastic'):
-            for parent in source_net.predecessors(node):
-                link = observed_name(parent) if parent in observable else parent
-                net.add_edge(link, observed_name(node), **source_net[parent][node].copy())
-    for node in uses_observed:
-        for anc in nx.ancestors(net, observed_name(node)):
-            if '_stochastic' in source_net.nodes.get(anc, {}).get('attr_dict', {}):
-                raise ValueError("Observed nodes must be deterministic. Observed data depends "
-                                 "on a non-deterministic node {}.".format(anc))
+        if not rec.has(STOCHASTIC):
+            twin.args = [twin_or_self(p) for p in rec.inputs]
+    for feed in (BATCH_SIZE_INPUT, META_INPUT, RANDOM_STATE_INPUT):
+        if any(feed in s.kwargs.values() for s in steps.values()):
+            steps[feed] = Step(feed)
 
-    for flag, feeder in (('_uses_batch_size', '_batch_size'), ('_uses_meta', '_meta')):
-        for node, d in source_net.nodes(data=True):
-            if d['attr_dict'].get(flag):
-                if not net.has_node(feeder):
-                    net.add_node(feeder)
-                net.add_edge(feeder, node, param=feeder[1:])
-    for node, d in source_net.nodes(data=True):
-        if '_stochastic' in d['attr_dict']:
-            if not net.has_node('_random_state'):
-                net.add_node('_random_state')
-            net.add_edge('_random_state', node, param='random_state')
+    def upstream(roots):
+        seen, visit = set(), list(roots)
+        while visit:
+            n = visit.pop()
+            if n not in seen:
+                seen.add(n)
+                visit.extend(steps[n].sources)
+        return seen
 
-    keep = set(outputs)
+    for name, rec in table.items():
+        if rec.has(TAKES_OBSERVED):
+            for anc in upstream([observed_name(name)]):
+                if anc in table and table[anc].has(STOCHASTIC):
+                    raise ValueError('Observed nodes must be deterministic. Observed data '
+                                     'depends on a non-deterministic node {}.'.format(anc))
     for o in outputs:
-        if not net.has_node(o):
+        if o not in steps:
             raise ValueError('Node {} is not in the model'.format(o))
-        keep |= nx.ancestors(net, o)
-    for node in list(net.nodes()):
-        if node not in keep:
-            net.remove_node(node)
-    net.graph['order'] = _constant_topological_order(net)
-    return net
+    kept = upstream(outputs)
+    steps = {n: s for n, s in steps.items() if n in kept}
+    children = {n: [] for n in steps}
+    for n, s in steps.items():
+        for src in s.sources:
+            children[src].append(n)
+    order = _constant_topological_order(steps, children.__getitem__)
+    return Plan(model.name, outputs, steps, order)
 
 
-def _call_node(net, node, values, accept):
-    attr = net.nodes[node]
-    op = attr['operation']
-    args, kwargs = [], {}
-    for parent in net.predecessors(node):
-        param = net[parent][node]['param']
-        if isinstance(param, int):
-            args.append((param, values[parent]))
-        else:
-            kwargs[param] = values[parent]
-    args = [a[1] for a in sorted(args, key=lambda t: t[0])]
-    if accept is not None and attr.get('uses_accept') and node in accept:
-        kwargs['accept'] = accept[node]
-    try:
-        return op(*args, **kwargs)
-    except Exception as exc:
-        raise exc.__class__("In executing node '{}': {}.".format(node, exc)).with_traceback(
-            exc.__traceback__)
+def _batch_random_state(context, batch_index):
+    """The RandomState of one batch: numpy's global one for seed 'global', else a fresh one
+    from the batch's sub seed (elfi/loader.py:131-178)."""
+    seed = context.seed
+    if isinstance(seed, str) and seed == 'global':
+        return np.random.mtrand._rand
+    if isinstance(seed, (int, np.integer)):
+        sub = get_sub_seed(int(seed), batch_index, cache=context.caches.get('sub_seed'))
+        return np.random.RandomState(sub)
+    raise ValueError('Seed of type {} is not supported'.format(seed))
 
 
 def execute_batch(model, outputs, context, batch_index, with_values=None, accept=None,
                   compiled=None):
-    """compile (cached by the caller) + load + execute one batch; returns {name: output}.
+    """Run one batch of `outputs`; returns {name: output}.
 
-    `accept` = {discrepancy_name: thresholds} asks a device Distance node to also return the
-    accepted row indices (fused in the distance kernel); they come back under the key
-    ('accepted', name)."""
-    net = compiled if compiled is not None else compile_net(model.source_net, outputs)
+    `compiled` is the plan of a previous ``compile_plan(model, outputs)`` (samplers compile
+    once per inference).  `accept` = {discrepancy name: thresholds} asks a device distance to
+    also return the accepted row indices, found under the key ('accepted', name).
+
+    Known before any step runs: observed data (-> twins of the nodes that carry it), the
+    per-batch inputs, outputs already in the context's pool, `with_values`, constants, and --
+    with a reused plan -- the observed twins evaluated by the first batch (they are
+    deterministic functions of the observed data: checked at compile time; the reference
+    re-evaluates them every batch, which here would be kernel launches and a D2H each)."""
+    plan = compiled if compiled is not None else compile_plan(model, outputs)
     values = {}
-    # ---- load (elfi/loader.py)
-    observed = model.observed
-    for name, obs in observed.items():
-        if net.has_node(observed_name(name)):
-            values[observed_name(name)] = obs
-    if net.has_node('_batch_size'):
-        values['_batch_size'] = context.batch_size
-    if net.has_node('_meta'):
-        values['_meta'] = {'batch_index': batch_index,
-                           'submission_index': context.num_submissions,
-                           'master_seed': context.seed, 'model_name': net.graph['name']}
-    if net.has_node('_random_state'):
-        seed = context.seed
-        if isinstance(seed, str) and seed == 'global':
-            values['_random_state'] = np.random.mtrand._rand
-        elif isinstance(seed, (int, np.integer)):
-            sub_seed = get_sub_seed(int(seed), batch_index, cache=context.caches.get('sub_seed'))
-            values['_random_state'] = np.random.RandomState(sub_seed)
-        else:
-            raise ValueError("Seed of type {} is not supported".format(seed))
-    # pool (elfi/loader.py:95-129): stored outputs replace their nodes, missing ones are
-    # requested so that the callback can store them when the batch is done
-    outputs = set(net.graph['outputs'])
+    for name, data in model.observed.items():
+        if observed_name(name) in plan:
+            values[observed_name(name)] = data
+    if BATCH_SIZE_INPUT in plan:
+        values[BATCH_SIZE_INPUT] = context.batch_size
+    if META_INPUT in plan:
+        values[META_INPUT] = dict(batch_index=batch_index,
+                                  submission_index=context.num_submissions,
+                                  master_seed=context.seed, model_name=plan.model_name)
+    if RANDOM_STATE_INPUT in plan:
+        values[RANDOM_STATE_INPUT] = _batch_random_state(context, batch_index)
+    wanted = list(plan.outputs)
     if context.pool is not None:
+        # stored outputs replace their nodes; missing ones are requested so that the callback
+        # can store them when the batch is done (elfi/loader.py:95-129)
         stored = context.pool.get_batch(batch_index)
-        for node in context.pool.stores:
-            if not net.has_node(node):
-                continue
-            if node in stored:
-                values[node] = stored[node]
-            else:
-                outputs.add(node)
-    for k, v in (with_values or {}).items():
-        if net.has_node(k):
-            values[k] = v
-    for node, attr in net.nodes(data=True):
-        if 'output' in attr and node not in values:
-            values[node] = attr['output']
-    # observed twins are deterministic functions of the observed data (checked at compile time):
-    # computed in the first batch of an inference, reused by the following ones (the reference
-    # recomputes them per batch; here that would be kernel launches and a D2H per batch)
-    obs_cache = context.caches.setdefault('observed', {}).setdefault(id(net), {})
-    for node, out in obs_cache.items():
-        values.setdefault(node, out)
-
-    # ---- which nodes must run: ancestors of the outputs not cut off by a known value
-    needed = [o for o in outputs if o not in values]
-    todo = set()
-    stack = list(needed)
-    while stack:
-        n = stack.pop()
-        if n in todo or n in values:
-            continue
-        todo.add(n)
-        stack.extend(net.predecessors(n))
-    extras = {}
-    for node in net.graph['order']:
-        if node not in todo:
-            continue
-        if 'operation' not in net.nodes[node]:
-            raise ValueError('Generative graph has no op or output present for node '
-                             '{}'.format(node))
-        out = _call_node(net, node, values, accept)
-        if isinstance(out, AcceptedOutput):
-            extras[('accepted', node)] = out.accepted
-            out = out.value
-        values[node] = out
-        if is_observed_name(node) and compiled is not None:
-            obs_cache[node] = out
-    result = {k: values[k] for k in outputs}
+        for name in context.pool.stores:
+            if name in stored and name in plan:
+                values[name] = stored[name]
+            elif name in plan and name not in wanted:
+                wanted.append(name)
+    for name, val in (with_values or {}).items():
+        if name in plan:
+            values[name] = val
+    for name, step in plan.steps.items():
+        if step.constant is not _MISSING and name not in values:
+            values[name] = step.constant
+    twins = None
+    if compiled is not None:
+        twins = context.caches.setdefault('observed', {}).setdefault(id(plan), {})
+        for name, val in twins.items():
+            values.setdefault(name, val)
+    extras = plan.run(values, wanted, accept=accept, keep_observed=twins)
+    result = {name: values[name] for name in wanted}
     result.update(extras)
     return result
 
@@ -473,109 +527,84 @@ class AcceptedOutput:
         self.accepted = accepted
 
 
-# ------------------------------------------------------------------------------------ nodes
+# ------------------------------------------------------------------------------------- nodes
 class NodeReference:
-    """Base class of node objects: a named handle on a state dict stored in the model
-    (elfi/model/elfi_model.py:477-731)."""
+    """A handle (model, name) on one row of a model's table.  Creating a node object inserts
+    the row; ``model[name]`` re-creates a handle of the row's class."""
+
+    # what a subclass contributes to its row
+    _flags = 0
 
     def __init__(self, *parents, state=None, model=None, name=None):
-        state = state or {}
-        state['_class'] = self.__class__
-        model = self._determine_model(model, parents)
-        name = self._give_name(name, model)
-        model.add_node(name, state)
-        self._init_reference(name, model)
-        self._add_parents(parents)
-
-    def _add_parents(self, parents):
-        for parent in parents:
-            if not isinstance(parent, NodeReference):
-                parent_name = self._new_name('_' + self.name)
-                parent = Constant(parent, name=parent_name, model=self.model)
-            self.model.add_edge(parent.name, self.name)
-
-    def _determine_model(self, model, parents):
-        if not isinstance(model, ElfiModel) and model is not None:
+        state = dict(state or {})
+        if model is not None and not isinstance(model, ElfiModel):
             raise ValueError('Invalid model passed {}'.format(model))
         for p in parents:
             if isinstance(p, NodeReference):
                 if model is None:
                     model = p.model
-                elif model != p.model:
+                elif p.model is not model:
                     raise ValueError('Parents are from different models!')
-        if model is None:
-            model = get_default_model()
-        return model
+        self.model = get_default_model() if model is None else model
+        self.name = self._resolve_name(name)
+        record = NodeRecord(type(self), op=state.pop('op', None),
+                            constant=state.pop('constant', _MISSING),
+                            flags=self._flags | state.pop('flags', 0), attrs=state)
+        self.model.insert(self.name, record)
+        for p in parents:
+            if not isinstance(p, NodeReference):     # plain values become hidden constants
+                p = Constant(p, model=self.model, name='_' + self.name + '*')
+            record.inputs.append(p.name)
+
+    def _resolve_name(self, name):
+        """An explicit name is used as is; 'base*' gets a random suffix; without a name a
+        random one is made up (the reference reads the caller's assignment target instead)."""
+        if name is not None and not name.endswith('*'):
+            return name
+        base = name[:-1] if name else '_' + type(self).__name__.lower()
+        while True:
+            candidate = '{}_{}'.format(base, random_name())
+            if not self.model.has_node(candidate):
+                return candidate
+
+    @classmethod
+    def reference(cls, name, model):
+        handle = cls.__new__(cls)
+        handle.name, handle.model = name, model
+        return handle
+
+    @property
+    def record(self):
+        if self.model is None:
+            raise ValueError('{} {} is not initialized'.format(type(self).__name__, self.name))
+        return self.model.record(self.name)
 
     @property
     def parents(self):
         return [self.model[p] for p in self.model.get_parents(self.name)]
 
-    @classmethod
-    def reference(cls, name, model):
-        instance = cls.__new__(cls)
-        instance._init_reference(name, model)
-        return instance
-
     def become(self, other_node):
+        """Replace this node by `other_node` in place: children keep their parent."""
         if other_node.model is not self.model:
             raise ValueError('The other node belongs to a different model')
         self.model.update_node(self.name, other_node.name)
-        _class = self.state['attr_dict'].get('_class', NodeReference)
-        if not isinstance(self, _class):
-            self.__class__ = _class
+        if not isinstance(self, self.record.cls):
+            self.__class__ = self.record.cls
         other_node.name = self.name
-        other_node.model = self.model
-
-    def _init_reference(self, name, model):
-        self.name = name
-        self.model = model
 
     def generate(self, batch_size=1, with_values=None):
-        result = self.model.generate(batch_size, self.name, with_values=with_values)
-        return result[self.name]
-
-    def _give_name(self, name, model):
-        if name is not None:
-            if name[-1] == '*':
-                name = self._new_name(name[:-1], model)
-            return name
-        # the reference inspects the caller's source line for `x = elfi.Node(...)`; here an
-        # explicit name is expected and a random one is generated otherwise
-        return self._new_name(model=model)
-
-    def _new_name(self, basename='', model=None):
-        model = model or self.model
-        if not basename:
-            basename = '_{}'.format(self.__class__.__name__.lower())
-        while True:
-            name = "{}_{}".format(basename, random_name())
-            if not model.has_node(name):
-                break
-        return name
-
-    @property
-    def state(self):
-        if self.model is None:
-            raise ValueError('{} {} is not initialized'.format(self.__class__.__name__, self.name))
-        return self.model.get_node(self.name)
-
-    def __getitem__(self, item):
-        return self.state[item]
-
-    def __setitem__(self, item, value):
-        self.state[item] = value
+        return self.model.generate(batch_size, self.name, with_values=with_values)[self.name]
 
     @property
     def uses_meta(self):
-        return self.state['attr_dict'].get('_uses_meta', False)
+        return self.record.has(TAKES_META)
 
     @uses_meta.setter
-    def uses_meta(self, val):
-        self.state['attr_dict']['_uses_meta'] = val
+    def uses_meta(self, on):
+        self.record.set(TAKES_META, bool(on))
 
     def __repr__(self):
-        return "{}(name='{}')".format(self.__class__.__name__, self.name)
+        return "{}(name='{}')".format(type(self).__name__, self.name)
 
     def __str__(self):
         return self.name
@@ -583,7 +612,7 @@ class NodeReference:
 
 class Constant(NodeReference):
     def __init__(self, value, **kwargs):
-        super().__init__(state=dict(_output=value), **kwargs)
+        super().__init__(state=dict(constant=value), **kwargs)
 
 
 class _HostOperation:
@@ -601,84 +630,87 @@ class _HostOperation:
 
 class Operation(NodeReference):
     def __init__(self, fn, *parents, **kwargs):
-        super().__init__(*parents, state=dict(_operation=_HostOperation(fn)), **kwargs)
+        super().__init__(*parents, state=dict(op=_HostOperation(fn)), **kwargs)
 
 
-def rvs_from_distribution(*params, batch_size, distribution, size=None, random_state=None):
-    """elfi/model/utils.py:6-34."""
-    size = (batch_size,) if size is None else (batch_size,) + size
-    return distribution.rvs(*params, size=size, random_state=random_state)
+def _draw(*params, batch_size, distribution, size=None, random_state=None):
+    """One batch of a random variable: `size` is the shape of a single draw."""
+    shape = (batch_size,) + (size or ())
+    return distribution.rvs(*params, size=shape, random_state=random_state)
 
 
 class RandomVariable(NodeReference):
+    """`distribution` is a scipy.stats name or any object with ``rvs(*params, size,
+    random_state)``."""
+    _flags = STOCHASTIC | TAKES_BATCH_SIZE
+
     def __init__(self, distribution, *params, size=None, **kwargs):
-        state = dict(distribution=distribution, size=size, _uses_batch_size=True,
-                     _stochastic=True)
-        if not (size is None or isinstance(size, tuple)):
+        if size is not None and not isinstance(size, tuple):
             size = (size,)
         dist = scipy_from_str(distribution) if isinstance(distribution, str) else distribution
         if not hasattr(dist, 'rvs'):
-            raise ValueError("Distribution {} must implement a rvs method".format(distribution))
-        state['_operation'] = partial(rvs_from_distribution, distribution=dist, size=size)
+            raise ValueError('Distribution {} must implement a rvs method'.format(distribution))
+        state = dict(op=partial(_draw, distribution=dist, size=size), distribution=distribution,
+                     size=size)
         super().__init__(*params, state=state, **kwargs)
 
     @property
     def distribution(self):
-        distribution = self.state['attr_dict']['distribution']
-        if isinstance(distribution, str):
-            distribution = scipy_from_str(distribution)
-        return distribution
+        dist = self.record.attrs['distribution']
+        return scipy_from_str(dist) if isinstance(dist, str) else dist
 
     @property
     def size(self):
-        return self.state['attr_dict']['size']
+        return self.record.attrs['size']
 
 
 class Prior(RandomVariable):
-    def __init__(self, distribution, *params, size=None, **kwargs):
-        super().__init__(distribution, *params, size=size, **kwargs)
-        self.state['attr_dict']['_parameter'] = True
+    _flags = RandomVariable._flags | PARAMETER
 
 
 class _Observable(NodeReference):
+    _flags = OBSERVABLE
+
     def _set_observed(self, observed):
         if observed is not None:
             self.model.observed[self.name] = observed
 
     @property
     def observed(self):
-        obs_name = observed_name(self.name)
-        return self.model.generate(0, obs_name)[obs_name]
+        twin = observed_name(self.name)
+        return self.model.generate(0, twin)[twin]
 
 
 class Simulator(_Observable):
     """fn(*params, batch_size, random_state) -> array of length batch_size."""
+    _flags = OBSERVABLE | STOCHASTIC | TAKES_BATCH_SIZE
 
     def __init__(self, fn, *params, observed=None, **kwargs):
-        state = dict(_operation=fn, _uses_batch_size=True, _stochastic=True, _observable=True)
-        super().__init__(*params, state=state, **kwargs)
+        super().__init__(*params, state=dict(op=fn), **kwargs)
         self._set_observed(observed)
+
+
+def _require_parents(parents):
+    if not parents:
+        raise ValueError('This node requires that at least one parent is specified.')
 
 
 class Summary(_Observable):
     """fn(*parents) -> summary statistic; may return a device array."""
 
     def __init__(self, fn, *parents, observed=None, **kwargs):
-        if not parents:
-            raise ValueError('This node requires that at least one parent is specified.')
-        state = dict(_operation=fn, _observable=True)
-        super().__init__(*parents, state=state, **kwargs)
+        _require_parents(parents)
+        super().__init__(*parents, state=dict(op=fn), **kwargs)
         self._set_observed(observed)
 
 
 class Discrepancy(NodeReference):
     """discrepancy(*summaries, observed=tuple) -> (B,) or (B, K)."""
+    _flags = TAKES_OBSERVED
 
     def __init__(self, discrepancy, *parents, **kwargs):
-        if not parents:
-            raise ValueError('This node requires that at least one parent is specified.')
-        state = kwargs.pop('state', None) or {}
-        state.update(dict(_operation=discrepancy, _uses_observed=True))
+        _require_parents(parents)
+        state = dict(kwargs.pop('state', None) or {}, op=discrepancy)
         super().__init__(*parents, state=state, **kwargs)
 
 
@@ -795,45 +827,49 @@ def host_distance_as_discrepancy(dist, *summaries, observed):
         "CUDA kernel; use elfi_b200.Discrepancy with your own callable.".format(dist))
 
 
+_REQUIRED_METRIC_KEYWORD = {'wminkowski': 'w', 'seuclidean': 'V', 'mahalanobis': 'VI'}
+
+
+def _device_metric_operation(metric, kw):
+    """The device operation for cdist metric `metric` with cdist keywords `kw`, or None when no
+    kernel computes that combination."""
+    given = set(kw)
+    if metric == 'euclidean' and given <= {'w'}:
+        return partial(device_euclidean_discrepancy, w=kw.get('w'))
+    if metric == 'seuclidean' and given == {'V'}:
+        return partial(device_seuclidean_discrepancy, V=np.asarray(kw['V'], dtype=np.float64))
+    if metric == 'minkowski' and given <= {'p'}:
+        return partial(device_metric_discrepancy, metric, p=kw.get('p', 2.0))
+    if metric in DEVICE_METRICS and not given:
+        return partial(device_metric_discrepancy, metric)
+    return None
+
+
 class Distance(Discrepancy):
-    """Distance('euclidean', *summaries[, w=]) -- elfi/model/elfi_model.py:974-1044."""
+    """Distance(metric, *summaries[, p=, w=, V=, VI=]): a cdist metric name (device kernel, fused
+    acceptance) or a callable ``f(XA, XB)`` (host operation).  Node semantics of
+    elfi/model/elfi_model.py:974-1044."""
 
     def __init__(self, distance, *summaries, **kwargs):
-        if not summaries:
-            raise ValueError("This node requires that at least one parent is specified.")
+        _require_parents(summaries)
         state = {}
-        if isinstance(distance, str):
-            if distance == 'wminkowski' and 'w' not in kwargs:
-                raise ValueError('Parameter w must be specified for distance=wminkowski.')
-            if distance == 'seuclidean' and 'V' not in kwargs:
-                raise ValueError('Parameter V must be specified for distance=seuclidean.')
-            if distance == 'mahalanobis' and 'VI' not in kwargs:
-                raise ValueError('Parameter VI must be specified for distance=mahalanobis.')
-            cd = {k: kwargs.pop(k) for k in ['p', 'w', 'V', 'VI'] if k in kwargs}
-            if distance == 'euclidean' and not (set(cd) - {'w'}):
-                op = partial(device_euclidean_discrepancy, w=cd.get('w'))
-                state['_uses_accept'] = True
-            elif distance == 'seuclidean' and set(cd) == {'V'}:
-                op = partial(device_seuclidean_discrepancy,
-                             V=np.asarray(cd['V'], dtype=np.float64))
-                state['_uses_accept'] = True
-            elif distance in DEVICE_METRICS and not (set(cd) - {'p'}) and \
-                    (distance == 'minkowski' or not cd):
-                op = partial(device_metric_discrepancy, distance, p=cd.get('p', 2.0))
-                state['_uses_accept'] = True
-            else:
-                op = partial(host_distance_as_discrepancy, distance)
+        if callable(distance):
+            def op(*summaries, observed, _f=distance):
+                d = _f(_stack_summaries(summaries), _stack_observed(observed))
+                return d.reshape(-1) if d.ndim == 2 and d.shape[1] == 1 else d
         else:
-            user_fn = distance
-
-            def op(*summaries, observed):
-                X = _stack_summaries(summaries)
-                d = user_fn(X, _stack_observed(observed))
-                if d.ndim == 2 and d.shape[1] == 1:
-                    d = d.reshape(-1)
-                return d
+            need = _REQUIRED_METRIC_KEYWORD.get(distance)
+            if need is not None and need not in kwargs:
+                raise ValueError('Parameter {} must be specified for distance={}.'.format(
+                    need, distance))
+            kw = {k: kwargs.pop(k) for k in ('p', 'w', 'V', 'VI') if k in kwargs}
+            op = _device_metric_operation(distance, kw)
+            if op is None:
+                op = partial(host_distance_as_discrepancy, distance)
+            else:
+                state['flags'] = TAKES_ACCEPT
         super().__init__(op, *summaries, state=state, **kwargs)
-        self.state['attr_dict']['distance'] = distance
+        self.record.attrs['distance'] = distance
 
 
 class AdaptiveDistance(Discrepancy):
@@ -842,16 +878,15 @@ class AdaptiveDistance(Discrepancy):
     store = [n, mean, M2] merged batch by batch from device column moments."""
 
     def __init__(self, *summaries, **kwargs):
-        if not summaries:
-            raise ValueError("This node requires that at least one parent is specified.")
-        state = dict(_uses_accept=True)
+        _require_parents(summaries)
+        state = dict(flags=TAKES_ACCEPT)
         super().__init__(self._nested_discrepancy, *summaries, state=state, **kwargs)
         self.init_state()
 
     # the operation is a bound method of a reference; look the state up at call time
     def _nested_discrepancy(self, *summaries, observed, accept=None):
         X = _stack_summaries(summaries)
-        ws = self.state['attr_dict']['w']
+        ws = self._s['w']
         D = X.shape[1]
         key = tuple(id(w) for w in ws)       # (K, D) squared weights: rebuilt when a round is added
         held = self._s.get('_W_dev')
@@ -867,7 +902,7 @@ class AdaptiveDistance(Discrepancy):
 
     @property
     def _s(self):
-        return self.state['attr_dict']
+        return self.record.attrs
 
     def init_state(self):
         self._s['w'] = [None]

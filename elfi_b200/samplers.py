@@ -172,7 +172,7 @@ class ModelPrior:
             combine = add if log else (lambda a, b: a * b)
             joint = em.Operation(lambda *a, _c=combine: reduce(_c, a), *nodes, model=model,
                                  name='_joint_{}*'.format(attr))
-            self._nets[log] = (joint.name, em.compile_net(model.source_net, [joint.name]))
+            self._nets[log] = (joint.name, em.compile_plan(model, [joint.name]))
 
     def _evaluate(self, x, log):
         x = np.asanyarray(x)
@@ -295,7 +295,7 @@ class ParameterInference:
         self.output_names = self._check_outputs(output_names)
         self.computation_context = em.ComputationContext(batch_size=batch_size, seed=seed,
                                                          pool=pool)
-        self._compiled = em.compile_net(self.model.source_net, self.output_names)
+        self._compiled = em.compile_plan(self.model, self.output_names)
         self._distributed = distributed
         self.comm = Comm(distributed)
         if self.comm.on and pool is not None and type(pool).__name__ == 'ArrayPool':

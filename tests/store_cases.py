@@ -21,10 +21,10 @@ def counted_ma2():
     import elfi_b200 as elfi
     from elfi_b200.examples import ma2
     m = ma2.get_model(seed_obs=4)
-    sim = Counter(m.get_state('MA2')['attr_dict']['_operation'])
-    m.get_state('MA2')['attr_dict']['_operation'] = sim
-    s1 = Counter(m.get_state('S1')['attr_dict']['_operation'])
-    m.get_state('S1')['attr_dict']['_operation'] = s1
+    sim = Counter(m.record('MA2').op)
+    m.record('MA2').op = sim
+    s1 = Counter(m.record('S1').op)
+    m.record('S1').op = s1
     return elfi, m, sim, s1
 
 

@@ -60,31 +60,39 @@ def test_compile_adds_observed_twins_and_feeders():
     from elfi_b200 import model as em
     from elfi_b200.examples import ma2
     m = ma2.get_model(seed_obs=1)
-    net = em.compile_net(m.source_net, ['d'])
+    plan = em.compile_plan(m, ['d'])
     for n in ('_MA2_observed', '_S1_observed', '_S2_observed', '_d_observed', '_batch_size',
               '_random_state', 't1', 't2', 'MA2', 'S1', 'S2', 'd'):
-        assert net.has_node(n), n
-    assert net['_d_observed']['d']['param'] == 'observed'
-    assert net['_random_state']['MA2']['param'] == 'random_state'
-    assert net['_MA2_observed']['_S1_observed']['param'] == 0
-    order = net.graph['order']
+        assert plan.has_node(n), n
+    assert plan.steps['d'].kwargs['observed'] == '_d_observed'
+    assert plan.steps['MA2'].kwargs['random_state'] == '_random_state'
+    assert plan.steps['MA2'].kwargs['batch_size'] == '_batch_size'
+    assert plan.steps['_S1_observed'].args[0] == '_MA2_observed'
+    assert plan.steps['_MA2_observed'].sources == []          # the observed data itself
+    assert plan.steps['_d_observed'].args == ['_S1_observed', '_S2_observed']
+    assert plan.steps['d'].fuses_accept and not plan.steps['_S1_observed'].fuses_accept
+    order = plan.order
+    assert sorted(order) == sorted(plan.steps)
     assert order.index('t1') < order.index('t2') < order.index('MA2') < order.index('S1') < \
         order.index('d')
-    # pruning: only ancestors of the requested outputs survive
-    net2 = em.compile_net(m.source_net, ['t1'])
-    assert not net2.has_node('MA2') and not net2.has_node('d')
+    # pruning: only what the requested outputs depend on survives
+    plan2 = em.compile_plan(m, ['t1'])
+    assert not plan2.has_node('MA2') and not plan2.has_node('d')
+    with pytest.raises(ValueError):
+        em.compile_plan(m, ['no_such_node'])
 
 
 def test_execution_order_is_reference_order():
     """Same order as elfi/executor.py:nx_constant_topological_sort (golden from the reference)."""
     from elfi_b200.model import _constant_topological_order
-    import networkx as nx
     g = json.load(open(os.path.join(GOLDEN, 'topo_orders.json')))
     for case in g:
-        G = nx.DiGraph()
-        G.add_nodes_from(case['nodes'])
-        G.add_edges_from(case['edges'])
-        assert _constant_topological_order(G) == case['order']
+        children = {n: [] for n in case['nodes']}
+        for u, v in case['edges']:
+            children[u].append(v)
+        assert _constant_topological_order(case['nodes'], children.__getitem__) == case['order']
+    with pytest.raises(ValueError):
+        _constant_topological_order('ab', {'a': 'b', 'b': 'a'}.__getitem__)   # a cycle
 
 
 def test_node_api_errors_and_become():
@@ -112,7 +120,19 @@ def test_node_api_errors_and_become():
     assert isinstance(m['d'], elfi.AdaptiveDistance)
     kopy = m.copy()
     assert kopy.name != m.name and kopy.has_node('d')
-    assert kopy.get_node('d')['attr_dict'] is m.get_node('d')['attr_dict']   # shared node state
+    assert kopy.record('d') is not m.record('d')
+    assert kopy.record('d').attrs is m.record('d').attrs      # shared node state
+    assert kopy.get_parents('d') == ['s'] and m.get_children('s') == ['d']
+    # hidden constants go with the node that used them; observed data goes with its node
+    n_before = len(m.nodes)
+    elfi.Prior('uniform', 0, 1, model=m, name='q')
+    assert len(m.nodes) == n_before + 3
+    m.remove_node('q')
+    assert len(m.nodes) == n_before
+    m.remove_node('sim')
+    assert 'sim' not in m.observed and m.get_parents('s') == []
+    with pytest.raises(ValueError):
+        m.parameter_names = ['nope']
 
 
 def test_unsupported_metric_fails_loudly():
