@@ -13,6 +13,6 @@ from .model import (AdaptiveDistance, Constant, Discrepancy, Distance, ElfiModel
                     get_default_model, new_model, set_default_model)
 from .samplers import (SMC, AdaptiveDistanceSMC, AdaptiveThresholdSMC,  # noqa: F401
                        DensityRatioEstimation, GMDistribution, ModelPrior, Rejection)
-from .store import ArrayPool, OutputPool  # noqa: F401
+from .store import OutputPool  # noqa: F401
 from .bo import (BOLFI, LCBSC, BayesianOptimization, BolfiPosterior, GPyRegression,  # noqa: F401
                  ExpIntVar, MaxVar, RandMaxVar, UniformAcquisition)

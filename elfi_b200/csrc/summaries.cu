@@ -248,6 +248,127 @@ struct MeanVarRegsConsumer {
     }
 };
 
+// Contiguous rows whose pitch is an odd multiple of 16 bytes (n = 2 mod 4; the Gaussian model
+// has n = 50: 400-byte rows).  Through the 2-D tensor map such a matrix costs ceil(n/16) boxes
+// per 32 rows, the last one nearly empty (n = 50: 4 boxes for 3.125 boxes of data -- the
+// kernel ran at 0.6 of the HBM peak against 0.8 at n = 64), and no box row is line aligned.
+// Here a tile is what it is in memory: 32 rows = ONE contiguous run of 32 * 8n bytes, fetched
+// by one 1-D bulk copy into the warp's ring slot.  No swizzle is needed: lane l reads 16-byte
+// chunk c of its row at l * 8n + 16c, and with 8n / 16 odd the eight lanes of a quarter-warp
+// fall into eight distinct 16-byte bank groups (LDS.128 without conflicts).  Arithmetic and
+// order are MeanVarRegs', i.e. the same bits as the row-stream consumers.
+constexpr int RG_WARPS = 8;
+constexpr int RG_SLACK = 256;   // the last box of lane 31 reads up to (16*NBOX - n) doubles past its row
+
+__host__ __device__ inline size_t rg_slot_bytes(int n) { return size_t(32) * n * 8; }
+
+template <int NBOX>
+__global__ void __launch_bounds__(RG_WARPS * 32, 1)
+meanvar_rowgroup_kernel(const double* __restrict__ X, int64_t B, int ns, SummaryParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n = p.n;
+    const uint32_t slot = uint32_t(rg_slot_bytes(n));
+    uint8_t* bars_generic = smem + size_t(RG_WARPS) * ns * slot + RG_SLACK;
+    const uint32_t box0 = smem_u32(smem) + uint32_t(warp) * ns * slot;
+    const uint32_t bar0 = smem_u32(bars_generic) + uint32_t(warp) * ns * 8;
+    const uint8_t* box0_generic = smem + size_t(warp) * ns * slot;
+    if (lane == 0) {
+        for (int s = 0; s < ns; ++s) mbar_init(bar0 + s * 8, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    const int64_t ntiles = (B + 31) / 32;
+    const int64_t gw = int64_t(blockIdx.x) * RG_WARPS + warp;
+    const int64_t GW = int64_t(gridDim.x) * RG_WARPS;
+    const int64_t my_tiles = gw < ntiles ? (ntiles - gw + GW - 1) / GW : 0;
+
+    int64_t p_tile = gw;   // producer cursor (lane 0)
+    int64_t p_q = 0;
+    int p_s = 0;
+    auto issue = [&]() {
+        const int64_t row0 = p_tile * 32;
+        const int64_t rows = (B - row0 < 32) ? (B - row0) : 32;
+        const uint32_t bytes = uint32_t(rows) * uint32_t(n) * 8u;
+        mbar_arrive_expect_tx(bar0 + p_s * 8, bytes);
+        bulk_load_1d(box0 + p_s * slot, X + row0 * n, bytes, bar0 + p_s * 8);
+        ++p_q;
+        p_tile += GW;
+        if (++p_s == ns) p_s = 0;
+    };
+    if (lane == 0) {
+        const int64_t pre = my_tiles < ns ? my_tiles : ns;
+        for (int64_t i = 0; i < pre; ++i) issue();
+    }
+
+    MeanVarRegs<NBOX> st;
+    const uint32_t row_off = uint32_t(lane) * uint32_t(n) * 8u;
+    int s = 0;
+    uint32_t parity = 0;
+    int64_t tile = gw;
+    for (int64_t q = 0; q < my_tiles; ++q) {
+        mbar_wait(bar0 + s * 8, parity);
+        const double2* row = reinterpret_cast<const double2*>(box0_generic + size_t(s) * slot + row_off);
+        st.begin(n);
+        double cur[16];
+#pragma unroll
+        for (int g = 0; g < NBOX; ++g) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double2 v = row[g * 8 + c];
+                cur[2 * c] = v.x;
+                cur[2 * c + 1] = v.y;
+            }
+            if (g == 0) st.template box<0>(cur);
+            if constexpr (NBOX > 1) if (g == 1) st.template box<1>(cur);
+            if constexpr (NBOX > 2) if (g == 2) st.template box<2>(cur);
+            if constexpr (NBOX > 3) if (g == 3) st.template box<3>(cur);
+        }
+        __syncwarp();
+        if (lane == 0 && p_q < my_tiles) issue();
+        double mean, var;
+        st.finish(mean, var);
+        const int64_t r = tile * 32 + lane;
+        if (r < B) {
+            if (p.col_a >= 0) p.out[r * p.ld_out + p.col_a] = mean;
+            if (p.col_b >= 0) p.out[r * p.ld_out + p.col_b] = var;
+        }
+        tile += GW;
+        if (++s == ns) { s = 0; parity ^= 1; }
+    }
+}
+
+static bool rowgroup_ok(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t n) {
+    static const bool off = [] {
+        const char* v = std::getenv("ELFI_B200_MEANVAR_ROWGROUP");
+        return v != nullptr && v[0] == '0';
+    }();
+    if (off || ld != n || n > 64 || (n & 3) != 2 || (reinterpret_cast<uintptr_t>(X) & 15)) return false;
+    return size_t(RG_WARPS) * 2 * rg_slot_bytes(int(n)) + RG_SLACK + RG_WARPS * 2 * 8 + 1024 <=
+           ctx->smem_optin;
+}
+
+template <int NBOX>
+static int rowgroup_launch(elfi_b200_ctx* ctx, const double* X, int64_t B, int64_t n,
+                           const SummaryParams& p, cudaStream_t stream) {
+    const size_t slot = rg_slot_bytes(int(n));
+    int ns = 4;
+    while (size_t(RG_WARPS) * ns * slot + RG_SLACK + size_t(RG_WARPS) * ns * 8 + 1024 > ctx->smem_optin)
+        --ns;
+    const size_t smem_bytes = size_t(RG_WARPS) * ns * slot + RG_SLACK + size_t(RG_WARPS) * ns * 8;
+    auto kern = meanvar_rowgroup_kernel<NBOX>;
+    ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem_bytes)));
+    const int64_t ntiles = (B + 31) / 32;
+    int64_t ctas = (ntiles + RG_WARPS - 1) / RG_WARPS;
+    if (ctas > ctx->sm_count) ctas = ctx->sm_count;
+    kern<<<dim3(unsigned(ctas)), dim3(RG_WARPS * 32), smem_bytes, stream>>>(X, B, ns, p);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
+}
+
 typedef TreeSum<RS_PW_DEPTH> RowTreeSum;
 
 // Rows of 129..7688 terms: the term-wise TreeSum front end is the default since it was timed on
@@ -394,6 +515,12 @@ int elfi_b200_summary_meanvar_f64(elfi_b200_ctx* ctx, const double* X, int64_t l
     p.n = int(n);
     p.col_a = col_mean;
     p.col_b = col_var;
+    if (rowgroup_ok(ctx, X, ldX, n)) {
+        if (n <= 16) return rowgroup_launch<1>(ctx, X, B, n, p, stream);
+        if (n <= 32) return rowgroup_launch<2>(ctx, X, B, n, p, stream);
+        if (n <= 48) return rowgroup_launch<3>(ctx, X, B, n, p, stream);
+        return rowgroup_launch<4>(ctx, X, B, n, p, stream);
+    }
     if (rowstream_ok(ctx, X, ldX, n)) {
         static const bool two_sweeps = std::getenv("ELFI_B200_MEANVAR_TWO_SWEEPS") != nullptr;
         if (!two_sweeps) {

@@ -226,12 +226,10 @@ class ModelPrior:
 def normalize_weights(weights):
     """elfi/methods/utils.py:80-88."""
     w = np.atleast_1d(weights)
-    if np.any(w < 0):
-        raise ValueError("Weights must be positive")
-    wsum = np.sum(weights)
-    if wsum == 0:
-        raise ValueError("All weights are zero")
-    return w / wsum
+    total = np.sum(weights)
+    if (w < 0).any() or total == 0:
+        raise ValueError('Weights must be non-negative and not all zero')
+    return w / total
 
 
 class GMDistribution:
@@ -298,11 +296,6 @@ class ParameterInference:
         self._compiled = em.compile_plan(self.model, self.output_names)
         self._distributed = distributed
         self.comm = Comm(distributed)
-        if self.comm.on and pool is not None and type(pool).__name__ == 'ArrayPool':
-            # an appendable .npy store is written in batch-index order by ONE writer; rank r's
-            # first batch index is r and all ranks would share the same files
-            raise ValueError('ArrayPool cannot be shared by the ranks of a distributed run; use an '
-                             'OutputPool (device-resident, per rank) or distributed=False')
         self.max_parallel_batches = max_parallel_batches or self.comm.size
         if self.max_parallel_batches <= 0:
             raise ValueError('Value for max_parallel_batches ({}) must be at least one.'.format(
@@ -401,33 +394,27 @@ class ParameterInference:
 
     @staticmethod
     def _resolve_model(model, target, default_reference_class=em.NodeReference):
-        if isinstance(model, em.ElfiModel) and target is None:
-            raise NotImplementedError("Please specify the target node of the inference method")
+        """(model, target node name) from either (node, anything) or (model, node or name)."""
         if isinstance(model, em.NodeReference):
-            target = model
-            model = target.model
-        if isinstance(target, str):
-            target = model[target]
-        if not isinstance(target, default_reference_class):
-            raise ValueError('Unknown target node class')
-        return model, target.name
+            model, target = model.model, model
+        elif target is None:
+            raise NotImplementedError('{}: the target node must be named when a model is '
+                                      'given'.format(model))
+        node = model[target] if isinstance(target, str) else target
+        if not isinstance(node, default_reference_class):
+            raise ValueError('{!r} is not a {}'.format(node, default_reference_class.__name__))
+        return model, node.name
 
     def _check_outputs(self, output_names):
-        checked, seen = [], set()
-        for name in output_names or []:
-            if isinstance(name, em.NodeReference):
-                name = name.name
-            if name in seen:
-                continue
+        """Node names (handles are accepted) in first-mention order, each once, all in the
+        model."""
+        names = [n.name if isinstance(n, em.NodeReference) else n for n in output_names or []]
+        for name in names:
             if not isinstance(name, str):
-                raise ValueError('All output names must be strings, object {} was given'.format(
-                    name))
+                raise ValueError('Outputs are named by strings; got {!r}'.format(name))
             if not self.model.has_node(name):
-                raise ValueError('Node {} output was requested, but it is not in the model.'
-                                 .format(name))
-            seen.add(name)
-            checked.append(name)
-        return checked
+                raise ValueError('Requested output {} is not a node of the model'.format(name))
+        return list(dict.fromkeys(names))
 
 
 class Sampler(ParameterInference):
@@ -820,18 +807,21 @@ class SMC(Sampler):
         self.bar = False
 
     def set_objective(self, n_samples, thresholds=None, quantiles=None):
-        if thresholds is None and quantiles is None:
-            raise ValueError("Either thresholds or quantiles is required to run ABC-SMC.")
-        rounds = (len(quantiles) if thresholds is None else len(thresholds)) - 1
-        self.state['round'] = len(self._populations)
-        rounds = rounds + self.state['round']
+        """One more population per entry of `thresholds` (or `quantiles`: the threshold of a
+        round is then that quantile of the previous population's discrepancies), continuing
+        after the populations already sampled."""
+        schedule = thresholds if thresholds is not None else quantiles
+        if schedule is None:
+            raise ValueError('ABC-SMC needs either thresholds or quantiles')
+        done = len(self._populations)
+        self.state['round'] = done
+        padded = np.concatenate((np.full(done, None), schedule))
         if thresholds is None:
-            thresholds = np.full((rounds + 1), None)
-            self._quantiles = np.concatenate((np.full((self.state['round']), None), quantiles))
+            self._quantiles, thresholds = padded, np.full(len(padded), None)
         else:
-            thresholds = np.concatenate((np.full((self.state['round']), None), thresholds))
-        self.objective.update(dict(n_samples=n_samples, n_batches=self.max_parallel_batches,
-                                   round=rounds, thresholds=thresholds))
+            thresholds = padded
+        self.objective.update(n_samples=n_samples, n_batches=self.max_parallel_batches,
+                              round=len(padded) - 1, thresholds=thresholds)
         self._init_new_round()
         self._update_objective()
 

@@ -1,8 +1,6 @@
 """Bodies of the output-pool tests, shared by the CPU-double and the GPU collections
 (modelled on the reference's tests/functional/test_simulation_reuse.py and
 tests/unit/test_store.py:101-167)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -75,83 +73,40 @@ def case_pool_usage():
     assert pool.device_bytes() == 0 and isinstance(pool.get_store('S1')[0], np.ndarray)
 
 
-def case_array_pool(tmp_path):
-    """ArrayPool: .npy-backed stores with a device write-back cache, save / open / move / delete."""
+def case_pool_spill():
+    """resident_limit: the oldest batches move to host memory, all nodes of a batch together; a
+    spilled pool feeds a new inference with the same result."""
     elfi, m, sim, s1 = counted_ma2()
-    from elfi_b200.store import ArrayPool, ArrayStore, NpyArray, OutputPool
-    prefix = str(tmp_path / 'pools')
-    pool = ArrayPool(['MA2', 'S1'], prefix=prefix)
-    N, bs, total = 50, 100, 1000
-    rej_pool = elfi.Rejection(m['d'], batch_size=bs, pool=pool, seed=3)
-    means = rej_pool.sample(N, n_sim=total, bar=False).sample_means_array
-    assert len(pool.stores['MA2']) == total // bs == len(pool.stores['S1']) == len(pool)
-    assert 't1' not in pool.stores
-    assert len(pool.stores['MA2'].array) == total        # host simulator output: written through
-    assert pool.stores['S1'].resident_bytes() == total * 8 and len(pool.stores['S1'].array) == 0
-    batch2 = {k: np.array(np.asarray(v.cpu() if hasattr(v, 'cpu') else v)) for k, v in pool[2].items()}
-
-    pool2 = OutputPool(['MA2', 'S1'])
-    elfi.Rejection(m['d'], batch_size=bs, pool=pool2, seed=pool.seed).sample(N, n_sim=total, bar=False)
-    for bi in range(total // bs):
-        assert np.array_equal(np.asarray(pool.stores['S1'][bi].cpu()),
-                              np.asarray(pool2.stores['S1'][bi].cpu()))
-
+    from elfi_b200 import device as dev
+    bs, n_batches = 200, 6
+    per_batch = bs * 8 * 3                                    # S1, S2, d: one double per row each
+    pool = elfi.OutputPool(['S1', 'S2', 'd'], resident_limit=2 * per_batch)
+    res = elfi.Rejection(m['d'], batch_size=bs, pool=pool, seed=11).sample(
+        30, n_sim=bs * n_batches, bar=False)
+    assert len(pool) == n_batches and pool.device_bytes() == 2 * per_batch
+    for node in ('S1', 'S2', 'd'):
+        store = pool.get_store(node)
+        assert store.resident_batches() == [n_batches - 2, n_batches - 1]
+        assert isinstance(store[0], np.ndarray) and dev.is_device_array(store[n_batches - 1])
     calls = sim.calls
-    rej_pool.sample(N, n_sim=total, bar=False)
-    rej_new = elfi.Rejection(m['d'], batch_size=bs, pool=pool)
-    assert np.array_equal(means, rej_new.sample(N, n_sim=total, bar=False).sample_means_array)
+    again = elfi.Rejection(m['d'], batch_size=bs, pool=pool).sample(30, n_sim=bs * n_batches,
+                                                                    bar=False)
+    # parameters are not pooled: they are drawn again (same seed, same values); nothing asks for
+    # the simulator since summaries and distance are read back (spilled batches from the host)
+    assert np.array_equal(again.discrepancies, res.discrepancies)
+    assert np.array_equal(again.samples_array, res.samples_array)
     assert sim.calls == calls
-
-    pool.flush()                                          # lazy spill of the device batches
-    assert pool.device_bytes() == 0 and len(pool.stores['S1'].array) == total
-    assert np.array_equal(np.load(os.path.join(pool.path, 'S1.npy')),
-                          np.concatenate([pool.stores['S1'][b] for b in range(total // bs)]))
-    pool.close()
-    pool = ArrayPool.open(pool.name, prefix=prefix)
-    assert len(pool) == total // bs
-    pool.close()
-    os.rename(pool.path, pool.path + '_move')
-    pool = ArrayPool.open(pool.name + '_move', prefix=prefix)
-    assert len(pool) == total // bs
-    assert np.array_equal(pool[2]['S1'], batch2['S1']) and np.array_equal(pool[2]['MA2'], batch2['MA2'])
-    # an opened pool feeds a new inference without simulating
-    calls = sim.calls
-    again = elfi.Rejection(m['d'], batch_size=bs, pool=pool).sample(N, n_sim=total, bar=False)
-    assert sim.calls == calls and np.array_equal(again.sample_means_array, means)
-
-    r = np.random.rand(3 * bs)
-    arr = NpyArray(os.path.join(pool.path, 'test.npy'), r)
-    pool.add_store('test', ArrayStore(arr, bs))
-    assert len(pool.get_store('test')) == 3 and np.array_equal(pool[2]['test'], r[-bs:])
-    pool.delete()
-    assert not os.path.exists(pool.path)
-
-
-def case_pool_restarts(tmp_path):
-    """save() then keep appending: a re-opened pool sees the saved batches and continues them."""
-    elfi, m, sim, s1 = counted_ma2()
-    from elfi_b200.store import ArrayPool
-    prefix = str(tmp_path / 'pools')
-    pool = ArrayPool(['t1', 'd'], name='test', prefix=prefix)
-    rej = elfi.Rejection(m, 'd', batch_size=10, pool=pool, seed=123)
-    rej.sample(1, n_sim=30, bar=False)
-    pool.save()
-    rej = elfi.Rejection(m, 'd', batch_size=10, pool=pool)
-    rej.set_objective(3, n_sim=60)
-    while not rej.finished:
-        rej.iterate()
-    pool.get_store('t1').array.fs.flush()       # data reaches the file, the header is not rewritten
-    assert len(pool) == 6 and len(pool.stores['t1'].array) == 60
-
-    pool2 = ArrayPool.open('test', prefix=prefix)
-    assert len(pool2) == 3 and len(pool2.stores['t1'].array) == 30
-    s9pool = elfi.Rejection(m, 'd', batch_size=10, pool=pool2).sample(3, n_sim=90, bar=False)
-    pool2.save()
-    pool2 = ArrayPool.open('test', prefix=prefix)
-    s9loaded = elfi.Rejection(m, 'd', batch_size=10, pool=pool2).sample(3, n_sim=90, bar=False)
-    s9 = elfi.Rejection(m, 'd', batch_size=10, seed=123).sample(3, n_sim=90, bar=False)
-    for a in (s9pool, s9loaded):
-        assert np.array_equal(a.samples['t1'], s9.samples['t1'])
-        assert np.array_equal(a.discrepancies, s9.discrepancies)
-    pool.delete()
-    pool2.delete()
+    pool.remove_batch(n_batches - 1)
+    assert len(pool) == n_batches - 1 and (n_batches - 1) not in pool and 0 in pool
+    pool.clear()
+    assert len(pool) == 0 and pool.device_bytes() == 0
+    with pytest.raises(ValueError):
+        pool.add_store('S1')
+    with pytest.raises(ValueError):
+        pool.set_context(None)
+    own = {}
+    pool2 = elfi.OutputPool({'d': own})                        # any dictionary works as a store
+    elfi.Rejection(m['d'], batch_size=bs, pool=pool2, seed=11).sample(5, n_sim=bs, bar=False)
+    assert list(own) == [0] and pool2.device_bytes() == bs * 8
+    pool2.to_host()
+    assert isinstance(own[0], np.ndarray) and pool2.device_bytes() == 0

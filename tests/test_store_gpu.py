@@ -1,5 +1,5 @@
-"""Output pools on the device (row N4): stored summaries / discrepancies stay in HBM across
-inferences and spill to .npy lazily.  Same bodies as tests/test_store_cpu_double.py."""
+"""Output pool on the device (row N4): stored summaries / discrepancies stay in HBM across
+inferences and spill to host memory lazily.  Same bodies as tests/test_store_cpu_double.py."""
 import pytest
 
 import store_cases as cases
@@ -11,9 +11,5 @@ def test_pool_usage_device_resident():
     cases.case_pool_usage()
 
 
-def test_array_pool_write_back_cache(tmp_path):
-    cases.case_array_pool(tmp_path)
-
-
-def test_pool_restarts(tmp_path):
-    cases.case_pool_restarts(tmp_path)
+def test_pool_spill_oldest_batches_first():
+    cases.case_pool_spill()

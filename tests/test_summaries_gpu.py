@@ -32,7 +32,10 @@ def test_autocov_lag_variants(lags):
 
 
 @pytest.mark.parametrize('B,n', [(1000, 50), (333, 16), (64, 17), (2000, 128), (500, 129),
-                                 (100, 300), (50, 5000), (31, 7), (12, 1)])
+                                 (100, 300), (50, 5000), (31, 7), (12, 1),
+                                 # contiguous rows with n = 2 mod 4: the 1-D bulk row-group kernel
+                                 (1, 50), (33, 2), (37, 18), (4097, 62), (10007, 34), (300001, 50),
+                                 (257, 6), (95, 14), (64, 46)])
 def test_meanvar_bit_exact(B, n):
     from elfi_b200 import ops
     rs = np.random.RandomState(B * 7 + n)
