@@ -257,20 +257,20 @@ struct MeanVarRegsConsumer {
 // chunk c of its row at l * 8n + 16c, and with 8n / 16 odd the eight lanes of a quarter-warp
 // fall into eight distinct 16-byte bank groups (LDS.128 without conflicts).  Arithmetic and
 // order are MeanVarRegs', i.e. the same bits as the row-stream consumers.
-constexpr int RG_WARPS = 8;
+constexpr int RG_WARPS = 8;         // 6 for the widest rows (two ring slots of 8 warps would not fit)
 constexpr int RG_SLACK = 256;   // the last box of lane 31 reads up to (16*NBOX - n) doubles past its row
 
 __host__ __device__ inline size_t rg_slot_bytes(int n) { return size_t(32) * n * 8; }
 
-template <int NBOX>
-__global__ void __launch_bounds__(RG_WARPS * 32, 1)
+template <int NBOX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 meanvar_rowgroup_kernel(const double* __restrict__ X, int64_t B, int ns, SummaryParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n = p.n;
     const uint32_t slot = uint32_t(rg_slot_bytes(n));
-    uint8_t* bars_generic = smem + size_t(RG_WARPS) * ns * slot + RG_SLACK;
+    uint8_t* bars_generic = smem + size_t(WARPS) * ns * slot + RG_SLACK;
     const uint32_t box0 = smem_u32(smem) + uint32_t(warp) * ns * slot;
     const uint32_t bar0 = smem_u32(bars_generic) + uint32_t(warp) * ns * 8;
     const uint8_t* box0_generic = smem + size_t(warp) * ns * slot;
@@ -281,8 +281,8 @@ meanvar_rowgroup_kernel(const double* __restrict__ X, int64_t B, int ns, Summary
     __syncwarp();
 
     const int64_t ntiles = (B + 31) / 32;
-    const int64_t gw = int64_t(blockIdx.x) * RG_WARPS + warp;
-    const int64_t GW = int64_t(gridDim.x) * RG_WARPS;
+    const int64_t gw = int64_t(blockIdx.x) * WARPS + warp;
+    const int64_t GW = int64_t(gridDim.x) * WARPS;
     const int64_t my_tiles = gw < ntiles ? (ntiles - gw + GW - 1) / GW : 0;
 
     int64_t p_tile = gw;   // producer cursor (lane 0)
@@ -340,33 +340,42 @@ meanvar_rowgroup_kernel(const double* __restrict__ X, int64_t B, int ns, Summary
     }
 }
 
+static size_t rg_smem_bytes(int warps, int ns, int64_t n) {
+    return size_t(warps) * ns * rg_slot_bytes(int(n)) + RG_SLACK + size_t(warps) * ns * 8;
+}
+
 static bool rowgroup_ok(elfi_b200_ctx* ctx, const double* X, int64_t ld, int64_t n) {
     static const bool off = [] {
         const char* v = std::getenv("ELFI_B200_MEANVAR_ROWGROUP");
         return v != nullptr && v[0] == '0';
     }();
     if (off || ld != n || n > 64 || (n & 3) != 2 || (reinterpret_cast<uintptr_t>(X) & 15)) return false;
-    return size_t(RG_WARPS) * 2 * rg_slot_bytes(int(n)) + RG_SLACK + RG_WARPS * 2 * 8 + 1024 <=
-           ctx->smem_optin;
+    return rg_smem_bytes(6, 2, n) + 1024 <= ctx->smem_optin;
+}
+
+template <int NBOX, int WARPS>
+static int rowgroup_launch_w(elfi_b200_ctx* ctx, const double* X, int64_t B, int64_t n,
+                             const SummaryParams& p, cudaStream_t stream) {
+    int ns = 4;
+    while (rg_smem_bytes(WARPS, ns, n) + 1024 > ctx->smem_optin) --ns;
+    const size_t smem_bytes = rg_smem_bytes(WARPS, ns, n);
+    auto kern = meanvar_rowgroup_kernel<NBOX, WARPS>;
+    ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem_bytes)));
+    const int64_t ntiles = (B + 31) / 32;
+    int64_t ctas = (ntiles + WARPS - 1) / WARPS;
+    if (ctas > ctx->sm_count) ctas = ctx->sm_count;
+    kern<<<dim3(unsigned(ctas)), dim3(WARPS * 32), smem_bytes, stream>>>(X, B, ns, p);
+    ELFI_CUDA_OK(cudaGetLastError());
+    return ELFI_B200_OK;
 }
 
 template <int NBOX>
 static int rowgroup_launch(elfi_b200_ctx* ctx, const double* X, int64_t B, int64_t n,
                            const SummaryParams& p, cudaStream_t stream) {
-    const size_t slot = rg_slot_bytes(int(n));
-    int ns = 4;
-    while (size_t(RG_WARPS) * ns * slot + RG_SLACK + size_t(RG_WARPS) * ns * 8 + 1024 > ctx->smem_optin)
-        --ns;
-    const size_t smem_bytes = size_t(RG_WARPS) * ns * slot + RG_SLACK + size_t(RG_WARPS) * ns * 8;
-    auto kern = meanvar_rowgroup_kernel<NBOX>;
-    ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(smem_bytes)));
-    const int64_t ntiles = (B + 31) / 32;
-    int64_t ctas = (ntiles + RG_WARPS - 1) / RG_WARPS;
-    if (ctas > ctx->sm_count) ctas = ctx->sm_count;
-    kern<<<dim3(unsigned(ctas)), dim3(RG_WARPS * 32), smem_bytes, stream>>>(X, B, ns, p);
-    ELFI_CUDA_OK(cudaGetLastError());
-    return ELFI_B200_OK;
+    if (rg_smem_bytes(RG_WARPS, 2, n) + 1024 <= ctx->smem_optin)
+        return rowgroup_launch_w<NBOX, RG_WARPS>(ctx, X, B, n, p, stream);
+    return rowgroup_launch_w<NBOX, 6>(ctx, X, B, n, p, stream);
 }
 
 typedef TreeSum<RS_PW_DEPTH> RowTreeSum;
