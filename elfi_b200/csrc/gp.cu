@@ -52,6 +52,11 @@ struct GemmArgs {
     int64_t M, N, K;
     double alpha, beta;
     int mode;   // 0 full; 1 lower tiles only (SYRK-style); 2 K limited to col0 + BN (B lower-tri)
+    // mode 2 only: B is lower triangular with EXACT zeros above the diagonal and only its first
+    // n_valid rows matter (rows >= n_valid belong to the identity padding and meet zero columns of
+    // A).  When tri_skip is set a warp skips the DMMA steps that would only multiply those zeros:
+    // k > c for all 8 columns c of a sub-tile, and whole sub-tiles of columns >= n_valid.
+    int tri_skip; int64_t n_valid;
     // When set, C is not stored: the CTA of column tile bx writes, for each of its rows r,
     // rowsq[bx * ld_rowsq + r] = sum over the tile's columns of (A B^T)[r][c]^2 (alpha must be 1,
     // beta 0) -- the predictive variance needs |W k_i|^2, not W k_i.
@@ -105,6 +110,21 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     double* C = g.C + bz * g.strideC;
     int64_t Kend = g.K;
     if (g.mode == 2 && col0 + BN < Kend) Kend = col0 + BN;
+    // A warp's TN sub-tiles of 8 columns are INTERLEAVED across the tile (sub-tile j of warp
+    // column wn starts at column j * 8 * WARPS_N + wn * 8), not contiguous: with a triangular B
+    // the work of a sub-tile grows with its column, and the four warp columns sit on the four
+    // SM sub-partitions -- contiguous ownership would leave the skipped DMMA slots of three tensor
+    // pipes idle while the fourth works through the longest K range.
+    constexpr int CSTR = 8 * WARPS_N;
+    int klast[TN];          // last k at which sub-tile j still meets a non-zero of B
+    int klast_min = 0x7fffffff;
+    const bool tri = g.mode == 2 && g.tri_skip != 0;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int64_t c0 = col0 + j * CSTR + wn * 8;
+        klast[j] = !tri ? 0x7fffffff : (c0 >= g.n_valid ? -1 : int(c0 + 7));
+        klast_min = klast[j] < klast_min ? klast[j] : klast_min;
+    }
 
     double acc[TM][TN][2];
 #pragma unroll
@@ -149,18 +169,42 @@ gemm_nt_dmma_kernel(GemmArgs g) {
             load_stage(nxt, (kt + GM_STAGES - 1) * GM_BK);   // reuses the buffer of slab kt - 1
         }
         const double* as = As + size_t(cur) * BM * GM_LDS + size_t(wm * Cfg::WTM) * GM_LDS;
-        const double* bs = Bs + size_t(cur) * BN * GM_LDS + size_t(wn * Cfg::WTN) * GM_LDS;
+        const double* bs = Bs + size_t(cur) * BN * GM_LDS + size_t(wn * 8) * GM_LDS;
+        const int k0 = int(kt) * GM_BK;
+        if (k0 + GM_BK - 1 <= klast_min) {
 #pragma unroll
-        for (int kk = 0; kk < GM_BK; kk += 4) {
-            double af[TM], bf[TN];
+            for (int kk = 0; kk < GM_BK; kk += 4) {
+                double af[TM], bf[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) af[i] = as[(i * 8 + grp) * GM_LDS + kk + tig];
+                for (int i = 0; i < TM; ++i) af[i] = as[(i * 8 + grp) * GM_LDS + kk + tig];
 #pragma unroll
-            for (int j = 0; j < TN; ++j) bf[j] = bs[(j * 8 + grp) * GM_LDS + kk + tig];
+                for (int j = 0; j < TN; ++j) bf[j] = bs[(j * CSTR + grp) * GM_LDS + kk + tig];
 #pragma unroll
-            for (int i = 0; i < TM; ++i)
+                for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < TN; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        } else {
+            // the slabs that cross the diagonal of B (and the padded columns): per 4-wide k step,
+            // only the sub-tiles that still meet non-zeros (warp-uniform conditions)
+#pragma unroll
+            for (int kk = 0; kk < GM_BK; kk += 4) {
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) any = any || (k0 + kk <= klast[j]);
+                if (!any) continue;
+                double af[TM];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) af[i] = as[(i * 8 + grp) * GM_LDS + kk + tig];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    if (k0 + kk <= klast[j]) {
+                        const double bfj = bs[(j * CSTR + grp) * GM_LDS + kk + tig];
+#pragma unroll
+                        for (int i = 0; i < TM; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bfj);
+                    }
+                }
+            }
         }
         if (++cur == GM_STAGES) cur = 0;
     }
@@ -197,7 +241,7 @@ gemm_nt_dmma_kernel(GemmArgs g) {
         for (int j = 0; j < TN; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int64_t c = col0 + wn * Cfg::WTN + j * 8 + tig * 2 + e;
+                const int64_t c = col0 + j * CSTR + wn * 8 + tig * 2 + e;
                 if (c >= g.N) continue;
                 double v = g.alpha * acc[i][j][e];
                 if (g.beta != 0.0) v += g.beta * C[r * g.ldc + c];
@@ -846,6 +890,13 @@ int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, 
         g.C = nullptr; g.ldc = n_pad;          // V = K* W^T is consumed in the epilogue
         g.rowsq = rowsq; g.ld_rowsq = mc;
         g.M = rows; g.N = n_pad; g.K = n_pad; g.alpha = 1.0; g.beta = 0.0; g.mode = 2;
+        static const bool tri_skip = [] {
+            const char* v = getenv("ELFI_B200_GEMM_TRI_SKIP");
+            return !(v != nullptr && v[0] == '0');
+        }();
+        g.tri_skip = tri_skip ? 1 : 0;
+        g.n_valid = n;
+        if (tri_skip) g.K = (n + 3) & ~int64_t(3);   // k >= n: zero columns of K*, identity rows of W
         int rc = launch_gemm(g, 1, stream);
         if (rc) return rc;
         predict_rows_sq_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(
