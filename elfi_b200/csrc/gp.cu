@@ -84,7 +84,7 @@ struct GemmCfg {
     static constexpr size_t SMEM = size_t(GM_STAGES) * (BM + BN) * LDS * sizeof(double);
 };
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int BK>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int BK, bool TRI>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N)
 gemm_nt_dmma_kernel(GemmArgs g) {
     using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, BK>;
@@ -118,7 +118,7 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     constexpr int CSTR = 8 * WARPS_N;
     int klast[TN];          // last k at which sub-tile j still meets a non-zero of B
     int klast_min = 0x7fffffff;
-    const bool tri = g.mode == 2 && g.tri_skip != 0;
+    const bool tri = TRI && g.mode == 2;   // TRI instances are launched for tri_skip products only
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
         const int64_t c0 = col0 + j * CSTR + wn * 8;
@@ -171,7 +171,7 @@ gemm_nt_dmma_kernel(GemmArgs g) {
         const double* as = As + size_t(cur) * BM * GM_LDS + size_t(wm * Cfg::WTM) * GM_LDS;
         const double* bs = Bs + size_t(cur) * BN * GM_LDS + size_t(wn * 8) * GM_LDS;
         const int k0 = int(kt) * GM_BK;
-        if (k0 + GM_BK - 1 <= klast_min) {
+        if (!TRI || k0 + GM_BK - 1 <= klast_min) {
 #pragma unroll
             for (int kk = 0; kk < GM_BK; kk += 4) {
                 double af[TM], bf[TN];
@@ -184,7 +184,7 @@ gemm_nt_dmma_kernel(GemmArgs g) {
 #pragma unroll
                     for (int j = 0; j < TN; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
-        } else {
+        } else if constexpr (TRI) {
             // the slabs that cross the diagonal of B (and the padded columns): per 4-wide k step,
             // only the sub-tiles that still meet non-zeros (warp-uniform conditions)
 #pragma unroll
@@ -252,10 +252,10 @@ gemm_nt_dmma_kernel(GemmArgs g) {
     }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int BK>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int BK, bool TRI = false>
 static int launch_gemm_cfg(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
     using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, BK>;
-    auto kern = gemm_nt_dmma_kernel<BM, BN, WARPS_M, WARPS_N, BK>;
+    auto kern = gemm_nt_dmma_kernel<BM, BN, WARPS_M, WARPS_N, BK, TRI>;
     static bool attr_set = false;
     if (!attr_set) {
         ELFI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -283,6 +283,10 @@ static int launch_gemm(const GemmArgs& g, int64_t batch, cudaStream_t stream) {
         const char* v = getenv("ELFI_B200_GEMM_BK32");
         return !(v != nullptr && v[0] == '0');
     }();
+    if (g.mode == 2 && g.tri_skip) {   // the guarded k-steps exist in these two instances only
+        if (wide_slab) return launch_gemm_cfg<GM_BM, GM_BN, 2, 4, 32, true>(g, batch, stream);
+        return launch_gemm_cfg<GM_BM, GM_BN, 2, 4, 16, true>(g, batch, stream);
+    }
     if (wide_slab) return launch_gemm_cfg<GM_BM, GM_BN, 2, 4, 32>(g, batch, stream);
     return launch_gemm_cfg<GM_BM, GM_BN, 2, 4, 16>(g, batch, stream);
 }
