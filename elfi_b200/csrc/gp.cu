@@ -873,9 +873,18 @@ int elfi_b200_gp_predict_f64(elfi_b200_ctx* ctx, const double* Xq, int64_t ldq, 
         ELFI_CUDA_OK(cudaGetLastError());
         return ELFI_B200_OK;
     }
-    // query chunks: Ks (mc x n_pad) and V (mc x n_pad) live in scratch
-    int64_t mc = 8192;
-    if (mc > m) mc = ((m + 127) / 128) * 128;
+    // Query chunks: Ks (mc x n_pad) lives in scratch.  Every chunk boundary costs the tail wave of
+    // its GEMM plus the K* / epilogue kernels' launch gaps, so chunks are as large as gridDim.y of
+    // the K* kernel allows (32768 rows = 0.5 GB of scratch at n_pad = 2048, nothing on a 180 GB
+    // part) and equal in size (a short last chunk would be 1-2 ragged waves).  Round 2 ran 8192-row
+    // chunks; ELFI_B200_GP_PREDICT_CHUNK restores any other size.
+    static const int64_t mc_max = [] {
+        const char* v = getenv("ELFI_B200_GP_PREDICT_CHUNK");
+        const long c = v ? atol(v) : 32768;
+        return int64_t(c < 128 ? 128 : (c > 65408 ? 65408 : c));
+    }();
+    const int64_t nchunks = (m + mc_max - 1) / mc_max;
+    const int64_t mc = ((m + nchunks - 1) / nchunks + 127) / 128 * 128;
     // scratch: Ks (mc x n_pad), then the per-column-tile sums of squares (ntiles x mc)
     const int ntiles = int(n_pad / GM_BN);
     const size_t bytes = (size_t(mc) * n_pad + size_t(ntiles) * mc) * 8 + 256;

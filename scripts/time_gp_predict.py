@@ -44,7 +44,7 @@ def child(tag):
                 b.record()
                 torch.cuda.synchronize()
                 ft.append(a.elapsed_time(b) / 3)
-            print(json.dumps(dict(name='gp_fit_n2000', tri_skip=tag, ms_median=float(np.median(ft)),
+            print(json.dumps(dict(name='gp_fit_n2000', variant=tag, ms_median=float(np.median(ft)),
                                   ms_min=float(min(ft)))), flush=True)
         g1, g2 = np.meshgrid(np.linspace(-2, 2, 400), np.linspace(-1, 1, 250))
         grid_h = np.column_stack([g1.ravel(), g2.ravel()])
@@ -78,7 +78,9 @@ def child(tag):
         sol = np.linalg.solve(Ky, np.column_stack([ye, Ks.T]))
         mean_h = Ks @ sol[:, 0]
         var_h = h['kernel_var'] + h['bias_var'] - np.einsum('ij,ji->i', Ks, sol[:, 1:])
-        res.append(dict(name='gp_predict_lcbsc_m1e5_n{}'.format(n), tri_skip=tag, ms_median=ms,
+        res.append(dict(name='gp_predict_lcbsc_m1e5_n{}'.format(n), variant=tag,
+                        env={k: v for k, v in os.environ.items() if k.startswith('ELFI_B200_G')},
+                        ms_median=ms,
                         ms_min=float(min(ts)), TFLOPs=flops / ms / 1e9,
                         frac_dmma_peak=flops / ms / 1e9 / dmma, dmma_peak_tflops=dmma,
                         max_rel_err_mean=float(np.max(np.abs(mean[sub] - mean_h) /
@@ -92,13 +94,17 @@ if __name__ == '__main__':
         child(sys.argv[2])
     else:
         os.makedirs(OUT, exist_ok=True)
-        for flag in ('1', '0'):
-            env = dict(os.environ, ELFI_B200_GEMM_TRI_SKIP=flag)
-            subprocess.check_call([sys.executable, os.path.abspath(__file__), '--child', flag], env=env)
+        # tag -> environment of the variant; the first one is the default configuration
+        variants = {'1': {}, '0': {'ELFI_B200_GEMM_TRI_SKIP': '0'}}
+        if '--chunks' in sys.argv:
+            variants = {'1': {}, '0': {'ELFI_B200_GP_PREDICT_CHUNK': '8192'}}
+        for tag, extra in variants.items():
+            env = dict(os.environ, **extra)
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), '--child', tag], env=env)
         for n in (2000, 2048, 700):
             a = np.load(os.path.join(OUT, 'gp_predict_1_n{}.npy'.format(n)))
             b = np.load(os.path.join(OUT, 'gp_predict_0_n{}.npy'.format(n)))
-            print(json.dumps(dict(name='skip_vs_noskip_n{}'.format(n),
+            print(json.dumps(dict(name='variant_vs_default_n{}'.format(n), variants=variants,
                                   identical=bool(np.array_equal(a, b)),
                                   max_abs_diff=float(np.max(np.abs(a - b))))), flush=True)
             os.remove(os.path.join(OUT, 'gp_predict_1_n{}.npy'.format(n)))
