@@ -17,3 +17,4 @@ print('bolfi', {k: d['bolfi_config4'].get(k) for k in ('fit_ms','rank5_update_ms
 PY
 tail -3 gpurun_out/r2ac_bench.err
 timeout 300 python scripts/time_gp_predict.py --chunks > gpurun_out/r2ac_gp_predict_chunks.jsonl 2> gpurun_out/r2ac_gp_predict_chunks.err; cut -c1-400 gpurun_out/r2ac_gp_predict_chunks.jsonl; tail -3 gpurun_out/r2ac_gp_predict_chunks.err
+timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_nt_dmma_kernel<.*true>' -c 1 -f -o gpurun_out/r2ac_gemm_tri python scripts/prof_gp_predict_once.py > gpurun_out/r2ac_ncu_gemm.log 2>&1; tail -2 gpurun_out/r2ac_ncu_gemm.log
