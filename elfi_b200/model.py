@@ -239,6 +239,9 @@ class ElfiModel:
         data = self._observed.pop(updating_name, None)
         old_inputs = self._records[name].inputs
         del self._records[updating_name]
+        for other in self._records.values():      # nothing may keep pointing at the vanished name
+            if updating_name in other.inputs:
+                other.inputs = [p for p in other.inputs if p != updating_name]
         self._records[name] = incoming
         self._observed.pop(name, None)
         if data is not None:
@@ -373,7 +376,11 @@ class Plan:
                 out = step.op(*[values[src] for src in step.args], **kwargs)
             except Exception as exc:
                 note = "In executing node '{}': {}.".format(name, exc)
-                raise type(exc)(note).with_traceback(exc.__traceback__)
+                try:
+                    tagged = type(exc)(note)
+                except Exception:                 # exception types with their own signature
+                    tagged = RuntimeError(note)
+                raise tagged.with_traceback(exc.__traceback__) from exc
             if isinstance(out, AcceptedOutput):
                 extras[('accepted', name)] = out.accepted
                 out = out.value

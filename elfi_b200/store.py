@@ -55,6 +55,7 @@ class OutputPool:
         self.resident_limit = resident_limit
         self.batch_size = None
         self.seed = None
+        self._resident = 0      # running count of device_bytes(), exact after _recount()
 
     # ---- the inference this pool belongs to ----------------------------------------------------
     @property
@@ -87,7 +88,9 @@ class OutputPool:
         self.stores[node] = BatchStore() if store is None else store
 
     def remove_store(self, node):
-        return self.stores.pop(node)
+        store = self.stores.pop(node)
+        self._recount()
+        return store
 
     def _live_stores(self):
         return [s for s in self.stores.values() if s is not None]
@@ -110,17 +113,21 @@ class OutputPool:
                 continue
             if self.stores[node] is None:
                 self.stores[node] = BatchStore()
-            self.stores[node].setdefault(batch_index, value)
-        if self.resident_limit is not None:
+            if batch_index not in self.stores[node]:
+                self.stores[node][batch_index] = value
+                self._resident += _device_nbytes(value)
+        if self.resident_limit is not None and self._resident > self.resident_limit:
             self._enforce_limit()
 
     def remove_batch(self, batch_index):
         for store in self._live_stores():
             store.pop(batch_index, None)
+        self._recount()
 
     def clear(self):
         for store in self._live_stores():
             store.clear()
+        self._recount()
 
     def __len__(self):
         """Number of batches (of the fullest store)."""
@@ -137,24 +144,31 @@ class OutputPool:
 
     # ---- HBM residency ---------------------------------------------------------------------------
     def device_bytes(self):
-        """HBM held by the stored outputs."""
-        return sum(s.device_bytes() if hasattr(s, 'device_bytes')
-                   else sum(_device_nbytes(v) for v in s.values())
-                   for s in self._live_stores())
+        """HBM held by the stored outputs (counted afresh: stores may have been edited directly)."""
+        return self._recount()
+
+    def _recount(self):
+        self._resident = sum(s.device_bytes() if hasattr(s, 'device_bytes')
+                             else sum(_device_nbytes(v) for v in s.values())
+                             for s in self._live_stores())
+        return self._resident
 
     def _spillable(self):
         return [s for s in self._live_stores() if hasattr(s, 'spill')]
 
     def _enforce_limit(self):
-        """Oldest batches first, all nodes of a batch together, until under the limit."""
-        excess = self.device_bytes() - self.resident_limit
+        """Oldest batches first, all nodes of a batch together, until under the limit.  (The
+        running byte count makes the common case -- under the limit -- free of any scan.)"""
+        excess = self._recount() - self.resident_limit
         if excess <= 0:
             return
         stores = self._spillable()
         for b in sorted(set(b for s in stores for b in s.resident_batches())):
             for s in stores:
                 if b in s:
-                    excess -= s.spill(b)
+                    freed = s.spill(b)
+                    excess -= freed
+                    self._resident -= freed
             if excess <= 0:
                 return
 
@@ -168,3 +182,4 @@ class OutputPool:
                 for b in list(s):
                     if dev.is_device_array(s[b]):
                         s[b] = dev.to_host(s[b])
+        self._recount()

@@ -216,3 +216,34 @@ def test_result_containers():
     assert opt.x_min['t1'] == 0.5 and opt.n_sim == 5
     import copy
     assert copy.copy(s).threshold == 0.3
+
+
+def test_become_drops_dangling_inputs_and_errors_name_the_node():
+    """A node that vanishes in become() leaves no dangling parent names behind, and an exception
+    raised inside an operation is re-raised naming the node -- also for exception types whose
+    constructor does not take a single message."""
+    import elfi_b200 as elfi
+
+    class Picky(Exception):
+        def __init__(self, a, b):
+            super().__init__(a, b)
+
+    def boom(x):
+        raise Picky(1, 2)
+
+    m = elfi.ElfiModel()
+    elfi.Constant(1.0, model=m, name='c')
+    elfi.Operation(lambda c: c + 1, m['c'], name='a')
+    elfi.Operation(lambda c: c + 2, m['c'], name='b')
+    elfi.Operation(lambda a, b: a + b, m['a'], m['b'], name='s')
+    elfi.Operation(lambda b: b, m['b'], name='user_of_b')
+    assert m.generate(1, ['s'])['s'] == 5.0
+    m['a'].become(m['b'])                       # 'a' takes b's operation; 'b' disappears
+    assert not m.has_node('b') and m.get_parents('s') == ['a'] and m.get_parents('user_of_b') == []
+    assert m.generate(1, ['a'])['a'] == 3.0
+    elfi.Operation(boom, m['c'], name='bad')
+    with pytest.raises(RuntimeError, match="node 'bad'"):
+        m.generate(1, ['bad'])
+    elfi.Operation(lambda c: 1 / 0, m['c'], name='div')
+    with pytest.raises(ZeroDivisionError, match="node 'div'"):
+        m.generate(1, ['div'])
