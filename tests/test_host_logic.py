@@ -247,3 +247,41 @@ def test_become_drops_dangling_inputs_and_errors_name_the_node():
     elfi.Operation(lambda c: 1 / 0, m['c'], name='div')
     with pytest.raises(ZeroDivisionError, match="node 'div'"):
         m.generate(1, ['div'])
+
+
+def test_observed_side_must_be_deterministic_and_twins_follow_observable_parents():
+    """compile_plan: a discrepancy's observed twin may only depend on deterministic nodes
+    (elfi/compiler.py:83-104 raises the same way); an Operation between a simulator and a summary
+    is not observable, so the summary's twin would re-run it on simulated data -> rejected."""
+    import elfi_b200 as elfi
+    from elfi_b200 import model as em
+
+    def sim(p, batch_size=1, random_state=None):
+        return random_state.normal(p[:, None] if np.ndim(p) else p, 1.0, size=(batch_size, 4))
+
+    m = elfi.ElfiModel()
+    elfi.Prior('uniform', 0, 1, model=m, name='p')
+    elfi.Simulator(sim, m['p'], observed=np.ones((1, 4)), name='y')
+    elfi.Summary(lambda y: y.mean(axis=1), m['y'], name='s')
+    elfi.Discrepancy(lambda s, observed: np.abs(s - observed[0]), m['s'], name='d')
+    plan = em.compile_plan(m, ['d'])
+    assert plan.steps['_s_observed'].args == ['_y_observed']
+    assert plan.steps['_d_observed'].args == ['_s_observed']
+    # twins carry no per-batch inputs: the simulator's twin is the observed data itself
+    assert plan.steps['_y_observed'].kwargs == {} and plan.steps['y'].kwargs.keys() == \
+        {'batch_size', 'random_state'}
+    out = m.generate(5, ['d', 's'], seed=3)
+    assert out['d'].shape == (5,) and np.array_equal(out['d'], np.abs(out['s'] - 1.0))
+    assert np.array_equal(m['s'].observed, [1.0])
+    # a prior feeding a discrepancy directly: its observed side would be random
+    elfi.Discrepancy(lambda p, observed: p, m['p'], name='bad')
+    with pytest.raises(ValueError, match='deterministic'):
+        em.compile_plan(m, ['bad'])
+    m.remove_node('bad')
+    # uses_meta: the batch's meta dict reaches the operation
+    seen = {}
+    elfi.Operation(lambda s, meta=None: seen.update(meta) or s, m['s'], name='tap')
+    m['tap'].uses_meta = True
+    m.generate(2, ['tap'], seed=9)
+    assert seen['batch_index'] == 0 and seen['master_seed'] == 9 and seen['model_name'] == m.name
+    assert em.compile_plan(m, ['tap']).has_node('_meta') and not plan.has_node('_meta')
