@@ -134,7 +134,8 @@ class OutputPool:
         return max((len(s) for s in self._live_stores()), default=0)
 
     def __contains__(self, batch_index):
-        return batch_index < len(self)
+        """Does any store hold this batch?  (Ranks of a distributed run hold every W-th index.)"""
+        return any(batch_index in s for s in self._live_stores())
 
     def __getitem__(self, batch_index):
         return self.get_batch(batch_index)
