@@ -131,6 +131,27 @@ def _worker(rank, world, port, out_dir):
         assert np.array_equal(pa.weights, pb.weights)
         assert np.array_equal(pa.cov, pb.cov)
 
+    # a rank-local OutputPool in a distributed run: rank r stores the batches it ran (indices
+    # r, r + W, ...) and a second inference over the same pool reads them back -- same result,
+    # no simulation (the file-backed ArrayPool of round 1 could not do this and was removed)
+    calls = {'n': 0}
+    mp_ = ma2.get_model(seed_obs=4)
+    sim_op = mp_.record('MA2').op
+
+    def counting(*a, **k):
+        calls['n'] += 1
+        return sim_op(*a, **k)
+    mp_.record('MA2').op = counting
+    pool = elfi.OutputPool(['t1', 't2', 'MA2'])
+    with_pool = elfi.Rejection(mp_['d'], batch_size=1000, seed=123, pool=pool).sample(
+        100, quantile=0.01, bar=False)
+    assert np.array_equal(with_pool.discrepancies, gold['out_d'])
+    assert sorted(pool.get_store('MA2')) == list(range(rank, 10, world)) and calls['n'] == 5
+    assert (rank in pool) and ((1 - rank) not in pool) and len(pool) == 5
+    again_p = elfi.Rejection(mp_['d'], batch_size=1000, pool=pool).sample(100, quantile=0.01,
+                                                                          bar=False)
+    assert calls['n'] == 5 and np.array_equal(again_p.discrepancies, gold['out_d'])
+
     # all ranks hold identical results
     np.save(os.path.join(out_dir, 'rank{}.npy'.format(rank)),
             np.concatenate([res.discrepancies, smc.weights, smc.samples_array.ravel(), ad.weights,
